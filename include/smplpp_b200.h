@@ -1,0 +1,261 @@
+/* smplpp_b200 — C ABI of the B200-native (sm_100a) SMPL forward + MoSh/MoSh++ IK hot path.
+ *
+ * This is the drop-in boundary for the data-parallel path of mmurooka/SMPLpp.  The reference exposes the
+ * path as plain C++ classes in libsmplpp.so (no FFI, no plugin registry); every entry point
+ * below names the reference interface it replaces (file:line, relative to the reference tree).  Signatures
+ * use only plain pointers, sizes and opaque handles: no libtorch / CUDA runtime types.
+ *
+ * Conventions
+ *   - all arrays are dense, row-major, float32 unless stated; `_dev` pointers are device memory on the
+ *     current CUDA device, `_host` pointers are host memory;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); device entry points only enqueue
+ *     work on it and never synchronise;
+ *   - every function returns SMPLPP_OK (0) or a negative error code; smplpp_last_error() returns the
+ *     reference-style message ("<module> Error: <text>", src/toolbox/Exception.cpp:77-91) of the last
+ *     failure on the calling thread;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     SMPLPP_ERR_CUDA.
+ */
+#ifndef SMPLPP_B200_H
+#define SMPLPP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMPLPP_OK 0
+#define SMPLPP_ERR_INVALID (-1) /* bad argument / shape (the reference throws smpl_error) */
+#define SMPLPP_ERR_CUDA (-2)    /* CUDA runtime failure, or no device */
+#define SMPLPP_ERR_ALLOC (-3)
+
+/* shape constants of include/smplpp/definition/def.h:8-14 */
+#define SMPLPP_VERTEX_NUM 6890
+#define SMPLPP_FACE_NUM 13776
+#define SMPLPP_JOINT_NUM 24
+#define SMPLPP_SHAPE_DIM 10
+#define SMPLPP_POSE_DIM 207
+#define SMPLPP_LATENT_DIM 32
+#define SMPLPP_VPOSER_HIDDEN 512
+#define SMPLPP_VPOSER_JOINTS 21
+
+typedef struct smplpp_model smplpp_model_t;
+typedef struct smplpp_vposer smplpp_vposer_t;
+typedef struct smplpp_tasks smplpp_tasks_t;
+
+const char * smplpp_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches evidence) */
+uint64_t smplpp_launch_count(void);
+int smplpp_device_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Model (replaces SMPL::init, src/SMPL.cpp:560-643: the tensors loaded from the model JSON)
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct smplpp_model_desc
+{
+  int64_t vertex_num;               /* 6890 for SMPL; any V >= 1 is accepted (Tester KATs use V = 1, 5) */
+  int64_t face_num;                 /* 13776; may be 0 when no normals / IK tasks are needed */
+  const int32_t * face_indices;     /* (face_num, 3), 1-BASED vertex ids as stored (SMPL.cpp:520) */
+  const float * shape_blend_shapes; /* (V, 3, 10) */
+  const float * pose_blend_shapes;  /* (V, 3, 207) */
+  const float * vertices_template;  /* (V, 3) */
+  const float * joint_regressor;    /* (24, V) */
+  const int64_t * kinematic_tree;   /* (2, 24): row 0 parents (root: any value outside 0..23) */
+  const float * weights;            /* (V, 24) dense; rows need not sum to 1 (homogeneous divide kept) */
+} smplpp_model_desc;
+
+int smplpp_model_create(const smplpp_model_desc * desc_host, smplpp_model_t ** out);
+void smplpp_model_destroy(smplpp_model_t * model);
+int64_t smplpp_model_vertex_num(const smplpp_model_t * model);
+/* max non-zeros per row of `weights` found at create time (4 for SMPL) */
+int smplpp_model_max_influences(const smplpp_model_t * model);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Forward pass (replaces SMPL::launch, src/SMPL.cpp:671-737 = BlendShape::blend + JointRegression::regress +
+ * WorldTransformation::transform + LinearBlendSkinning::skinning, and the getters SMPL.cpp:386-516)
+ *
+ *   beta_dev   (B, 10) with row stride `beta_stride` floats; beta_stride == 0 shares one beta by all frames
+ *   theta_dev  (B, 25, 3): row 0 = root translation, rows 1..24 = axis-angle (SMPL.cpp:685-686, 726-727)
+ *   vertices   (B, V, 3)        SMPL::getVertex           (nullable)
+ *   joints     (B, 24, 3)       SMPL::getRestJoint        (nullable)
+ *   transforms (B, 24, 4, 4)    WorldTransformation::getTransformation (nullable)
+ *   rest_shape (B, V, 3)        SMPL::getRestShape        (nullable; forces the unfused path for that output)
+ *   workspace  smplpp_forward_workspace_bytes(B) bytes of device scratch owned by the caller
+ * ------------------------------------------------------------------------------------------------------- */
+size_t smplpp_forward_workspace_bytes(const smplpp_model_t * model, int64_t batch);
+
+int smplpp_forward(const smplpp_model_t * model, void * stream, int64_t batch, const float * beta_dev,
+                   int64_t beta_stride, const float * theta_dev, float * vertices_dev, float * joints_dev,
+                   float * transforms_dev, float * rest_shape_dev, void * workspace_dev, size_t workspace_bytes);
+
+/* Same call with HOST buffers: stages through pinned memory, copies in, runs, copies out, synchronises.
+ * This is the call a user of smplpp::SMPL::launch + getVertex makes; bench.py's `e2e` times it. */
+int smplpp_forward_host(const smplpp_model_t * model, int64_t batch, const float * beta_host, int64_t beta_stride,
+                        const float * theta_host, float * vertices_host, float * joints_host);
+
+/* Pipeline variant selection for smplpp_forward: 0 = auto, 1 = FFMA fused blend+skinning,
+ * 2 = tcgen05 3xTF32 fused blend+skinning, 3 = unfused (blend GEMM -> rest shape -> standalone skinning). */
+int smplpp_set_forward_variant(int variant);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * The four pipeline modules on caller-supplied tensors (any V), mirroring the setter/compute/getter triples
+ * of BlendShape.h:221-244, JointRegression.h:194-204, WorldTransformation.h:174-191,
+ * LinearBlendSkinning.h:175-198.  All pointers are device pointers.
+ * ------------------------------------------------------------------------------------------------------- */
+/* BlendShape::blend (src/BlendShape.cpp:620-647): theta (B,24,3) axis-angle */
+int smplpp_blend_shape(void * stream, int64_t batch, int64_t vertex_num, const float * beta, const float * theta,
+                       const float * shape_basis, const float * pose_basis, float * shape_blend_shape,
+                       float * pose_blend_shape, float * pose_rotation);
+/* JointRegression::regress (src/JointRegression.cpp:507-598) */
+int smplpp_joint_regression(void * stream, int64_t batch, int64_t vertex_num, const float * templ,
+                            const float * joint_regressor, const float * shape_blend_shape,
+                            const float * pose_blend_shape, float * rest_shape, float * joints);
+/* WorldTransformation::transform (src/WorldTransformation.cpp:421-468); kinematic_tree (2,24) int64 on device */
+int smplpp_world_transformation(void * stream, int64_t batch, const int64_t * kinematic_tree, const float * joints,
+                                const float * pose_rotation, float * transforms);
+/* LinearBlendSkinning::skinning (src/LinearBlendSkinning.cpp:445-483); root_pos (B,3) nullable.
+ * weights (V,24) dense.  This is the standalone HBM-bound skinning kernel (roofline row of SURVEY §8d). */
+int smplpp_linear_blend_skinning(void * stream, int64_t batch, int64_t vertex_num, const float * weights,
+                                 const float * rest_shape, const float * transforms, const float * root_pos,
+                                 float * vertices);
+/* Same kernel driven from a model handle (pre-packed sparse weights): rest_shape (B,V,3), transforms (B,24,4,4) */
+int smplpp_model_skinning(const smplpp_model_t * model, void * stream, int64_t batch, const float * rest_shape,
+                          const float * transforms, const float * root_pos, float * vertices);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Normals (replaces SMPL::calcNormal / calcVertexNormal, src/SMPL.cpp:518-535) — batched over frames.
+ *   face_normals   (B, n_faces, 3)  for the listed 0-based face rows
+ *   vertex_normals (B, n_verts, 3)  for the listed 0-based vertex ids
+ * ------------------------------------------------------------------------------------------------------- */
+int smplpp_normals(const smplpp_model_t * model, void * stream, int64_t batch, const float * vertices_dev,
+                   int64_t n_faces, const int64_t * face_idx_dev, float * face_normals_dev, int64_t n_verts,
+                   const int64_t * vert_idx_dev, float * vertex_normals_dev);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * VPoser decoder (replaces VPoserDecoderImpl, src/VPoser.cpp:143-238)
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct smplpp_vposer_desc
+{
+  const float * w0; /* decoder_net.0.weight (512, 32)  */
+  const float * b0; /* decoder_net.0.bias   (512)      */
+  const float * w3; /* decoder_net.3.weight (512, 512) */
+  const float * b3; /* decoder_net.3.bias   (512)      */
+  const float * w5; /* decoder_net.5.weight (126, 512) */
+  const float * b5; /* decoder_net.5.bias   (126)      */
+} smplpp_vposer_desc;
+
+int smplpp_vposer_create(const smplpp_vposer_desc * desc_host, smplpp_vposer_t ** out);
+void smplpp_vposer_destroy(smplpp_vposer_t * vposer);
+/* VPoserDecoderImpl::forward (VPoser.cpp:163-167): latent (B,32) -> axis_angle (B,21,3);
+ * jacobian (B,63,32) = d axis_angle / d latent (nullable; what autograd yields in the reference). */
+int smplpp_vposer_decode(const smplpp_vposer_t * vposer, void * stream, int64_t batch, const float * latent_dev,
+                         float * axis_angle_dev, float * jacobian_dev);
+/* convertRotMatToAxisAngle (VPoser.cpp:25-120): (n,3,3) -> (n,3) */
+int smplpp_rotmat_to_axis_angle(void * stream, int64_t n, const float * rotmat_dev, float * axis_angle_dev);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * IK tasks (replaces smplpp::IkTask, include/smplpp/IkTask.h:13-85, src/IkTask.cpp, and
+ * calcTriangleVertexWeights, include/smplpp/toolbox/GeometryUtils.h:42-52)
+ *
+ * A task set fixes the attachment faces of n markers (IkTask::faceIdx_, 0-based rows of face_indices);
+ * create() gathers the 1-ring topology needed by calcActualNormal and packs the blend-shape rows of those
+ * vertices so that the IK kernels never touch the full 17 MB pose basis.
+ * Per-frame task state lives in caller-owned device arrays (see smplpp_ik_step).
+ * ------------------------------------------------------------------------------------------------------- */
+int smplpp_tasks_create(const smplpp_model_t * model, int32_t n_tasks, const int64_t * face_idx_host,
+                        smplpp_tasks_t ** out);
+void smplpp_tasks_destroy(smplpp_tasks_t * tasks);
+int32_t smplpp_tasks_count(const smplpp_tasks_t * tasks);
+/* number of distinct mesh vertices the task set depends on (face corners + their 1-rings) */
+int32_t smplpp_tasks_vertex_count(const smplpp_tasks_t * tasks);
+
+/* calcTriangleVertexWeights on n (pos (n,3), triangle (n,3,3)) pairs -> weights (n,3) */
+int smplpp_triangle_vertex_weights(void * stream, int64_t n, const float * pos_dev, const float * triangles_dev,
+                                   float * weights_dev);
+
+typedef struct smplpp_ik_options
+{
+  int32_t enable_vposer;   /* node.cpp:316-322: state = [trans 3 | root 3 | latent 32 | hands 6] (44) else 75 */
+  int32_t optimize_beta;   /* node.cpp:652-656: per-frame beta columns (10) with |dbeta| <= delta_beta_limit */
+  int32_t enable_qp;       /* node.cpp:907: box-QP (phi / beta bounds); 0 = plain LLT (node.cpp:933-938) */
+  int32_t enable_phi;      /* 1: tasks with phi_limit > 0 get their 2 phi columns (node.cpp:716-733) */
+  int32_t skip_if_too_few; /* node.cpp:785: skip frames with fewer than n/2 valid markers (motion mode) */
+  int32_t update_state;    /* apply node.cpp:946-968 to theta / beta */
+  float normal_offset;     /* IkTask::normalOffset_ (0.015 in mocap modes, node.cpp:560) */
+  float normal_task_weight;/* IkTask::normalTaskWeight_ (0 in mocap modes, node.cpp:558) */
+  float phi_limit;         /* IkTask::phiLimit_ (node.cpp:695-700) */
+  float delta_theta_reg;   /* 1e-3 node.cpp:887 */
+  float delta_phi_reg;     /* 1e-1 node.cpp:888 */
+  float delta_beta_reg;    /* 1e-3 node.cpp:889 */
+  float delta_beta_limit;  /* 0.5  node.cpp:925 */
+  float vposer_latent_reg; /* 1e-5 node.cpp:897 */
+  float vposer_hand_reg;   /* 1e3  node.cpp:900 */
+  int32_t reserved[3];
+} smplpp_ik_options;
+
+void smplpp_ik_options_default(smplpp_ik_options * opt); /* the constants of node/node.cpp cited above */
+
+/* state dimension helpers: theta_dim = 75 or 44; dim = theta_dim + 2 n (phi) + (optimize_beta ? 10 : 0) */
+int32_t smplpp_ik_theta_dim(const smplpp_ik_options * opt);
+int32_t smplpp_ik_dim(const smplpp_ik_options * opt, int32_t n_tasks);
+
+/* IkTask::calcActualPos / calcActualNormal batched (src/IkTask.cpp:59-86) on an existing vertex buffer:
+ *   vertices (B,V,3), vertex_weights (B,n,3) -> positions (B,n,3) [+ normal_offset * normal], normals (B,n,3) */
+int smplpp_task_positions(const smplpp_model_t * model, const smplpp_tasks_t * tasks, void * stream, int64_t batch,
+                          const float * vertices_dev, const float * vertex_weights_dev, float normal_offset,
+                          float * positions_dev, float * normals_dev);
+
+/* One IK iteration for B independent frames (replaces node/node.cpp:753-968 per frame):
+ *   theta assembly (+VPoser) -> sparse forward on the task vertices -> tangents + re-weighting (:803-804) ->
+ *   residual e (:807-820) -> analytic Jacobian J (what the one-hot backward rows of :823-873 yield) ->
+ *   A = J'J + damping (+ prior), b = J'e in fp64 (:884-904) -> Cholesky / box-QP (:907-939) -> update (:946-968).
+ *
+ *   theta_state     (B, theta_dim)  in/out   g_theta
+ *   beta            (B, 10) stride beta_stride (0 = shared, read-only unless optimize_beta)   g_beta
+ *   vertex_weights  (B, n, 3)       in/out   IkTask::vertexWeights_
+ *   target_pos      (B, n, 3)                IkTask::targetPos_
+ *   target_normal   (B, n, 3)       nullable (default (0,0,1), IkTask.cpp:13-16)
+ *   pos_task_weight (B, n)          nullable (default 1; 0 marks a missing marker, node.cpp:682-683)
+ *   status          (B) int32       out: 0 ok, 1 skipped (too few markers), 2 numerical issue (LLT pivot <= 0
+ *                                        or non-finite residual), 3 QP iteration cap
+ *   e_out (B,4n) f32, jac_out (B,4n,dim) f32, a_out (B,dim,dim) f64, b_out (B,dim) f64, delta_out (B,dim) f64:
+ *   optional materialised intermediates (the "Jacobian getter" path; nullable)
+ *   workspace: smplpp_ik_workspace_bytes(...) bytes of device scratch
+ */
+size_t smplpp_ik_workspace_bytes(const smplpp_tasks_t * tasks, const smplpp_ik_options * opt, int64_t batch);
+
+int smplpp_ik_step(const smplpp_model_t * model, const smplpp_vposer_t * vposer, const smplpp_tasks_t * tasks,
+                   const smplpp_ik_options * opt, void * stream, int64_t batch, float * theta_state_dev,
+                   float * beta_dev, int64_t beta_stride, float * vertex_weights_dev, const float * target_pos_dev,
+                   const float * target_normal_dev, const float * pos_task_weight_dev, int32_t * status_dev,
+                   float * e_out_dev, float * jac_out_dev, double * a_out_dev, double * b_out_dev,
+                   double * delta_out_dev, void * workspace_dev, size_t workspace_bytes);
+
+/* Shared-beta stage (MoSh++ shape estimation over many frames).  Frames couple only through the
+ * 10 shape unknowns, so the step is split around ONE all-reduce of 111 doubles:
+ *   (1) smplpp_ik_shared_beta_reduce: per-frame normal equations with the beta columns, Schur complement
+ *       S_f = A_bb - A_bf A_ff^-1 A_fb, r_f = b_b - A_bf A_ff^-1 b_f, summed over the local frames into
+ *       reduced_dev = [S (10x10) | r (10) | sum ||e||^2 (1)]  (fp64);
+ *   (2) the caller all-reduces reduced_dev over ranks (NCCL sum; nothing to do on one GPU);
+ *   (3) smplpp_ik_shared_beta_apply: every rank solves the same 10-dim box QP (|dbeta| <= limit), back-
+ *       substitutes x_f = -A_ff^-1 (b_f + A_fb dbeta) and updates theta_state and the shared beta (10).
+ * The per-frame factors are kept in `workspace` between (1) and (3). */
+size_t smplpp_ik_shared_beta_workspace_bytes(const smplpp_tasks_t * tasks, const smplpp_ik_options * opt,
+                                             int64_t batch);
+int smplpp_ik_shared_beta_reduce(const smplpp_model_t * model, const smplpp_vposer_t * vposer,
+                                 const smplpp_tasks_t * tasks, const smplpp_ik_options * opt, void * stream,
+                                 int64_t batch, const float * theta_state_dev, const float * shared_beta_dev,
+                                 float * vertex_weights_dev, const float * target_pos_dev,
+                                 const float * pos_task_weight_dev, int32_t * status_dev, double * reduced_dev,
+                                 void * workspace_dev, size_t workspace_bytes);
+int smplpp_ik_shared_beta_apply(const smplpp_tasks_t * tasks, const smplpp_ik_options * opt, void * stream,
+                                int64_t batch, float * theta_state_dev, float * shared_beta_dev,
+                                const int32_t * status_dev, const double * reduced_dev, void * workspace_dev,
+                                size_t workspace_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMPLPP_B200_H */

@@ -1,0 +1,426 @@
+"""Host-side mirror of the reference's operator interface for the hot path, over the C-ABI library.
+
+Same class and method names, argument meaning and error behaviour as the reference:
+    smplpp::SMPL                 include/smplpp/SMPL.h:210-270        -> SMPL
+    smplpp::BlendShape           include/smplpp/BlendShape.h:221-244  -> BlendShape
+    smplpp::JointRegression      include/smplpp/JointRegression.h     -> JointRegression
+    smplpp::WorldTransformation  include/smplpp/WorldTransformation.h -> WorldTransformation
+    smplpp::LinearBlendSkinning  include/smplpp/LinearBlendSkinning.h -> LinearBlendSkinning
+Tensors are torch CUDA float32 tensors (torch is used for device memory and streams only; every computation
+is a call into smplpp_b200/libsmplpp_b200.so).  Shape violations raise SmplppError with the reference's
+message text (e.g. "BlendShape Error: Failed to set beta!", src/BlendShape.cpp:340).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import capi
+from .capi import SmplppError, check, lib
+
+JOINT_NUM = 24
+SHAPE_BASIS_DIM = 10
+POSE_BASIS_DIM = 207
+FACE_INDEX_NUM = 13776
+LATENT_DIM = 32
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _dev_f32(x, device) -> torch.Tensor:
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=torch.float32).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32), device=device)
+
+
+def _np_f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _require_cuda(device: torch.device) -> None:
+    if device.type != "cuda" or not torch.cuda.is_available():
+        raise SmplppError("SMPL Error: Failed to fetch device index! (smplpp_b200 needs a CUDA device; "
+                          "there is no CPU fallback)")
+
+
+class SMPL:
+    """smplpp::SMPL (src/SMPL.cpp).  `launch` runs K1 (pose features + chain) and K2 (fused blend + skinning)."""
+
+    def __init__(self, params=None, device="cuda:0"):
+        self.m__device = torch.device(device)
+        self.m__modelPath = None
+        self._h = None
+        self._params = params
+        self._beta = self._theta = None
+        self._vertices = self._joints = self._rest = self._transforms = None
+        self._ws = None
+        if params is not None:
+            self.init()
+
+    # -- setters / getters of SMPL.h:250-264 --
+    def setDevice(self, device):
+        device = torch.device(device)
+        if device.index is None:
+            raise SmplppError("SMPL Error: Failed to fetch device index!")  # SMPL.cpp:299
+        self.m__device = device
+
+    def getDevice(self):
+        return self.m__device
+
+    def setModelPath(self, path: str):
+        import os
+        if not os.path.exists(path):
+            raise SmplppError("SMPL Error: Failed to initialize model path!")  # SMPL.cpp:337
+        self.m__modelPath = path
+
+    def init(self):
+        """SMPL::init (src/SMPL.cpp:560-643): load the model arrays and pack them on the device."""
+        _require_cuda(self.m__device)
+        p = self._params
+        if p is None:
+            if self.m__modelPath is None:
+                raise SmplppError("SMPL Error: Cannot initialize a SMPL model!")  # SMPL.cpp:616
+            p = load_model_file(self.m__modelPath)
+            self._params = p
+        arrs = dict(
+            face_indices=np.ascontiguousarray(p.face_indices, dtype=np.int32),
+            shape=_np_f32(p.shape_blend_shapes), pose=_np_f32(p.pose_blend_shapes),
+            templ=_np_f32(p.vertices_template), jreg=_np_f32(p.joint_regressor),
+            tree=np.ascontiguousarray(p.kinematic_tree, dtype=np.int64), weights=_np_f32(p.weights))
+        V = arrs["templ"].shape[0]
+        if arrs["shape"].shape != (V, 3, SHAPE_BASIS_DIM):
+            raise SmplppError("SMPL Error: Shape parameter dimensions are invalid: %d != %d"
+                              % (arrs["shape"].shape[-1], SHAPE_BASIS_DIM))  # SMPL.cpp:581
+        if arrs["pose"].shape != (V, 3, POSE_BASIS_DIM):
+            raise SmplppError("SMPL Error: Pose parameter dimensions are invalid: %d != %d"
+                              % (arrs["pose"].shape[-1], POSE_BASIS_DIM))  # SMPL.cpp:588
+        desc = capi.ModelDesc(
+            V, arrs["face_indices"].shape[0], arrs["face_indices"].ctypes.data_as(capi.c_i32p),
+            arrs["shape"].ctypes.data_as(capi.c_f32p), arrs["pose"].ctypes.data_as(capi.c_f32p),
+            arrs["templ"].ctypes.data_as(capi.c_f32p), arrs["jreg"].ctypes.data_as(capi.c_f32p),
+            arrs["tree"].ctypes.data_as(capi.c_i64p), arrs["weights"].ctypes.data_as(capi.c_f32p))
+        h = C.c_void_p()
+        with torch.cuda.device(self.m__device):
+            check(lib().smplpp_model_create(C.byref(desc), C.byref(h)))
+        self._h = h
+        self.vertex_num = V
+        self._faces_host = arrs["face_indices"]
+        self._face_dev = None
+        self._adjacent = None
+
+    def __del__(self):
+        if getattr(self, "_h", None) is not None and capi._lib is not None:
+            capi._lib.smplpp_model_destroy(self._h)
+            self._h = None
+
+    @property
+    def handle(self):
+        if self._h is None:
+            raise SmplppError("SMPL Error: Cannot launch a SMPL model!")
+        return self._h
+
+    def _workspace(self, batch: int) -> torch.Tensor:
+        need = lib().smplpp_forward_workspace_bytes(self.handle, C.c_int64(batch))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.m__device)
+        return self._ws
+
+    def launch(self, beta, theta, want_transforms: bool = False):
+        """SMPL::launch (src/SMPL.cpp:671-737).  beta (N,10) [or (10,)/(1,10) shared by all frames],
+        theta (N,25,3): row 0 root translation, rows 1..24 axis-angle."""
+        theta = _dev_f32(theta, self.m__device)
+        beta = _dev_f32(beta, self.m__device)
+        if theta.dim() != 3 or theta.shape[1:] != (JOINT_NUM + 1, 3):
+            raise SmplppError("SMPL Error: Cannot launch a SMPL model!")  # SMPL.cpp:676
+        n = theta.shape[0]
+        if beta.dim() == 1:
+            beta = beta.view(1, -1)
+        if beta.shape[-1] != SHAPE_BASIS_DIM or beta.shape[0] not in (1, n):
+            raise SmplppError("BlendShape Error: Failed to set beta!")  # BlendShape.cpp:340
+        stride = 0 if (beta.shape[0] == 1 and n > 1) else SHAPE_BASIS_DIM
+        self._beta, self._theta, self._beta_stride = beta, theta, stride
+        V = self.vertex_num
+        self._vertices = torch.empty((n, V, 3), dtype=torch.float32, device=self.m__device)
+        self._joints = torch.empty((n, JOINT_NUM, 3), dtype=torch.float32, device=self.m__device)
+        self._transforms = (torch.empty((n, JOINT_NUM, 4, 4), dtype=torch.float32, device=self.m__device)
+                            if want_transforms else None)
+        self._rest = None
+        ws = self._workspace(n)
+        with torch.cuda.device(self.m__device):
+            check(lib().smplpp_forward(self.handle, _stream(self.m__device), C.c_int64(n), _ptr(beta),
+                                       C.c_int64(stride), _ptr(theta), _ptr(self._vertices), _ptr(self._joints),
+                                       _ptr(self._transforms), None, _ptr(ws), C.c_size_t(ws.numel())))
+
+    def launch_host(self, beta: np.ndarray, theta: np.ndarray, want_joints: bool = True):
+        """Host-buffer variant of launch + getVertex (+getRestJoint): numpy in, numpy out, copies included."""
+        beta, theta = _np_f32(beta), _np_f32(theta)
+        n = theta.shape[0]
+        if beta.ndim == 1:
+            beta = beta.reshape(1, -1)
+        stride = 0 if (beta.shape[0] == 1 and n > 1) else SHAPE_BASIS_DIM
+        verts = np.empty((n, self.vertex_num, 3), np.float32)
+        joints = np.empty((n, JOINT_NUM, 3), np.float32) if want_joints else None
+        with torch.cuda.device(self.m__device):
+            check(lib().smplpp_forward_host(self.handle, C.c_int64(n), beta.ctypes.data_as(capi.c_f32p),
+                                            C.c_int64(stride), theta.ctypes.data_as(capi.c_f32p),
+                                            verts.ctypes.data_as(capi.c_f32p),
+                                            joints.ctypes.data_as(capi.c_f32p) if want_joints else None))
+        return verts, joints
+
+    def _launched(self, what):
+        if self._vertices is None:
+            raise SmplppError(what)
+
+    def getVertex(self) -> torch.Tensor:
+        self._launched("LinearBlendSknning Error: Failed to get vertices of new pose!")  # LinearBlendSkinning.cpp:409
+        return self._vertices.clone()
+
+    def getVertexRaw(self, idx):
+        """Batch element 0 only, like the reference (LinearBlendSkinning.cpp:419-427)."""
+        self._launched("LinearBlendSknning Error: Failed to get vertices of new pose!")
+        return self._vertices[0, idx]
+
+    def getRestJoint(self) -> torch.Tensor:
+        self._launched("JointRegression Error: Failed to get joints!")
+        return self._joints.clone()
+
+    def getRestShape(self) -> torch.Tensor:
+        """SMPL::getRestShape: T + S beta + P c (JointRegression.cpp:557); computed on demand (unfused pass)."""
+        self._launched("JointRegression Error: Failed to get rest shape!")
+        if self._rest is None:
+            n = self._theta.shape[0]
+            self._rest = torch.empty((n, self.vertex_num, 3), dtype=torch.float32, device=self.m__device)
+            ws = self._workspace(n)
+            with torch.cuda.device(self.m__device):
+                check(lib().smplpp_forward(self.handle, _stream(self.m__device), C.c_int64(n), _ptr(self._beta),
+                                           C.c_int64(self._beta_stride), _ptr(self._theta), None, None, None,
+                                           _ptr(self._rest), _ptr(ws), C.c_size_t(ws.numel())))
+        return self._rest.clone()
+
+    def getTransformation(self) -> torch.Tensor:
+        """WorldTransformation::getTransformation (N,24,4,4) of the last launch(want_transforms=True)."""
+        if self._transforms is None:
+            raise SmplppError("WorldTransformation Error: Failed to get transformations!")
+        return self._transforms.clone()
+
+    def getFaceIndex(self) -> torch.Tensor:
+        if self._faces_host.shape != (FACE_INDEX_NUM, 3) and self.vertex_num == 6890:
+            raise SmplppError("SMPL Error: Failed to get face indices!")  # SMPL.cpp:404
+        return torch.as_tensor(self._faces_host.copy(), device=self.m__device)
+
+    def getFaceIndexRaw(self, idx: int) -> torch.Tensor:
+        return torch.as_tensor(self._faces_host[idx])
+
+    def getAdjacentFaces(self, idx: int) -> dict:
+        """SMPL::getAdjacentFaces (SMPL.cpp:619-640): {faceIdx: 1/deg}."""
+        if self._adjacent is None:
+            adj = [[] for _ in range(self.vertex_num)]
+            for f, tri in enumerate((self._faces_host.astype(np.int64) - 1).tolist()):
+                for v in tri:
+                    if f not in adj[v]:
+                        adj[v].append(f)
+            self._adjacent = adj
+        faces = self._adjacent[idx]
+        return {f: np.float32(1.0) / np.float32(len(faces)) for f in faces}
+
+    def normals(self, face_idx=None, vert_idx=None):
+        """Batched SMPL::calcNormal / calcVertexNormal (SMPL.cpp:518-535) for all launched frames."""
+        self._launched("LinearBlendSknning Error: Failed to get vertices of new pose!")
+        n = self._vertices.shape[0]
+        dev = self.m__device
+        fi = torch.as_tensor(np.asarray([] if face_idx is None else face_idx, dtype=np.int64), device=dev)
+        vi = torch.as_tensor(np.asarray([] if vert_idx is None else vert_idx, dtype=np.int64), device=dev)
+        fn = torch.empty((n, fi.numel(), 3), dtype=torch.float32, device=dev)
+        vn = torch.empty((n, vi.numel(), 3), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().smplpp_normals(self.handle, _stream(dev), C.c_int64(n), _ptr(self._vertices),
+                                       C.c_int64(fi.numel()), _ptr(fi), _ptr(fn), C.c_int64(vi.numel()), _ptr(vi),
+                                       _ptr(vn)))
+        return fn, vn
+
+    def calcNormal(self, faceIdx: int) -> torch.Tensor:
+        return self.normals(face_idx=[faceIdx])[0][0, 0]
+
+    def calcVertexNormal(self, idx: int) -> torch.Tensor:
+        return self.normals(vert_idx=[idx])[1][0, 0]
+
+
+def load_model_file(path: str):
+    """Model arrays from the reference's JSON (keys of src/SMPL.cpp:573-611) or the .npz twin written by
+    scripts/preprocess.py:109-121."""
+    from .synth import SmplParams
+    if path.endswith(".npz"):
+        z = np.load(path)
+        get = lambda k: z[k]  # noqa: E731
+    else:
+        with open(path) as f:
+            j = json.load(f)
+        get = lambda k: np.asarray(j[k])  # noqa: E731
+    return SmplParams(
+        face_indices=np.asarray(get("face_indices"), dtype=np.int32),
+        shape_blend_shapes=np.asarray(get("shape_blend_shapes"), dtype=np.float32),
+        pose_blend_shapes=np.asarray(get("pose_blend_shapes"), dtype=np.float32),
+        vertices_template=np.asarray(get("vertices_template"), dtype=np.float32),
+        joint_regressor=np.asarray(get("joint_regressor"), dtype=np.float32),
+        kinematic_tree=np.asarray(get("kinematic_tree"), dtype=np.int64),
+        weights=np.asarray(get("weights"), dtype=np.float32))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the four pipeline modules (setter -> compute -> getter, like the reference)
+# ----------------------------------------------------------------------------------------------------------------
+
+class _Module:
+    def __init__(self, device="cuda:0"):
+        self.m__device = torch.device(device)
+
+    def setDevice(self, device):
+        self.m__device = torch.device(device)
+
+    def _set(self, name, value, shape_tail, err):
+        t = _dev_f32(value, self.m__device)
+        if tuple(t.shape[-len(shape_tail):]) != tuple(shape_tail):
+            raise SmplppError(err)
+        setattr(self, name, t)
+
+
+class BlendShape(_Module):
+    """smplpp::BlendShape (src/BlendShape.cpp)."""
+
+    def setBeta(self, beta):
+        self._set("_beta", beta, (SHAPE_BASIS_DIM,), "BlendShape Error: Failed to set beta!")
+
+    def setTheta(self, theta):
+        self._set("_theta", theta, (JOINT_NUM, 3), "BlendShape Error: Failed to set theta!")
+
+    def setShapeBlendBasis(self, basis):
+        self._set("_shape_basis", basis, (3, SHAPE_BASIS_DIM), "BlendShape Error: Failed to set shape blend basis!")
+
+    def setPoseBlendBasis(self, basis):
+        self._set("_pose_basis", basis, (3, POSE_BASIS_DIM), "BlendShape Error: Failed to set pose blend basis!")
+
+    def blend(self):
+        _require_cuda(self.m__device)
+        n, v = self._theta.shape[0], self._pose_basis.shape[0]
+        dev = self.m__device
+        self._shape_bs = torch.empty((n, v, 3), dtype=torch.float32, device=dev)
+        self._pose_bs = torch.empty((n, v, 3), dtype=torch.float32, device=dev)
+        self._pose_rot = torch.empty((n, JOINT_NUM, 3, 3), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().smplpp_blend_shape(_stream(dev), C.c_int64(n), C.c_int64(v), _ptr(self._beta), _ptr(self._theta),
+                                           _ptr(self._shape_basis), _ptr(self._pose_basis), _ptr(self._shape_bs),
+                                           _ptr(self._pose_bs), _ptr(self._pose_rot)))
+
+    def getShapeBlendShape(self):
+        return self._shape_bs.clone()
+
+    def getPoseBlendShape(self):
+        return self._pose_bs.clone()
+
+    def getPoseRotation(self):
+        return self._pose_rot.clone()
+
+
+class JointRegression(_Module):
+    """smplpp::JointRegression (src/JointRegression.cpp)."""
+
+    def setTemplateRestShape(self, t):
+        self._set("_templ", t, (3,), "JointRegression Error: Failed to set template shape!")
+
+    def setJointRegressor(self, r):
+        t = _dev_f32(r, self.m__device)
+        if t.shape[0] != JOINT_NUM:
+            raise SmplppError("JointRegression Error: Failed to set joint regressor!")
+        self._jreg = t
+
+    def setShapeBlendShape(self, s):
+        self._set("_shape_bs", s, (3,), "JointRegression Error: Failed to set shape blend shape!")
+
+    def setPoseBlendShape(self, p):
+        self._set("_pose_bs", p, (3,), "JointRegression Error: Failed to set pose blend shape!")
+
+    def regress(self):
+        _require_cuda(self.m__device)
+        n, v = self._shape_bs.shape[0], self._templ.shape[0]
+        dev = self.m__device
+        self._rest = torch.empty((n, v, 3), dtype=torch.float32, device=dev)
+        self._joints = torch.empty((n, JOINT_NUM, 3), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().smplpp_joint_regression(_stream(dev), C.c_int64(n), C.c_int64(v), _ptr(self._templ),
+                                                _ptr(self._jreg), _ptr(self._shape_bs), _ptr(self._pose_bs),
+                                                _ptr(self._rest), _ptr(self._joints)))
+
+    def getRestShape(self):
+        return self._rest.clone()
+
+    def getJoint(self):
+        return self._joints.clone()
+
+
+class WorldTransformation(_Module):
+    """smplpp::WorldTransformation (src/WorldTransformation.cpp)."""
+
+    def setKinematicTree(self, tree):
+        t = torch.as_tensor(np.asarray(tree, dtype=np.int64) if not isinstance(tree, torch.Tensor) else tree)
+        if tuple(t.shape) != (2, JOINT_NUM):
+            raise SmplppError("WorldTransformation Error: Failed to set kinematic tree!")
+        self._tree = t.to(device=self.m__device, dtype=torch.int64).contiguous()
+
+    def setJoint(self, j):
+        self._set("_joints", j, (JOINT_NUM, 3), "WorldTransformation Error: Failed to set joints!")
+
+    def setPoseRotation(self, r):
+        self._set("_rot", r, (JOINT_NUM, 3, 3), "WorldTransformation Error: Failed to set pose rotations!")
+
+    def transform(self):
+        _require_cuda(self.m__device)
+        n = self._joints.shape[0]
+        dev = self.m__device
+        self._xf = torch.empty((n, JOINT_NUM, 4, 4), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().smplpp_world_transformation(_stream(dev), C.c_int64(n), _ptr(self._tree), _ptr(self._joints),
+                                                    _ptr(self._rot), _ptr(self._xf)))
+
+    def getTransformation(self):
+        return self._xf.clone()
+
+
+class LinearBlendSkinning(_Module):
+    """smplpp::LinearBlendSkinning (src/LinearBlendSkinning.cpp)."""
+
+    _root = None
+
+    def setWeight(self, w):
+        self._set("_weights", w, (JOINT_NUM,), "LinearBlendSkinning Error: Failed to set weights!")
+
+    def setRestShape(self, r):
+        self._set("_rest", r, (3,), "LinearBlendSkinning Error: Failed to set rest shape!")
+
+    def setTransformation(self, t):
+        self._set("_xf", t, (JOINT_NUM, 4, 4), "LinearBlendSkinning Error: Failed to set transformations!")
+
+    def setRootPos(self, p):
+        self._root = _dev_f32(p, self.m__device).reshape(-1, 3).contiguous()
+
+    def skinning(self):
+        _require_cuda(self.m__device)
+        n, v = self._rest.shape[0], self._weights.shape[0]
+        dev = self.m__device
+        self._verts = torch.empty((n, v, 3), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().smplpp_linear_blend_skinning(_stream(dev), C.c_int64(n), C.c_int64(v), _ptr(self._weights),
+                                                     _ptr(self._rest), _ptr(self._xf), _ptr(self._root),
+                                                     _ptr(self._verts)))
+
+    def getVertex(self):
+        return self._verts.clone()

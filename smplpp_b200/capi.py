@@ -1,0 +1,81 @@
+"""ctypes loader for the C-ABI library (include/smplpp_b200.h).  Fails loudly when the library is missing:
+there is no CPU fallback and no alternate implementation."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsmplpp_b200.so")
+
+c_f32p = C.POINTER(C.c_float)
+c_f64p = C.POINTER(C.c_double)
+c_i64p = C.POINTER(C.c_int64)
+c_i32p = C.POINTER(C.c_int32)
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [
+        ("vertex_num", C.c_int64), ("face_num", C.c_int64), ("face_indices", c_i32p),
+        ("shape_blend_shapes", c_f32p), ("pose_blend_shapes", c_f32p), ("vertices_template", c_f32p),
+        ("joint_regressor", c_f32p), ("kinematic_tree", c_i64p), ("weights", c_f32p),
+    ]
+
+
+class VposerDesc(C.Structure):
+    _fields_ = [("w0", c_f32p), ("b0", c_f32p), ("w3", c_f32p), ("b3", c_f32p), ("w5", c_f32p), ("b5", c_f32p)]
+
+
+class IkOptions(C.Structure):
+    _fields_ = [
+        ("enable_vposer", C.c_int32), ("optimize_beta", C.c_int32), ("enable_qp", C.c_int32),
+        ("enable_phi", C.c_int32), ("skip_if_too_few", C.c_int32), ("update_state", C.c_int32),
+        ("normal_offset", C.c_float), ("normal_task_weight", C.c_float), ("phi_limit", C.c_float),
+        ("delta_theta_reg", C.c_float), ("delta_phi_reg", C.c_float), ("delta_beta_reg", C.c_float),
+        ("delta_beta_limit", C.c_float), ("vposer_latent_reg", C.c_float), ("vposer_hand_reg", C.c_float),
+        ("reserved", C.c_int32 * 3),
+    ]
+
+
+# every symbol declared in include/smplpp_b200.h (tests check that the .so exports all of them)
+EXPORTS = [
+    "smplpp_last_error", "smplpp_launch_count", "smplpp_device_count",
+    "smplpp_model_create", "smplpp_model_destroy", "smplpp_model_vertex_num", "smplpp_model_max_influences",
+    "smplpp_forward_workspace_bytes", "smplpp_forward", "smplpp_forward_host", "smplpp_set_forward_variant",
+    "smplpp_blend_shape", "smplpp_joint_regression", "smplpp_world_transformation", "smplpp_linear_blend_skinning",
+    "smplpp_model_skinning", "smplpp_normals",
+    "smplpp_vposer_create", "smplpp_vposer_destroy", "smplpp_vposer_decode", "smplpp_rotmat_to_axis_angle",
+    "smplpp_tasks_create", "smplpp_tasks_destroy", "smplpp_tasks_count", "smplpp_tasks_vertex_count",
+    "smplpp_triangle_vertex_weights", "smplpp_ik_options_default", "smplpp_ik_theta_dim", "smplpp_ik_dim",
+    "smplpp_task_positions", "smplpp_ik_workspace_bytes", "smplpp_ik_step",
+    "smplpp_ik_shared_beta_workspace_bytes", "smplpp_ik_shared_beta_reduce", "smplpp_ik_shared_beta_apply",
+]
+
+_lib = None
+
+
+class SmplppError(RuntimeError):
+    """Counterpart of smplpp::Exception (src/toolbox/Exception.h:122): message "<module> Error: <text>"."""
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SmplppError(
+                "smplpp_b200: CUDA extension %s is missing — run `python -m smplpp_b200.build` "
+                "(there is no CPU fallback)" % LIB_PATH)
+        _lib = C.CDLL(LIB_PATH)
+        _lib.smplpp_last_error.restype = C.c_char_p
+        _lib.smplpp_launch_count.restype = C.c_uint64
+        _lib.smplpp_model_vertex_num.restype = C.c_int64
+        for name in ("smplpp_forward_workspace_bytes", "smplpp_ik_workspace_bytes",
+                     "smplpp_ik_shared_beta_workspace_bytes"):
+            if hasattr(_lib, name):
+                getattr(_lib, name).restype = C.c_size_t
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise SmplppError(lib().smplpp_last_error().decode() or ("smplpp_b200 error %d" % rc))

@@ -1,0 +1,105 @@
+// Shared declarations of the smplpp_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/smplpp_b200.h"
+
+namespace sb
+{
+constexpr int kJoints = SMPLPP_JOINT_NUM;
+constexpr int kShapeDim = SMPLPP_SHAPE_DIM;
+constexpr int kPoseDim = SMPLPP_POSE_DIM;
+// K of the fused blend contraction: 207 pose features | 10 betas | 1 (template) | zero padding
+constexpr int kBlendK = 224;
+constexpr int kBlendKUsed = kPoseDim + kShapeDim + 1; // 218
+constexpr int kXformFloats = 12;                      // 3x4 row-major [R | t] per joint
+
+extern thread_local std::string g_last_error;
+extern std::atomic<uint64_t> g_launch_count;
+
+int fail(int code, const char * module, const std::string & msg);
+
+#define SB_CUDA(expr)                                                                                   \
+  do                                                                                                    \
+  {                                                                                                     \
+    cudaError_t err__ = (expr);                                                                         \
+    if(err__ != cudaSuccess)                                                                            \
+      return ::sb::fail(SMPLPP_ERR_CUDA, "CUDA", std::string(#expr) + ": " + cudaGetErrorString(err__)); \
+  } while(0)
+
+#define SB_LAUNCHED()                                                              \
+  do                                                                               \
+  {                                                                                \
+    ::sb::g_launch_count.fetch_add(1, std::memory_order_relaxed);                  \
+    cudaError_t err__ = cudaPeekAtLastError();                                     \
+    if(err__ != cudaSuccess)                                                       \
+      return ::sb::fail(SMPLPP_ERR_CUDA, "CUDA", std::string("kernel launch: ") + cudaGetErrorString(err__)); \
+  } while(0)
+
+inline cudaStream_t as_stream(void * s)
+{
+  return static_cast<cudaStream_t>(s);
+}
+
+template<typename T>
+inline T * align_up_ptr(void * p, size_t a = 256)
+{
+  return reinterpret_cast<T *>((reinterpret_cast<uintptr_t>(p) + a - 1) / a * a);
+}
+
+inline size_t align_up(size_t n, size_t a = 256)
+{
+  return (n + a - 1) / a * a;
+}
+
+// Device-resident constants of one model.  Immutable after create => shareable across streams/threads.
+struct ModelDev
+{
+  int V = 0;      // vertices
+  int Vpad = 0;   // V rounded up to the blend tile (64 vertices)
+  int F = 0;      // faces
+  int kmax = 0;   // max skinning influences per vertex
+  // fused blend basis, K-major: row (3 v + k) holds [pose basis 207 | shape basis 10 | template | 0 x 6]
+  float * basis = nullptr; // (3 Vpad, 224)
+  // skinning weights, ELL, structure-of-arrays over influences: [kmax][Vpad]
+  uint8_t * lbs_joint = nullptr;
+  float * lbs_weight = nullptr;
+  float * lbs_wsum = nullptr; // (Vpad) sum_j W[v,j]  (homogeneous coordinate h[3])
+  // joints = J_T + J_S beta  (Jreg (T + S beta), JointRegression.cpp:588-590)
+  float * joint_template = nullptr; // (24, 3)
+  float * joint_shape = nullptr;    // (24, 3, 10)
+  int parent[kJoints];              // -1 for the root
+  int depth[kJoints];
+  int max_depth = 0;
+  // topology
+  int32_t * faces = nullptr;     // (F, 3) 0-based
+  int32_t * adj_offset = nullptr; // (V + 1) CSR: vertex -> adjacent faces
+  int32_t * adj_faces = nullptr;
+  // originals kept for the task builder and the generic module kernels
+  float * weights_dense = nullptr; // (V, 24)
+};
+} // namespace sb
+
+struct smplpp_model
+{
+  sb::ModelDev d;
+  // host copies used by smplpp_tasks_create
+  std::vector<int32_t> h_faces;      // 0-based
+  std::vector<int32_t> h_adj_offset; // CSR
+  std::vector<int32_t> h_adj_faces;
+  std::vector<float> h_basis;        // (3V, 224) same row layout as d.basis (unpadded V)
+  std::vector<float> h_weights;      // (V, 24)
+  std::vector<float> h_joint_template, h_joint_shape;
+  // pinned staging for smplpp_forward_host
+  void * pinned = nullptr;
+  size_t pinned_bytes = 0;
+  void * dev_scratch = nullptr;
+  size_t dev_scratch_bytes = 0;
+  cudaStream_t host_stream = nullptr;
+};

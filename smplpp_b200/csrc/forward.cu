@@ -1,0 +1,981 @@
+// SMPL forward pass on sm_100a: pose features + kinematic chain (K1), fused blend-shape contraction +
+// linear blend skinning (K2, FFMA variant), standalone skinning (K3) and the generic per-module kernels.
+//
+// Reference semantics (file:line in the reference tree):
+//   rodrigues           src/BlendShape.cpp:803-844     (a = ||theta + 1e-8||, u = theta / a)
+//   pose feature        src/BlendShape.cpp:865-928     (vec(R_1..R_23) - vec(I))
+//   pose / shape blend  src/BlendShape.cpp:764, 670-683
+//   rest shape, joints  src/JointRegression.cpp:551-598 (joints exclude the pose blend)
+//   kinematic chain     src/WorldTransformation.cpp:508-677
+//   skinning            src/LinearBlendSkinning.cpp:445-553 (homogeneous divide kept, root translation added)
+#include "common.cuh"
+#include "forward.cuh"
+
+using namespace sb;
+
+namespace sb
+{
+int g_forward_variant = 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------------------
+
+// BlendShape::rodrigues for one joint.  R row-major.
+__device__ __forceinline__ void rodrigues3(float x, float y, float z, float * R)
+{
+  const float eps = 1e-8f;
+  float ax = x + eps, ay = y + eps, az = z + eps;
+  float a = sqrtf(ax * ax + ay * ay + az * az);
+  float ux = x / a, uy = y / a, uz = z / a;
+  float s, c;
+  sincosf(a, &s, &c);
+  float oc = 1.f - c;
+  // K = [u]x ; K^2 computed entry-wise exactly as matmul(skew, skew)
+  R[0] = 1.f + oc * (-(uz * uz) - uy * uy);
+  R[1] = s * (-uz) + oc * (uy * ux);
+  R[2] = s * uy + oc * (uz * ux);
+  R[3] = s * uz + oc * (ux * uy);
+  R[4] = 1.f + oc * (-(uz * uz) - ux * ux);
+  R[5] = s * (-ux) + oc * (uz * uy);
+  R[6] = s * (-uy) + oc * (ux * uz);
+  R[7] = s * ux + oc * (uy * uz);
+  R[8] = 1.f + oc * (-(uy * uy) - ux * ux);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K1: pose features + joints + kinematic chain.  One warp per frame, lane j = joint j (24 of 32 lanes).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kChainWarps = 8;
+
+__global__ void __launch_bounds__(kChainWarps * 32)
+    pose_chain_kernel(ChainTopo topo, const float * __restrict__ joint_template,
+                      const float * __restrict__ joint_shape, int B, const float * __restrict__ beta,
+                      long long beta_stride, const float * __restrict__ theta, float * __restrict__ coef,
+                      float * __restrict__ xforms, float * __restrict__ joints_out, float * __restrict__ xforms44_out)
+{
+  __shared__ float sG[kChainWarps][kJoints][12];
+  __shared__ float sJ[kChainWarps][kJoints][3];
+  __shared__ float sC[kChainWarps][kBlendK];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long b = static_cast<long long>(blockIdx.x) * kChainWarps + warp;
+  if(b >= B) return; // whole warp leaves together; only __syncwarp below
+
+  const float * bp = beta + b * beta_stride;
+  float R[9], Jt[3] = {0.f, 0.f, 0.f}, t[3];
+  if(lane < kJoints)
+  {
+    const float * th = theta + (b * (kJoints + 1) + 1 + lane) * 3;
+    rodrigues3(th[0], th[1], th[2], R);
+#pragma unroll
+    for(int k = 0; k < 3; k++)
+    {
+      float acc = joint_template[lane * 3 + k];
+#pragma unroll
+      for(int i = 0; i < kShapeDim; i++) acc = fmaf(joint_shape[(lane * 3 + k) * kShapeDim + i], bp[i], acc);
+      Jt[k] = acc;
+      sJ[warp][lane][k] = acc;
+    }
+  }
+  __syncwarp();
+  const int parent = lane < kJoints ? topo.parent[lane] : -1;
+  const int depth = lane < kJoints ? topo.depth[lane] : -1;
+  if(lane < kJoints)
+  {
+#pragma unroll
+    for(int k = 0; k < 3; k++) t[k] = parent >= 0 ? Jt[k] - sJ[warp][parent][k] : Jt[k];
+  }
+  // global transforms, level by level (parents always precede: WorldTransformation.cpp:583-610)
+  float G[12];
+  for(int d = 0; d <= topo.max_depth; d++)
+  {
+    if(depth == d)
+    {
+      if(parent < 0)
+      {
+#pragma unroll
+        for(int r = 0; r < 3; r++)
+        {
+          G[4 * r + 0] = R[3 * r + 0];
+          G[4 * r + 1] = R[3 * r + 1];
+          G[4 * r + 2] = R[3 * r + 2];
+          G[4 * r + 3] = t[r];
+        }
+      }
+      else
+      {
+        const float * P = sG[warp][parent];
+#pragma unroll
+        for(int r = 0; r < 3; r++)
+        {
+          float p0 = P[4 * r + 0], p1 = P[4 * r + 1], p2 = P[4 * r + 2], p3 = P[4 * r + 3];
+#pragma unroll
+          for(int c = 0; c < 3; c++) G[4 * r + c] = p0 * R[c] + p1 * R[3 + c] + p2 * R[6 + c];
+          G[4 * r + 3] = p0 * t[0] + p1 * t[1] + p2 * t[2] + p3;
+        }
+      }
+#pragma unroll
+      for(int e = 0; e < 12; e++) sG[warp][lane][e] = G[e];
+    }
+    __syncwarp();
+  }
+  if(lane < kJoints)
+  {
+    // relativeTransform (WorldTransformation.cpp:657-677): t' = tg - Rg * Jt
+#pragma unroll
+    for(int r = 0; r < 3; r++) G[4 * r + 3] -= G[4 * r + 0] * Jt[0] + G[4 * r + 1] * Jt[1] + G[4 * r + 2] * Jt[2];
+    if(xforms)
+    {
+      float4 * dst = reinterpret_cast<float4 *>(xforms + (b * kJoints + lane) * 12);
+      dst[0] = make_float4(G[0], G[1], G[2], G[3]);
+      dst[1] = make_float4(G[4], G[5], G[6], G[7]);
+      dst[2] = make_float4(G[8], G[9], G[10], G[11]);
+    }
+    if(xforms44_out)
+    {
+      float4 * dst = reinterpret_cast<float4 *>(xforms44_out + (b * kJoints + lane) * 16);
+      dst[0] = make_float4(G[0], G[1], G[2], G[3]);
+      dst[1] = make_float4(G[4], G[5], G[6], G[7]);
+      dst[2] = make_float4(G[8], G[9], G[10], G[11]);
+      dst[3] = make_float4(0.f, 0.f, 0.f, 1.f);
+    }
+    if(joints_out)
+    {
+#pragma unroll
+      for(int k = 0; k < 3; k++) joints_out[(b * kJoints + lane) * 3 + k] = Jt[k];
+    }
+  }
+  if(coef)
+  {
+    if(lane >= 1 && lane < kJoints)
+    {
+#pragma unroll
+      for(int e = 0; e < 9; e++) sC[warp][9 * (lane - 1) + e] = R[e] - ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f);
+    }
+    if(lane < kShapeDim) sC[warp][kPoseDim + lane] = bp[lane];
+    if(lane >= kShapeDim && lane < kShapeDim + 1 + (kBlendK - kBlendKUsed))
+      sC[warp][kPoseDim + lane] = lane == kShapeDim ? 1.f : 0.f;
+    __syncwarp();
+    for(int i = lane; i < kBlendK; i += 32) coef[b * kBlendK + i] = sC[warp][i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K2 (FFMA): rest = coef (B x 224) . basis^T (224 x 3V) with skinning fused in the epilogue.
+//   tile 64 frames x 64 vertices (192 columns), 256 threads, 4 frames x 4 vertices per thread.
+// ------------------------------------------------------------------------------------------------------------
+namespace k2
+{
+constexpr int BM = 64, BNV = 64, BN = BNV * 3, BK = 16, THREADS = 256;
+constexpr int TM = 4, TNV = 4, TN = TNV * 3;
+constexpr int AS_LD = BM + 4, BS_LD = BN + 4;
+constexpr int GS_LD = kJoints * 12;
+constexpr size_t SMEM_AB = sizeof(float) * 2 * BK * (AS_LD + BS_LD);
+constexpr size_t SMEM_G = sizeof(float) * BM * GS_LD;
+constexpr size_t SMEM_TOTAL = SMEM_AB + SMEM_G;
+} // namespace k2
+
+__device__ __forceinline__ void cp_async16(void * smem, const void * gmem)
+{
+  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit()
+{
+  asm volatile("cp.async.commit_group;\n" ::);
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+  asm volatile("cp.async.wait_all;\n" ::);
+}
+
+template<bool kSkin>
+__global__ void __launch_bounds__(k2::THREADS, 2)
+    blend_skin_ffma_kernel(const float * __restrict__ basis, const uint8_t * __restrict__ lbs_joint,
+                           const float * __restrict__ lbs_weight, const float * __restrict__ lbs_wsum, int V, int Vpad,
+                           int kmax, int B, const float * __restrict__ coef, const float * __restrict__ xforms,
+                           const float * __restrict__ theta, float * __restrict__ out)
+{
+  using namespace k2;
+  extern __shared__ __align__(16) float smem[];
+  float * As = smem;                    // [2][BK][AS_LD]
+  float * Bs = smem + 2 * BK * AS_LD;   // [2][BK][BS_LD]
+  float * Gs = smem + 2 * BK * (AS_LD + BS_LD); // [BM][24*12]
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int v0 = blockIdx.x * BNV;
+  const int m0 = blockIdx.y * BM;
+
+  if(kSkin)
+  {
+    // prefetch the tile's 64 x 24 relative transforms; consumed only in the epilogue
+    for(int i = tid; i < BM * GS_LD / 4; i += THREADS)
+    {
+      int row = i / (GS_LD / 4), q = i % (GS_LD / 4);
+      int b = min(m0 + row, B - 1);
+      cp_async16(Gs + row * GS_LD + q * 4, xforms + static_cast<size_t>(b) * GS_LD + q * 4);
+    }
+    cp_async_commit();
+  }
+
+  // global -> register staging of one K chunk
+  const int a_row = tid >> 2, a_q = tid & 3;
+  const float * a_src = coef + static_cast<size_t>(min(m0 + a_row, B - 1)) * kBlendK + a_q * 4;
+  const float * b_src[3];
+  int b_row[3], b_q[3];
+#pragma unroll
+  for(int i = 0; i < 3; i++)
+  {
+    int idx = tid + i * THREADS;
+    b_row[i] = idx >> 2;
+    b_q[i] = idx & 3;
+    b_src[i] = basis + (static_cast<size_t>(v0) * 3 + b_row[i]) * kBlendK + b_q[i] * 4;
+  }
+  float4 a_reg, b_reg[3];
+  auto load_chunk = [&](int kc) {
+    a_reg = __ldg(reinterpret_cast<const float4 *>(a_src + kc * BK));
+#pragma unroll
+    for(int i = 0; i < 3; i++) b_reg[i] = __ldg(reinterpret_cast<const float4 *>(b_src[i] + kc * BK));
+  };
+  auto store_chunk = [&](int buf) {
+    float * as = As + buf * BK * AS_LD + (a_q * 4) * AS_LD + a_row;
+    as[0] = a_reg.x;
+    as[AS_LD] = a_reg.y;
+    as[2 * AS_LD] = a_reg.z;
+    as[3 * AS_LD] = a_reg.w;
+#pragma unroll
+    for(int i = 0; i < 3; i++)
+    {
+      float * bs = Bs + buf * BK * BS_LD + (b_q[i] * 4) * BS_LD + b_row[i];
+      bs[0] = b_reg[i].x;
+      bs[BS_LD] = b_reg[i].y;
+      bs[2 * BS_LD] = b_reg[i].z;
+      bs[3 * BS_LD] = b_reg[i].w;
+    }
+  };
+
+  float acc[TM][TN];
+#pragma unroll
+  for(int i = 0; i < TM; i++)
+#pragma unroll
+    for(int j = 0; j < TN; j++) acc[i][j] = 0.f;
+
+  constexpr int NK = kBlendK / BK;
+  load_chunk(0);
+  store_chunk(0);
+  __syncthreads();
+  for(int kc = 0; kc < NK; kc++)
+  {
+    const int buf = kc & 1;
+    if(kc + 1 < NK) load_chunk(kc + 1);
+    const float * as = As + buf * BK * AS_LD + ty * TM;
+    const float * bs = Bs + buf * BK * BS_LD + tx * TN;
+#pragma unroll
+    for(int k = 0; k < BK; k++)
+    {
+      float4 a4 = *reinterpret_cast<const float4 *>(as + k * AS_LD);
+      float4 b0 = *reinterpret_cast<const float4 *>(bs + k * BS_LD);
+      float4 b1 = *reinterpret_cast<const float4 *>(bs + k * BS_LD + 4);
+      float4 b2 = *reinterpret_cast<const float4 *>(bs + k * BS_LD + 8);
+      float a[TM] = {a4.x, a4.y, a4.z, a4.w};
+      float bb[TN] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w};
+#pragma unroll
+      for(int i = 0; i < TM; i++)
+#pragma unroll
+        for(int j = 0; j < TN; j++) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    if(kc + 1 < NK)
+    {
+      store_chunk(buf ^ 1);
+      __syncthreads();
+    }
+  }
+
+  // ---- epilogue ----
+  const int vbase = v0 + tx * TNV;
+  if(kSkin)
+  {
+    cp_async_wait_all();
+    __syncthreads();
+    uint8_t jn[TNV][4];
+    float jw[TNV][4], inv_ws[TNV];
+    if(kmax <= 4)
+    {
+#pragma unroll
+      for(int jv = 0; jv < TNV; jv++)
+      {
+#pragma unroll
+        for(int k = 0; k < 4; k++)
+        {
+          bool on = k < kmax;
+          jn[jv][k] = on ? lbs_joint[static_cast<size_t>(k) * Vpad + vbase + jv] : 0;
+          jw[jv][k] = on ? lbs_weight[static_cast<size_t>(k) * Vpad + vbase + jv] : 0.f;
+        }
+        inv_ws[jv] = 1.f / lbs_wsum[vbase + jv];
+      }
+    }
+#pragma unroll
+    for(int i = 0; i < TM; i++)
+    {
+      const int b = m0 + ty * TM + i;
+      if(b >= B) continue;
+      const float * g = Gs + (ty * TM + i) * GS_LD;
+      const float * tr = theta + static_cast<size_t>(b) * (kJoints + 1) * 3;
+      const float trx = tr[0], try_ = tr[1], trz = tr[2];
+      float o[TN];
+#pragma unroll
+      for(int jv = 0; jv < TNV; jv++)
+      {
+        const float rx = acc[i][3 * jv], ry = acc[i][3 * jv + 1], rz = acc[i][3 * jv + 2];
+        float ox = 0.f, oy = 0.f, oz = 0.f, iw;
+        if(kmax <= 4)
+        {
+#pragma unroll
+          for(int k = 0; k < 4; k++)
+          {
+            const float4 * gj = reinterpret_cast<const float4 *>(g + jn[jv][k] * 12);
+            float4 r0 = gj[0], r1 = gj[1], r2 = gj[2];
+            float w = jw[jv][k];
+            ox = fmaf(w, fmaf(r0.x, rx, fmaf(r0.y, ry, fmaf(r0.z, rz, r0.w))), ox);
+            oy = fmaf(w, fmaf(r1.x, rx, fmaf(r1.y, ry, fmaf(r1.z, rz, r1.w))), oy);
+            oz = fmaf(w, fmaf(r2.x, rx, fmaf(r2.y, ry, fmaf(r2.z, rz, r2.w))), oz);
+          }
+          iw = inv_ws[jv];
+        }
+        else
+        {
+          const int v = vbase + jv;
+          for(int k = 0; k < kmax; k++)
+          {
+            const float4 * gj = reinterpret_cast<const float4 *>(g + lbs_joint[static_cast<size_t>(k) * Vpad + v] * 12);
+            float4 r0 = gj[0], r1 = gj[1], r2 = gj[2];
+            float w = lbs_weight[static_cast<size_t>(k) * Vpad + v];
+            ox = fmaf(w, fmaf(r0.x, rx, fmaf(r0.y, ry, fmaf(r0.z, rz, r0.w))), ox);
+            oy = fmaf(w, fmaf(r1.x, rx, fmaf(r1.y, ry, fmaf(r1.z, rz, r1.w))), oy);
+            oz = fmaf(w, fmaf(r2.x, rx, fmaf(r2.y, ry, fmaf(r2.z, rz, r2.w))), oz);
+          }
+          iw = 1.f / lbs_wsum[v];
+        }
+        o[3 * jv] = fmaf(ox, iw, trx);
+        o[3 * jv + 1] = fmaf(oy, iw, try_);
+        o[3 * jv + 2] = fmaf(oz, iw, trz);
+      }
+      float * dst = out + (static_cast<size_t>(b) * V + vbase) * 3;
+      if(vbase + TNV <= V)
+      {
+#pragma unroll
+        for(int q = 0; q < TN / 2; q++) reinterpret_cast<float2 *>(dst)[q] = make_float2(o[2 * q], o[2 * q + 1]);
+      }
+      else
+      {
+        for(int q = 0; q < TN; q++)
+          if(vbase + q / 3 < V) dst[q] = o[q];
+      }
+    }
+  }
+  else
+  {
+#pragma unroll
+    for(int i = 0; i < TM; i++)
+    {
+      const int b = m0 + ty * TM + i;
+      if(b >= B) continue;
+      float * dst = out + (static_cast<size_t>(b) * V + vbase) * 3;
+      if(vbase + TNV <= V)
+      {
+#pragma unroll
+        for(int q = 0; q < TN / 2; q++) reinterpret_cast<float2 *>(dst)[q] = make_float2(acc[i][2 * q], acc[i][2 * q + 1]);
+      }
+      else
+      {
+        for(int q = 0; q < TN; q++)
+          if(vbase + q / 3 < V) dst[q] = acc[i][q];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K3: standalone linear blend skinning (HBM-bound).  CTA = 512 vertices x FR frames; 2 vertices per thread.
+//   kAffine: transforms are 3x4 [R|t'] rows (12 floats/joint, internal format); else full 4x4 (16 floats/joint,
+//   LinearBlendSkinning's input format) including the homogeneous row.
+// ------------------------------------------------------------------------------------------------------------
+namespace k3
+{
+constexpr int THREADS = 256, VPT = 2, FR = 8;
+}
+
+template<bool kAffine>
+__global__ void __launch_bounds__(k3::THREADS)
+    lbs_kernel(const uint8_t * __restrict__ lbs_joint, const float * __restrict__ lbs_weight,
+               const float * __restrict__ lbs_wsum, int V, int Vpad, int kmax, int B, const float * __restrict__ rest,
+               const float * __restrict__ xforms, const float * __restrict__ root, int root_stride,
+               float * __restrict__ out)
+{
+  using namespace k3;
+  constexpr int XF = kAffine ? 12 : 16;
+  __shared__ __align__(16) float Gs[FR][kJoints * XF];
+  const int tid = threadIdx.x;
+  const int b0 = blockIdx.y * FR;
+  const int nfr = min(FR, B - b0);
+  for(int i = tid; i < nfr * kJoints * XF / 4; i += THREADS)
+    reinterpret_cast<float4 *>(&Gs[0][0])[i] =
+        __ldg(reinterpret_cast<const float4 *>(xforms + static_cast<size_t>(b0) * kJoints * XF) + i);
+  const int v = (blockIdx.x * THREADS + tid) * VPT;
+  uint8_t jn[VPT][4];
+  float jw[VPT][4], iw[VPT];
+  const bool fast = kmax <= 4;
+  if(v < V && fast)
+  {
+#pragma unroll
+    for(int u = 0; u < VPT; u++)
+    {
+      int vv = min(v + u, V - 1);
+#pragma unroll
+      for(int k = 0; k < 4; k++)
+      {
+        bool on = k < kmax;
+        jn[u][k] = on ? lbs_joint[static_cast<size_t>(k) * Vpad + vv] : 0;
+        jw[u][k] = on ? lbs_weight[static_cast<size_t>(k) * Vpad + vv] : 0.f;
+      }
+      iw[u] = 1.f / lbs_wsum[vv];
+    }
+  }
+  __syncthreads();
+  if(v >= V) return;
+  const bool pair = v + 1 < V;
+  for(int f = 0; f < nfr; f++)
+  {
+    const size_t base = (static_cast<size_t>(b0 + f) * V + v) * 3;
+    float r[6];
+    if(pair)
+    {
+      const float2 * src = reinterpret_cast<const float2 *>(rest + base);
+      float2 p0 = __ldcs(src), p1 = __ldcs(src + 1), p2 = __ldcs(src + 2);
+      r[0] = p0.x, r[1] = p0.y, r[2] = p1.x, r[3] = p1.y, r[4] = p2.x, r[5] = p2.y;
+    }
+    else
+    {
+      r[0] = rest[base], r[1] = rest[base + 1], r[2] = rest[base + 2];
+      r[3] = r[4] = r[5] = 0.f;
+    }
+    float tx = 0.f, ty = 0.f, tz = 0.f;
+    if(root)
+    {
+      const float * rp = root + static_cast<size_t>(b0 + f) * root_stride;
+      tx = rp[0], ty = rp[1], tz = rp[2];
+    }
+    float o[6];
+#pragma unroll
+    for(int u = 0; u < VPT; u++)
+    {
+      const float rx = r[3 * u], ry = r[3 * u + 1], rz = r[3 * u + 2];
+      float ox = 0.f, oy = 0.f, oz = 0.f, ow = 0.f;
+      auto accum = [&](int j, float w) {
+        const float4 * gj = reinterpret_cast<const float4 *>(&Gs[f][j * XF]);
+        float4 r0 = gj[0], r1 = gj[1], r2 = gj[2];
+        ox = fmaf(w, fmaf(r0.x, rx, fmaf(r0.y, ry, fmaf(r0.z, rz, r0.w))), ox);
+        oy = fmaf(w, fmaf(r1.x, rx, fmaf(r1.y, ry, fmaf(r1.z, rz, r1.w))), oy);
+        oz = fmaf(w, fmaf(r2.x, rx, fmaf(r2.y, ry, fmaf(r2.z, rz, r2.w))), oz);
+        if(!kAffine)
+        {
+          float4 r3 = gj[3];
+          ow = fmaf(w, fmaf(r3.x, rx, fmaf(r3.y, ry, fmaf(r3.z, rz, r3.w))), ow);
+        }
+      };
+      float inv;
+      if(fast)
+      {
+#pragma unroll
+        for(int k = 0; k < 4; k++) accum(jn[u][k], jw[u][k]);
+        inv = kAffine ? iw[u] : 1.f / ow;
+      }
+      else
+      {
+        int vv = min(v + u, V - 1);
+        for(int k = 0; k < kmax; k++)
+          accum(lbs_joint[static_cast<size_t>(k) * Vpad + vv], lbs_weight[static_cast<size_t>(k) * Vpad + vv]);
+        inv = kAffine ? 1.f / lbs_wsum[vv] : 1.f / ow;
+      }
+      o[3 * u] = fmaf(ox, inv, tx);
+      o[3 * u + 1] = fmaf(oy, inv, ty);
+      o[3 * u + 2] = fmaf(oz, inv, tz);
+    }
+    if(pair)
+    {
+      float2 * dst = reinterpret_cast<float2 *>(out + base);
+      __stcs(dst, make_float2(o[0], o[1]));
+      __stcs(dst + 1, make_float2(o[2], o[3]));
+      __stcs(dst + 2, make_float2(o[4], o[5]));
+    }
+    else
+    {
+      out[base] = o[0], out[base + 1] = o[1], out[base + 2] = o[2];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Generic per-module kernels (any V, caller tensors; used by the module-level API and the Tester KATs).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void rodrigues_kernel(long long n, const float * __restrict__ theta, float * __restrict__ rot)
+{
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  float R[9];
+  rodrigues3(theta[3 * i], theta[3 * i + 1], theta[3 * i + 2], R);
+#pragma unroll
+  for(int e = 0; e < 9; e++) rot[9 * i + e] = R[e];
+}
+
+// one thread per (b, v, k): pose blend 207-dot and shape blend 10-dot
+__global__ void blend_generic_kernel(int B, int V, const float * __restrict__ beta, const float * __restrict__ rot,
+                                     const float * __restrict__ shape_basis, const float * __restrict__ pose_basis,
+                                     float * __restrict__ shape_bs, float * __restrict__ pose_bs)
+{
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if(i >= static_cast<long long>(B) * V * 3) return;
+  int b = static_cast<int>(i / (static_cast<long long>(V) * 3));
+  long long vk = i % (static_cast<long long>(V) * 3);
+  const float * pb = pose_basis + vk * kPoseDim;
+  const float * r = rot + static_cast<size_t>(b) * kJoints * 9 + 9; // skip the root rotation
+  float acc = 0.f;
+  for(int d = 0; d < kPoseDim; d++)
+  {
+    int e = d % 9;
+    float c = r[d] - ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f);
+    acc = fmaf(c, pb[d], acc);
+  }
+  pose_bs[i] = acc;
+  const float * sb_ = shape_basis + vk * kShapeDim;
+  float s = 0.f;
+  for(int d = 0; d < kShapeDim; d++) s = fmaf(beta[b * kShapeDim + d], sb_[d], s);
+  shape_bs[i] = s;
+}
+
+__global__ void linear_combine_kernel(long long n, long long vk_count, const float * __restrict__ templ,
+                                      const float * __restrict__ shape_bs, const float * __restrict__ pose_bs,
+                                      float * __restrict__ rest)
+{
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  rest[i] = templ[i % vk_count] + shape_bs[i] + pose_bs[i];
+}
+
+// one warp per (b, j, k): joints = Jreg . (T + S)
+__global__ void joint_regress_kernel(int B, int V, const float * __restrict__ templ, const float * __restrict__ jreg,
+                                     const float * __restrict__ shape_bs, float * __restrict__ joints)
+{
+  int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if(w >= B * kJoints * 3) return;
+  int b = w / (kJoints * 3), j = (w / 3) % kJoints, k = w % 3;
+  float acc = 0.f;
+  for(int v = lane; v < V; v += 32)
+    acc = fmaf(jreg[static_cast<size_t>(j) * V + v], templ[3 * v + k] + shape_bs[(static_cast<size_t>(b) * V + v) * 3 + k], acc);
+#pragma unroll
+  for(int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if(lane == 0) joints[w] = acc;
+}
+
+// WorldTransformation::transform on caller-supplied rotations (any 3x3, the Tester KAT feeds non-rotations)
+__global__ void world_transform_kernel(int B, const long long * __restrict__ kine_tree, const float * __restrict__ joints,
+                                       const float * __restrict__ rot, float * __restrict__ out)
+{
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if(b >= B) return;
+  float G[kJoints][12];
+  const float * J = joints + static_cast<size_t>(b) * kJoints * 3;
+  const float * R = rot + static_cast<size_t>(b) * kJoints * 9;
+  for(int j = 0; j < kJoints; j++)
+  {
+    long long p = kine_tree[j];
+    const float * Rj = R + 9 * j;
+    if(j == 0 || p < 0 || p >= kJoints)
+    {
+      for(int r = 0; r < 3; r++)
+      {
+        for(int c = 0; c < 3; c++) G[j][4 * r + c] = Rj[3 * r + c];
+        G[j][4 * r + 3] = J[3 * j + r];
+      }
+    }
+    else
+    {
+      float t[3] = {J[3 * j] - J[3 * p], J[3 * j + 1] - J[3 * p + 1], J[3 * j + 2] - J[3 * p + 2]};
+      for(int r = 0; r < 3; r++)
+      {
+        float p0 = G[p][4 * r], p1 = G[p][4 * r + 1], p2 = G[p][4 * r + 2], p3 = G[p][4 * r + 3];
+        for(int c = 0; c < 3; c++) G[j][4 * r + c] = p0 * Rj[c] + p1 * Rj[3 + c] + p2 * Rj[6 + c];
+        G[j][4 * r + 3] = p0 * t[0] + p1 * t[1] + p2 * t[2] + p3;
+      }
+    }
+  }
+  float * o = out + static_cast<size_t>(b) * kJoints * 16;
+  for(int j = 0; j < kJoints; j++)
+  {
+    for(int r = 0; r < 3; r++)
+    {
+      for(int c = 0; c < 3; c++) o[16 * j + 4 * r + c] = G[j][4 * r + c];
+      o[16 * j + 4 * r + 3] =
+          G[j][4 * r + 3] - (G[j][4 * r] * J[3 * j] + G[j][4 * r + 1] * J[3 * j + 1] + G[j][4 * r + 2] * J[3 * j + 2]);
+    }
+    o[16 * j + 12] = 0.f, o[16 * j + 13] = 0.f, o[16 * j + 14] = 0.f, o[16 * j + 15] = 1.f;
+  }
+}
+
+// dense-weight skinning with the full homogeneous row (LinearBlendSkinning.cpp:463-467, 545-550)
+__global__ void lbs_dense_kernel(int B, int V, const float * __restrict__ weights, const float * __restrict__ rest,
+                                 const float * __restrict__ xf, const float * __restrict__ root,
+                                 float * __restrict__ out)
+{
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if(i >= static_cast<long long>(B) * V) return;
+  int b = static_cast<int>(i / V), v = static_cast<int>(i % V);
+  float rx = rest[3 * i], ry = rest[3 * i + 1], rz = rest[3 * i + 2];
+  float M[16];
+  for(int e = 0; e < 16; e++) M[e] = 0.f;
+  for(int j = 0; j < kJoints; j++)
+  {
+    float w = weights[static_cast<size_t>(v) * kJoints + j];
+    const float * g = xf + (static_cast<size_t>(b) * kJoints + j) * 16;
+    for(int e = 0; e < 16; e++) M[e] = fmaf(w, g[e], M[e]);
+  }
+  float h[4];
+  for(int r = 0; r < 4; r++) h[r] = M[4 * r] * rx + M[4 * r + 1] * ry + M[4 * r + 2] * rz + M[4 * r + 3];
+  for(int k = 0; k < 3; k++) out[3 * i + k] = h[k] / h[3] + (root ? root[3 * b + k] : 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Normals (SMPL::calcNormal / calcVertexNormal, src/SMPL.cpp:518-535), batched: one thread per (frame, item).
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void normalize3(float & x, float & y, float & z)
+{
+  // torch::nn::functional::normalize: v / max(||v||, 1e-12)
+  float n = fmaxf(sqrtf(x * x + y * y + z * z), 1e-12f);
+  x /= n, y /= n, z /= n;
+}
+
+__device__ __forceinline__ void face_normal(const float * __restrict__ verts, const int32_t * __restrict__ faces, int f,
+                                            float & nx, float & ny, float & nz)
+{
+  const float * a = verts + 3 * faces[3 * f], *b = verts + 3 * faces[3 * f + 1], *c = verts + 3 * faces[3 * f + 2];
+  float e1x = b[0] - a[0], e1y = b[1] - a[1], e1z = b[2] - a[2];
+  float e2x = c[0] - a[0], e2y = c[1] - a[1], e2z = c[2] - a[2];
+  nx = e1y * e2z - e1z * e2y;
+  ny = e1z * e2x - e1x * e2z;
+  nz = e1x * e2y - e1y * e2x;
+  normalize3(nx, ny, nz);
+}
+
+__global__ void normals_kernel(const int32_t * __restrict__ faces, const int32_t * __restrict__ adj_offset,
+                               const int32_t * __restrict__ adj_faces, int V, int F, int B,
+                               const float * __restrict__ verts, int nF, const long long * __restrict__ face_idx,
+                               float * __restrict__ fn, int nV, const long long * __restrict__ vert_idx,
+                               float * __restrict__ vn)
+{
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int per = nF + nV;
+  if(i >= static_cast<long long>(B) * per) return;
+  int b = static_cast<int>(i / per), it = static_cast<int>(i % per);
+  const float * vb = verts + static_cast<size_t>(b) * V * 3;
+  if(it < nF)
+  {
+    long long f = face_idx[it];
+    float x = 0.f, y = 0.f, z = 0.f;
+    if(f >= 0 && f < F) face_normal(vb, faces, static_cast<int>(f), x, y, z);
+    float * o = fn + (static_cast<size_t>(b) * nF + it) * 3;
+    o[0] = x, o[1] = y, o[2] = z;
+  }
+  else
+  {
+    it -= nF;
+    long long v = vert_idx[it];
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    if(v >= 0 && v < V)
+    {
+      int s = adj_offset[v], e = adj_offset[v + 1];
+      float w = 1.f / static_cast<float>(e - s);
+      for(int k = s; k < e; k++)
+      {
+        float x, y, z;
+        face_normal(vb, faces, adj_faces[k], x, y, z);
+        ax = fmaf(w, x, ax), ay = fmaf(w, y, ay), az = fmaf(w, z, az);
+      }
+      normalize3(ax, ay, az);
+    }
+    float * o = vn + (static_cast<size_t>(b) * nV + it) * 3;
+    o[0] = ax, o[1] = ay, o[2] = az;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+namespace sb
+{
+ChainTopo make_topo(const ModelDev & d)
+{
+  ChainTopo t;
+  for(int j = 0; j < kJoints; j++)
+  {
+    t.parent[j] = d.parent[j];
+    t.depth[j] = d.depth[j];
+  }
+  t.max_depth = d.max_depth;
+  return t;
+}
+
+int launch_pose_chain(const ModelDev & d, cudaStream_t st, int B, const float * beta, long long beta_stride,
+                      const float * theta, float * coef, float * xforms, float * joints, float * xforms44)
+{
+  int grid = (B + kChainWarps - 1) / kChainWarps;
+  pose_chain_kernel<<<grid, kChainWarps * 32, 0, st>>>(make_topo(d), d.joint_template, d.joint_shape, B, beta,
+                                                       beta_stride, theta, coef, xforms, joints, xforms44);
+  SB_LAUNCHED();
+  return SMPLPP_OK;
+}
+
+int launch_blend_skin_ffma(const ModelDev & d, cudaStream_t st, int B, const float * coef, const float * xforms,
+                           const float * theta, float * out, bool skin)
+{
+  static bool configured = false;
+  if(!configured)
+  {
+    SB_CUDA(cudaFuncSetAttribute(blend_skin_ffma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(k2::SMEM_TOTAL)));
+    SB_CUDA(cudaFuncSetAttribute(blend_skin_ffma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(k2::SMEM_AB)));
+    configured = true;
+  }
+  dim3 grid(d.Vpad / k2::BNV, (B + k2::BM - 1) / k2::BM);
+  if(skin)
+    blend_skin_ffma_kernel<true><<<grid, k2::THREADS, k2::SMEM_TOTAL, st>>>(
+        d.basis, d.lbs_joint, d.lbs_weight, d.lbs_wsum, d.V, d.Vpad, d.kmax, B, coef, xforms, theta, out);
+  else
+    blend_skin_ffma_kernel<false><<<grid, k2::THREADS, k2::SMEM_AB, st>>>(
+        d.basis, d.lbs_joint, d.lbs_weight, d.lbs_wsum, d.V, d.Vpad, d.kmax, B, coef, xforms, theta, out);
+  SB_LAUNCHED();
+  return SMPLPP_OK;
+}
+
+int launch_lbs(const ModelDev & d, cudaStream_t st, int B, const float * rest, const float * xforms, bool affine,
+               const float * root, int root_stride, float * out)
+{
+  dim3 grid((d.V + k3::THREADS * k3::VPT - 1) / (k3::THREADS * k3::VPT), (B + k3::FR - 1) / k3::FR);
+  if(affine)
+    lbs_kernel<true><<<grid, k3::THREADS, 0, st>>>(d.lbs_joint, d.lbs_weight, d.lbs_wsum, d.V, d.Vpad, d.kmax, B, rest,
+                                                   xforms, root, root_stride, out);
+  else
+    lbs_kernel<false><<<grid, k3::THREADS, 0, st>>>(d.lbs_joint, d.lbs_weight, d.lbs_wsum, d.V, d.Vpad, d.kmax, B, rest,
+                                                    xforms, root, root_stride, out);
+  SB_LAUNCHED();
+  return SMPLPP_OK;
+}
+} // namespace sb
+
+extern "C" int smplpp_set_forward_variant(int variant)
+{
+  if(variant < 0 || variant > 3) return fail(SMPLPP_ERR_INVALID, "SMPL", "unknown forward variant");
+  g_forward_variant = variant;
+  return SMPLPP_OK;
+}
+
+extern "C" size_t smplpp_forward_workspace_bytes(const smplpp_model_t * model, int64_t batch)
+{
+  if(!model || batch < 1) return 0;
+  size_t bpad = align_up(static_cast<size_t>(batch), 128);
+  size_t bytes = 512;
+  bytes += align_up(bpad * kBlendK * sizeof(float));         // coefficients (A operand)
+  bytes += align_up(bpad * kJoints * 12 * sizeof(float));    // relative transforms 3x4
+  bytes += align_up(static_cast<size_t>(batch) * model->d.V * 3 * sizeof(float)); // rest shape (unfused variant)
+  return bytes;
+}
+
+extern "C" int smplpp_forward(const smplpp_model_t * model, void * stream, int64_t batch, const float * beta,
+                              int64_t beta_stride, const float * theta, float * vertices, float * joints,
+                              float * transforms, float * rest_shape, void * workspace, size_t workspace_bytes)
+{
+  if(!model || batch < 1 || !beta || !theta) return fail(SMPLPP_ERR_INVALID, "SMPL", "Cannot launch a SMPL model!");
+  if(batch > (1ll << 24)) return fail(SMPLPP_ERR_INVALID, "SMPL", "Cannot launch a SMPL model! (batch too large)");
+  if(!workspace || workspace_bytes < smplpp_forward_workspace_bytes(model, batch))
+    return fail(SMPLPP_ERR_INVALID, "SMPL", "Cannot launch a SMPL model! (workspace too small)");
+  const ModelDev & d = model->d;
+  const int B = static_cast<int>(batch);
+  cudaStream_t st = as_stream(stream);
+  size_t bpad = align_up(static_cast<size_t>(batch), 128);
+  char * ws = align_up_ptr<char>(workspace);
+  float * coef = reinterpret_cast<float *>(ws);
+  ws += align_up(bpad * kBlendK * sizeof(float));
+  float * xforms = reinterpret_cast<float *>(ws);
+  ws += align_up(bpad * kJoints * 12 * sizeof(float));
+  float * rest_ws = reinterpret_cast<float *>(ws);
+
+  const bool need_verts = vertices != nullptr;
+  const bool need_rest = rest_shape != nullptr;
+  int rc = launch_pose_chain(d, st, B, beta, beta_stride, theta, (need_verts || need_rest) ? coef : nullptr, xforms,
+                             joints, transforms);
+  if(rc != SMPLPP_OK) return rc;
+  int variant = g_forward_variant;
+  if(variant == 0) variant = tc_blend_available() ? 2 : 1;
+  if(need_rest || (need_verts && variant == 3))
+  {
+    float * rest = need_rest ? rest_shape : rest_ws;
+    rc = launch_blend_skin_ffma(d, st, B, coef, xforms, theta, rest, false);
+    if(rc != SMPLPP_OK) return rc;
+    if(need_verts) rc = launch_lbs(d, st, B, rest, xforms, true, theta, (kJoints + 1) * 3, vertices);
+    return rc;
+  }
+  if(need_verts)
+  {
+    if(variant == 2)
+      rc = launch_blend_skin_tc(d, st, B, coef, xforms, theta, vertices);
+    else
+      rc = launch_blend_skin_ffma(d, st, B, coef, xforms, theta, vertices, true);
+  }
+  return rc;
+}
+
+extern "C" int smplpp_forward_host(const smplpp_model_t * model_c, int64_t batch, const float * beta_host,
+                                   int64_t beta_stride, const float * theta_host, float * vertices_host,
+                                   float * joints_host)
+{
+  smplpp_model_t * model = const_cast<smplpp_model_t *>(model_c);
+  if(!model || batch < 1 || !beta_host || !theta_host)
+    return fail(SMPLPP_ERR_INVALID, "SMPL", "Cannot launch a SMPL model!");
+  const size_t V = model->d.V;
+  const size_t n_beta = beta_stride == 0 ? kShapeDim : static_cast<size_t>(batch) * beta_stride;
+  const size_t n_theta = static_cast<size_t>(batch) * (kJoints + 1) * 3;
+  const size_t n_vert = vertices_host ? static_cast<size_t>(batch) * V * 3 : 0;
+  const size_t n_joint = joints_host ? static_cast<size_t>(batch) * kJoints * 3 : 0;
+  const size_t io_floats = n_beta + n_theta + n_vert + n_joint + 64;
+  const size_t ws_bytes = smplpp_forward_workspace_bytes(model, batch);
+  const size_t dev_bytes = align_up(io_floats * sizeof(float)) + ws_bytes;
+  if(model->pinned_bytes < io_floats * sizeof(float))
+  {
+    if(model->pinned) cudaFreeHost(model->pinned);
+    model->pinned = nullptr;
+    model->pinned_bytes = 0;
+    SB_CUDA(cudaMallocHost(&model->pinned, io_floats * sizeof(float)));
+    model->pinned_bytes = io_floats * sizeof(float);
+  }
+  if(model->dev_scratch_bytes < dev_bytes)
+  {
+    if(model->dev_scratch) cudaFree(model->dev_scratch);
+    model->dev_scratch = nullptr;
+    model->dev_scratch_bytes = 0;
+    SB_CUDA(cudaMalloc(&model->dev_scratch, dev_bytes));
+    model->dev_scratch_bytes = dev_bytes;
+  }
+  cudaStream_t st = model->host_stream;
+  float * hp = static_cast<float *>(model->pinned);
+  float * dp = static_cast<float *>(model->dev_scratch);
+  // inputs: pageable host -> pinned -> device
+  memcpy(hp, beta_host, n_beta * sizeof(float));
+  memcpy(hp + n_beta, theta_host, n_theta * sizeof(float));
+  SB_CUDA(cudaMemcpyAsync(dp, hp, (n_beta + n_theta) * sizeof(float), cudaMemcpyHostToDevice, st));
+  float * d_beta = dp;
+  float * d_theta = dp + n_beta;
+  float * d_vert = d_theta + n_theta + ((4 - (n_beta + n_theta) % 4) % 4);
+  float * d_joint = d_vert + n_vert;
+  void * d_ws = reinterpret_cast<char *>(dp) + align_up(io_floats * sizeof(float));
+  int rc = smplpp_forward(model, st, batch, d_beta, beta_stride, d_theta, vertices_host ? d_vert : nullptr,
+                          joints_host ? d_joint : nullptr, nullptr, nullptr, d_ws, ws_bytes);
+  if(rc != SMPLPP_OK) return rc;
+  float * h_out = hp + n_beta + n_theta;
+  if(n_vert + n_joint)
+    SB_CUDA(cudaMemcpyAsync(h_out, d_vert, (n_vert + n_joint) * sizeof(float), cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  if(vertices_host) memcpy(vertices_host, h_out, n_vert * sizeof(float));
+  if(joints_host) memcpy(joints_host, h_out + n_vert, n_joint * sizeof(float));
+  return SMPLPP_OK;
+}
+
+// ---- module-level API ----
+
+extern "C" int smplpp_blend_shape(void * stream, int64_t batch, int64_t V, const float * beta, const float * theta,
+                                  const float * shape_basis, const float * pose_basis, float * shape_bs, float * pose_bs,
+                                  float * pose_rot)
+{
+  if(batch < 1 || V < 1 || !beta) return fail(SMPLPP_ERR_INVALID, "BlendShape", "Failed to set beta!");
+  if(!theta) return fail(SMPLPP_ERR_INVALID, "BlendShape", "Failed to set theta!");
+  if(!shape_basis || !pose_basis || !shape_bs || !pose_bs || !pose_rot)
+    return fail(SMPLPP_ERR_INVALID, "BlendShape", "Cannot blend pose-dependented shape!");
+  cudaStream_t st = as_stream(stream);
+  long long n = batch * kJoints;
+  rodrigues_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(n, theta, pose_rot);
+  SB_LAUNCHED();
+  long long total = batch * V * 3;
+  blend_generic_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, st>>>(
+      static_cast<int>(batch), static_cast<int>(V), beta, pose_rot, shape_basis, pose_basis, shape_bs, pose_bs);
+  SB_LAUNCHED();
+  return SMPLPP_OK;
+}
+
+extern "C" int smplpp_joint_regression(void * stream, int64_t batch, int64_t V, const float * templ, const float * jreg,
+                                       const float * shape_bs, const float * pose_bs, float * rest, float * joints)
+{
+  if(batch < 1 || V < 1 || !templ || !shape_bs || !pose_bs || !rest)
+    return fail(SMPLPP_ERR_INVALID, "JointRegression", "Cannot linearly combine shapes!");
+  if(!jreg || !joints) return fail(SMPLPP_ERR_INVALID, "JointRegression", "Cannot regress vertices to joints!");
+  cudaStream_t st = as_stream(stream);
+  long long n = batch * V * 3;
+  linear_combine_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(n, V * 3, templ, shape_bs, pose_bs, rest);
+  SB_LAUNCHED();
+  long long warps = batch * kJoints * 3;
+  joint_regress_kernel<<<static_cast<unsigned>((warps * 32 + 127) / 128), 128, 0, st>>>(
+      static_cast<int>(batch), static_cast<int>(V), templ, jreg, shape_bs, joints);
+  SB_LAUNCHED();
+  return SMPLPP_OK;
+}
+
+extern "C" int smplpp_world_transformation(void * stream, int64_t batch, const int64_t * kine_tree, const float * joints,
+                                           const float * pose_rot, float * transforms)
+{
+  if(batch < 1 || !kine_tree || !joints || !pose_rot || !transforms)
+    return fail(SMPLPP_ERR_INVALID, "WorldTransformation", "Cannot transform bones locally!");
+  world_transform_kernel<<<static_cast<unsigned>((batch + 63) / 64), 64, 0, as_stream(stream)>>>(
+      static_cast<int>(batch), reinterpret_cast<const long long *>(kine_tree), joints, pose_rot, transforms);
+  SB_LAUNCHED();
+  return SMPLPP_OK;
+}
+
+extern "C" int smplpp_linear_blend_skinning(void * stream, int64_t batch, int64_t V, const float * weights,
+                                            const float * rest, const float * transforms, const float * root_pos,
+                                            float * vertices)
+{
+  if(batch < 1 || V < 1 || !weights) return fail(SMPLPP_ERR_INVALID, "LinearBlendSkinning", "Failed to set weights!");
+  if(!rest || !transforms || !vertices)
+    return fail(SMPLPP_ERR_INVALID, "LinearBlendSkinning", "Cannot convert Cartesian coordinates to homogeneous one!");
+  long long n = batch * V;
+  lbs_dense_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, as_stream(stream)>>>(
+      static_cast<int>(batch), static_cast<int>(V), weights, rest, transforms, root_pos, vertices);
+  SB_LAUNCHED();
+  return SMPLPP_OK;
+}
+
+extern "C" int smplpp_model_skinning(const smplpp_model_t * model, void * stream, int64_t batch, const float * rest,
+                                     const float * transforms, const float * root_pos, float * vertices)
+{
+  if(!model || batch < 1 || !rest || !transforms || !vertices)
+    return fail(SMPLPP_ERR_INVALID, "LinearBlendSkinning", "Failed to get vertices of new pose!");
+  return launch_lbs(model->d, as_stream(stream), static_cast<int>(batch), rest, transforms, false, root_pos, 3, vertices);
+}
+
+extern "C" int smplpp_normals(const smplpp_model_t * model, void * stream, int64_t batch, const float * vertices,
+                              int64_t n_faces, const int64_t * face_idx, float * face_normals, int64_t n_verts,
+                              const int64_t * vert_idx, float * vertex_normals)
+{
+  if(!model || batch < 1 || !vertices || n_faces < 0 || n_verts < 0 || (n_faces > 0 && (!face_idx || !face_normals))
+     || (n_verts > 0 && (!vert_idx || !vertex_normals)))
+    return fail(SMPLPP_ERR_INVALID, "SMPL", "Failed to get face indices!");
+  long long total = batch * (n_faces + n_verts);
+  if(total == 0) return SMPLPP_OK;
+  const ModelDev & d = model->d;
+  normals_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, as_stream(stream)>>>(
+      d.faces, d.adj_offset, d.adj_faces, d.V, d.F, static_cast<int>(batch), vertices, static_cast<int>(n_faces),
+      reinterpret_cast<const long long *>(face_idx), face_normals, static_cast<int>(n_verts),
+      reinterpret_cast<const long long *>(vert_idx), vertex_normals);
+  SB_LAUNCHED();
+  return SMPLPP_OK;
+}

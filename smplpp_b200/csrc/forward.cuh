@@ -1,0 +1,31 @@
+// Internal launch helpers shared by forward.cu, blend_tc.cu and ik.cu.
+#pragma once
+#include "common.cuh"
+
+namespace sb
+{
+struct ChainTopo
+{
+  int parent[kJoints];
+  int depth[kJoints];
+  int max_depth;
+};
+
+ChainTopo make_topo(const ModelDev & d);
+
+// K1: rodrigues + pose features + joints + kinematic chain (one warp per frame)
+int launch_pose_chain(const ModelDev & d, cudaStream_t st, int B, const float * beta, long long beta_stride,
+                      const float * theta, float * coef, float * xforms, float * joints, float * xforms44);
+// K2 (FFMA): fused blend contraction (+ skinning when skin == true, else writes the rest shape)
+int launch_blend_skin_ffma(const ModelDev & d, cudaStream_t st, int B, const float * coef, const float * xforms,
+                           const float * theta, float * out, bool skin);
+// K2 (tcgen05 3xTF32): same contract as the skin == true FFMA kernel
+bool tc_blend_available();
+int launch_blend_skin_tc(const ModelDev & d, cudaStream_t st, int B, const float * coef, const float * xforms,
+                         const float * theta, float * out);
+// K3: standalone skinning; affine: xforms are (B,24,3,4) else (B,24,4,4)
+int launch_lbs(const ModelDev & d, cudaStream_t st, int B, const float * rest, const float * xforms, bool affine,
+               const float * root, int root_stride, float * out);
+
+extern int g_forward_variant;
+} // namespace sb

@@ -205,7 +205,15 @@ def make_smpl_params(seed: int = 0) -> SmplParams:
     rad = _radial_surface(cand, center)
     wgt = np.clip(rad, 0.05, None) ** 2
     keep = rng.random(cand.shape[0]) < wgt / wgt.max()
-    dirs = cand[keep][:VERTEX_NUM]
+    cand, rad = cand[keep], rad[keep]
+    # thin out near-coincident surface points (keeps the smallest triangles well above fp32 noise)
+    from scipy.spatial import cKDTree
+    pts = center + rad[:, None] * cand
+    drop = np.zeros(cand.shape[0], dtype=bool)
+    for i, j in sorted(cKDTree(pts).query_pairs(0.006)):
+        if not drop[i]:
+            drop[j] = True
+    dirs = cand[~drop][:VERTEX_NUM]
     assert dirs.shape[0] == VERTEX_NUM, dirs.shape
     hull = ConvexHull(dirs)
     assert hull.vertices.shape[0] == VERTEX_NUM
@@ -323,6 +331,10 @@ def make_marker_tasks(params: SmplParams, seed: int = 2):
     faces = params.face_indices.astype(np.int64) - 1
     verts = params.vertices_template.astype(np.float64)
     cent = verts[faces].mean(axis=1)
+    tri = verts[faces]
+    area = 0.5 * np.linalg.norm(np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]), axis=1)
+    edge = np.max([np.linalg.norm(tri[:, a] - tri[:, b], axis=1) for a, b in ((0, 1), (1, 2), (2, 0))], axis=0)
+    good = (area > np.quantile(area, 0.3)) & (edge < 0.05)  # well-shaped faces only
     face_idx = np.empty(len(MARKER_NAMES), dtype=np.int64)
     used = set()
     for m, name in enumerate(MARKER_NAMES):
@@ -330,7 +342,7 @@ def make_marker_tasks(params: SmplParams, seed: int = 2):
         target = _JOINTS[j] + np.asarray(off)
         orderf = np.argsort(np.linalg.norm(cent - target, axis=1))
         for f in orderf:
-            if int(f) not in used:
+            if int(f) not in used and good[f]:
                 used.add(int(f))
                 face_idx[m] = f
                 break
