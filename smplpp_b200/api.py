@@ -424,3 +424,92 @@ class LinearBlendSkinning(_Module):
 
     def getVertex(self):
         return self._verts.clone()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# VPoser decoder (include/smplpp/VPoser.h:33-90)
+# ----------------------------------------------------------------------------------------------------------------
+
+_VPOSER_KEYS = ("decoder_net.0.weight", "decoder_net.0.bias", "decoder_net.3.weight", "decoder_net.3.bias",
+                "decoder_net.5.weight", "decoder_net.5.bias")
+_VPOSER_SHAPES = ((512, LATENT_DIM), (512,), (512, 512), (512,), (126, 512), (126,))
+
+
+class VPoserDecoder:
+    """smplpp::VPoserDecoder (src/VPoser.cpp:143-238).  forward(latent (B,32)) -> (B,21,3) axis-angle."""
+
+    hiddenDim_ = 512
+    jointNum_ = 21
+
+    def __init__(self, params: Optional[dict] = None, device="cuda:0"):
+        self.m__device = torch.device(device)
+        self._h = None
+        if params is not None:
+            self.loadParams(params)
+
+    def to(self, device):
+        self.m__device = torch.device(device)
+        return self
+
+    def eval(self):  # Dropout is the identity in eval mode; the kernels implement exactly that
+        return self
+
+    def loadParamsFromJson(self, jsonPath: str):
+        """VPoserDecoderImpl::loadParamsFromJson (VPoser.cpp:169-238)."""
+        import os
+        if not os.path.exists(jsonPath):
+            raise SmplppError("VPoser Error: Cannot find a JSON file!")  # VPoser.cpp:182
+        with open(jsonPath) as f:
+            j = json.load(f)
+        self.loadParams({k: np.asarray(j[k], dtype=np.float32) for k in _VPOSER_KEYS})
+
+    def loadParams(self, params: dict):
+        _require_cuda(self.m__device)
+        arrs = []
+        for key, shape in zip(_VPOSER_KEYS, _VPOSER_SHAPES):
+            a = _np_f32(params[key])
+            if a.shape != shape:
+                raise SmplppError("VPoser Error: invalid dimension of %s from JSON file!" % key)  # VPoser.cpp:190
+            arrs.append(a)
+        desc = capi.VposerDesc(*[a.ctypes.data_as(capi.c_f32p) for a in arrs])
+        h = C.c_void_p()
+        with torch.cuda.device(self.m__device):
+            check(lib().smplpp_vposer_create(C.byref(desc), C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        if getattr(self, "_h", None) is not None and capi._lib is not None:
+            capi._lib.smplpp_vposer_destroy(self._h)
+            self._h = None
+
+    @property
+    def handle(self):
+        if self._h is None:
+            raise SmplppError("VPoser Error: Cannot find a JSON file!")
+        return self._h
+
+    def forward(self, latent, jacobian: bool = False):
+        z = _dev_f32(latent, self.m__device)
+        if z.dim() != 2 or z.shape[1] != LATENT_DIM:
+            raise SmplppError("VPoser Error: invalid latent tensor!")
+        b = z.shape[0]
+        aa = torch.empty((b, self.jointNum_, 3), dtype=torch.float32, device=self.m__device)
+        jac = torch.empty((b, 63, LATENT_DIM), dtype=torch.float32, device=self.m__device) if jacobian else None
+        with torch.cuda.device(self.m__device):
+            check(lib().smplpp_vposer_decode(self.handle, _stream(self.m__device), C.c_int64(b), _ptr(z), _ptr(aa),
+                                             _ptr(jac)))
+        return (aa, jac) if jacobian else aa
+
+    __call__ = forward
+
+
+def convertRotMatToAxisAngle(rotMat) -> torch.Tensor:
+    """smplpp::convertRotMatToAxisAngle (src/VPoser.cpp:25-120): (N,3,3) -> (N,3)."""
+    dev = rotMat.device if isinstance(rotMat, torch.Tensor) and rotMat.is_cuda else torch.device("cuda:0")
+    _require_cuda(dev)
+    r = _dev_f32(rotMat, dev)
+    n = r.shape[0]
+    out = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().smplpp_rotmat_to_axis_angle(_stream(dev), C.c_int64(n), _ptr(r), _ptr(out)))
+    return out

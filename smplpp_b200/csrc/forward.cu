@@ -295,6 +295,7 @@ __global__ void __launch_bounds__(k2::THREADS, 2)
 
   // ---- epilogue ----
   const int vbase = v0 + tx * TNV;
+  const bool vec_ok = (V & 1) == 0; // float2 stores need (b V + v) 3 even
   if(kSkin)
   {
     cp_async_wait_all();
@@ -363,7 +364,7 @@ __global__ void __launch_bounds__(k2::THREADS, 2)
         o[3 * jv + 2] = fmaf(oz, iw, trz);
       }
       float * dst = out + (static_cast<size_t>(b) * V + vbase) * 3;
-      if(vbase + TNV <= V)
+      if(vbase + TNV <= V && vec_ok)
       {
 #pragma unroll
         for(int q = 0; q < TN / 2; q++) reinterpret_cast<float2 *>(dst)[q] = make_float2(o[2 * q], o[2 * q + 1]);
@@ -383,7 +384,7 @@ __global__ void __launch_bounds__(k2::THREADS, 2)
       const int b = m0 + ty * TM + i;
       if(b >= B) continue;
       float * dst = out + (static_cast<size_t>(b) * V + vbase) * 3;
-      if(vbase + TNV <= V)
+      if(vbase + TNV <= V && vec_ok)
       {
 #pragma unroll
         for(int q = 0; q < TN / 2; q++) reinterpret_cast<float2 *>(dst)[q] = make_float2(acc[i][2 * q], acc[i][2 * q + 1]);
@@ -445,7 +446,8 @@ __global__ void __launch_bounds__(k3::THREADS)
   }
   __syncthreads();
   if(v >= V) return;
-  const bool pair = v + 1 < V;
+  const bool has2 = v + 1 < V;
+  const bool pair = has2 && (V & 1) == 0; // float2 path needs 8-byte aligned rows
   for(int f = 0; f < nfr; f++)
   {
     const size_t base = (static_cast<size_t>(b0 + f) * V + v) * 3;
@@ -459,7 +461,9 @@ __global__ void __launch_bounds__(k3::THREADS)
     else
     {
       r[0] = rest[base], r[1] = rest[base + 1], r[2] = rest[base + 2];
-      r[3] = r[4] = r[5] = 0.f;
+      r[3] = has2 ? rest[base + 3] : 0.f;
+      r[4] = has2 ? rest[base + 4] : 0.f;
+      r[5] = has2 ? rest[base + 5] : 0.f;
     }
     float tx = 0.f, ty = 0.f, tz = 0.f;
     if(root)
@@ -513,6 +517,7 @@ __global__ void __launch_bounds__(k3::THREADS)
     else
     {
       out[base] = o[0], out[base + 1] = o[1], out[base + 2] = o[2];
+      if(has2) out[base + 3] = o[3], out[base + 4] = o[4], out[base + 5] = o[5];
     }
   }
 }

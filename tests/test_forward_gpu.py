@@ -1,0 +1,239 @@
+"""GPU parity tests of the forward path (K1 pose chain, K2 fused blend + skinning, K3 skinning, module kernels,
+normals) against the oracle and the reference golden vectors.  Everything goes through the C-ABI library."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import TOL_VERTEX_M
+
+pytestmark = pytest.mark.gpu
+
+f32 = np.float32
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=f32), device="cuda:0")
+
+
+# ---- known-answer vectors of src/toolbox/Tester.cpp through the module-level API ----
+
+def test_kat_blend_shape(kat):
+    from smplpp_b200 import api
+    i, e = kat["blendShape"]["inputs"], kat["blendShape"]["expected"]
+    m = api.BlendShape()
+    m.setBeta(np.asarray(i["beta"]))
+    m.setTheta(np.asarray(i["theta"]))
+    m.setShapeBlendBasis(np.asarray(i["shapeBlendBasis"]))
+    m.setPoseBlendBasis(np.asarray(i["poseBlendBasis"]))
+    m.blend()
+    assert np.allclose(m.getShapeBlendShape().cpu().numpy().reshape(-1), np.asarray(e["shapeBlendShape"]).reshape(-1),
+                       atol=2e-6)
+    assert np.allclose(m.getPoseBlendShape().cpu().numpy().reshape(-1), np.asarray(e["poseBlendShape"]).reshape(-1),
+                       atol=5e-6)
+    assert np.allclose(m.getPoseRotation().cpu().numpy()[0, :5], np.asarray(e["poseRotation"]), atol=1.5e-6)
+
+
+def test_kat_joint_regression(kat):
+    from smplpp_b200 import api
+    i, e = kat["jointRegression"]["inputs"], kat["jointRegression"]["expected"]
+    m = api.JointRegression()
+    m.setShapeBlendShape(np.asarray(i["shapeBlendShape"]))
+    m.setPoseBlendShape(np.asarray(i["poseBlendShape"]))
+    m.setTemplateRestShape(np.asarray(i["templateShape"]))
+    m.setJointRegressor(np.asarray(i["jointRegressor"]))
+    m.regress()
+    assert np.allclose(m.getRestShape().cpu().numpy(), np.asarray(e["restShape"]), atol=1.5e-6)
+    assert np.allclose(m.getJoint().cpu().numpy()[0], np.asarray(e["joints"]), atol=2e-6)
+
+
+def test_kat_world_transformation(kat):
+    from smplpp_b200 import api
+    i, e = kat["worldTransformation"]["inputs"], kat["worldTransformation"]["expected"]
+    m = api.WorldTransformation()
+    m.setKinematicTree(np.asarray(i["kineTree"], dtype=np.int64))
+    m.setJoint(np.asarray(i["joints"]))
+    m.setPoseRotation(np.asarray(i["poseRotation"]))
+    m.transform()
+    got = m.getTransformation().cpu().numpy()[0, :5]
+    assert np.allclose(got, np.asarray(e["transformations"]), atol=2e-6, rtol=2e-6)
+
+
+def test_kat_linear_blend_skinning(kat):
+    from smplpp_b200 import api
+    i, e = kat["linearBlendSkinning"]["inputs"], kat["linearBlendSkinning"]["expected"]
+    m = api.LinearBlendSkinning()
+    m.setWeight(np.asarray(i["weights"]))
+    m.setRestShape(np.asarray(i["restShape"]))
+    m.setTransformation(np.asarray(i["transformations"]))
+    m.skinning()
+    assert np.allclose(m.getVertex().cpu().numpy().reshape(-1), np.asarray(e["vertices"]).reshape(-1), atol=1.5e-6)
+
+
+# ---- full model: golden vectors of the compiled reference ----
+
+@pytest.mark.parametrize("variant", [1, 3])
+def test_forward_vs_reference_golden(smpl_gpu, golden_forward, variant):
+    from smplpp_b200 import capi
+    g = golden_forward
+    capi.check(capi.lib().smplpp_set_forward_variant(variant))
+    try:
+        smpl_gpu.launch(g["beta"], g["theta"])
+        v = smpl_gpu.getVertex().cpu().numpy()
+        j = smpl_gpu.getRestJoint().cpu().numpy()
+        rest = smpl_gpu.getRestShape().cpu().numpy()
+    finally:
+        capi.check(capi.lib().smplpp_set_forward_variant(0))
+    assert np.abs(v - g["vertices"]).max() <= TOL_VERTEX_M
+    assert np.abs(j - g["joints"]).max() <= TOL_VERTEX_M
+    assert np.abs(rest - g["rest_shape"]).max() <= TOL_VERTEX_M
+    # in practice the fp32 FFMA path sits two orders below the stated tolerance
+    assert np.abs(v - g["vertices"]).max() < 2e-6
+
+
+def test_normals_vs_reference_golden(smpl_gpu, golden_forward):
+    g = golden_forward
+    smpl_gpu.launch(g["beta"][:1], g["theta"][:1])
+    fn, vn = smpl_gpu.normals(g["normal_face_idx"], g["normal_vert_idx"])
+    assert np.abs(fn.cpu().numpy()[0] - g["face_normals"]).max() < 5e-5
+    assert np.abs(vn.cpu().numpy()[0] - g["vertex_normals"]).max() < 5e-5
+    assert np.abs(smpl_gpu.calcNormal(int(g["normal_face_idx"][3])).cpu().numpy() - g["face_normals"][3]).max() < 5e-5
+
+
+# ---- full model vs the oracle on seeded inputs (ragged batch sizes cross every tile boundary) ----
+
+@pytest.mark.parametrize("batch,seed,shared_beta", [(1, 10, False), (70, 11, False), (129, 12, True)])
+def test_forward_vs_oracle(smpl_gpu, oracle_model, batch, seed, shared_beta):
+    from oracle import smpl_oracle as so
+    from smplpp_b200 import synth
+    beta, theta = synth.make_forward_inputs(batch, seed)
+    if shared_beta:
+        beta = np.repeat(beta[:1], batch, axis=0)
+    v_o, j_o, rest_o, xf_o = so.forward_numpy(oracle_model, beta, theta)
+    smpl_gpu.launch(beta[:1] if shared_beta else beta, theta, want_transforms=True)
+    v = smpl_gpu.getVertex().cpu().numpy()
+    assert np.abs(v - v_o).max() <= TOL_VERTEX_M
+    assert np.abs(smpl_gpu.getRestJoint().cpu().numpy() - j_o).max() <= TOL_VERTEX_M
+    assert np.abs(smpl_gpu.getRestShape().cpu().numpy() - rest_o).max() <= TOL_VERTEX_M
+    assert np.abs(smpl_gpu.getTransformation().cpu().numpy() - xf_o).max() <= TOL_VERTEX_M
+
+
+def test_edge_poses_vs_oracle(smpl_gpu, oracle_model):
+    """theta = 0 (Rodrigues with a = sqrt(3) 1e-8), tiny angles, angles near pi and 2 pi."""
+    from oracle import smpl_oracle as so
+    rng = np.random.default_rng(3)
+    theta = np.zeros((6, 25, 3), f32)
+    theta[1, 1:] = 1e-7
+    theta[2, 1:] = rng.normal(size=(24, 3)) * 1e-4
+    axis = rng.normal(size=(24, 3))
+    axis /= np.linalg.norm(axis, axis=1, keepdims=True)
+    theta[3, 1:] = axis * np.pi
+    theta[4, 1:] = axis * (2 * np.pi - 1e-3)
+    theta[5, 1:] = axis * 5.0
+    theta[:, 0] = rng.uniform(-1, 1, size=(6, 3))
+    beta = rng.normal(size=(6, 10)).astype(f32) * 2
+    v_o, j_o, _, _ = so.forward_numpy(oracle_model, beta, theta)
+    smpl_gpu.launch(beta, theta)
+    assert np.abs(smpl_gpu.getVertex().cpu().numpy() - v_o).max() <= TOL_VERTEX_M
+    assert np.isfinite(smpl_gpu.getVertex().cpu().numpy()).all()
+
+
+def test_model_skinning_vs_oracle(smpl_gpu, oracle_model, params):
+    """K3 standalone (packed sparse weights, 4x4 transforms incl. homogeneous row) vs LinearBlendSkinning."""
+    import ctypes as C
+    from oracle import smpl_oracle as so
+    from smplpp_b200 import api, capi, synth
+    beta, theta = synth.make_forward_inputs(19, 13)
+    with torch.no_grad():
+        r = so.smpl_launch(oracle_model, torch.as_tensor(beta), torch.as_tensor(theta))
+    rest, xf = dev(r.rest_shape.numpy()), dev(r.transforms.numpy())
+    root = dev(theta[:, 0])
+    out = torch.empty_like(rest)
+    capi.check(capi.lib().smplpp_model_skinning(smpl_gpu.handle, None, C.c_int64(19), api._ptr(rest), api._ptr(xf),
+                                                api._ptr(root), api._ptr(out)))
+    torch.cuda.synchronize()
+    assert np.abs(out.cpu().numpy() - r.vertices.numpy()).max() <= TOL_VERTEX_M
+
+
+def test_dense_weights_small_model():
+    """A model whose skinning rows are dense (24 non-zeros, sums != 1) and V not a multiple of the tile."""
+    from oracle import smpl_oracle as so
+    from smplpp_b200 import api, synth
+    rng = np.random.default_rng(7)
+    V = 77
+    tree = np.stack([synth.PARENTS.copy(), np.arange(24)])
+    tree[0, 0] = 4294967295
+    faces = np.stack([rng.permutation(V)[:3] for _ in range(40)]).astype(np.int32) + 1
+    p = synth.SmplParams(
+        face_indices=faces, shape_blend_shapes=rng.normal(size=(V, 3, 10)).astype(f32) * 0.01,
+        pose_blend_shapes=rng.normal(size=(V, 3, 207)).astype(f32) * 0.002,
+        vertices_template=rng.normal(size=(V, 3)).astype(f32) * 0.3,
+        joint_regressor=rng.dirichlet(np.ones(V), size=24).astype(f32), kinematic_tree=tree,
+        weights=rng.uniform(0.1, 1.0, size=(V, 24)).astype(f32))
+    m = api.SMPL(p)
+    assert m.vertex_num == V
+    beta, theta = synth.make_forward_inputs(5, 14)
+    om = so.SmplModel.from_params(p)
+    v_o, j_o, rest_o, _ = so.forward_numpy(om, beta, theta)
+    m.launch(beta, theta)
+    assert np.abs(m.getVertex().cpu().numpy() - v_o).max() <= TOL_VERTEX_M
+    assert np.abs(m.getRestShape().cpu().numpy() - rest_o).max() <= TOL_VERTEX_M
+    assert np.abs(m.getRestJoint().cpu().numpy() - j_o).max() <= TOL_VERTEX_M
+
+
+# ---- BASELINE config 2 (B = 4096): size-independent properties ----
+
+def test_full_batch_properties(smpl_gpu, oracle_model):
+    from oracle import smpl_oracle as so
+    from smplpp_b200 import synth
+    B = 4096
+    beta, theta = synth.make_forward_inputs(B, 11)
+    smpl_gpu.launch(beta, theta)
+    v = smpl_gpu.getVertex()
+    assert torch.isfinite(v).all()
+    # (a) batch invariance: any frame of the big batch equals the same frame launched alone
+    pick = [0, 63, 64, 1000, 4095]
+    smpl_gpu.launch(beta[pick], theta[pick])
+    assert (smpl_gpu.getVertex() - v[pick]).abs().max().item() == 0.0
+    # (b) spot-check against the oracle
+    v_o, _, _, _ = so.forward_numpy(oracle_model, beta[pick], theta[pick])
+    assert np.abs(v[pick].cpu().numpy() - v_o).max() <= TOL_VERTEX_M
+    # (c) translation equivariance: moving theta row 0 moves every vertex by the same vector
+    shift = np.array([0.25, -1.5, 3.0], f32)
+    theta2 = theta.copy()
+    theta2[:, 0] += shift
+    smpl_gpu.launch(beta, theta2)
+    d = smpl_gpu.getVertex() - v
+    assert (d - torch.as_tensor(shift, device=d.device)).abs().max().item() < 2e-6
+    # (d) rest pose: theta = 0 gives T + S beta (+ translation)
+    theta0 = np.zeros_like(theta[:8])
+    theta0[:, 0] = theta[:8, 0]
+    smpl_gpu.launch(beta[:8], theta0)
+    rest = smpl_gpu.getRestShape()
+    assert (smpl_gpu.getVertex() - (rest + torch.as_tensor(theta0[:, :1], device=rest.device))).abs().max().item() < 2e-6
+
+
+def test_launch_host_matches_device(smpl_gpu):
+    from smplpp_b200 import synth
+    beta, theta = synth.make_forward_inputs(33, 15)
+    smpl_gpu.launch(beta, theta)
+    v = smpl_gpu.getVertex().cpu().numpy()
+    j = smpl_gpu.getRestJoint().cpu().numpy()
+    vh, jh = smpl_gpu.launch_host(beta, theta)
+    assert np.array_equal(v, vh) and np.array_equal(j, jh)
+
+
+def test_error_messages(smpl_gpu):
+    """Shape violations raise with the reference's message text (smpl_error, Exception.cpp:77-91)."""
+    from smplpp_b200 import api
+    with pytest.raises(api.SmplppError, match="Cannot launch a SMPL model!"):
+        smpl_gpu.launch(np.zeros((2, 10), f32), np.zeros((2, 24, 3), f32))
+    with pytest.raises(api.SmplppError, match="BlendShape Error: Failed to set beta!"):
+        smpl_gpu.launch(np.zeros((2, 9), f32), np.zeros((2, 25, 3), f32))
+    m = api.BlendShape()
+    with pytest.raises(api.SmplppError, match="Failed to set theta!"):
+        m.setTheta(np.zeros((1, 23, 3), f32))
+    fresh = api.SMPL()
+    with pytest.raises(api.SmplppError, match="Failed to initialize model path!"):
+        fresh.setModelPath("/nonexistent/smpl_male.json")
+    with pytest.raises(api.SmplppError, match="Cannot initialize a SMPL model!"):
+        fresh.init()
