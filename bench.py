@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path (BASELINE.json: "SMPL FK+LBS meshes/s and IK frame-iters/s ...; % HBM roofline").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One step = one pass of the SMPL forward path (K1 pose chain + K2 fused blend-shape contraction & skinning)
+over one batch of B = 4096 synthetic poses per GPU (BASELINE configs[1]); for N > 1 (torchrun, one rank per
+GPU) every rank owns its own 4096 frames: frames are independent, there is no data-path collective (weak
+scaling).  Rank 0 prints ONE JSON line.  The same line carries
+  roofline      dominant kernel (fused blend+skinning) against the measured HBM peak, plus `lbs` for the
+                standalone skinning kernel (the HBM-bound row of SURVEY.md §8d, 166 512 algorithmic B/mesh)
+  e2e           the same metric through the C-ABI host-buffer call smplpp_forward_host (H2D + D2H inside)
+  ik            IK frame-iterations/s of the batched MoSh step (configs[2]-shaped) when available
+  cpu_baseline  the reference's own libtorch CPU implementation (oracle/_ref) on this box's host cores
+`--impl reference` times only that CPU implementation and prints the line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 4096
+VERTS = 6890
+# algorithmic bytes per mesh (stated in DESIGN.md)
+BYTES_FUSED = VERTS * 3 * 4 + (25 * 3 + 10) * 4  # vertices out + theta, beta in
+BYTES_LBS = 2 * VERTS * 3 * 4 + 24 * 12 * 4  # rest in + vertices out + 24 transforms
+FLOPS_BLEND = 2 * 218 * VERTS * 3  # pose (207) + shape (10) + template (1) contraction
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                if out.returncode == 0 and out.stdout.strip():
+                    self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_reference_forward(batch_total: int, threads: int | None = None, chunk: int = 256, reps: int = 3):
+    """Times the reference's own libtorch CPU forward (unmodified sources, oracle/_ref) on host cores.
+    Returns (meshes/s, cores, sample description)."""
+    from oracle import ref_lib
+    from smplpp_b200 import synth
+    if not ref_lib.available():
+        raise RuntimeError("oracle/_ref/libsmplpp_ref.so is missing (built by `make -C oracle` in the build container)")
+    if threads:
+        ref_lib.set_num_threads(threads)
+    cores = ref_lib.get_num_threads()
+    ref = ref_lib.RefSMPL(ref_lib.model_json_path(0))
+    beta, theta = synth.make_forward_inputs(chunk, 11)
+    ref.forward(beta, theta, batched=True, want=("vertices",))  # warm-up
+    best = None
+    done = 0
+    t_all = time.perf_counter()
+    while done < batch_total:
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ref.forward(beta, theta, batched=True, want=("vertices",))
+        dt = (time.perf_counter() - t0) / reps
+        best = dt if best is None else min(best, dt)
+        done += chunk * reps
+        if time.perf_counter() - t_all > 25:
+            break
+    sample = ("SMPL::launch+getVertex of the unmodified reference sources (libtorch CPU, batched build N=%d, "
+              "same synthetic model/inputs), %d meshes timed" % (chunk, done))
+    return chunk / best, cores, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    per_step = 1024  # bounded sample of the B=4096 workload per step
+    from oracle import ref_lib
+    from smplpp_b200 import synth
+    cores = os.cpu_count() or 1
+    ref_lib.set_num_threads(cores)
+    ref = ref_lib.RefSMPL(ref_lib.model_json_path(0))
+    beta, theta = synth.make_forward_inputs(256, 11)
+    for _ in range(max(1, args.warmup)):
+        ref.forward(beta, theta, batched=True, want=("vertices",))
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for _ in range(per_step // 256):
+            ref.forward(beta, theta, batched=True, want=("vertices",))
+    dt = time.perf_counter() - t0
+    value = args.steps * per_step / dt
+    line = {
+        "impl": "reference", "metric": "SMPL FK+LBS meshes/s", "value": value, "unit": "meshes/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1] batched SMPL forward (pose-blend GEMM + joint chain + LBS), reference CPU "
+                               "path; each step = bounded sample of %d of the 4096 poses" % per_step},
+        "cpu_baseline": {"value": value, "unit": "meshes/s", "cores": ref_lib.get_num_threads(), "kind": "reference",
+                         "sample": "unmodified reference sources (oracle/_ref, libtorch CPU, batched build N=256), "
+                                   "%d meshes per step" % per_step},
+        "e2e": {"value": value, "unit": "meshes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH, help="frames per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ik", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from smplpp_b200 import api, capi, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    B = args.batch
+    params = synth.make_smpl_params(0)
+    smpl = api.SMPL(params, device=dev)
+    beta_h, theta_h = synth.make_forward_inputs(B, 11 + rank)
+    beta, theta = torch.as_tensor(beta_h, device=dev), torch.as_tensor(theta_h, device=dev)
+    lib = capi.lib()
+    import ctypes as C
+    ws_bytes = lib.smplpp_forward_workspace_bytes(smpl.handle, C.c_int64(B))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    verts = torch.empty((B, VERTS, 3), dtype=torch.float32, device=dev)
+    joints = torch.empty((B, 24, 3), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step():
+        capi.check(lib.smplpp_forward(smpl.handle, C.c_void_p(stream.cuda_stream), C.c_int64(B),
+                                      C.c_void_p(beta.data_ptr()), C.c_int64(10), C.c_void_p(theta.data_ptr()),
+                                      C.c_void_p(verts.data_ptr()), C.c_void_p(joints.data_ptr()), None, None,
+                                      C.c_void_p(ws.data_ptr()), C.c_size_t(ws_bytes)))
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = lib.smplpp_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step()
+        ev1.record(stream)
+        barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = int(lib.smplpp_launch_count() - launches0)
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step * 1e-3)
+
+    # ---- per-kernel device times (CUDA events on the launching stream), same workload ----
+    def time_kernel(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(reps):
+            fn()
+        b.record(stream)
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    # dominant kernel: time the step with and without it (K1 alone = joints only)
+    def k1_only():
+        capi.check(lib.smplpp_forward(smpl.handle, C.c_void_p(stream.cuda_stream), C.c_int64(B),
+                                      C.c_void_p(beta.data_ptr()), C.c_int64(10), C.c_void_p(theta.data_ptr()),
+                                      None, C.c_void_p(joints.data_ptr()), None, None, C.c_void_p(ws.data_ptr()),
+                                      C.c_size_t(ws_bytes)))
+
+    ms_k1 = time_kernel(k1_only, 20)
+    ms_full = time_kernel(step, 20)
+    ms_k2 = max(ms_full - ms_k1, 1e-6)
+    peak, peak_src = measured_peaks()
+    ach = BYTES_FUSED * B / (ms_k2 * 1e-3) / 1e9
+    roofline = {"kernel": "blend_skin (fused pose/shape blend contraction + linear blend skinning)", "bound": "hbm",
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "peak_source": peak_src, "ms_per_launch": ms_k2,
+                "fp32_tflops_algorithmic": FLOPS_BLEND * B / (ms_k2 * 1e-3) / 1e12}
+
+    # standalone skinning kernel (the HBM-bound row): rest shape + 4x4 transforms -> vertices
+    rest = torch.empty((B, VERTS, 3), dtype=torch.float32, device=dev)
+    xf = torch.empty((B, 24, 4, 4), dtype=torch.float32, device=dev)
+    capi.check(lib.smplpp_forward(smpl.handle, C.c_void_p(stream.cuda_stream), C.c_int64(B),
+                                  C.c_void_p(beta.data_ptr()), C.c_int64(10), C.c_void_p(theta.data_ptr()), None, None,
+                                  C.c_void_p(xf.data_ptr()), C.c_void_p(rest.data_ptr()), C.c_void_p(ws.data_ptr()),
+                                  C.c_size_t(ws_bytes)))
+    root = theta[:, 0].contiguous()
+
+    def lbs_only():
+        capi.check(lib.smplpp_model_skinning(smpl.handle, C.c_void_p(stream.cuda_stream), C.c_int64(B),
+                                             C.c_void_p(rest.data_ptr()), C.c_void_p(xf.data_ptr()),
+                                             C.c_void_p(root.data_ptr()), C.c_void_p(verts.data_ptr())))
+
+    ms_lbs = time_kernel(lbs_only, 20)
+    ach_lbs = BYTES_LBS * B / (ms_lbs * 1e-3) / 1e9
+    roofline["lbs"] = {"kernel": "lbs_kernel (standalone skinning)", "bound": "hbm", "achieved": ach_lbs, "peak": peak,
+                       "unit": "GB/s", "frac": ach_lbs / peak, "ms_per_launch": ms_lbs,
+                       "meshes_per_s": B / (ms_lbs * 1e-3)}
+    del rest, xf
+
+    # ---- e2e through the C-ABI host-buffer call (pinned staging, H2D + D2H inside the timed region) ----
+    e2e_steps = max(3, min(args.steps, 10))
+    smpl.launch_host(beta_h, theta_h)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        smpl.launch_host(beta_h, theta_h)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    e2e = {"value": world * B / e2e_s, "unit": "meshes/s", "h2d_bytes_per_step": int(beta_h.nbytes + theta_h.nbytes),
+           "d2h_bytes_per_step": int(B * VERTS * 3 * 4 + B * 24 * 3 * 4),
+           "api": "smplpp_forward_host (smplpp::SMPL::launch + getVertex + getRestJoint with host buffers)"}
+
+    ik = None
+    if not args.no_ik:
+        try:
+            from smplpp_b200 import ik_bench
+            ik = ik_bench.run(dev, rank, world, max_over_ranks, barrier)
+        except ImportError:
+            ik = None
+
+    line = {
+        "metric": "SMPL FK+LBS meshes/s", "value": value, "unit": "meshes/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: batched SMPL forward B=%d poses/GPU fp32 (pose-blend GEMM + joint chain + "
+                               "LBS), synthetic smpl_male-shaped model (6890 verts, 207 pose dims, 10 betas)" % B,
+                   "frames_per_gpu": B, "l2": "no flush: every step writes %d MB of vertices (> 126 MB L2); the 18 MB "
+                                              "blend basis is model state that stays resident" % (B * VERTS * 12 >> 20),
+                   "variant": "auto"},
+        "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roofline, "e2e": e2e,
+    }
+    if ik is not None:
+        line["ik"] = ik
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        try:
+            v, cores, sample = cpu_reference_forward(1024)
+            line["cpu_baseline"] = {"value": v, "unit": "meshes/s", "cores": cores, "kind": "reference", "sample": sample}
+        except Exception as ex:  # the oracle library is test infrastructure; say so instead of failing the bench
+            line["cpu_baseline"] = {"value": None, "unit": "meshes/s", "cores": 0, "kind": "reference",
+                                    "sample": "unavailable: %s" % ex}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

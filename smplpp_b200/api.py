@@ -513,3 +513,187 @@ def convertRotMatToAxisAngle(rotMat) -> torch.Tensor:
     with torch.cuda.device(dev):
         check(lib().smplpp_rotmat_to_axis_angle(_stream(dev), C.c_int64(n), _ptr(r), _ptr(out)))
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# IK (include/smplpp/IkTask.h:13-85 and the loop body of node/node.cpp:753-968, batched over frames)
+# ----------------------------------------------------------------------------------------------------------------
+
+def ik_options(**kw) -> capi.IkOptions:
+    """smplpp_ik_options with the constants of node/node.cpp (see include/smplpp_b200.h); override by keyword."""
+    o = capi.IkOptions()
+    lib().smplpp_ik_options_default(C.byref(o))
+    for k, v in kw.items():
+        if not hasattr(o, k):
+            raise SmplppError("IkTask Error: unknown IK option %s" % k)
+        setattr(o, k, v)
+    return o
+
+
+def calcTriangleVertexWeights(pos, vertices) -> torch.Tensor:
+    """smplpp::calcTriangleVertexWeights (GeometryUtils.h:42-52), batched: pos (N,3), vertices (N,3,3) -> (N,3)."""
+    dev = torch.device("cuda:0")
+    _require_cuda(dev)
+    p = _dev_f32(pos, dev).reshape(-1, 3)
+    t = _dev_f32(vertices, dev).reshape(-1, 3, 3)
+    out = torch.empty_like(p)
+    with torch.cuda.device(dev):
+        check(lib().smplpp_triangle_vertex_weights(_stream(dev), C.c_int64(p.shape[0]), _ptr(p), _ptr(t), _ptr(out)))
+    return out
+
+
+class IkTaskSet:
+    """n smplpp::IkTask objects (one attachment face each) handled as one batch over B frames.
+
+    Per-task fields of IkTask.h:59-84 that the node varies per frame (targetPos_, posTaskWeight_,
+    vertexWeights_) are (B,n,...) device tensors owned by the caller; the ones it sets once per mode
+    (normalTaskWeight_, phiLimit_, normalOffset_) live in the options."""
+
+    def __init__(self, smpl: SMPL, face_idx, vposer: Optional[VPoserDecoder] = None):
+        self.smpl, self.vposer = smpl, vposer
+        self.face_idx = np.ascontiguousarray(face_idx, dtype=np.int64)
+        self.n = int(self.face_idx.shape[0])
+        h = C.c_void_p()
+        with torch.cuda.device(smpl.m__device):
+            check(lib().smplpp_tasks_create(smpl.handle, C.c_int32(self.n), self.face_idx.ctypes.data_as(capi.c_i64p),
+                                            C.byref(h)))
+        self._h = h
+        self._ws = None
+
+    def __del__(self):
+        if getattr(self, "_h", None) is not None and capi._lib is not None:
+            capi._lib.smplpp_tasks_destroy(self._h)
+            self._h = None
+
+    @property
+    def vertex_count(self) -> int:
+        return int(lib().smplpp_tasks_vertex_count(self._h))
+
+    def default_vertex_weights(self, batch: int) -> torch.Tensor:
+        """IkTask::vertexWeights_ default 1/3 (IkTask.h:78)."""
+        return torch.full((batch, self.n, 3), 1.0 / 3.0, dtype=torch.float32, device=self.smpl.m__device)
+
+    def positions(self, vertices: torch.Tensor, vertex_weights: torch.Tensor, normal_offset: float = 0.0,
+                  want_normals: bool = False):
+        """IkTask::calcActualPos (+calcActualNormal) for every frame of a (B,V,3) vertex buffer."""
+        dev = self.smpl.m__device
+        v = _dev_f32(vertices, dev)
+        w = _dev_f32(vertex_weights, dev)
+        b = v.shape[0]
+        pos = torch.empty((b, self.n, 3), dtype=torch.float32, device=dev)
+        nrm = torch.empty((b, self.n, 3), dtype=torch.float32, device=dev) if want_normals else None
+        with torch.cuda.device(dev):
+            check(lib().smplpp_task_positions(self.smpl.handle, self._h, _stream(dev), C.c_int64(b), _ptr(v), _ptr(w),
+                                              C.c_float(normal_offset), _ptr(pos), _ptr(nrm)))
+        return (pos, nrm) if want_normals else pos
+
+    def _workspace(self, nbytes: int) -> torch.Tensor:
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.smpl.m__device)
+        return self._ws
+
+    def step(self, opt: capi.IkOptions, theta_state: torch.Tensor, beta: torch.Tensor, vertex_weights: torch.Tensor,
+             target_pos: torch.Tensor, pos_task_weight: Optional[torch.Tensor] = None,
+             target_normal: Optional[torch.Tensor] = None, outputs: bool = False):
+        """One IK iteration for all frames (node/node.cpp:753-968 per frame).  theta_state (B,75|44), beta
+        ((B,10) or (10,) shared) and vertex_weights (B,n,3) are updated IN PLACE.  Returns status (B,) int32 and,
+        with outputs=True, a dict of e (B,4n), J (B,4n,dim), A (B,dim,dim), b, delta in the reference layout."""
+        dev = self.smpl.m__device
+        for name, t in (("theta_state", theta_state), ("beta", beta), ("vertex_weights", vertex_weights),
+                        ("target_pos", target_pos)):
+            if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise SmplppError("IkTask Error: %s must be a contiguous float32 CUDA tensor" % name)
+        b = theta_state.shape[0]
+        theta_dim = int(lib().smplpp_ik_theta_dim(C.byref(opt)))
+        if theta_state.shape != (b, theta_dim):
+            raise SmplppError("IkTask Error: theta state must be (B, %d)" % theta_dim)
+        if vertex_weights.shape != (b, self.n, 3) or target_pos.shape != (b, self.n, 3):
+            raise SmplppError("IkTask Error: task tensors must be (B, %d, 3)" % self.n)
+        stride = 0 if beta.numel() == SHAPE_BASIS_DIM and b > 1 else SHAPE_BASIS_DIM
+        dim = int(lib().smplpp_ik_dim(C.byref(opt), C.c_int32(self.n)))
+        status = torch.empty((b,), dtype=torch.int32, device=dev)
+        out = None
+        if outputs:
+            out = dict(e=torch.empty((b, 4 * self.n), dtype=torch.float32, device=dev),
+                       J=torch.empty((b, 4 * self.n, dim), dtype=torch.float32, device=dev),
+                       A=torch.empty((b, dim, dim), dtype=torch.float64, device=dev),
+                       b=torch.empty((b, dim), dtype=torch.float64, device=dev),
+                       delta=torch.empty((b, dim), dtype=torch.float64, device=dev))
+        need = lib().smplpp_ik_workspace_bytes(self._h, C.byref(opt), C.c_int64(b))
+        ws = self._workspace(need)
+        vp = self.vposer.handle if (opt.enable_vposer and self.vposer is not None) else None
+        with torch.cuda.device(dev):
+            check(lib().smplpp_ik_step(
+                self.smpl.handle, vp, self._h, C.byref(opt), _stream(dev), C.c_int64(b), _ptr(theta_state), _ptr(beta),
+                C.c_int64(stride), _ptr(vertex_weights), _ptr(target_pos), _ptr(target_normal), _ptr(pos_task_weight),
+                _ptr(status), _ptr(out["e"]) if out else None, _ptr(out["J"]) if out else None,
+                _ptr(out["A"]) if out else None, _ptr(out["b"]) if out else None, _ptr(out["delta"]) if out else None,
+                _ptr(ws), C.c_size_t(ws.numel())))
+        return (status, out) if outputs else status
+
+    def shared_beta_step(self, opt: capi.IkOptions, theta_state: torch.Tensor, shared_beta: torch.Tensor,
+                         vertex_weights: torch.Tensor, target_pos: torch.Tensor,
+                         pos_task_weight: Optional[torch.Tensor] = None, process_group=None, return_reduced=False):
+        """MoSh++ shape stage over the frames of ALL ranks: per-frame Schur complement onto the 10 shared betas,
+        ONE all-reduce of 111 doubles (only collective of the path), identical 10-dim box QP on every rank,
+        back-substitution.  theta_state (B,75|44) and shared_beta (10,) are updated in place."""
+        import torch.distributed as dist
+        dev = self.smpl.m__device
+        b = theta_state.shape[0]
+        status = torch.empty((b,), dtype=torch.int32, device=dev)
+        reduced = torch.empty((111,), dtype=torch.float64, device=dev)
+        need = lib().smplpp_ik_shared_beta_workspace_bytes(self._h, C.byref(opt), C.c_int64(b))
+        ws = self._workspace(need)
+        vp = self.vposer.handle if (opt.enable_vposer and self.vposer is not None) else None
+        with torch.cuda.device(dev):
+            check(lib().smplpp_ik_shared_beta_reduce(
+                self.smpl.handle, vp, self._h, C.byref(opt), _stream(dev), C.c_int64(b), _ptr(theta_state),
+                _ptr(shared_beta), _ptr(vertex_weights), _ptr(target_pos), _ptr(pos_task_weight), _ptr(status),
+                _ptr(reduced), _ptr(ws), C.c_size_t(ws.numel())))
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1:
+                dist.all_reduce(reduced, op=dist.ReduceOp.SUM, group=process_group)
+            check(lib().smplpp_ik_shared_beta_apply(self._h, C.byref(opt), _stream(dev), C.c_int64(b), _ptr(theta_state),
+                                                    _ptr(shared_beta), _ptr(status), _ptr(reduced), _ptr(ws),
+                                                    C.c_size_t(ws.numel())))
+        return (status, reduced) if return_reduced else status
+
+
+class IkTask:
+    """smplpp::IkTask for ONE face on batch element 0 of the last SMPL::launch — the reference's object-level
+    interface (IkTask.h:20-84), kept for callers that drive single tasks; batched work uses IkTaskSet."""
+
+    def __init__(self, smpl: SMPL, faceIdx: int, targetPos=None, targetNormal=None):
+        self.smpl_, self.faceIdx_ = smpl, int(faceIdx)
+        dev = smpl.m__device
+        self.posTaskWeight_, self.normalTaskWeight_, self.phiLimit_, self.normalOffset_ = 1.0, 1.0, 0.04, 0.0
+        self.targetPos_ = torch.zeros(3, device=dev) if targetPos is None else _dev_f32(targetPos, dev)
+        self.targetNormal_ = (torch.tensor([0.0, 0.0, 1.0], device=dev) if targetNormal is None
+                              else _dev_f32(targetNormal, dev))
+        self.vertexWeights_ = torch.full((3,), 1.0 / 3.0, device=dev)
+        self.tangents_ = torch.zeros(3, 2, device=dev)
+        self.phi_ = torch.zeros(2, device=dev)
+        self._set = IkTaskSet(smpl, [self.faceIdx_])
+
+    def _face_vertices(self):
+        ids = torch.as_tensor(self.smpl_._faces_host[self.faceIdx_].astype(np.int64) - 1, device=self.smpl_.m__device)
+        return self.smpl_.getVertexRaw(ids)
+
+    def calcTangents(self):
+        fv = self._face_vertices()
+        t1 = fv[1] - fv[0]
+        normal = torch.linalg.cross(t1, fv[2] - fv[0])
+        t2 = torch.linalg.cross(normal, t1)
+        self.tangents_ = torch.stack([torch.nn.functional.normalize(t1, dim=-1),
+                                      torch.nn.functional.normalize(t2, dim=-1)], 1)
+
+    def calcVertexWeights(self, actualPos):
+        pos = _dev_f32(actualPos, self.smpl_.m__device) + self.tangents_ @ self.phi_
+        self.vertexWeights_ = calcTriangleVertexWeights(pos.view(1, 3), self._face_vertices().view(1, 3, 3))[0]
+
+    def calcActualPos(self) -> torch.Tensor:
+        v = self.smpl_._vertices[:1]
+        return self._set.positions(v, self.vertexWeights_.view(1, 1, 3), float(self.normalOffset_))[0, 0]
+
+    def calcActualNormal(self) -> torch.Tensor:
+        v = self.smpl_._vertices[:1]
+        return self._set.positions(v, self.vertexWeights_.view(1, 1, 3), 0.0, want_normals=True)[1][0, 0]

@@ -1,0 +1,46 @@
+// IK task set: attachment faces of n markers, the 1-ring topology needed by IkTask::calcActualNormal
+// (reference src/IkTask.cpp:74-86 -> SMPL::calcVertexNormal src/SMPL.cpp:527-535) and a compact copy of the
+// blend basis / skinning rows of the vertices the tasks depend on.
+#pragma once
+#include "common.cuh"
+
+namespace sb
+{
+// Device-side view handed to kernels by value.
+struct TasksDev
+{
+  int n = 0;        // tasks (markers)
+  int nU = 0;       // distinct mesh vertices used: corners first (nCorner), then 1-ring-only vertices
+  int nCorner = 0;  // distinct corner vertices
+  int nUpad = 0;    // nU rounded up to 64 (tile of the sparse forward)
+  int nItems = 0;   // (task, corner, adjacent face) triples
+  int nPairs = 0;   // (task, vertex) pairs; per task: corners 0,1,2 first, then ring vertices
+  int maxPairs = 0; // max pairs of one task
+  int kmax = 0;     // skinning influences per vertex (as in the model)
+  const int32_t * corner = nullptr;       // (n, 3)   local vertex id of the face corners
+  const int32_t * item_off = nullptr;     // (3n + 1) CSR (task, corner) -> items
+  const int32_t * item_verts = nullptr;   // (nItems, 3) local vertex ids of the adjacent face, in face order
+  const int32_t * pair_off = nullptr;     // (n + 1)  CSR task -> pairs
+  const int32_t * pair_vert = nullptr;    // (nPairs) local vertex id
+  const int32_t * pair_ref_off = nullptr; // (nPairs + 1) CSR pair -> references
+  const int32_t * pair_refs = nullptr;    // item * 4 + slot (slot = position of the vertex in the item's face)
+  const uint32_t * task_joint_mask = nullptr; // (n) joints that move any vertex of the task (corners only: bit 24+)
+  const uint32_t * task_joint_mask_corner = nullptr; // (n) same, restricted to the three corners
+  // compact model rows of the nU vertices (same layouts as ModelDev, V -> nU)
+  const float * basis = nullptr;       // (3 nUpad, 224)
+  const uint8_t * lbs_joint = nullptr; // [kmax][nUpad]
+  const float * lbs_weight = nullptr;  // [kmax][nUpad]
+  const float * lbs_wsum = nullptr;    // (nUpad)
+};
+} // namespace sb
+
+struct smplpp_tasks
+{
+  sb::TasksDev d;
+  sb::ModelDev sub;      // sparse-forward view (basis/lbs arrays alias the TasksDev ones)
+  sb::ModelDev sub_corner; // same arrays, V = nCorner (no normals needed)
+  std::vector<void *> allocations;
+  std::vector<int64_t> h_face_idx;
+  std::vector<int32_t> h_sub_vert; // local -> global vertex id
+  std::vector<int32_t> h_corner;
+};

@@ -1,0 +1,228 @@
+"""GPU parity tests of the IK step (sparse forward, analytic Jacobian, fp64 normal equations, Cholesky / box QP,
+update) against golden vectors of the compiled reference harness and against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import TOL_JACOBIAN_REL, TOL_RESIDUAL_M, TOL_VERTEX_M
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+
+MODES = {
+    "motion": dict(normal_task_weight=0.0, phi_limit=0.0, normal_offset=0.015, optimize_beta=0, enable_qp=1,
+                   enable_phi=0),
+    "body": dict(normal_task_weight=0.0, phi_limit=0.04, normal_offset=0.015, optimize_beta=1, enable_qp=1,
+                 enable_phi=1),
+    "interactive": dict(normal_task_weight=1.0, phi_limit=0.0, normal_offset=0.0, optimize_beta=0, enable_qp=1,
+                        enable_phi=0),
+    "llt": dict(normal_task_weight=0.0, phi_limit=0.0, normal_offset=0.0, optimize_beta=0, enable_qp=0, enable_phi=0),
+}
+
+
+def cu(a, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device="cuda:0").contiguous()
+
+
+@pytest.fixture(scope="module")
+def task_set(smpl_gpu, marker_tasks, vposer_params):
+    from smplpp_b200 import api
+    _, face_idx, _ = marker_tasks
+    return api.IkTaskSet(smpl_gpu, face_idx, vposer=api.VPoserDecoder(vposer_params))
+
+
+def test_task_positions_vs_oracle(smpl_gpu, task_set, oracle_model, marker_tasks):
+    """IkTask::calcActualPos / calcActualNormal batched, with and without the 15 mm normal offset."""
+    from oracle import smpl_oracle as so
+    from smplpp_b200 import synth
+    _, face_idx, vw = marker_tasks
+    beta, theta = synth.make_forward_inputs(3, 40)
+    smpl_gpu.launch(beta, theta)
+    w = cu(np.repeat(vw[None], 3, axis=0))
+    for off in (0.0, 0.015):
+        pos, nrm = task_set.positions(smpl_gpu.getVertex(), w, off, want_normals=True)
+        with torch.no_grad():
+            r = so.smpl_launch(oracle_model, torch.as_tensor(beta), torch.as_tensor(theta))
+            for b in range(3):
+                for m in (0, 7, 40):
+                    t = so.IkTask(int(face_idx[m]), normal_offset=off, vertex_weights=torch.as_tensor(vw[m]))
+                    assert np.abs(pos[b, m].cpu().numpy() - t.calc_actual_pos(oracle_model, r.vertices[b]).numpy()).max() \
+                        <= TOL_VERTEX_M
+                    assert np.abs(nrm[b, m].cpu().numpy()
+                                  - t.calc_actual_normal(oracle_model, r.vertices[b]).numpy()).max() < 5e-5
+
+
+def test_triangle_vertex_weights_property():
+    """tests/src/TestGeometryUtils.cpp:39-96 on the CUDA kernel."""
+    from smplpp_b200 import api
+    rng = np.random.default_rng(0)
+    tri = rng.uniform(-1, 1, size=(1000, 3, 3)).astype(f32)
+    w = rng.dirichlet(np.ones(3), size=1000).astype(f32)
+    w[:7] = [(1, 0, 0), (0, 1, 0), (0, 0, 1), (.5, .5, 0), (0, .5, .5), (.5, 0, .5), (1 / 3, 1 / 3, 1 / 3)]
+    pos = np.einsum("ni,nik->nk", w, tri)
+    got = api.calcTriangleVertexWeights(pos, tri).cpu().numpy()
+    assert np.abs(got.sum(1) - 1).max() < 1e-5
+    assert np.abs(np.einsum("ni,nik->nk", got, tri) - pos).max() < 1e-3
+
+
+@pytest.mark.parametrize("mode", list(MODES))
+def test_ik_step_vs_reference_golden(task_set, golden_ik, mode):
+    from smplpp_b200 import api
+    g = golden_ik
+    n = task_set.n
+    opt = api.ik_options(skip_if_too_few=0, **MODES[mode])
+    theta = cu(g["theta_in"].reshape(1, 75))
+    beta = cu(g["beta_in"].reshape(1, 10))
+    vw = cu(g["vertex_weights_in"].reshape(1, n, 3))
+    tgt = cu(g[mode + "_target"].reshape(1, n, 3))
+    pw = cu(g[mode + "_pos_task_weight"].reshape(1, n).astype(f32)) if (mode + "_pos_task_weight") in g else None
+    status, out = task_set.step(opt, theta, beta, vw, tgt, pos_task_weight=pw, outputs=True)
+    assert int(status[0]) == 0
+    e, J = out["e"][0].cpu().numpy(), out["J"][0].cpu().numpy()
+    Jref = g[mode + "_J"]
+    assert np.abs(e - g[mode + "_e"]).max() < (2e-5 if mode == "interactive" else TOL_VERTEX_M)
+    assert np.abs(J - Jref).max() / np.abs(Jref).max() <= TOL_JACOBIAN_REL
+    # per-block relative error too (theta / phi / beta columns have different scales)
+    for lo, hi in ((0, 3), (3, 75), (75, 75 + 2 * n), (75 + 2 * n, J.shape[1])):
+        if hi > lo and np.abs(Jref[:, lo:hi]).max() > 0:
+            assert np.abs(J[:, lo:hi] - Jref[:, lo:hi]).max() / np.abs(Jref[:, lo:hi]).max() <= 2 * TOL_JACOBIAN_REL
+    bref = g[mode + "_b"]
+    assert np.abs(out["b"][0].cpu().numpy() - bref).max() / np.abs(bref).max() < 1e-4
+    assert np.abs(out["delta"][0].cpu().numpy() - g[mode + "_delta"]).max() < 2e-4
+    assert np.abs(theta[0].cpu().numpy() - g[mode + "_theta_out"]).max() < 2e-4
+    assert np.abs(beta[0].cpu().numpy() - g[mode + "_beta_out"]).max() < 2e-4
+    assert np.abs(vw[0].cpu().numpy() - g[mode + "_vertex_weights_out"]).max() < 1e-4
+    # A is J'J + damping: check it against the fp64 product of OUR J (bit-level definition of node.cpp:884-893)
+    A = out["A"][0].cpu().numpy()
+    J64 = J.astype(np.float64)
+    A_chk = J64.T @ J64
+    esq = float(e.astype(np.float64) @ e.astype(np.float64))
+    dim = J.shape[1]
+    reg = np.concatenate([np.full(75, 1e-3), np.full(2 * n, 1e-1), np.full(dim - 75 - 2 * n, 1e-3)])
+    A_chk[np.diag_indices(dim)] += reg.astype(np.float32).astype(np.float64) + esq
+    assert np.abs(A - A_chk).max() < 1e-9 * max(1.0, np.abs(A_chk).max())
+
+
+def test_ik_step_vposer_vs_reference_golden(task_set, golden_ik):
+    from smplpp_b200 import api
+    g = golden_ik
+    n = task_set.n
+    opt = api.ik_options(skip_if_too_few=0, enable_vposer=1, **MODES["motion"])
+    theta = cu(g["vposer_theta_in"].reshape(1, 44))
+    beta = cu(g["beta_in"].reshape(1, 10))
+    vw = cu(g["vertex_weights_in"].reshape(1, n, 3))
+    tgt = cu(g["target_pos"].reshape(1, n, 3))
+    status, out = task_set.step(opt, theta, beta, vw, tgt, outputs=True)
+    assert int(status[0]) == 0
+    J, Jref = out["J"][0].cpu().numpy(), g["vposer_J"]
+    assert np.abs(out["e"][0].cpu().numpy() - g["vposer_e"]).max() < 5e-5
+    assert np.abs(J - Jref).max() / np.abs(Jref).max() <= 2 * TOL_JACOBIAN_REL
+    assert np.abs(out["delta"][0].cpu().numpy() - g["vposer_delta"]).max() < 5e-4
+    assert np.abs(theta[0].cpu().numpy() - g["vposer_theta_out"]).max() < 5e-4
+
+
+def test_ik_converges_like_oracle(task_set, oracle_model, marker_tasks, smpl_gpu):
+    """Run K iterations of the motion-mode step on 3 frames and compare the marker residual trajectory with the
+    oracle's (converged residual within 1e-4 m)."""
+    from oracle import smpl_oracle as so
+    from smplpp_b200 import api, synth
+    _, face_idx, vw0 = marker_tasks
+    n, B, K = task_set.n, 2, 6
+    gt = synth.make_motion(40, 20)[[5, 30]]
+    beta = (np.random.default_rng(5).normal(size=10) * 0.5).astype(f32)
+    smpl_gpu.launch(beta, gt)
+    w0 = cu(np.repeat(vw0[None], B, axis=0))
+    target = task_set.positions(smpl_gpu.getVertex(), w0, 0.015).contiguous()
+    x0 = np.repeat(synth.make_motion(40, 20)[:1].reshape(1, 75), B, axis=0)
+    opt = api.ik_options(**MODES["motion"])
+    theta, vw = cu(x0), w0.clone()
+    beta_d = cu(beta)
+    res_gpu = []
+    for _ in range(K):
+        status, out = task_set.step(opt, theta, beta_d, vw, target, outputs=True)
+        assert (status == 0).all()
+        res_gpu.append(np.linalg.norm(out["e"].cpu().numpy().reshape(B, n, 4)[:, :, :3], axis=2).mean(axis=1))
+    tgt_h = target.cpu().numpy()
+    for b in range(B):
+        tasks = [so.IkTask(int(face_idx[i]), target_pos=torch.as_tensor(tgt_h[b, i]), normal_task_weight=0.0,
+                           phi_limit=0.0, normal_offset=0.015, vertex_weights=torch.as_tensor(vw0[i])) for i in range(n)]
+        x = x0[b].copy()
+        for k in range(K):
+            r = so.ik_iteration(oracle_model, tasks, x, beta, skip_if_too_few=True)
+            res_o = np.linalg.norm(r.e.reshape(n, 4)[:, :3], axis=1).mean()
+            assert abs(res_o - res_gpu[k][b]) < TOL_RESIDUAL_M
+            x = r.theta_state
+        assert np.abs(theta[b].cpu().numpy() - x).max() < 5e-3
+    assert res_gpu[-1].max() < res_gpu[0].min()
+
+
+def test_ik_skip_and_missing_markers(task_set, marker_tasks, smpl_gpu):
+    """node.cpp:785: a motion-mode frame with fewer than n/2 valid markers is left untouched (status 1)."""
+    from smplpp_b200 import api, synth
+    n = task_set.n
+    x0 = synth.initial_theta(False).reshape(1, 75).repeat(2, axis=0)
+    theta = cu(x0)
+    beta = cu(np.zeros(10, f32))
+    vw = task_set.default_vertex_weights(2)
+    tgt = cu(np.random.default_rng(1).normal(size=(2, n, 3)).astype(f32) * 0.3)
+    pw = np.ones((2, n), f32)
+    pw[1, : n - 10] = 0.0
+    status = task_set.step(api.ik_options(**MODES["motion"]), theta, beta, vw, tgt, pos_task_weight=cu(pw))
+    assert status.cpu().tolist() == [0, 1]
+    assert np.array_equal(theta[1].cpu().numpy(), x0[1])
+    assert not np.array_equal(theta[0].cpu().numpy(), x0[0])
+
+
+def test_shared_beta_single_frame_equals_joint_qp(task_set, oracle_model, marker_tasks, golden_ik):
+    """With ONE frame the shared-beta stage (Schur complement + 10-dim box QP + back-substitution) must equal
+    the reference's joint QP over [theta | beta] with |dbeta| <= 0.5 (phi pinned)."""
+    from oracle import smpl_oracle as so
+    from smplpp_b200 import api
+    g = golden_ik
+    _, face_idx, _ = marker_tasks
+    n = task_set.n
+    tasks = [so.IkTask(int(face_idx[i]), target_pos=torch.as_tensor(g["target_pos"][i]), normal_task_weight=0.0,
+                       phi_limit=0.0, normal_offset=0.015, vertex_weights=torch.as_tensor(g["vertex_weights_in"][i]))
+             for i in range(n)]
+    r = so.ik_iteration(oracle_model, tasks, g["theta_in"], g["beta_in"], optimize_beta=True)
+    opt = api.ik_options(skip_if_too_few=0, **MODES["motion"])
+    theta = cu(g["theta_in"].reshape(1, 75))
+    sbeta = cu(g["beta_in"].reshape(10))
+    vw = cu(g["vertex_weights_in"].reshape(1, n, 3))
+    status = task_set.shared_beta_step(opt, theta, sbeta, vw, cu(g["target_pos"].reshape(1, n, 3)))
+    assert int(status[0]) == 0
+    assert np.abs(sbeta.cpu().numpy() - r.beta).max() < 2e-4
+    assert np.abs(theta[0].cpu().numpy() - r.theta_state).max() < 2e-4
+
+
+def test_shared_beta_many_frames_kkt(task_set, marker_tasks, smpl_gpu):
+    """Many frames: the reduced 111 doubles are a deterministic sum, the solve satisfies the box-QP KKT
+    conditions, and two identical runs agree bitwise."""
+    from smplpp_b200 import api, synth
+    _, face_idx, vw0 = marker_tasks
+    n, B = task_set.n, 37
+    gt = synth.make_motion(B, 23)
+    beta_true = (np.random.default_rng(6).normal(size=10)).astype(f32)
+    smpl_gpu.launch(beta_true, gt)
+    w0 = cu(np.repeat(vw0[None], B, axis=0))
+    target = task_set.positions(smpl_gpu.getVertex(), w0, 0.015).contiguous()
+    opt = api.ik_options(**MODES["motion"])
+    outs = []
+    for _ in range(2):
+        theta = cu(gt.reshape(B, 75))
+        sbeta = cu(np.zeros(10, f32))
+        vw = w0.clone()
+        status, red = task_set.shared_beta_step(opt, theta, sbeta, vw, target, return_reduced=True)
+        assert (status == 0).all()
+        outs.append((theta.cpu().numpy(), sbeta.cpu().numpy(), red.cpu().numpy()))
+    assert all(np.array_equal(a, b) for a, b in zip(outs[0], outs[1]))
+    red = outs[0][2]
+    S = red[:100].reshape(10, 10) + (1e-3 + red[110]) * np.eye(10)
+    x = outs[0][1].astype(np.float64)  # beta started at 0 => beta == dbeta
+    grad = S @ x + red[100:110]
+    assert np.abs(S - S.T).max() < 1e-9 * np.abs(S).max()
+    free = np.abs(x) < 0.5 - 1e-6
+    assert np.abs(grad[free]).max(initial=0.0) < 1e-5 * max(1.0, np.abs(red[100:110]).max())
+    assert (grad[x >= 0.5 - 1e-6] <= 1e-6).all() and (grad[x <= -0.5 + 1e-6] >= -1e-6).all()
+    # moving towards the true shape
+    assert np.linalg.norm(x - beta_true) < np.linalg.norm(beta_true)

@@ -38,7 +38,7 @@ def test_decoder_vs_oracle_batch(vposer_gpu, oracle_vposer):
     from scipy.spatial.transform import Rotation
     ang = np.linalg.norm(ref.reshape(-1, 3), axis=1)
     err = np.abs(aa - ref).reshape(-1, 3).max(axis=1)
-    assert err[ang < 2.6].max() < 2e-5
+    assert err[ang < 2.6].max() < 5e-5
     r_gpu = Rotation.from_rotvec(aa.reshape(-1, 3).astype(np.float64)).as_matrix()
     r_ref = Rotation.from_rotvec(ref.reshape(-1, 3).astype(np.float64)).as_matrix()
     assert np.abs(r_gpu - r_ref).max() < 2e-5
