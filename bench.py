@@ -266,7 +266,14 @@ def main():
                                   C.c_size_t(ws_bytes)))
     root = theta[:, 0].contiguous()
 
+    xf34 = xf[:, :, :3, :].contiguous()
+
     def lbs_only():
+        capi.check(lib.smplpp_model_skinning34(smpl.handle, C.c_void_p(stream.cuda_stream), C.c_int64(B),
+                                               C.c_void_p(rest.data_ptr()), C.c_void_p(xf34.data_ptr()),
+                                               C.c_void_p(root.data_ptr()), C.c_void_p(verts.data_ptr())))
+
+    def lbs_only44():
         capi.check(lib.smplpp_model_skinning(smpl.handle, C.c_void_p(stream.cuda_stream), C.c_int64(B),
                                              C.c_void_p(rest.data_ptr()), C.c_void_p(xf.data_ptr()),
                                              C.c_void_p(root.data_ptr()), C.c_void_p(verts.data_ptr())))
@@ -275,8 +282,8 @@ def main():
     ach_lbs = BYTES_LBS * B / (ms_lbs * 1e-3) / 1e9
     roofline["lbs"] = {"kernel": "lbs_kernel (standalone skinning)", "bound": "hbm", "achieved": ach_lbs, "peak": peak,
                        "unit": "GB/s", "frac": ach_lbs / peak, "ms_per_launch": ms_lbs,
-                       "meshes_per_s": B / (ms_lbs * 1e-3)}
-    del rest, xf
+                       "meshes_per_s": B / (ms_lbs * 1e-3), "ms_per_launch_4x4_transforms": time_kernel(lbs_only44, 20)}
+    del rest, xf, xf34
 
     # ---- e2e through the C-ABI host-buffer call (pinned staging, H2D + D2H inside the timed region) ----
     e2e_steps = max(3, min(args.steps, 10))

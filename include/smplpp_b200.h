@@ -123,6 +123,10 @@ int smplpp_linear_blend_skinning(void * stream, int64_t batch, int64_t vertex_nu
 /* Same kernel driven from a model handle (pre-packed sparse weights): rest_shape (B,V,3), transforms (B,24,4,4) */
 int smplpp_model_skinning(const smplpp_model_t * model, void * stream, int64_t batch, const float * rest_shape,
                           const float * transforms, const float * root_pos, float * vertices);
+/* Same with affine 3x4 transforms [R | t] (B,24,3,4): the bottom row (0,0,0,1) of the reference's 4x4 is implied,
+ * the homogeneous divide uses sum_j W[v,j].  This is the layout the fused pipeline keeps internally. */
+int smplpp_model_skinning34(const smplpp_model_t * model, void * stream, int64_t batch, const float * rest_shape,
+                            const float * transforms34, const float * root_pos, float * vertices);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Normals (replaces SMPL::calcNormal / calcVertexNormal, src/SMPL.cpp:518-535) — batched over frames.

@@ -43,7 +43,7 @@ EXPORTS = [
     "smplpp_model_create", "smplpp_model_destroy", "smplpp_model_vertex_num", "smplpp_model_max_influences",
     "smplpp_forward_workspace_bytes", "smplpp_forward", "smplpp_forward_host", "smplpp_set_forward_variant",
     "smplpp_blend_shape", "smplpp_joint_regression", "smplpp_world_transformation", "smplpp_linear_blend_skinning",
-    "smplpp_model_skinning", "smplpp_normals",
+    "smplpp_model_skinning", "smplpp_model_skinning34", "smplpp_normals",
     "smplpp_vposer_create", "smplpp_vposer_destroy", "smplpp_vposer_decode", "smplpp_rotmat_to_axis_angle",
     "smplpp_tasks_create", "smplpp_tasks_destroy", "smplpp_tasks_count", "smplpp_tasks_vertex_count",
     "smplpp_triangle_vertex_weights", "smplpp_ik_options_default", "smplpp_ik_theta_dim", "smplpp_ik_dim",

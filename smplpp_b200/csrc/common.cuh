@@ -19,6 +19,8 @@ constexpr int kPoseDim = SMPLPP_POSE_DIM;
 constexpr int kBlendK = 224;
 constexpr int kBlendKUsed = kPoseDim + kShapeDim + 1; // 218
 constexpr int kXformFloats = 12;                      // 3x4 row-major [R | t] per joint
+constexpr int kGroupVerts = 4;                        // consecutive vertices handled by one skinning lane
+constexpr int kGroupJoints = 8;                       // max distinct joints of a group on the register-reuse path
 
 extern thread_local std::string g_last_error;
 extern std::atomic<uint64_t> g_launch_count;
@@ -71,6 +73,12 @@ struct ModelDev
   uint8_t * lbs_joint = nullptr;
   float * lbs_weight = nullptr;
   float * lbs_wsum = nullptr; // (Vpad) sum_j W[v,j]  (homogeneous coordinate h[3])
+  // per group of 4 consecutive vertices (one lane of the skinning kernel): the union of the joints influencing
+  // the group (<= kGroupJoints, 0xFF padded; count = -1 marks an overflowing group) and dense weights over it.
+  // A lane then fetches each transform ONCE for its 4 vertices: ~3.7 instead of 16 transform fetches per group.
+  int8_t * group_nj = nullptr;      // (Vpad / 4)
+  uint8_t * group_joint = nullptr;  // (Vpad / 4, kGroupJoints)
+  float * group_w = nullptr;        // (Vpad / 4, kGroupJoints, 4)  [joint slot][vertex in group]
   // joints = J_T + J_S beta  (Jreg (T + S beta), JointRegression.cpp:588-590)
   float * joint_template = nullptr; // (24, 3)
   float * joint_shape = nullptr;    // (24, 3, 10)

@@ -405,119 +405,172 @@ __global__ void __launch_bounds__(k2::THREADS, 2)
 // ------------------------------------------------------------------------------------------------------------
 namespace k3
 {
-constexpr int THREADS = 256, VPT = 2, FR = 8;
+constexpr int THREADS = 256, VPL = kGroupVerts, VPC = THREADS * VPL; // 4 vertices per lane, 1024 per CTA
+constexpr int FR = 16;                                               // frames per CTA (weights stay in registers)
 }
 
-template<bool kAffine>
-__global__ void __launch_bounds__(k3::THREADS)
+// Shared-memory bandwidth bounds skinning: every (vertex, frame, influence) needs 12-16 floats of a transform.  A lane
+// therefore owns 4 CONSECUTIVE vertices and walks the union of their joints (3.7 on average for a coherent mesh):
+// each transform row is fetched once and applied to all 4 vertices from registers.
+// kVec2: 8-byte global accesses (needs even V); otherwise scalar accesses.
+template<bool kAffine, bool kVec2>
+__global__ void __launch_bounds__(k3::THREADS, 2)
     lbs_kernel(const uint8_t * __restrict__ lbs_joint, const float * __restrict__ lbs_weight,
-               const float * __restrict__ lbs_wsum, int V, int Vpad, int kmax, int B, const float * __restrict__ rest,
-               const float * __restrict__ xforms, const float * __restrict__ root, int root_stride,
-               float * __restrict__ out)
+               const float * __restrict__ lbs_wsum, const int8_t * __restrict__ group_nj,
+               const uint8_t * __restrict__ group_joint, const float * __restrict__ group_w, int V, int Vpad, int kmax,
+               int B, const float * __restrict__ rest, const float * __restrict__ xforms,
+               const float * __restrict__ root, int root_stride, float * __restrict__ out)
 {
   using namespace k3;
   constexpr int XF = kAffine ? 12 : 16;
-  __shared__ __align__(16) float Gs[FR][kJoints * XF];
+  // per-joint stride in shared memory: 12 and 20 floats both map the 8 joint residues to distinct 4-bank groups
+  constexpr int XFP = kAffine ? 12 : 20;
+  __shared__ __align__(16) float Gs[FR][kJoints * XFP];
   const int tid = threadIdx.x;
   const int b0 = blockIdx.y * FR;
   const int nfr = min(FR, B - b0);
   for(int i = tid; i < nfr * kJoints * XF / 4; i += THREADS)
-    reinterpret_cast<float4 *>(&Gs[0][0])[i] =
-        __ldg(reinterpret_cast<const float4 *>(xforms + static_cast<size_t>(b0) * kJoints * XF) + i);
-  const int v = (blockIdx.x * THREADS + tid) * VPT;
-  uint8_t jn[VPT][4];
-  float jw[VPT][4], iw[VPT];
-  const bool fast = kmax <= 4;
-  if(v < V && fast)
   {
+    const int fr = i / (kJoints * XF / 4), rem = i % (kJoints * XF / 4);
+    const int j = rem / (XF / 4), q = rem % (XF / 4);
+    *reinterpret_cast<float4 *>(&Gs[fr][j * XFP + 4 * q]) =
+        __ldg(reinterpret_cast<const float4 *>(xforms + static_cast<size_t>(b0) * kJoints * XF) + i);
+  }
+  const int v = (blockIdx.x * THREADS + tid) * VPL; // first of this lane's 4 vertices
+  const int g = v / VPL;
+  const int nvalid = min(VPL, V - v);               // <= 0: lane idle
+  int nj = -1;
+  float gw[kGroupJoints][VPL], iw[VPL];
+  unsigned gj_lo = 0, gj_hi = 0;
+  if(nvalid > 0)
+  {
+    nj = group_nj ? group_nj[g] : -1;
 #pragma unroll
-    for(int u = 0; u < VPT; u++)
+    for(int u = 0; u < VPL; u++) iw[u] = 1.f / lbs_wsum[min(v + u, V - 1)];
+    if(nj >= 0)
     {
-      int vv = min(v + u, V - 1);
+      const uint2 jj = __ldg(reinterpret_cast<const uint2 *>(group_joint + static_cast<size_t>(g) * kGroupJoints));
+      gj_lo = jj.x, gj_hi = jj.y;
 #pragma unroll
-      for(int k = 0; k < 4; k++)
+      for(int k = 0; k < kGroupJoints; k++)
       {
-        bool on = k < kmax;
-        jn[u][k] = on ? lbs_joint[static_cast<size_t>(k) * Vpad + vv] : 0;
-        jw[u][k] = on ? lbs_weight[static_cast<size_t>(k) * Vpad + vv] : 0.f;
+        const float4 w = __ldg(reinterpret_cast<const float4 *>(group_w + (static_cast<size_t>(g) * kGroupJoints + k) * VPL));
+        gw[k][0] = w.x, gw[k][1] = w.y, gw[k][2] = w.z, gw[k][3] = w.w;
       }
-      iw[u] = 1.f / lbs_wsum[vv];
     }
   }
   __syncthreads();
-  if(v >= V) return;
-  const bool has2 = v + 1 < V;
-  const bool pair = has2 && (V & 1) == 0; // float2 path needs 8-byte aligned rows
-  for(int f = 0; f < nfr; f++)
-  {
+  if(nvalid <= 0) return;
+  const bool full = nvalid == VPL;
+  // software pipeline: the loads of frame f + 1 are in flight while frame f is skinned
+  float rn[3 * VPL];
+  auto load_frame = [&](int f) {
     const size_t base = (static_cast<size_t>(b0 + f) * V + v) * 3;
-    float r[6];
-    if(pair)
+    if(kVec2 && full)
     {
       const float2 * src = reinterpret_cast<const float2 *>(rest + base);
-      float2 p0 = __ldcs(src), p1 = __ldcs(src + 1), p2 = __ldcs(src + 2);
-      r[0] = p0.x, r[1] = p0.y, r[2] = p1.x, r[3] = p1.y, r[4] = p2.x, r[5] = p2.y;
+#pragma unroll
+      for(int q = 0; q < 6; q++)
+      {
+        const float2 t = __ldcs(src + q);
+        rn[2 * q] = t.x, rn[2 * q + 1] = t.y;
+      }
     }
     else
     {
-      r[0] = rest[base], r[1] = rest[base + 1], r[2] = rest[base + 2];
-      r[3] = has2 ? rest[base + 3] : 0.f;
-      r[4] = has2 ? rest[base + 4] : 0.f;
-      r[5] = has2 ? rest[base + 5] : 0.f;
+#pragma unroll
+      for(int q = 0; q < 3 * VPL; q++) rn[q] = q < 3 * nvalid ? rest[base + q] : 0.f;
     }
+  };
+  load_frame(0);
+  for(int f = 0; f < nfr; f++)
+  {
+    const size_t base = (static_cast<size_t>(b0 + f) * V + v) * 3;
+    float r[3 * VPL];
+#pragma unroll
+    for(int q = 0; q < 3 * VPL; q++) r[q] = rn[q];
+    if(f + 1 < nfr) load_frame(f + 1);
     float tx = 0.f, ty = 0.f, tz = 0.f;
     if(root)
     {
       const float * rp = root + static_cast<size_t>(b0 + f) * root_stride;
       tx = rp[0], ty = rp[1], tz = rp[2];
     }
-    float o[6];
+    float o[3 * VPL], ow[VPL];
 #pragma unroll
-    for(int u = 0; u < VPT; u++)
+    for(int q = 0; q < 3 * VPL; q++) o[q] = 0.f;
+#pragma unroll
+    for(int u = 0; u < VPL; u++) ow[u] = 0.f;
+    if(nj >= 0)
     {
-      const float rx = r[3 * u], ry = r[3 * u + 1], rz = r[3 * u + 2];
-      float ox = 0.f, oy = 0.f, oz = 0.f, ow = 0.f;
-      auto accum = [&](int j, float w) {
-        const float4 * gj = reinterpret_cast<const float4 *>(&Gs[f][j * XF]);
-        float4 r0 = gj[0], r1 = gj[1], r2 = gj[2];
-        ox = fmaf(w, fmaf(r0.x, rx, fmaf(r0.y, ry, fmaf(r0.z, rz, r0.w))), ox);
-        oy = fmaf(w, fmaf(r1.x, rx, fmaf(r1.y, ry, fmaf(r1.z, rz, r1.w))), oy);
-        oz = fmaf(w, fmaf(r2.x, rx, fmaf(r2.y, ry, fmaf(r2.z, rz, r2.w))), oz);
-        if(!kAffine)
+#pragma unroll
+      for(int k = 0; k < kGroupJoints; k++)
+      {
+        if(k < nj)
         {
-          float4 r3 = gj[3];
-          ow = fmaf(w, fmaf(r3.x, rx, fmaf(r3.y, ry, fmaf(r3.z, rz, r3.w))), ow);
-        }
-      };
-      float inv;
-      if(fast)
-      {
+          const int j = ((k < 4 ? gj_lo : gj_hi) >> (8 * (k & 3))) & 0xff;
+          const float4 * gjp = reinterpret_cast<const float4 *>(&Gs[f][j * XFP]);
+          const float4 r0 = gjp[0], r1 = gjp[1], r2 = gjp[2];
+          float4 r3 = make_float4(0.f, 0.f, 0.f, 1.f);
+          if(!kAffine) r3 = gjp[3];
 #pragma unroll
-        for(int k = 0; k < 4; k++) accum(jn[u][k], jw[u][k]);
-        inv = kAffine ? iw[u] : 1.f / ow;
+          for(int u = 0; u < VPL; u++)
+          {
+            const float w = gw[k][u];
+            const float rx = r[3 * u], ry = r[3 * u + 1], rz = r[3 * u + 2];
+            o[3 * u] = fmaf(w, fmaf(r0.x, rx, fmaf(r0.y, ry, fmaf(r0.z, rz, r0.w))), o[3 * u]);
+            o[3 * u + 1] = fmaf(w, fmaf(r1.x, rx, fmaf(r1.y, ry, fmaf(r1.z, rz, r1.w))), o[3 * u + 1]);
+            o[3 * u + 2] = fmaf(w, fmaf(r2.x, rx, fmaf(r2.y, ry, fmaf(r2.z, rz, r2.w))), o[3 * u + 2]);
+            if(!kAffine) ow[u] = fmaf(w, fmaf(r3.x, rx, fmaf(r3.y, ry, fmaf(r3.z, rz, r3.w))), ow[u]);
+          }
+        }
       }
-      else
-      {
-        int vv = min(v + u, V - 1);
-        for(int k = 0; k < kmax; k++)
-          accum(lbs_joint[static_cast<size_t>(k) * Vpad + vv], lbs_weight[static_cast<size_t>(k) * Vpad + vv]);
-        inv = kAffine ? 1.f / lbs_wsum[vv] : 1.f / ow;
-      }
-      o[3 * u] = fmaf(ox, inv, tx);
-      o[3 * u + 1] = fmaf(oy, inv, ty);
-      o[3 * u + 2] = fmaf(oz, inv, tz);
-    }
-    if(pair)
-    {
-      float2 * dst = reinterpret_cast<float2 *>(out + base);
-      __stcs(dst, make_float2(o[0], o[1]));
-      __stcs(dst + 1, make_float2(o[2], o[3]));
-      __stcs(dst + 2, make_float2(o[4], o[5]));
     }
     else
     {
-      out[base] = o[0], out[base + 1] = o[1], out[base + 2] = o[2];
-      if(has2) out[base + 3] = o[3], out[base + 4] = o[4], out[base + 5] = o[5];
+      // generic path: per-vertex influence slots (more than kGroupJoints joints in the group, or no group tables)
+      for(int u = 0; u < nvalid; u++)
+      {
+        const float rx = r[3 * u], ry = r[3 * u + 1], rz = r[3 * u + 2];
+        float ox = 0.f, oy = 0.f, oz = 0.f, o4 = 0.f;
+        for(int k = 0; k < kmax; k++)
+        {
+          const float w = lbs_weight[static_cast<size_t>(k) * Vpad + v + u];
+          const float4 * gjp = reinterpret_cast<const float4 *>(&Gs[f][lbs_joint[static_cast<size_t>(k) * Vpad + v + u] * XFP]);
+          const float4 r0 = gjp[0], r1 = gjp[1], r2 = gjp[2];
+          ox = fmaf(w, fmaf(r0.x, rx, fmaf(r0.y, ry, fmaf(r0.z, rz, r0.w))), ox);
+          oy = fmaf(w, fmaf(r1.x, rx, fmaf(r1.y, ry, fmaf(r1.z, rz, r1.w))), oy);
+          oz = fmaf(w, fmaf(r2.x, rx, fmaf(r2.y, ry, fmaf(r2.z, rz, r2.w))), oz);
+          if(!kAffine)
+          {
+            const float4 r3 = gjp[3];
+            o4 = fmaf(w, fmaf(r3.x, rx, fmaf(r3.y, ry, fmaf(r3.z, rz, r3.w))), o4);
+          }
+        }
+#pragma unroll
+        for(int uu = 0; uu < VPL; uu++)
+          if(uu == u) o[3 * uu] = ox, o[3 * uu + 1] = oy, o[3 * uu + 2] = oz, ow[uu] = o4;
+      }
+    }
+#pragma unroll
+    for(int u = 0; u < VPL; u++)
+    {
+      const float inv = kAffine ? iw[u] : 1.f / ow[u];
+      o[3 * u] = fmaf(o[3 * u], inv, tx);
+      o[3 * u + 1] = fmaf(o[3 * u + 1], inv, ty);
+      o[3 * u + 2] = fmaf(o[3 * u + 2], inv, tz);
+    }
+    if(kVec2 && full)
+    {
+      float2 * dst = reinterpret_cast<float2 *>(out + base);
+#pragma unroll
+      for(int q = 0; q < 6; q++) __stcs(dst + q, make_float2(o[2 * q], o[2 * q + 1]));
+    }
+    else
+    {
+#pragma unroll
+      for(int q = 0; q < 3 * VPL; q++)
+        if(q < 3 * nvalid) out[base + q] = o[q];
     }
   }
 }
@@ -767,13 +820,21 @@ int launch_blend_skin_ffma(const ModelDev & d, cudaStream_t st, int B, const flo
 int launch_lbs(const ModelDev & d, cudaStream_t st, int B, const float * rest, const float * xforms, bool affine,
                const float * root, int root_stride, float * out)
 {
-  dim3 grid((d.V + k3::THREADS * k3::VPT - 1) / (k3::THREADS * k3::VPT), (B + k3::FR - 1) / k3::FR);
-  if(affine)
-    lbs_kernel<true><<<grid, k3::THREADS, 0, st>>>(d.lbs_joint, d.lbs_weight, d.lbs_wsum, d.V, d.Vpad, d.kmax, B, rest,
-                                                   xforms, root, root_stride, out);
+  dim3 grid((d.V + k3::VPC - 1) / k3::VPC, (B + k3::FR - 1) / k3::FR);
+  const bool vec2 = (d.V & 1) == 0 && (reinterpret_cast<uintptr_t>(rest) & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0;
+#define SB_LBS(AFF, VEC)                                                                                               \
+  lbs_kernel<AFF, VEC><<<grid, k3::THREADS, 0, st>>>(d.lbs_joint, d.lbs_weight, d.lbs_wsum, d.group_nj, d.group_joint, \
+                                                     d.group_w, d.V, d.Vpad, d.kmax, B, rest, xforms, root,           \
+                                                     root_stride, out)
+  if(affine && vec2)
+    SB_LBS(true, true);
+  else if(affine)
+    SB_LBS(true, false);
+  else if(vec2)
+    SB_LBS(false, true);
   else
-    lbs_kernel<false><<<grid, k3::THREADS, 0, st>>>(d.lbs_joint, d.lbs_weight, d.lbs_wsum, d.V, d.Vpad, d.kmax, B, rest,
-                                                    xforms, root, root_stride, out);
+    SB_LBS(false, false);
+#undef SB_LBS
   SB_LAUNCHED();
   return SMPLPP_OK;
 }
@@ -983,4 +1044,12 @@ extern "C" int smplpp_normals(const smplpp_model_t * model, void * stream, int64
       reinterpret_cast<const long long *>(vert_idx), vertex_normals);
   SB_LAUNCHED();
   return SMPLPP_OK;
+}
+
+extern "C" int smplpp_model_skinning34(const smplpp_model_t * model, void * stream, int64_t batch, const float * rest,
+                                       const float * transforms34, const float * root_pos, float * vertices)
+{
+  if(!model || batch < 1 || !rest || !transforms34 || !vertices)
+    return fail(SMPLPP_ERR_INVALID, "LinearBlendSkinning", "Failed to get vertices of new pose!");
+  return launch_lbs(model->d, as_stream(stream), static_cast<int>(batch), rest, transforms34, true, root_pos, 3, vertices);
 }

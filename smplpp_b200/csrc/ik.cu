@@ -267,7 +267,9 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
   float * s_cornN = s_itemN + (p.use_ring ? 4 * t.nItems : 0); // 3n*4
   float * s_task = s_cornN + (p.use_ring ? 12 * n : 0);        // n*TS
   float * s_C4 = s_task + TS * n;                              // nPairs*12
-  float * s_Q = s_C4 + 12 * t.nPairs;                          // 2*ROWS*224
+  float * s_sw = s_C4 + 12 * t.nPairs;                         // nUse*kmax   normalised skinning weights w_j / sum w
+  float * s_xw = s_sw + p.nUse * t.kmax;                       // nUse*kmax*3 wn_j * x_uj (vertex carried by bone j)
+  uint8_t * s_sj = reinterpret_cast<uint8_t *>(s_xw + 3 * p.nUse * t.kmax); // nUse*kmax joint ids
   __shared__ int s_valid, s_bad;
 
   if(tid == 0) s_valid = 0, s_bad = 0;
@@ -277,6 +279,12 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
     const float * gv = p.verts + static_cast<size_t>(f) * p.nUse * 3;
     const float * gr = p.rest + static_cast<size_t>(f) * p.nUse * 3;
     for(int i = tid; i < 3 * p.nUse; i += THREADS) s_verts[i] = gv[i], s_rest[i] = gr[i];
+    for(int i = tid; i < p.nUse * t.kmax; i += THREADS)
+    {
+      const int u = i / t.kmax, sl = i % t.kmax;
+      s_sw[i] = t.lbs_weight[static_cast<size_t>(sl) * t.nUpad + u] / t.lbs_wsum[u];
+      s_sj[i] = t.lbs_joint[static_cast<size_t>(sl) * t.nUpad + u];
+    }
   }
   __syncthreads();
 
@@ -505,61 +513,74 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
     }
   }
   __syncthreads();
-  // ---- G4: per (task, vertex) pair: C4 = d(residual rows) / d(vertex)  (ROWS x 3) ----
-  for(int m = 0; m < n; m++)
+  // ---- G4: per (task, vertex) pair: C4 = d(residual rows) / d(vertex)  (ROWS x 3); also wn_j * x_uj ----
+  for(int i = tid; i < p.nUse * t.kmax; i += THREADS)
   {
-    const int p0 = t.pair_off[m];
-    const int np = p.use_ring ? t.pair_off[m + 1] - p0 : 3;
-    const float * ts = s_task + TS * m;
-    for(int q = tid; q < np; q += THREADS)
+    const int u = i / t.kmax;
+    const int j = s_sj[i];
+    const float wj = s_sw[i];
+    const float * G = s_G + 12 * j;
+    const f3 ru = ld3(s_rest + 3 * u);
+    s_xw[3 * i] = wj * (G[0] * ru.x + G[1] * ru.y + G[2] * ru.z + s_tp[3 * j]);
+    s_xw[3 * i + 1] = wj * (G[4] * ru.x + G[5] * ru.y + G[6] * ru.z + s_tp[3 * j + 1]);
+    s_xw[3 * i + 2] = wj * (G[8] * ru.x + G[9] * ru.y + G[10] * ru.z + s_tp[3 * j + 2]);
+  }
+  for(int pr = tid; pr < t.nPairs; pr += THREADS)
+  {
+    const int m = t.pair_task[pr];
+    const int q = pr - t.pair_off[m];
+    float * C = s_C4 + 12 * pr;
+    if(!p.use_ring && q >= 3)
     {
-      const int pr = p0 + q;
-      float D[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if(p.use_ring)
-      {
-        const f3 nh = mk3(ts[3], ts[4], ts[5]);
-        const float inv_s = ts[6];
-        for(int rf = t.pair_ref_off[pr]; rf < t.pair_ref_off[pr + 1]; rf++)
-        {
-          const int it = t.pair_refs[rf] >> 2, slot = t.pair_refs[rf] & 3;
-          // corner index of the item: items of (m, c) are contiguous
-          int c = 0;
-          while(it >= t.item_off[3 * m + c + 1]) c++;
-          const int ci = 3 * m + c;
-          const float wg = 1.f / static_cast<float>(t.item_off[ci + 1] - t.item_off[ci]);
-          const float scale = ts[c] * wg;
-          f3 v0 = ld3(s_verts + 3 * t.item_verts[3 * it]), v1 = ld3(s_verts + 3 * t.item_verts[3 * it + 1]),
-             v2 = ld3(s_verts + 3 * t.item_verts[3 * it + 2]);
-          f3 e1 = v1 - v0, e2 = v2 - v0;
-          f3 a = slot == 0 ? (e2 - e1) : (slot == 1 ? mk3(-e2.x, -e2.y, -e2.z) : e1);
-          const f3 ng = ld3(s_itemN + 4 * it), nci = ld3(s_cornN + 4 * ci);
-          const float inv_g = s_itemN[4 * it + 3], inv_q = s_cornN[4 * ci + 3];
-          const f3 ax[3] = {mk3(0.f, a.z, -a.y), mk3(-a.z, 0.f, a.x), mk3(a.y, -a.x, 0.f)}; // a x e_c
 #pragma unroll
-          for(int cc = 0; cc < 3; cc++)
-          {
-            f3 y = proj_apply(nh, inv_s, proj_apply(nci, inv_q, proj_apply(ng, inv_g, ax[cc])));
-            D[cc] += scale * y.x, D[3 + cc] += scale * y.y, D[6 + cc] += scale * y.z;
-          }
+      for(int e = 0; e < 12; e++) C[e] = 0.f;
+      continue;
+    }
+    const float * ts = s_task + TS * m;
+    float D[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if(p.use_ring)
+    {
+      const f3 nh = mk3(ts[3], ts[4], ts[5]);
+      const float inv_s = ts[6];
+      for(int rf = t.pair_ref_off[pr]; rf < t.pair_ref_off[pr + 1]; rf++)
+      {
+        const int it = t.pair_refs[rf] >> 2, slot = t.pair_refs[rf] & 3;
+        // corner index of the item: items of (m, c) are contiguous
+        int c = 0;
+        while(it >= t.item_off[3 * m + c + 1]) c++;
+        const int ci = 3 * m + c;
+        const float wg = 1.f / static_cast<float>(t.item_off[ci + 1] - t.item_off[ci]);
+        const float scale = ts[c] * wg;
+        f3 v0 = ld3(s_verts + 3 * t.item_verts[3 * it]), v1 = ld3(s_verts + 3 * t.item_verts[3 * it + 1]),
+           v2 = ld3(s_verts + 3 * t.item_verts[3 * it + 2]);
+        f3 e1 = v1 - v0, e2 = v2 - v0;
+        f3 a = slot == 0 ? (e2 - e1) : (slot == 1 ? mk3(-e2.x, -e2.y, -e2.z) : e1);
+        const f3 ng = ld3(s_itemN + 4 * it), nci = ld3(s_cornN + 4 * ci);
+        const float inv_g = s_itemN[4 * it + 3], inv_q = s_cornN[4 * ci + 3];
+        const f3 ax[3] = {mk3(0.f, a.z, -a.y), mk3(-a.z, 0.f, a.x), mk3(a.y, -a.x, 0.f)}; // a x e_c
+#pragma unroll
+        for(int cc = 0; cc < 3; cc++)
+        {
+          f3 y = proj_apply(nh, inv_s, proj_apply(nci, inv_q, proj_apply(ng, inv_g, ax[cc])));
+          D[cc] += scale * y.x, D[3 + cc] += scale * y.y, D[6 + cc] += scale * y.z;
         }
       }
-      const float posw = ts[7];
-      const float wc = q < 3 ? ts[q] : 0.f; // pairs 0..2 of a task are its corners 0..2
-      float * C = s_C4 + 12 * pr;
+    }
+    const float posw = ts[7];
+    const float wc = q < 3 ? ts[q] : 0.f; // pairs 0..2 of a task are its corners 0..2
 #pragma unroll
-      for(int r = 0; r < 3; r++)
+    for(int r = 0; r < 3; r++)
 #pragma unroll
-        for(int c = 0; c < 3; c++) C[3 * r + c] = posw * (((r == c) ? wc : 0.f) + p.normal_offset * D[3 * r + c]);
-      if(ROWS == 4)
-      {
-        const float nw = p.normal_task_weight;
+      for(int c = 0; c < 3; c++) C[3 * r + c] = posw * (((r == c) ? wc : 0.f) + p.normal_offset * D[3 * r + c]);
+    if(ROWS == 4)
+    {
+      const float nw = p.normal_task_weight;
 #pragma unroll
-        for(int c = 0; c < 3; c++) C[9 + c] = nw * (ts[8] * D[c] + ts[9] * D[3 + c] + ts[10] * D[6 + c]);
-      }
-      else
-      {
-        C[9] = C[10] = C[11] = 0.f;
-      }
+      for(int c = 0; c < 3; c++) C[9 + c] = nw * (ts[8] * D[c] + ts[9] * D[3 + c] + ts[10] * D[6 + c]);
+    }
+    else
+    {
+      C[9] = C[10] = C[11] = 0.f;
     }
   }
   __syncthreads();
@@ -602,21 +623,12 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
       for(int q = 0; q < np; q++)
       {
         const int u = t.pair_vert[p0 + q];
-        const f3 ru = ld3(s_rest + 3 * u);
-        const float iw = 1.f / t.lbs_wsum[u];
         f3 y = mk3(0.f, 0.f, 0.f);
         for(int sl = 0; sl < t.kmax; sl++)
         {
-          const float wj = t.lbs_weight[static_cast<size_t>(sl) * t.nUpad + u];
-          const int j = t.lbs_joint[static_cast<size_t>(sl) * t.nUpad + u];
-          if(wj != 0.f && ((p.anc_mask[j] >> k) & 1u))
-          {
-            const float * G = s_G + 12 * j;
-            f3 x = mk3(G[0] * ru.x + G[1] * ru.y + G[2] * ru.z + s_tp[3 * j],
-                       G[4] * ru.x + G[5] * ru.y + G[6] * ru.z + s_tp[3 * j + 1],
-                       G[8] * ru.x + G[9] * ru.y + G[10] * ru.z + s_tp[3 * j + 2]);
-            y = y + (wj * iw) * (x - tgk);
-          }
+          const int i = u * t.kmax + sl;
+          const float wj = s_sw[i];
+          if(wj != 0.f && ((p.anc_mask[s_sj[i]] >> k) & 1u)) y = y + (ld3(s_xw + 3 * i) - wj * tgk);
         }
         const float * C = s_C4 + 12 * (p0 + q);
 #pragma unroll
@@ -661,15 +673,15 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
       for(int q = 0; q < np; q++)
       {
         const int u = t.pair_vert[p0 + q];
-        const float iw = 1.f / t.lbs_wsum[u];
         f3 y = mk3(0.f, 0.f, 0.f);
         for(int sl = 0; sl < t.kmax; sl++)
         {
-          const float wj = t.lbs_weight[static_cast<size_t>(sl) * t.nUpad + u];
-          const int j = t.lbs_joint[static_cast<size_t>(sl) * t.nUpad + u];
+          const int i = u * t.kmax + sl;
+          const float wj = s_sw[i];
+          const int j = s_sj[i];
           if(wj != 0.f)
-            y = y + (wj * iw) * mk3(s_dTp[(3 * j) * kShapeDim + ib], s_dTp[(3 * j + 1) * kShapeDim + ib],
-                                    s_dTp[(3 * j + 2) * kShapeDim + ib]);
+            y = y + wj * mk3(s_dTp[(3 * j) * kShapeDim + ib], s_dTp[(3 * j + 1) * kShapeDim + ib],
+                             s_dTp[(3 * j + 2) * kShapeDim + ib]);
         }
         const float * C = s_C4 + 12 * (p0 + q);
 #pragma unroll
@@ -681,80 +693,91 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
   }
   __syncthreads();
   // ---- CA4 = C4 . A_u in place, A_u = sum_j wn_j Rg_j (the rotation part of the skinning matrix) ----
-  for(int m = 0; m < n; m++)
+  for(int pr = tid; pr < t.nPairs; pr += THREADS)
   {
-    const int p0 = t.pair_off[m];
-    const int np = p.use_ring ? t.pair_off[m + 1] - p0 : 3;
-    for(int q = tid; q < np; q += THREADS)
+    if(!p.use_ring && pr - t.pair_off[t.pair_task[pr]] >= 3) continue; // ring-only vertices are not loaded
+    const int u = t.pair_vert[pr];
+    float A[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for(int sl = 0; sl < t.kmax; sl++)
     {
-      const int u = t.pair_vert[p0 + q];
-      const float iw = 1.f / t.lbs_wsum[u];
-      float A[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      for(int sl = 0; sl < t.kmax; sl++)
-      {
-        const float wj = t.lbs_weight[static_cast<size_t>(sl) * t.nUpad + u] * iw;
-        const float * G = s_G + 12 * t.lbs_joint[static_cast<size_t>(sl) * t.nUpad + u];
+      const float wj = s_sw[u * t.kmax + sl];
+      const float * G = s_G + 12 * s_sj[u * t.kmax + sl];
 #pragma unroll
-        for(int r = 0; r < 3; r++)
+      for(int r = 0; r < 3; r++)
 #pragma unroll
-          for(int c = 0; c < 3; c++) A[3 * r + c] = fmaf(wj, G[4 * r + c], A[3 * r + c]);
-      }
-      float * C = s_C4 + 12 * (p0 + q);
-      float out[12];
-#pragma unroll
-      for(int r = 0; r < 4; r++)
-#pragma unroll
-        for(int c = 0; c < 3; c++) out[3 * r + c] = C[3 * r] * A[c] + C[3 * r + 1] * A[3 + c] + C[3 * r + 2] * A[6 + c];
-#pragma unroll
-      for(int e = 0; e < 12; e++) C[e] = out[e];
+        for(int c = 0; c < 3; c++) A[3 * r + c] = fmaf(wj, G[4 * r + c], A[3 * r + c]);
     }
+    float * C = s_C4 + 12 * pr;
+    float out[12];
+#pragma unroll
+    for(int r = 0; r < 4; r++)
+#pragma unroll
+      for(int c = 0; c < 3; c++) out[3 * r + c] = C[3 * r] * A[c] + C[3 * r + 1] * A[3 + c] + C[3 * r + 2] * A[6 + c];
+#pragma unroll
+    for(int e = 0; e < 12; e++) C[e] = out[e];
   }
   __syncthreads();
-  // ---- P5d: pose-blend (and shape-blend) columns: Q_m = sum_u CA4_u P_u (ROWS x 224), J += Q_m dvec(R_k)/dtheta ----
+  // ---- P5d: pose-blend (and shape-blend) columns: Q_m = sum_u CA4_u P_u (ROWS x 218), J += Q_m dvec(R_k)/dtheta.
+  //      Warp w owns joints 3w+1..3w+3 (27 lanes, 9 basis columns each); warp 7 also owns the 10 shape columns.
+  //      The 9-term contraction per (joint, axis) is a segmented shuffle reduction: no block barrier per task. ----
   {
+    const int warp = tid >> 5, lane = tid & 31;
     const int bcol = 75 + p.phi_cols;
-    for(int m = 0; m < n; m++)
+    int k = 3 * warp + 1 + lane / 9, e = lane % 9, d = -1, ib = -1;
+    if(lane < 27 && k < kJoints) d = 9 * (k - 1) + e;
+    if(warp == 7 && lane >= 18 && lane < 18 + kShapeDim && p.beta_cols) ib = lane - 18, d = kPoseDim + ib;
+    const bool joint_lane = d >= 0 && ib < 0;
+    float dv[3] = {0.f, 0.f, 0.f};
+    if(joint_lane) dv[0] = s_dR[27 * k + e], dv[1] = s_dR[27 * k + 9 + e], dv[2] = s_dR[27 * k + 18 + e];
+    const bool warp_active = __any_sync(0xffffffffu, d >= 0);
+    if(warp_active)
     {
-      float * Q = s_Q + (m & 1) * ROWS * kBlendK;
-      if(tid < kBlendK)
+      for(int m = 0; m < n; m++)
       {
         float q4[ROWS];
 #pragma unroll
         for(int r = 0; r < ROWS; r++) q4[r] = 0.f;
         const int p0 = t.pair_off[m];
         const int np = p.use_ring ? t.pair_off[m + 1] - p0 : 3;
-        for(int q = 0; q < np; q++)
+        if(d >= 0)
         {
-          const int u = t.pair_vert[p0 + q];
-          const float * bu = t.basis + static_cast<size_t>(3 * u) * kBlendK + tid;
-          const float b0 = __ldg(bu), b1 = __ldg(bu + kBlendK), b2 = __ldg(bu + 2 * kBlendK);
-          const float * C = s_C4 + 12 * (p0 + q);
+          for(int q = 0; q < np; q++)
+          {
+            const int u = t.pair_vert[p0 + q];
+            const float * bu = t.basis + static_cast<size_t>(3 * u) * kBlendK + d;
+            const float b0 = __ldg(bu), b1 = __ldg(bu + kBlendK), b2 = __ldg(bu + 2 * kBlendK);
+            const float * C = s_C4 + 12 * (p0 + q);
 #pragma unroll
-          for(int r = 0; r < ROWS; r++) q4[r] = fmaf(C[3 * r], b0, fmaf(C[3 * r + 1], b1, fmaf(C[3 * r + 2], b2, q4[r])));
+            for(int r = 0; r < ROWS; r++) q4[r] = fmaf(C[3 * r], b0, fmaf(C[3 * r + 1], b1, fmaf(C[3 * r + 2], b2, q4[r])));
+          }
         }
-#pragma unroll
-        for(int r = 0; r < ROWS; r++) Q[r * kBlendK + tid] = q4[r];
-      }
-      __syncthreads();
-      if(tid < 69)
-      {
-        const int k = 1 + tid / 3, c = tid % 3;
-        const float * dv = s_dR + 27 * k + 9 * c;
+        float val[ROWS][3];
 #pragma unroll
         for(int r = 0; r < ROWS; r++)
+#pragma unroll
+          for(int c = 0; c < 3; c++)
+          {
+            float v = q4[r] * dv[c];
+#pragma unroll
+            for(int o = 1; o < 16; o <<= 1)
+            {
+              const float other = __shfl_down_sync(0xffffffffu, v, o);
+              if(e + o < 9) v += other;
+            }
+            val[r][c] = v;
+          }
+        if(joint_lane && e == 0)
         {
-          const float * qr = Q + r * kBlendK + 9 * (k - 1);
-          float acc = 0.f;
 #pragma unroll
-          for(int e = 0; e < 9; e++) acc = fmaf(qr[e], dv[e], acc);
-          Jf[(4 * m + r) * p.ldfull + 3 + 3 * k + c] += acc;
+          for(int r = 0; r < ROWS; r++)
+#pragma unroll
+            for(int c = 0; c < 3; c++) Jf[(4 * m + r) * p.ldfull + 3 + 3 * k + c] += val[r][c];
         }
-      }
-      else if(p.beta_cols && tid >= 96 && tid < 96 + kShapeDim)
-      {
-        const int ib = tid - 96;
+        if(ib >= 0)
+        {
 #pragma unroll
-        for(int r = 0; r < ROWS; r++) Jf[(4 * m + r) * p.ldfull + bcol + ib] += Q[r * kBlendK + kPoseDim + ib];
+          for(int r = 0; r < ROWS; r++) Jf[(4 * m + r) * p.ldfull + bcol + ib] += q4[r];
+        }
       }
     }
   }
@@ -1464,7 +1487,7 @@ extern "C" int smplpp_tasks_create(const smplpp_model_t * model, int32_t n, cons
   const int nUpad = (nU + 63) / 64 * 64;
   const int nItems = static_cast<int>(item_verts.size() / 3);
   // pairs: corners 0,1,2 first, then the other ring vertices in order of first appearance
-  std::vector<int32_t> pair_off(n + 1, 0), pair_vert, pair_ref_off(1, 0), pair_refs;
+  std::vector<int32_t> pair_off(n + 1, 0), pair_vert, pair_task, pair_ref_off(1, 0), pair_refs;
   int maxPairs = 0;
   for(int m = 0; m < n; m++)
   {
@@ -1478,6 +1501,7 @@ extern "C" int smplpp_tasks_create(const smplpp_model_t * model, int32_t n, cons
     for(int32_t u : verts_m)
     {
       pair_vert.push_back(u);
+      pair_task.push_back(m);
       for(int it = item_off[3 * m]; it < item_off[3 * m + 3]; it++)
         for(int s = 0; s < 3; s++)
           if(item_verts[3 * it + s] == u) pair_refs.push_back(it * 4 + s);
@@ -1534,6 +1558,7 @@ extern "C" int smplpp_tasks_create(const smplpp_model_t * model, int32_t n, cons
   if(rc == SMPLPP_OK) rc = upload_vec(t, &d.item_verts, item_verts);
   if(rc == SMPLPP_OK) rc = upload_vec(t, &d.pair_off, pair_off);
   if(rc == SMPLPP_OK) rc = upload_vec(t, &d.pair_vert, pair_vert);
+  if(rc == SMPLPP_OK) rc = upload_vec(t, &d.pair_task, pair_task);
   if(rc == SMPLPP_OK) rc = upload_vec(t, &d.pair_ref_off, pair_ref_off);
   if(rc == SMPLPP_OK) rc = upload_vec(t, &d.pair_refs, pair_refs);
   if(rc == SMPLPP_OK) rc = upload_vec(t, &d.task_joint_mask, mask_all);
@@ -1554,6 +1579,7 @@ extern "C" int smplpp_tasks_create(const smplpp_model_t * model, int32_t n, cons
   t->sub.lbs_joint = const_cast<uint8_t *>(d.lbs_joint);
   t->sub.lbs_weight = const_cast<float *>(d.lbs_weight);
   t->sub.lbs_wsum = const_cast<float *>(d.lbs_wsum);
+  t->sub.group_nj = nullptr, t->sub.group_joint = nullptr, t->sub.group_w = nullptr; // per-vertex slot path
   t->sub_corner = t->sub;
   t->sub_corner.V = nCorner;
   t->h_sub_vert = sub_vert;
@@ -1715,8 +1741,8 @@ size_t jac_smem_bytes(const TasksDev & t, const IkLayout & L)
   if(L.use_ring) fl += 4 * static_cast<size_t>(t.nItems) + 12 * static_cast<size_t>(t.n);
   fl += c1::TS * static_cast<size_t>(t.n);
   fl += 12 * static_cast<size_t>(t.nPairs);
-  fl += 2 * 4 * static_cast<size_t>(kBlendK);
-  return fl * sizeof(float) + 64;
+  fl += 4 * static_cast<size_t>(L.nUse) * t.kmax; // normalised weights + wn * x
+  return fl * sizeof(float) + static_cast<size_t>(L.nUse) * t.kmax + 64;
 }
 
 size_t solve_smem_bytes(const IkLayout & L, bool schur)

@@ -165,6 +165,41 @@ extern "C" int smplpp_model_create(const smplpp_model_desc * desc, smplpp_model_
     if(upload(&d.lbs_weight, lw) != SMPLPP_OK) return SMPLPP_ERR_CUDA;
     if(upload(&d.lbs_wsum, ws) != SMPLPP_OK) return SMPLPP_ERR_CUDA;
   }
+  {
+    const int groups = Vpad / kGroupVerts;
+    std::vector<int8_t> nj(groups, 0);
+    std::vector<uint8_t> gj(static_cast<size_t>(groups) * kGroupJoints, 0);
+    std::vector<float> gw(static_cast<size_t>(groups) * kGroupJoints * kGroupVerts, 0.f);
+    for(int g = 0; g < groups; g++)
+    {
+      std::vector<int> list;
+      for(int v = g * kGroupVerts; v < std::min(V, (g + 1) * kGroupVerts); v++)
+        for(int j = 0; j < kJoints; j++)
+          if(desc->weights[static_cast<size_t>(v) * kJoints + j] != 0.f && std::find(list.begin(), list.end(), j) == list.end())
+            list.push_back(j);
+      std::sort(list.begin(), list.end());
+      if(static_cast<int>(list.size()) > kGroupJoints)
+      {
+        nj[g] = -1;
+        continue;
+      }
+      nj[g] = static_cast<int8_t>(list.size());
+      for(size_t k = 0; k < list.size(); k++)
+      {
+        gj[static_cast<size_t>(g) * kGroupJoints + k] = static_cast<uint8_t>(list[k]);
+        for(int u = 0; u < kGroupVerts; u++)
+        {
+          const int v = g * kGroupVerts + u;
+          if(v < V)
+            gw[(static_cast<size_t>(g) * kGroupJoints + k) * kGroupVerts + u] =
+                desc->weights[static_cast<size_t>(v) * kJoints + list[k]];
+        }
+      }
+    }
+    if(upload(&d.group_nj, nj) != SMPLPP_OK) return SMPLPP_ERR_CUDA;
+    if(upload(&d.group_joint, gj) != SMPLPP_OK) return SMPLPP_ERR_CUDA;
+    if(upload(&d.group_w, gw) != SMPLPP_OK) return SMPLPP_ERR_CUDA;
+  }
   if(upload(&d.weights_dense, m->h_weights) != SMPLPP_OK) return SMPLPP_ERR_CUDA;
 
   // topology: 0-based faces + vertex -> adjacent faces (SMPL.cpp:619-640; uniform weights 1/deg)
@@ -209,6 +244,9 @@ extern "C" void smplpp_model_destroy(smplpp_model_t * m)
   cudaFree(d.lbs_joint);
   cudaFree(d.lbs_weight);
   cudaFree(d.lbs_wsum);
+  cudaFree(d.group_nj);
+  cudaFree(d.group_joint);
+  cudaFree(d.group_w);
   cudaFree(d.joint_template);
   cudaFree(d.joint_shape);
   cudaFree(d.faces);

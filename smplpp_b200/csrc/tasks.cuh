@@ -22,6 +22,7 @@ struct TasksDev
   const int32_t * item_verts = nullptr;   // (nItems, 3) local vertex ids of the adjacent face, in face order
   const int32_t * pair_off = nullptr;     // (n + 1)  CSR task -> pairs
   const int32_t * pair_vert = nullptr;    // (nPairs) local vertex id
+  const int32_t * pair_task = nullptr;    // (nPairs) owning task
   const int32_t * pair_ref_off = nullptr; // (nPairs + 1) CSR pair -> references
   const int32_t * pair_refs = nullptr;    // item * 4 + slot (slot = position of the vertex in the item's face)
   const uint32_t * task_joint_mask = nullptr; // (n) joints that move any vertex of the task (corners only: bit 24+)

@@ -1,0 +1,125 @@
+"""IK leg of bench.py: frame-iterations/s of the batched MoSh step (BASELINE configs[2]-[4] shaped workloads).
+
+Synthetic 'sample_walk-shaped' mocap is generated ON THE DEVICE from the seed: ground-truth theta(t) (smooth
+random walk) -> product forward pass -> 41 marker positions (15 mm normal offset) + 1 mm noise + 3.4 % dropout.
+Every frame starts from the common initial pose (batched frames cannot warm-start from their predecessor)."""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+import torch
+
+from . import api, synth
+
+
+def make_problem(smpl, tasks, frames: int, seed: int, dev):
+    _, _, vw0 = synth.make_marker_tasks(smpl._params)
+    n = tasks.n
+    rng = np.random.default_rng(seed)
+    # per-frame random poses around the walking clip statistics (cheap to generate for millions of frames)
+    base = synth.make_motion(min(frames, 4096), seed)
+    reps = (frames + base.shape[0] - 1) // base.shape[0]
+    gt = np.tile(base, (reps, 1, 1))[:frames].copy()
+    gt[:, 2:] += rng.normal(scale=0.02, size=(frames, 23, 3)).astype(np.float32)
+    beta = (rng.normal(size=10) * 0.5).astype(np.float32)
+    w0 = torch.as_tensor(np.repeat(vw0[None], frames, axis=0), device=dev).contiguous()
+    target = torch.empty((frames, n, 3), dtype=torch.float32, device=dev)
+    for s in range(0, frames, 4096):
+        e = min(frames, s + 4096)
+        smpl.launch(beta, gt[s:e])
+        target[s:e] = tasks.positions(smpl._vertices, w0[s:e], 0.015)
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    target += 1e-3 * torch.randn(target.shape, generator=gen, device=dev)
+    valid = (torch.rand((frames, n), generator=gen, device=dev) >= 0.034).float()
+    target *= valid.unsqueeze(-1)  # node.cpp:682-683: missing marker -> weight 0, target zeroed
+    x0 = torch.as_tensor(gt[:1].reshape(1, 75), device=dev).repeat(frames, 1).contiguous()
+    return dict(beta=torch.as_tensor(beta, device=dev), w0=w0, target=target.contiguous(), valid=valid.contiguous(),
+                x0=x0, gt=gt)
+
+
+def time_steps(fn, iters, warmup, barrier, max_over_ranks, dev):
+    stream = torch.cuda.current_stream(dev)
+    for _ in range(warmup):
+        fn()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(iters):
+        fn()
+    b.record(stream)
+    barrier()
+    return max_over_ranks(a.elapsed_time(b)) / iters
+
+
+def run(dev, rank, world, max_over_ranks, barrier, frames: int = 16384, iters: int = 10, warmup: int = 3):
+    params = synth.make_smpl_params(0)
+    smpl = api.SMPL(params, device=dev)
+    vposer = api.VPoserDecoder(synth.make_vposer_params(1), device=dev)
+    _, face_idx, _ = synth.make_marker_tasks(params)
+    tasks = api.IkTaskSet(smpl, face_idx, vposer=vposer)
+    prob = make_problem(smpl, tasks, frames, 20 + rank, dev)
+    out = {"unit": "frame-iters/s", "frames_per_gpu": frames, "markers": tasks.n, "task_vertices": tasks.vertex_count,
+           "iterations_timed": iters}
+
+    # (1) MoSh direct (configs[2]): theta + translation per frame (D = 75), fixed beta, normal offset 15 mm
+    opt = api.ik_options()
+    theta, vw = prob["x0"].clone(), prob["w0"].clone()
+
+    def step_direct():
+        tasks.step(opt, theta, prob["beta"], vw, prob["target"], pos_task_weight=prob["valid"])
+
+    ms = time_steps(step_direct, iters, warmup, barrier, max_over_ranks, dev)
+    out["mosh_direct"] = {"value": world * frames / (ms * 1e-3), "ms_per_iter": ms, "unknowns_per_frame": 75}
+    # residual after the timed iterations (sanity: the solver is converging on real work)
+    status, o = tasks.step(opt, theta, prob["beta"], vw, prob["target"], pos_task_weight=prob["valid"], outputs=False), None
+    del o
+    out["mosh_direct"]["frames_ok"] = int((status == 0).sum().item())
+
+    # (2) MoSh++ with the VPoser latent prior (configs[3]): D = 44, decoder + 63x32 Jacobian in the step
+    optv = api.ik_options(enable_vposer=1)
+    xv = torch.zeros((frames, 44), dtype=torch.float32, device=dev)
+    xv[:, :6] = prob["x0"][:, :6]
+    vw2 = prob["w0"].clone()
+
+    def step_vposer():
+        tasks.step(optv, xv, prob["beta"], vw2, prob["target"], pos_task_weight=prob["valid"])
+
+    ms = time_steps(step_vposer, max(3, iters // 2), 2, barrier, max_over_ranks, dev)
+    out["moshpp_vposer"] = {"value": world * frames / (ms * 1e-3), "ms_per_iter": ms, "unknowns_per_frame": 44}
+
+    # (3) shared-beta stage (configs[3]/[4]): Schur complement per frame + ONE all-reduce of 111 doubles
+    sbeta = torch.zeros(10, dtype=torch.float32, device=dev)
+    th3, vw3 = prob["x0"].clone(), prob["w0"].clone()
+
+    def step_shared():
+        tasks.shared_beta_step(opt, th3, sbeta, vw3, prob["target"], pos_task_weight=prob["valid"])
+
+    ms = time_steps(step_shared, max(3, iters // 2), 2, barrier, max_over_ranks, dev)
+    out["shared_beta"] = {"value": world * frames / (ms * 1e-3), "ms_per_iter": ms,
+                          "collective": "all_reduce(sum) of 111 float64 per iteration" if world > 1 else "none (1 GPU)"}
+    out["value"] = out["mosh_direct"]["value"]
+    return out
+
+
+def cpu_reference_ik(frames: int = 2, iters: int = 2):
+    """Reference CPU path (oracle/_ref harness restating node.cpp:753-968 on the compiled reference objects):
+    frame-iterations/s on a bounded sample."""
+    from oracle import ref_lib
+    params = synth.make_smpl_params(0)
+    _, face_idx, vw = synth.make_marker_tasks(params)
+    ref = ref_lib.RefSMPL(ref_lib.model_json_path(0))
+    gt = synth.make_motion(frames + 1, 20)
+    beta = np.zeros(10, np.float32)
+    n = len(face_idx)
+    tgt = np.random.default_rng(0).normal(size=(n, 3)).astype(np.float32) * 0.3
+    t0 = time.perf_counter()
+    for f in range(frames):
+        x = gt[f].reshape(-1).copy()
+        w = vw.copy()
+        for _ in range(iters):
+            r = ref.ik_iteration(x, beta, face_idx, w, tgt, normal_task_weight=0.0, phi_limit=0.0, normal_offset=0.015)
+            x, w = r["theta_state"], r["vertex_weights"]
+    dt = time.perf_counter() - t0
+    return frames * iters / dt, ref_lib.get_num_threads(), "%d frames x %d iterations, 41 markers, direct theta (D=75)" % (
+        frames, iters)

@@ -215,6 +215,14 @@ def make_smpl_params(seed: int = 0) -> SmplParams:
             drop[j] = True
     dirs = cand[~drop][:VERTEX_NUM]
     assert dirs.shape[0] == VERTEX_NUM, dirs.shape
+    # SMPL-like spatially coherent vertex numbering (the artist mesh numbers vertices region by region):
+    # order by nearest bone, then by the position along that bone
+    pts0 = center + _radial_surface(dirs, center)[:, None] * dirs
+    dbone = np.stack([_point_segment_dist(pts0, _JOINTS[PARENTS[j]], _JOINTS[j]) if j else
+                      np.linalg.norm(pts0 - _JOINTS[0], axis=1) for j in range(JOINT_NUM)], axis=1)
+    near = dbone.argmin(axis=1)
+    along = np.einsum("ij,ij->i", pts0 - _JOINTS[near], _JOINTS[near] - _JOINTS[np.maximum(PARENTS[near], 0)])
+    dirs = dirs[np.lexsort((np.round(along, 2), near))]
     hull = ConvexHull(dirs)
     assert hull.vertices.shape[0] == VERTEX_NUM
     faces = hull.simplices.astype(np.int64)

@@ -152,6 +152,12 @@ def test_model_skinning_vs_oracle(smpl_gpu, oracle_model, params):
                                                 api._ptr(root), api._ptr(out)))
     torch.cuda.synchronize()
     assert np.abs(out.cpu().numpy() - r.vertices.numpy()).max() <= TOL_VERTEX_M
+    xf34 = xf[:, :, :3, :].contiguous()
+    out34 = torch.empty_like(rest)
+    capi.check(capi.lib().smplpp_model_skinning34(smpl_gpu.handle, None, C.c_int64(19), api._ptr(rest), api._ptr(xf34),
+                                                  api._ptr(root), api._ptr(out34)))
+    torch.cuda.synchronize()
+    assert np.abs(out34.cpu().numpy() - r.vertices.numpy()).max() <= TOL_VERTEX_M
 
 
 def test_dense_weights_small_model():
