@@ -96,7 +96,9 @@ int smplpp_forward_host(const smplpp_model_t * model, int64_t batch, const float
                         const float * theta_host, float * vertices_host, float * joints_host);
 
 /* Pipeline variant selection for smplpp_forward: 0 = auto, 1 = FFMA fused blend+skinning,
- * 2 = tcgen05 3xTF32 fused blend+skinning, 3 = unfused (blend GEMM -> rest shape -> standalone skinning). */
+ * 2 = tcgen05 3xTF32 fused blend+skinning, 3 = unfused (blend GEMM -> rest shape -> standalone skinning),
+ * 4 = tcgen05 3xBF16 fused blend+skinning (faster, ~1.5e-6 m contraction error instead of ~3e-8 m).
+ * The tcgen05 variants need an even vertex count >= 128 and <= 4 skinning influences per vertex. */
 int smplpp_set_forward_variant(int variant);
 
 /* ---------------------------------------------------------------------------------------------------------

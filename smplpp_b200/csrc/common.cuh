@@ -91,6 +91,12 @@ struct ModelDev
   int32_t * adj_faces = nullptr;
   // originals kept for the task builder and the generic module kernels
   float * weights_dense = nullptr; // (V, 24)
+  // tcgen05 blend variant (blend_tc.cu): split basis [part hi|lo][tile][plane x|y|z][128][224] as bf16 ([0]) and
+  // tf32-rounded fp32 ([1]) with their TMA tensor maps (CUtensorMap is 128 bytes, 64-byte aligned)
+  void * basis_split[2] = {nullptr, nullptr};
+  alignas(64) unsigned char tmapA[2][128] = {};
+  int tc_tiles = 0;
+  bool tc_ready = false;
 };
 } // namespace sb
 

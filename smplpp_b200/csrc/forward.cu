@@ -842,7 +842,7 @@ int launch_lbs(const ModelDev & d, cudaStream_t st, int B, const float * rest, c
 
 extern "C" int smplpp_set_forward_variant(int variant)
 {
-  if(variant < 0 || variant > 3) return fail(SMPLPP_ERR_INVALID, "SMPL", "unknown forward variant");
+  if(variant < 0 || variant > 4) return fail(SMPLPP_ERR_INVALID, "SMPL", "unknown forward variant");
   g_forward_variant = variant;
   return SMPLPP_OK;
 }
@@ -854,6 +854,7 @@ extern "C" size_t smplpp_forward_workspace_bytes(const smplpp_model_t * model, i
   size_t bytes = 512;
   bytes += align_up(bpad * kBlendK * sizeof(float));         // coefficients (A operand)
   bytes += align_up(bpad * kJoints * 12 * sizeof(float));    // relative transforms 3x4
+  bytes += tc_coef_split_bytes(batch);                      // hi / lo coefficient parts (tcgen05 variants)
   bytes += align_up(static_cast<size_t>(batch) * model->d.V * 3 * sizeof(float)); // rest shape (unfused variant)
   return bytes;
 }
@@ -875,6 +876,8 @@ extern "C" int smplpp_forward(const smplpp_model_t * model, void * stream, int64
   ws += align_up(bpad * kBlendK * sizeof(float));
   float * xforms = reinterpret_cast<float *>(ws);
   ws += align_up(bpad * kJoints * 12 * sizeof(float));
+  void * coef_split = ws;
+  ws += tc_coef_split_bytes(batch);
   float * rest_ws = reinterpret_cast<float *>(ws);
 
   const bool need_verts = vertices != nullptr;
@@ -883,7 +886,9 @@ extern "C" int smplpp_forward(const smplpp_model_t * model, void * stream, int64
                              joints, transforms);
   if(rc != SMPLPP_OK) return rc;
   int variant = g_forward_variant;
-  if(variant == 0) variant = tc_blend_available() ? 2 : 1;
+  if(variant == 0) variant = model->d.tc_ready ? 2 : 1;
+  if((variant == 2 || variant == 4) && !model->d.tc_ready)
+    return fail(SMPLPP_ERR_INVALID, "SMPL", "tcgen05 blend variant is not available for this model");
   if(need_rest || (need_verts && variant == 3))
   {
     float * rest = need_rest ? rest_shape : rest_ws;
@@ -894,8 +899,8 @@ extern "C" int smplpp_forward(const smplpp_model_t * model, void * stream, int64
   }
   if(need_verts)
   {
-    if(variant == 2)
-      rc = launch_blend_skin_tc(d, st, B, coef, xforms, theta, vertices);
+    if(variant == 2 || variant == 4)
+      rc = launch_blend_skin_tc(d, st, B, coef, coef_split, xforms, theta, vertices, variant == 2);
     else
       rc = launch_blend_skin_ffma(d, st, B, coef, xforms, theta, vertices, true);
   }

@@ -19,10 +19,13 @@ int launch_pose_chain(const ModelDev & d, cudaStream_t st, int B, const float * 
 // K2 (FFMA): fused blend contraction (+ skinning when skin == true, else writes the rest shape)
 int launch_blend_skin_ffma(const ModelDev & d, cudaStream_t st, int B, const float * coef, const float * xforms,
                            const float * theta, float * out, bool skin);
-// K2 (tcgen05 3xTF32): same contract as the skin == true FFMA kernel
+// K2' (tcgen05 split precision, blend_tc.cu): same contract as the skin == true FFMA kernel; tf32: 3xTF32, else 3xBF16
 bool tc_blend_available();
-int launch_blend_skin_tc(const ModelDev & d, cudaStream_t st, int B, const float * coef, const float * xforms,
-                         const float * theta, float * out);
+int tc_prepare_model(ModelDev & d);
+void tc_release_model(ModelDev & d);
+size_t tc_coef_split_bytes(int64_t batch);
+int launch_blend_skin_tc(const ModelDev & d, cudaStream_t st, int B, const float * coef, void * coef_split,
+                         const float * xforms, const float * theta, float * out, bool tf32);
 // K3: standalone skinning; affine: xforms are (B,24,3,4) else (B,24,4,4)
 int launch_lbs(const ModelDev & d, cudaStream_t st, int B, const float * rest, const float * xforms, bool affine,
                const float * root, int root_stride, float * out);

@@ -4,7 +4,7 @@
 #include <cmath>
 #include <cstring>
 
-#include "common.cuh"
+#include "forward.cuh"
 
 namespace sb
 {
@@ -231,6 +231,7 @@ extern "C" int smplpp_model_create(const smplpp_model_desc * desc, smplpp_model_
   if(upload(&d.adj_offset, m->h_adj_offset) != SMPLPP_OK) return SMPLPP_ERR_CUDA;
   if(upload(&d.adj_faces, m->h_adj_faces) != SMPLPP_OK) return SMPLPP_ERR_CUDA;
 
+  if(tc_prepare_model(d) != SMPLPP_OK) return SMPLPP_ERR_CUDA;
   SB_CUDA(cudaStreamCreateWithFlags(&m->host_stream, cudaStreamNonBlocking));
   *out = m;
   return SMPLPP_OK;
@@ -253,6 +254,7 @@ extern "C" void smplpp_model_destroy(smplpp_model_t * m)
   cudaFree(d.adj_offset);
   cudaFree(d.adj_faces);
   cudaFree(d.weights_dense);
+  tc_release_model(d);
   if(m->pinned) cudaFreeHost(m->pinned);
   if(m->dev_scratch) cudaFree(m->dev_scratch);
   if(m->host_stream) cudaStreamDestroy(m->host_stream);
