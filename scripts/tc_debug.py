@@ -12,7 +12,8 @@ beta, theta = synth.make_forward_inputs(B, 11)
 v_o, j_o, _, _ = so.forward_numpy(so.SmplModel.from_params(params), beta[:64], theta[:64])
 lib = capi.lib()
 ref = None
-for var in (1, 2, 4):
+for var, order in ((1, 1), (2, 0), (2, 1), (4, 0), (4, 1)):
+    capi.check(lib.smplpp_set_forward_variant(100 + order))
     capi.check(lib.smplpp_set_forward_variant(var))
     try:
         smpl.launch(beta, theta)
@@ -23,8 +24,8 @@ for var in (1, 2, 4):
         continue
     if ref is None:
         ref = v
-    print("variant %d: max|v - oracle| = %.3g (64 frames), max|v - ffma| = %.3g, finite=%s" % (
-        var, np.abs(v[:64] - v_o).max(), np.abs(v - ref).max(), np.isfinite(v).all()))
+    print("variant %d order %d: max|v - oracle| = %.3g (64 frames), max|v - ffma| = %.3g, finite=%s" % (
+        var, order, np.abs(v[:64] - v_o).max(), np.abs(v - ref).max(), np.isfinite(v).all()))
     if not np.isfinite(v).all() or np.abs(v - ref).max() > 1e-4:
         d = np.abs(v - ref).max(axis=2)
         bad = np.argwhere(~(d < 1e-4))
@@ -34,7 +35,10 @@ for var in (1, 2, 4):
     t = []
     for _ in range(5):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); smpl.launch(beta, theta); b.record(); torch.cuda.synchronize()
-        t.append(a.elapsed_time(b))
-    print("  launch ms (incl. K1): min %.3f  -> %.2f M meshes/s" % (min(t), B / min(t) / 1e3))
+        a.record()
+        for _ in range(10):
+            smpl.launch(beta, theta)
+        b.record(); torch.cuda.synchronize()
+        t.append(a.elapsed_time(b) / 10)
+    print("  launch ms (incl. K1, 10 back to back): min %.3f  -> %.2f M meshes/s" % (min(t), B / min(t) / 1e3))
 capi.check(lib.smplpp_set_forward_variant(0))

@@ -39,7 +39,8 @@ constexpr int XF_FLOATS = XF_FR * kJoints * kXformFloats;
 constexpr int XF_BYTES = XF_FLOATS * 4;            // 36864
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 32 * (2 + EPI_WARPS);
-constexpr int STG_FLOATS = 2 * 32 * 3;             // per warp: 2 frames x 32 vertices x 3
+constexpr int STG_FR = 4;                          // frames staged per warp between two warp syncs
+constexpr int STG_FLOATS = STG_FR * 32 * 3;        // per warp: 4 frames x 32 vertices x 3
 constexpr int OFF_XF = STAGES * STAGE;
 constexpr int OFF_STG = OFF_XF + 2 * XF_BYTES;
 constexpr int OFF_BAR = OFF_STG + EPI_WARPS * STG_FLOATS * 4;
@@ -52,7 +53,7 @@ static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 struct Params
 {
-  int V, B, Bpad, ntiles, nkb, ke, ell_stride, kmax;
+  int V, B, Bpad, ntiles, nkb, ke, ell_stride, kmax, frames_fastest;
   const float * basis;
   const uint8_t * lbs_joint;
   const float * lbs_weight;
@@ -131,15 +132,16 @@ __global__ void split_coef_kernel(const float * __restrict__ coef, int B, int Bp
 // ------------------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void skin_vertex(const float * __restrict__ xfr, const int (&joff)[4], const float (&jw)[4],
-                                            float rx, float ry, float rz, float & ox, float & oy, float & oz)
+// xfr: shared-memory byte address of the frame's 24 x (3x4) transforms; joff: byte offsets of the vertex's joints
+__device__ __forceinline__ void skin_vertex(uint32_t xfr, const int (&joff)[4], const float (&jw)[4], float rx, float ry,
+                                            float rz, float & ox, float & oy, float & oz)
 {
   ox = oy = oz = 0.f;
 #pragma unroll
   for(int k = 0; k < 4; k++)
   {
-    const float4 * g = reinterpret_cast<const float4 *>(xfr + joff[k]);
-    const float4 r0 = g[0], r1 = g[1], r2 = g[2];
+    const uint32_t g = xfr + joff[k];
+    const float4 r0 = ptx::lds128(g), r1 = ptx::lds128(g + 16), r2 = ptx::lds128(g + 32);
     const float w = jw[k];
     ox = fmaf(w, fmaf(r0.x, rx, fmaf(r0.y, ry, fmaf(r0.z, rz, r0.w))), ox);
     oy = fmaf(w, fmaf(r1.x, rx, fmaf(r1.y, ry, fmaf(r1.z, rz, r1.w))), oy);
@@ -166,8 +168,9 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
   uint32_t * tmem_slot = reinterpret_cast<uint32_t *>(xf_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x;
-  const int f0 = blockIdx.y * NF;
+  // kFramesFastest: consecutive CTAs share the (3x larger) basis tile instead of the coefficient tile
+  const int tile = p.frames_fastest ? blockIdx.y : blockIdx.x;
+  const int f0 = (p.frames_fastest ? blockIdx.x : blockIdx.y) * NF;
 
   if(warp == 0 && lane == 0)
   {
@@ -278,19 +281,24 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
     for(int k = 0; k < 4; k++)
     {
       const bool on = k < p.kmax;
-      joff[k] = on ? p.lbs_joint[static_cast<size_t>(k) * p.ell_stride + vc] * kXformFloats : 0;
+      joff[k] = on ? p.lbs_joint[static_cast<size_t>(k) * p.ell_stride + vc] * (kXformFloats * 4) : 0;
       jw[k] = on ? p.lbs_weight[static_cast<size_t>(k) * p.ell_stride + vc] : 0.f;
     }
     const float iw = 1.f / p.lbs_wsum[vc];
-    float * my_stg = stg + ew * STG_FLOATS;
+    const uint32_t my_stg = ptx::smem_u32(stg + ew * STG_FLOATS);
+    const uint32_t xf_addr = ptx::smem_u32(xf);
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
 
     ptx::mbar_wait(tmem_full, 0);
     ptx::tc_fence_after();
     for(int sb = 0; sb < nsb; sb++)
     {
+      // root translation (theta row 0, SMPL.cpp:726-727) of this window's frames: lane l holds frame sb * 32 + l;
+      // issued before the wait so that the global-load latency hides behind it, broadcast per frame by shuffles
+      const float * trp = p.theta + static_cast<size_t>(min(f0 + sb * XF_FR + lane, p.B - 1)) * ((kJoints + 1) * 3);
+      const float wtx = __ldg(trp), wty = __ldg(trp + 1), wtz = __ldg(trp + 2);
       ptx::mbar_wait(&xf_full[sb & 1], (sb >> 1) & 1);
-      const float * xfb = xf + (sb & 1) * XF_FLOATS;
+      const uint32_t xfb = xf_addr + (sb & 1) * XF_BYTES;
 #pragma unroll 1
       for(int gg = 0; gg < 2; gg++)
       {
@@ -302,31 +310,32 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
         ptx::tmem_ld_x8(lane_taddr + 2 * NF + fl, Z);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for(int pr = 0; pr < 4; pr++)
+        for(int hf = 0; hf < 8 / STG_FR; hf++)
         {
 #pragma unroll
-          for(int t = 0; t < 2; t++)
+          for(int t = 0; t < STG_FR; t++)
           {
-            const int fi = 2 * pr + t;
-            const int f = min(f0 + fl + fi, p.B - 1);
-            const float * tr = p.theta + static_cast<size_t>(f) * ((kJoints + 1) * 3);
-            const float trx = __ldg(tr), try_ = __ldg(tr + 1), trz = __ldg(tr + 2);
+            const int fi = STG_FR * hf + t;
+            const float trx = __shfl_sync(0xffffffffu, wtx, g * 8 + fi);
+            const float try_ = __shfl_sync(0xffffffffu, wty, g * 8 + fi);
+            const float trz = __shfl_sync(0xffffffffu, wtz, g * 8 + fi);
             float ox, oy, oz;
-            skin_vertex(xfb + (g * 8 + fi) * (kJoints * kXformFloats), joff, jw, X[fi] + T[0], Y[fi] + T[1], Z[fi] + T[2],
-                        ox, oy, oz);
-            my_stg[t * 96 + lane * 3 + 0] = fmaf(ox, iw, trx);
-            my_stg[t * 96 + lane * 3 + 1] = fmaf(oy, iw, try_);
-            my_stg[t * 96 + lane * 3 + 2] = fmaf(oz, iw, trz);
+            skin_vertex(xfb + (g * 8 + fi) * (kJoints * kXformFloats * 4), joff, jw, X[fi] + T[0], Y[fi] + T[1],
+                        Z[fi] + T[2], ox, oy, oz);
+            const uint32_t sa = my_stg + (t * 96 + lane * 3) * 4;
+            ptx::sts32(sa, fmaf(ox, iw, trx));
+            ptx::sts32(sa + 4, fmaf(oy, iw, try_));
+            ptx::sts32(sa + 8, fmaf(oz, iw, trz));
           }
           __syncwarp();
 #pragma unroll
-          for(int i = 0; i < 3; i++)
+          for(int i = 0; i < STG_FR * 48 / 32; i++)
           {
-            const int idx = 32 * i + lane; // float2 index over 2 frames x 48
-            const int t = idx >= 48 ? 1 : 0;
+            const int idx = 32 * i + lane; // float2 index over STG_FR frames x 48
+            const int t = idx / 48;
             const int w = idx - 48 * t;
-            const int f = f0 + fl + 2 * pr + t;
-            const float2 val = reinterpret_cast<const float2 *>(my_stg)[idx];
+            const int f = f0 + fl + STG_FR * hf + t;
+            const float2 val = ptx::lds64(my_stg + idx * 8);
             if(f < p.B && 2 * w < 3 * nvalid)
               __stcs(reinterpret_cast<float2 *>(p.out + (static_cast<size_t>(f) * p.V + wv0) * 3) + w, val);
           }
@@ -386,6 +395,8 @@ bool encode_kmajor(CUtensorMap * out, bool tf32, void * base, uint64_t rows, uin
 
 namespace sb
 {
+int g_tc_grid_order = 1;
+
 bool tc_blend_available()
 {
   static int ok = -1;
@@ -493,7 +504,9 @@ int launch_blend_skin_tc(const ModelDev & d, cudaStream_t st, int B, const float
   p.xforms = xforms;
   p.theta = theta;
   p.out = out;
+  p.frames_fastest = g_tc_grid_order;
   dim3 grid(d.tc_tiles, Bpad / tc::NF);
+  if(p.frames_fastest) grid = dim3(Bpad / tc::NF, d.tc_tiles);
   const CUtensorMap & tmA = *reinterpret_cast<const CUtensorMap *>(d.tmapA[tf32 ? 1 : 0]);
   if(tf32)
     blend_skin_tc_kernel<true><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(tmA, tmB, p);

@@ -842,6 +842,12 @@ int launch_lbs(const ModelDev & d, cudaStream_t st, int B, const float * rest, c
 
 extern "C" int smplpp_set_forward_variant(int variant)
 {
+  // 100 / 101: tuning switch for the grid order of the tcgen05 kernel (tile-fastest / frames-fastest)
+  if(variant == 100 || variant == 101)
+  {
+    g_tc_grid_order = variant - 100;
+    return SMPLPP_OK;
+  }
   if(variant < 0 || variant > 4) return fail(SMPLPP_ERR_INVALID, "SMPL", "unknown forward variant");
   g_forward_variant = variant;
   return SMPLPP_OK;

@@ -31,4 +31,5 @@ int launch_lbs(const ModelDev & d, cudaStream_t st, int B, const float * rest, c
                const float * root, int root_stride, float * out);
 
 extern int g_forward_variant;
+extern int g_tc_grid_order; // 1: frame tiles fastest in the tcgen05 kernel's grid (CTAs in flight share the basis tile)
 } // namespace sb

@@ -27,6 +27,24 @@ __device__ __forceinline__ bool elect_one()
   return pred != 0;
 }
 
+// ---- explicit shared-state-space accesses (keeps the compiler from falling back to generic LD/ST) ----
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float2 lds64(uint32_t addr)
+{
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, float v)
+{
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
 // ---- mbarrier ----
 __device__ __forceinline__ void mbar_init(uint64_t * bar, uint32_t count)
 {
