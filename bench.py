@@ -285,18 +285,33 @@ def main():
                        "meshes_per_s": B / (ms_lbs * 1e-3), "ms_per_launch_4x4_transforms": time_kernel(lbs_only44, 20)}
     del rest, xf, xf34
 
-    # ---- e2e through the C-ABI host-buffer call (pinned staging, H2D + D2H inside the timed region) ----
+    # ---- e2e through the C-ABI host-buffer call: inputs in page-locked host memory, H2D + forward + D2H of the
+    # vertices and joints inside the timed region (chunked two-stream pipeline, csrc/host_pipe.cu) ----
     e2e_steps = max(3, min(args.steps, 10))
-    smpl.launch_host(beta_h, theta_h)
+    pin_beta, pin_theta = api.pinned_empty(beta_h.shape), api.pinned_empty(theta_h.shape)
+    pin_beta[...], pin_theta[...] = beta_h, theta_h
+    pin_v, pin_j = api.pinned_empty((B, VERTS, 3)), api.pinned_empty((B, 24, 3))
+    for _ in range(2):
+        smpl.launch_host(pin_beta, pin_theta, out_vertices=pin_v, out_joints=pin_j)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        smpl.launch_host(beta_h, theta_h)
+        smpl.launch_host(pin_beta, pin_theta, out_vertices=pin_v, out_joints=pin_j)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    e2e_check = float(np.abs(pin_v[::997] - verts[::997].cpu().numpy()).max())  # same numbers as the device path
     e2e = {"value": world * B / e2e_s, "unit": "meshes/s", "h2d_bytes_per_step": int(beta_h.nbytes + theta_h.nbytes),
-           "d2h_bytes_per_step": int(B * VERTS * 3 * 4 + B * 24 * 3 * 4),
-           "api": "smplpp_forward_host (smplpp::SMPL::launch + getVertex + getRestJoint with host buffers)"}
+           "d2h_bytes_per_step": int(B * VERTS * 3 * 4 + B * 24 * 3 * 4), "ms_per_step": 1e3 * e2e_s,
+           "d2h_gbs": (B * VERTS * 12 + B * 288) / e2e_s / 1e9, "max_abs_diff_vs_device_path": e2e_check,
+           "api": "smplpp_forward_host (smplpp::SMPL::launch + getVertex + getRestJoint), page-locked host buffers"}
+    # the same call with ordinary pageable numpy arrays (staged through pinned chunks by host threads)
+    pg_v, pg_j = np.empty((B, VERTS, 3), np.float32), np.empty((B, 24, 3), np.float32)
+    smpl.launch_host(beta_h, theta_h, out_vertices=pg_v, out_joints=pg_j)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        smpl.launch_host(beta_h, theta_h, out_vertices=pg_v, out_joints=pg_j)
+    e2e["pageable_value"] = world * B / max_over_ranks((time.perf_counter() - t0) / 3)
+    del pin_v, pg_v
 
     ik = None
     if not args.no_ik:

@@ -90,10 +90,23 @@ int smplpp_forward(const smplpp_model_t * model, void * stream, int64_t batch, c
                    int64_t beta_stride, const float * theta_dev, float * vertices_dev, float * joints_dev,
                    float * transforms_dev, float * rest_shape_dev, void * workspace_dev, size_t workspace_bytes);
 
-/* Same call with HOST buffers: stages through pinned memory, copies in, runs, copies out, synchronises.
- * This is the call a user of smplpp::SMPL::launch + getVertex makes; bench.py's `e2e` times it. */
+/* Same call with HOST buffers: copies in, runs, copies out, synchronises.  This is the call a user of
+ * smplpp::SMPL::launch + getVertex + getRestJoint makes (node/node.cpp:777, 1114-1117); bench.py's `e2e` times it.
+ * The batch is processed in chunks on a compute stream while a copy stream drains the previous chunk, so the
+ * device->host link (82 680 B per mesh) is the only thing the call waits for.  Page-locked buffers (from
+ * smplpp_host_alloc / smplpp_host_register, or any cudaHostAlloc memory) are DMA targets themselves; pageable
+ * buffers are staged through pinned chunk buffers and copied by host threads (SMPLPP_HOST_THREADS, default
+ * cores/2) while the next chunk is in flight.  SMPLPP_HOST_CHUNK sets the frames per chunk (default 256).
+ * Not re-entrant per model handle (the reference's SMPL object is not thread-safe either, SMPL.h:210-270). */
 int smplpp_forward_host(const smplpp_model_t * model, int64_t batch, const float * beta_host, int64_t beta_stride,
                         const float * theta_host, float * vertices_host, float * joints_host);
+
+/* Page-locked host memory for the host-buffer calls (the counterpart of torch's pinned tensors a libtorch caller
+ * of the reference would use for `.to(device, non_blocking)` / `.cpu()`). */
+int smplpp_host_alloc(void ** out, size_t bytes);
+void smplpp_host_free(void * ptr);
+int smplpp_host_register(void * ptr, size_t bytes);
+int smplpp_host_unregister(void * ptr);
 
 /* Pipeline variant selection for smplpp_forward: 0 = auto, 1 = FFMA fused blend+skinning,
  * 2 = tcgen05 3xTF32 fused blend+skinning, 3 = unfused (blend GEMM -> rest shape -> standalone skinning),

@@ -53,6 +53,30 @@ def _require_cuda(device: torch.device) -> None:
                           "there is no CPU fallback)")
 
 
+class _PinnedBlock:
+    """Owns one smplpp_host_alloc allocation; freed when the last numpy view goes away."""
+
+    def __init__(self, nbytes: int):
+        self.ptr = C.c_void_p()
+        check(lib().smplpp_host_alloc(C.byref(self.ptr), C.c_size_t(max(1, nbytes))))
+        self.nbytes = nbytes
+
+    def __del__(self):
+        if getattr(self, "ptr", None) and capi._lib is not None:
+            capi._lib.smplpp_host_free(self.ptr)
+            self.ptr = None
+
+
+def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
+    """numpy array in page-locked host memory (smplpp_host_alloc): the DMA source/target of the host-buffer calls."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape))
+    block = _PinnedBlock(n * dtype.itemsize)
+    buf = (C.c_char * max(1, block.nbytes)).from_address(block.ptr.value)
+    buf._smplpp_owner = block  # keeps the allocation alive as long as the buffer (numpy's base) is
+    return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+
+
 class SMPL:
     """smplpp::SMPL (src/SMPL.cpp).  `launch` runs K1 (pose features + chain) and K2 (fused blend + skinning)."""
 
@@ -161,20 +185,30 @@ class SMPL:
                                        C.c_int64(stride), _ptr(theta), _ptr(self._vertices), _ptr(self._joints),
                                        _ptr(self._transforms), None, _ptr(ws), C.c_size_t(ws.numel())))
 
-    def launch_host(self, beta: np.ndarray, theta: np.ndarray, want_joints: bool = True):
-        """Host-buffer variant of launch + getVertex (+getRestJoint): numpy in, numpy out, copies included."""
+    def launch_host(self, beta: np.ndarray, theta: np.ndarray, want_joints: bool = True, out_vertices=None,
+                    out_joints=None):
+        """Host-buffer variant of launch + getVertex (+getRestJoint): numpy in, numpy out, copies included.
+        `out_vertices` / `out_joints` may be caller-owned float32 arrays (page-locked ones from `pinned_empty`
+        are DMA targets themselves; pageable ones are staged)."""
         beta, theta = _np_f32(beta), _np_f32(theta)
+        if theta.ndim != 3 or theta.shape[1:] != (JOINT_NUM + 1, 3):
+            raise SmplppError("SMPL Error: Cannot launch a SMPL model!")  # SMPL.cpp:676
         n = theta.shape[0]
         if beta.ndim == 1:
             beta = beta.reshape(1, -1)
+        if beta.shape[-1] != SHAPE_BASIS_DIM or beta.shape[0] not in (1, n):
+            raise SmplppError("BlendShape Error: Failed to set beta!")  # BlendShape.cpp:340
         stride = 0 if (beta.shape[0] == 1 and n > 1) else SHAPE_BASIS_DIM
-        verts = np.empty((n, self.vertex_num, 3), np.float32)
-        joints = np.empty((n, JOINT_NUM, 3), np.float32) if want_joints else None
+        verts = out_vertices if out_vertices is not None else np.empty((n, self.vertex_num, 3), np.float32)
+        joints = out_joints if out_joints is not None else (np.empty((n, JOINT_NUM, 3), np.float32) if want_joints else None)
+        for a, shape in ((verts, (n, self.vertex_num, 3)), (joints, (n, JOINT_NUM, 3))):
+            if a is not None and (a.dtype != np.float32 or a.shape != shape or not a.flags.c_contiguous):
+                raise SmplppError("SMPL Error: Cannot launch a SMPL model! (output buffer shape/dtype)")
         with torch.cuda.device(self.m__device):
             check(lib().smplpp_forward_host(self.handle, C.c_int64(n), beta.ctypes.data_as(capi.c_f32p),
                                             C.c_int64(stride), theta.ctypes.data_as(capi.c_f32p),
                                             verts.ctypes.data_as(capi.c_f32p),
-                                            joints.ctypes.data_as(capi.c_f32p) if want_joints else None))
+                                            joints.ctypes.data_as(capi.c_f32p) if joints is not None else None))
         return verts, joints
 
     def _launched(self, what):

@@ -42,6 +42,7 @@ EXPORTS = [
     "smplpp_last_error", "smplpp_launch_count", "smplpp_device_count",
     "smplpp_model_create", "smplpp_model_destroy", "smplpp_model_vertex_num", "smplpp_model_max_influences",
     "smplpp_forward_workspace_bytes", "smplpp_forward", "smplpp_forward_host", "smplpp_set_forward_variant",
+    "smplpp_host_alloc", "smplpp_host_free", "smplpp_host_register", "smplpp_host_unregister",
     "smplpp_blend_shape", "smplpp_joint_regression", "smplpp_world_transformation", "smplpp_linear_blend_skinning",
     "smplpp_model_skinning", "smplpp_model_skinning34", "smplpp_normals",
     "smplpp_vposer_create", "smplpp_vposer_destroy", "smplpp_vposer_decode", "smplpp_rotmat_to_axis_angle",

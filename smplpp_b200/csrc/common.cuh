@@ -110,10 +110,23 @@ struct smplpp_model
   std::vector<float> h_basis;        // (3V, 224) same row layout as d.basis (unpadded V)
   std::vector<float> h_weights;      // (V, 24)
   std::vector<float> h_joint_template, h_joint_shape;
-  // pinned staging for smplpp_forward_host
-  void * pinned = nullptr;
-  size_t pinned_bytes = 0;
-  void * dev_scratch = nullptr;
-  size_t dev_scratch_bytes = 0;
-  cudaStream_t host_stream = nullptr;
+  // smplpp_forward_host: chunked, double-buffered pipeline (compute stream + copy stream)
+  struct HostPipe
+  {
+    cudaStream_t compute = nullptr, copy = nullptr;
+    cudaEvent_t done[2] = {nullptr, nullptr};    // chunk computed (compute stream)
+    cudaEvent_t drained[2] = {nullptr, nullptr}; // chunk copied out (copy stream)
+    void * dev_in = nullptr;                     // beta | theta of the whole batch
+    size_t dev_in_bytes = 0;
+    void * dev_out[2] = {nullptr, nullptr};      // vertices of one chunk
+    size_t dev_out_bytes = 0;
+    void * dev_joints = nullptr;                 // joints of the whole batch
+    size_t dev_joints_bytes = 0;
+    void * ws = nullptr;                         // forward workspace of one chunk
+    size_t ws_bytes = 0;
+    void * pin_in = nullptr;                     // staging for pageable inputs
+    size_t pin_in_bytes = 0;
+    void * pin_out[2] = {nullptr, nullptr};      // staging for pageable outputs (one chunk each)
+    size_t pin_out_bytes = 0;
+  } pipe;
 };

@@ -913,61 +913,6 @@ extern "C" int smplpp_forward(const smplpp_model_t * model, void * stream, int64
   return rc;
 }
 
-extern "C" int smplpp_forward_host(const smplpp_model_t * model_c, int64_t batch, const float * beta_host,
-                                   int64_t beta_stride, const float * theta_host, float * vertices_host,
-                                   float * joints_host)
-{
-  smplpp_model_t * model = const_cast<smplpp_model_t *>(model_c);
-  if(!model || batch < 1 || !beta_host || !theta_host)
-    return fail(SMPLPP_ERR_INVALID, "SMPL", "Cannot launch a SMPL model!");
-  const size_t V = model->d.V;
-  const size_t n_beta = beta_stride == 0 ? kShapeDim : static_cast<size_t>(batch) * beta_stride;
-  const size_t n_theta = static_cast<size_t>(batch) * (kJoints + 1) * 3;
-  const size_t n_vert = vertices_host ? static_cast<size_t>(batch) * V * 3 : 0;
-  const size_t n_joint = joints_host ? static_cast<size_t>(batch) * kJoints * 3 : 0;
-  const size_t io_floats = n_beta + n_theta + n_vert + n_joint + 64;
-  const size_t ws_bytes = smplpp_forward_workspace_bytes(model, batch);
-  const size_t dev_bytes = align_up(io_floats * sizeof(float)) + ws_bytes;
-  if(model->pinned_bytes < io_floats * sizeof(float))
-  {
-    if(model->pinned) cudaFreeHost(model->pinned);
-    model->pinned = nullptr;
-    model->pinned_bytes = 0;
-    SB_CUDA(cudaMallocHost(&model->pinned, io_floats * sizeof(float)));
-    model->pinned_bytes = io_floats * sizeof(float);
-  }
-  if(model->dev_scratch_bytes < dev_bytes)
-  {
-    if(model->dev_scratch) cudaFree(model->dev_scratch);
-    model->dev_scratch = nullptr;
-    model->dev_scratch_bytes = 0;
-    SB_CUDA(cudaMalloc(&model->dev_scratch, dev_bytes));
-    model->dev_scratch_bytes = dev_bytes;
-  }
-  cudaStream_t st = model->host_stream;
-  float * hp = static_cast<float *>(model->pinned);
-  float * dp = static_cast<float *>(model->dev_scratch);
-  // inputs: pageable host -> pinned -> device
-  memcpy(hp, beta_host, n_beta * sizeof(float));
-  memcpy(hp + n_beta, theta_host, n_theta * sizeof(float));
-  SB_CUDA(cudaMemcpyAsync(dp, hp, (n_beta + n_theta) * sizeof(float), cudaMemcpyHostToDevice, st));
-  float * d_beta = dp;
-  float * d_theta = dp + n_beta;
-  float * d_vert = d_theta + n_theta + ((4 - (n_beta + n_theta) % 4) % 4);
-  float * d_joint = d_vert + n_vert;
-  void * d_ws = reinterpret_cast<char *>(dp) + align_up(io_floats * sizeof(float));
-  int rc = smplpp_forward(model, st, batch, d_beta, beta_stride, d_theta, vertices_host ? d_vert : nullptr,
-                          joints_host ? d_joint : nullptr, nullptr, nullptr, d_ws, ws_bytes);
-  if(rc != SMPLPP_OK) return rc;
-  float * h_out = hp + n_beta + n_theta;
-  if(n_vert + n_joint)
-    SB_CUDA(cudaMemcpyAsync(h_out, d_vert, (n_vert + n_joint) * sizeof(float), cudaMemcpyDeviceToHost, st));
-  SB_CUDA(cudaStreamSynchronize(st));
-  if(vertices_host) memcpy(vertices_host, h_out, n_vert * sizeof(float));
-  if(joints_host) memcpy(joints_host, h_out + n_vert, n_joint * sizeof(float));
-  return SMPLPP_OK;
-}
-
 // ---- module-level API ----
 
 extern "C" int smplpp_blend_shape(void * stream, int64_t batch, int64_t V, const float * beta, const float * theta,

@@ -30,6 +30,9 @@ int launch_blend_skin_tc(const ModelDev & d, cudaStream_t st, int B, const float
 int launch_lbs(const ModelDev & d, cudaStream_t st, int B, const float * rest, const float * xforms, bool affine,
                const float * root, int root_stride, float * out);
 
+// frees the streams, events and buffers of smplpp_forward_host (host_pipe.cu)
+void release_host_pipe(smplpp_model * m);
+
 extern int g_forward_variant;
 extern int g_tc_grid_order; // 1: frame tiles fastest in the tcgen05 kernel's grid (CTAs in flight share the basis tile)
 } // namespace sb

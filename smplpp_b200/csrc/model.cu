@@ -232,7 +232,6 @@ extern "C" int smplpp_model_create(const smplpp_model_desc * desc, smplpp_model_
   if(upload(&d.adj_faces, m->h_adj_faces) != SMPLPP_OK) return SMPLPP_ERR_CUDA;
 
   if(tc_prepare_model(d) != SMPLPP_OK) return SMPLPP_ERR_CUDA;
-  SB_CUDA(cudaStreamCreateWithFlags(&m->host_stream, cudaStreamNonBlocking));
   *out = m;
   return SMPLPP_OK;
 }
@@ -255,9 +254,7 @@ extern "C" void smplpp_model_destroy(smplpp_model_t * m)
   cudaFree(d.adj_faces);
   cudaFree(d.weights_dense);
   tc_release_model(d);
-  if(m->pinned) cudaFreeHost(m->pinned);
-  if(m->dev_scratch) cudaFree(m->dev_scratch);
-  if(m->host_stream) cudaStreamDestroy(m->host_stream);
+  release_host_pipe(m);
   delete m;
 }
 
