@@ -279,10 +279,14 @@ def main():
                                              C.c_void_p(root.data_ptr()), C.c_void_p(verts.data_ptr())))
 
     ms_lbs = time_kernel(lbs_only, 20)
+    capi.check(lib.smplpp_set_forward_variant(200))  # the per-warp TMA pipeline variant, for comparison
+    ms_lbs_tma = time_kernel(lbs_only, 20)
+    capi.check(lib.smplpp_set_forward_variant(201))
     ach_lbs = BYTES_LBS * B / (ms_lbs * 1e-3) / 1e9
     roofline["lbs"] = {"kernel": "lbs_kernel (standalone skinning)", "bound": "hbm", "achieved": ach_lbs, "peak": peak,
                        "unit": "GB/s", "frac": ach_lbs / peak, "ms_per_launch": ms_lbs,
-                       "meshes_per_s": B / (ms_lbs * 1e-3), "ms_per_launch_4x4_transforms": time_kernel(lbs_only44, 20)}
+                       "meshes_per_s": B / (ms_lbs * 1e-3), "ms_per_launch_tma_pipeline_variant": ms_lbs_tma,
+                       "ms_per_launch_4x4_transforms": time_kernel(lbs_only44, 20)}
     del rest, xf, xf34
 
     # ---- e2e through the C-ABI host-buffer call: inputs in page-locked host memory, H2D + forward + D2H of the

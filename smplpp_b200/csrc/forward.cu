@@ -16,6 +16,7 @@ using namespace sb;
 namespace sb
 {
 int g_forward_variant = 0;
+int g_lbs_variant = 1;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -820,6 +821,8 @@ int launch_blend_skin_ffma(const ModelDev & d, cudaStream_t st, int B, const flo
 int launch_lbs(const ModelDev & d, cudaStream_t st, int B, const float * rest, const float * xforms, bool affine,
                const float * root, int root_stride, float * out)
 {
+  if(affine && g_lbs_variant == 0 && lbs_tma_usable(d, rest, out, xforms))
+    return launch_lbs_tma(d, st, B, rest, xforms, root, root_stride, out);
   dim3 grid((d.V + k3::VPC - 1) / k3::VPC, (B + k3::FR - 1) / k3::FR);
   const bool vec2 = (d.V & 1) == 0 && (reinterpret_cast<uintptr_t>(rest) & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0;
 #define SB_LBS(AFF, VEC)                                                                                               \
@@ -846,6 +849,13 @@ extern "C" int smplpp_set_forward_variant(int variant)
   if(variant == 100 || variant == 101)
   {
     g_tc_grid_order = variant - 100;
+    return SMPLPP_OK;
+  }
+  // 200 / 201: standalone skinning kernel (per-warp TMA pipelines when usable / register-pipelined kernel, the default:
+  // both are bound by FFMA issue, not by memory — see DESIGN.md §4)
+  if(variant == 200 || variant == 201)
+  {
+    g_lbs_variant = variant - 200;
     return SMPLPP_OK;
   }
   if(variant < 0 || variant > 4) return fail(SMPLPP_ERR_INVALID, "SMPL", "unknown forward variant");

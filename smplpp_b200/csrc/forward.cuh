@@ -30,6 +30,11 @@ int launch_blend_skin_tc(const ModelDev & d, cudaStream_t st, int B, const float
 int launch_lbs(const ModelDev & d, cudaStream_t st, int B, const float * rest, const float * xforms, bool affine,
                const float * root, int root_stride, float * out);
 
+// K3' (lbs_tma.cu): per-warp TMA pipelines; needs even V, 16-byte aligned tensors, affine (3x4) transforms
+bool lbs_tma_usable(const ModelDev & d, const float * rest, const float * out, const float * xforms);
+int launch_lbs_tma(const ModelDev & d, cudaStream_t st, int B, const float * rest, const float * xforms, const float * root,
+                   int root_stride, float * out);
+extern int g_lbs_variant; // 0: TMA pipeline when usable, 1: register-pipelined kernel (default)
 // frees the streams, events and buffers of smplpp_forward_host (host_pipe.cu)
 void release_host_pipe(smplpp_model * m);
 

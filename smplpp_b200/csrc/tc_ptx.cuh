@@ -45,6 +45,21 @@ __device__ __forceinline__ void sts32(uint32_t addr, float v)
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 
+__device__ __forceinline__ void sts64(uint32_t addr, float2 v)
+{
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v)
+{
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float lds32(uint32_t addr)
+{
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
 // ---- mbarrier ----
 __device__ __forceinline__ void mbar_init(uint64_t * bar, uint32_t count)
 {
@@ -110,6 +125,26 @@ __device__ __forceinline__ void bulk_load_1d(void * smem_dst, const void * gmem_
                :
                : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gmem_src)), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+
+// 1-D bulk copy shared -> global (bytes % 16 == 0, both addresses 16-byte aligned), tracked by the issuing
+// thread's bulk async-group; the writer must fence_proxy_async() its st.shared before the copy is issued
+__device__ __forceinline__ void bulk_store_1d(void * gmem_dst, uint32_t smem_src, uint32_t bytes)
+{
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               :
+               : "l"(reinterpret_cast<uint64_t>(gmem_dst)), "r"(smem_src), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit()
+{
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// waits until at most kPending of this thread's bulk groups still READ their shared-memory source
+template<int kPending>
+__device__ __forceinline__ void bulk_wait_read()
+{
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
 }
 
 // ---- tcgen05 ----

@@ -191,6 +191,46 @@ def test_model_skinning_vs_oracle(smpl_gpu, oracle_model, params):
     assert np.abs(out34.cpu().numpy() - r.vertices.numpy()).max() <= TOL_VERTEX_M
 
 
+@pytest.mark.parametrize("batch", [1, 2, 19, 50])
+def test_skinning_tma_pipeline(smpl_gpu, oracle_model, batch):
+    """K3' (per-warp TMA pipelines, lbs_tma.cu) against LinearBlendSkinning (oracle) and against the
+    register-pipelined kernel bit for bit: odd frames start 8 bytes off a 16-byte boundary, the last slice is short
+    (6890 = 53 x 128 + 106), the last chunk ends exactly at the end of the allocation, 16-frame CTAs are ragged."""
+    import ctypes as C
+    from oracle import smpl_oracle as so
+    from smplpp_b200 import api, capi, synth
+    beta, theta = synth.make_forward_inputs(batch, 31 + batch)
+    with torch.no_grad():
+        r = so.smpl_launch(oracle_model, torch.as_tensor(beta), torch.as_tensor(theta))
+    V = r.rest_shape.shape[1]
+    xf34 = dev(r.transforms.numpy()[:, :, :3, :].copy())
+    root = dev(theta[:, 0])
+    # exact-size allocations (torch rounds to 512 B; the tail guard words make an overrun visible)
+    rest = dev(r.rest_shape.numpy())
+    guard = torch.full((batch * V * 3 + 64,), 7.0, dtype=torch.float32, device="cuda:0")
+    outs = {}
+    for var in (201, 200):  # register kernel, then TMA pipeline (auto)
+        capi.check(capi.lib().smplpp_set_forward_variant(var))
+        guard.fill_(7.0)
+        out = guard[:batch * V * 3].view(batch, V, 3)
+        try:
+            capi.check(capi.lib().smplpp_model_skinning34(smpl_gpu.handle, None, C.c_int64(batch), api._ptr(rest),
+                                                          api._ptr(xf34), api._ptr(root), api._ptr(out)))
+            torch.cuda.synchronize()
+        finally:
+            capi.check(capi.lib().smplpp_set_forward_variant(201))
+        assert (guard[batch * V * 3:] == 7.0).all()
+        outs[var] = out.cpu().numpy().copy()
+    assert np.abs(outs[200] - r.vertices.numpy()).max() <= TOL_VERTEX_M
+    assert np.array_equal(outs[200], outs[201])
+    # no root translation
+    out = torch.empty_like(rest)
+    capi.check(capi.lib().smplpp_model_skinning34(smpl_gpu.handle, None, C.c_int64(batch), api._ptr(rest), api._ptr(xf34),
+                                                  None, api._ptr(out)))
+    torch.cuda.synchronize()
+    assert np.abs(out.cpu().numpy() + theta[:, :1] - r.vertices.numpy()).max() <= TOL_VERTEX_M
+
+
 def test_dense_weights_small_model():
     """A model whose skinning rows are dense (24 non-zeros, sums != 1) and V not a multiple of the tile."""
     from oracle import smpl_oracle as so
