@@ -110,8 +110,10 @@ int smplpp_host_unregister(void * ptr);
 
 /* Pipeline variant selection for smplpp_forward: 0 = auto, 1 = FFMA fused blend+skinning,
  * 2 = tcgen05 3xTF32 fused blend+skinning, 3 = unfused (blend GEMM -> rest shape -> standalone skinning),
- * 4 = tcgen05 3xBF16 fused blend+skinning (faster, ~1.5e-6 m contraction error instead of ~3e-8 m).
- * The tcgen05 variants need an even vertex count >= 128 and <= 4 skinning influences per vertex. */
+ * 4 = tcgen05 3xBF16 fused blend+skinning (faster, ~1.5e-6 m contraction error instead of ~3e-8 m),
+ * 5 = tcgen05 3xFP16 blend + skinning matrices on the tensor cores as well (the default when available).
+ * Variants 2 and 4 need an even vertex count >= 128 and <= 4 skinning influences per vertex; variant 5 needs an
+ * even vertex count >= 128 only. */
 int smplpp_set_forward_variant(int variant);
 
 /* ---------------------------------------------------------------------------------------------------------

@@ -97,6 +97,12 @@ struct ModelDev
   alignas(64) unsigned char tmapA[2][128] = {};
   int tc_tiles = 0;
   bool tc_ready = false;
+  // tcgen05 blend + tensor-core skinning (skin_tc.cu): fp16 hi | lo split basis scaled by 2^tc2_basis_exp
+  void * basis_f16 = nullptr;
+  alignas(64) unsigned char tmapA16[128] = {};
+  int tc2_basis_exp = 0;
+  int tc2_tiles = 0;
+  bool tc2_ready = false;
 };
 } // namespace sb
 

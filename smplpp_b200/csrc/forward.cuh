@@ -26,6 +26,12 @@ void tc_release_model(ModelDev & d);
 size_t tc_coef_split_bytes(int64_t batch);
 int launch_blend_skin_tc(const ModelDev & d, cudaStream_t st, int B, const float * coef, void * coef_split,
                          const float * xforms, const float * theta, float * out, bool tf32);
+// K2'' (skin_tc.cu): fp16 split-precision blend AND skinning matrices on tcgen05 (any number of influences per vertex)
+int tc2_prepare_model(ModelDev & d, float basis_max_abs);
+void tc2_release_model(ModelDev & d);
+size_t tc2_frame_operand_bytes(int64_t batch);
+int launch_blend_skin_tc2(const ModelDev & d, cudaStream_t st, int B, const float * coef, const float * xforms, void * scratch,
+                          const float * theta, float * out);
 // K3: standalone skinning; affine: xforms are (B,24,3,4) else (B,24,4,4)
 int launch_lbs(const ModelDev & d, cudaStream_t st, int B, const float * rest, const float * xforms, bool affine,
                const float * root, int root_stride, float * out);

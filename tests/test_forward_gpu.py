@@ -71,7 +71,7 @@ def test_kat_linear_blend_skinning(kat):
 
 # ---- full model: golden vectors of the compiled reference ----
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5])
 def test_forward_vs_reference_golden(smpl_gpu, golden_forward, variant):
     from smplpp_b200 import capi
     g = golden_forward
@@ -91,7 +91,7 @@ def test_forward_vs_reference_golden(smpl_gpu, golden_forward, variant):
     assert np.abs(v - g["vertices"]).max() < (5e-6 if variant == 4 else 2e-6)
 
 
-@pytest.mark.parametrize("variant", [2, 4])
+@pytest.mark.parametrize("variant", [2, 4, 5])
 @pytest.mark.parametrize("batch", [1, 127, 300])
 def test_forward_tensor_core_variants_match_ffma(smpl_gpu, variant, batch):
     """Ragged frame counts through the tcgen05 kernel (128-frame tiles, 32-frame transform windows) against the
