@@ -671,7 +671,7 @@ class IkTaskSet:
         """MoSh++ shape stage over the frames of ALL ranks: per-frame Schur complement onto the 10 shared betas,
         ONE all-reduce of 111 doubles (only collective of the path), identical 10-dim box QP on every rank,
         back-substitution.  theta_state (B,75|44) and shared_beta (10,) are updated in place."""
-        import torch.distributed as dist
+        from . import parallel
         dev = self.smpl.m__device
         b = theta_state.shape[0]
         status = torch.empty((b,), dtype=torch.int32, device=dev)
@@ -684,8 +684,7 @@ class IkTaskSet:
                 self.smpl.handle, vp, self._h, C.byref(opt), _stream(dev), C.c_int64(b), _ptr(theta_state),
                 _ptr(shared_beta), _ptr(vertex_weights), _ptr(target_pos), _ptr(pos_task_weight), _ptr(status),
                 _ptr(reduced), _ptr(ws), C.c_size_t(ws.numel())))
-            if dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1:
-                dist.all_reduce(reduced, op=dist.ReduceOp.SUM, group=process_group)
+            parallel.all_reduce_shared_beta(reduced, process_group)  # NCCL over NVLink on the B200 box; 888 bytes
             check(lib().smplpp_ik_shared_beta_apply(self._h, C.byref(opt), _stream(dev), C.c_int64(b), _ptr(theta_state),
                                                     _ptr(shared_beta), _ptr(status), _ptr(reduced), _ptr(ws),
                                                     C.c_size_t(ws.numel())))

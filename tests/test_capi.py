@@ -72,3 +72,17 @@ def test_synthetic_model_shapes(params, vposer_params, marker_tasks):
     names, face_idx, vw = marker_tasks
     assert len(names) == 41 and names == sorted(names) and len(set(face_idx.tolist())) == 41
     assert np.allclose(vw.sum(1), 1.0, atol=1e-6)
+
+
+def test_cpp_facade_builds_and_fails_loudly_without_gpu(lib):
+    """include/smplpp_b200/smplpp.hpp (the reference's class names over the C ABI) compiles with plain g++ and, on a
+    machine without a device, stops with the library's no-CPU-fallback error instead of computing anything."""
+    import subprocess
+    import torch
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "cpp")])
+    exe = os.path.join(ROOT, "tests", "cpp", "facade_smoke")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and "facade smoke: OK" in r.stdout, r.stdout + r.stderr
+    else:
+        assert r.returncode == 3 and "no CPU fallback" in r.stdout, r.stdout + r.stderr

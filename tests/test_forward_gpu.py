@@ -342,3 +342,15 @@ def test_error_messages(smpl_gpu):
         fresh.setModelPath("/nonexistent/smpl_male.json")
     with pytest.raises(api.SmplppError, match="Cannot initialize a SMPL model!"):
         fresh.init()
+
+
+def test_cpp_facade_smoke():
+    """The header-only C++ facade (smplpp::SMPL over the C ABI) end to end on the GPU: tests/cpp/facade_smoke.cpp."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", "facade_smoke")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(root, "tests", "cpp")])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "facade smoke: OK" in r.stdout, r.stdout + r.stderr
