@@ -279,13 +279,15 @@ def main():
                                              C.c_void_p(root.data_ptr()), C.c_void_p(verts.data_ptr())))
 
     ms_lbs = time_kernel(lbs_only, 20)
-    capi.check(lib.smplpp_set_forward_variant(200))  # the per-warp TMA pipeline variant, for comparison
-    ms_lbs_tma = time_kernel(lbs_only, 20)
-    capi.check(lib.smplpp_set_forward_variant(201))
+    ms_lbs_var = {}
+    for code, name in ((200, "ffma_tma_pipeline"), (201, "ffma_register_kernel")):  # the FFMA predecessors, for comparison
+        capi.check(lib.smplpp_set_forward_variant(code))
+        ms_lbs_var[name] = time_kernel(lbs_only, 20)
+    capi.check(lib.smplpp_set_forward_variant(202))
     ach_lbs = BYTES_LBS * B / (ms_lbs * 1e-3) / 1e9
-    roofline["lbs"] = {"kernel": "lbs_kernel (standalone skinning)", "bound": "hbm", "achieved": ach_lbs, "peak": peak,
+    roofline["lbs"] = {"kernel": "lbs_tc_kernel (standalone skinning, skinning matrices on tcgen05)", "bound": "hbm", "achieved": ach_lbs, "peak": peak,
                        "unit": "GB/s", "frac": ach_lbs / peak, "ms_per_launch": ms_lbs,
-                       "meshes_per_s": B / (ms_lbs * 1e-3), "ms_per_launch_tma_pipeline_variant": ms_lbs_tma,
+                       "meshes_per_s": B / (ms_lbs * 1e-3), "ms_per_launch_other_variants": ms_lbs_var,
                        "ms_per_launch_4x4_transforms": time_kernel(lbs_only44, 20)}
     del rest, xf, xf34
 

@@ -16,7 +16,7 @@ xf34 = torch.randn((B, 24, 3, 4), device="cuda", generator=g)
 root = torch.randn((B, 3), device="cuda", generator=g)
 out = torch.empty_like(rest)
 st = torch.cuda.current_stream()
-for var, name in ((200, "tma pipeline"), (201, "register kernel")):
+for var, name in ((202, "tcgen05"), (200, "ffma tma pipeline"), (201, "ffma register kernel")):
     capi.check(lib.smplpp_set_forward_variant(var))
     def run():
         capi.check(lib.smplpp_model_skinning34(smpl.handle, C.c_void_p(st.cuda_stream), C.c_int64(B), api._ptr(rest),
@@ -31,4 +31,4 @@ for var, name in ((200, "tma pipeline"), (201, "register kernel")):
     b.record(); torch.cuda.synchronize()
     ms = a.elapsed_time(b) / reps
     print("%-16s B=%d: %.4f ms  %.0f GB/s algorithmic (166512 B/mesh)" % (name, B, ms, 166512 * B / ms / 1e6))
-capi.check(lib.smplpp_set_forward_variant(201))
+capi.check(lib.smplpp_set_forward_variant(202))

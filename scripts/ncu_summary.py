@@ -33,6 +33,9 @@ METRICS = [
     "launch__shared_mem_per_block_dynamic", "launch__shared_mem_per_block_static", "launch__grid_size",
     "launch__block_size", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
     "smsp__cycles_active.avg", "sm__cycles_elapsed.max",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__warps_eligible.avg.per_cycle_active",
+    "l1tex__m_xbar2l1tex_read_bytes.sum", "l1tex__m_l1tex2xbar_write_bytes_mem_global_op_tma_st.sum",
+    "lts__t_sectors_op_read.sum", "lts__t_sectors_op_write.sum",
 ]
 
 

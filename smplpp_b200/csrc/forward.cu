@@ -16,7 +16,7 @@ using namespace sb;
 namespace sb
 {
 int g_forward_variant = 0;
-int g_lbs_variant = 1;
+int g_lbs_variant = 2;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -821,6 +821,8 @@ int launch_blend_skin_ffma(const ModelDev & d, cudaStream_t st, int B, const flo
 int launch_lbs(const ModelDev & d, cudaStream_t st, int B, const float * rest, const float * xforms, bool affine,
                const float * root, int root_stride, float * out)
 {
+  if(affine && g_lbs_variant == 2 && lbs_tc_usable(d, rest, out, xforms))
+    return launch_lbs_tc(d, st, B, rest, xforms, kXformFloats, root, root_stride, out);
   if(affine && g_lbs_variant == 0 && lbs_tma_usable(d, rest, out, xforms))
     return launch_lbs_tma(d, st, B, rest, xforms, root, root_stride, out);
   dim3 grid((d.V + k3::VPC - 1) / k3::VPC, (B + k3::FR - 1) / k3::FR);
@@ -851,9 +853,9 @@ extern "C" int smplpp_set_forward_variant(int variant)
     g_tc_grid_order = variant - 100;
     return SMPLPP_OK;
   }
-  // 200 / 201: standalone skinning kernel (per-warp TMA pipelines when usable / register-pipelined kernel, the default:
-  // both are bound by FFMA issue, not by memory — see DESIGN.md §4)
-  if(variant == 200 || variant == 201)
+  // 200 / 201 / 202: standalone skinning kernel (FFMA per-warp TMA pipelines / FFMA register-pipelined kernel / skinning
+  // matrices on tcgen05, the default; the FFMA kernels are bound by FFMA issue at ~3.2 TB/s)
+  if(variant >= 200 && variant <= 202)
   {
     g_lbs_variant = variant - 200;
     return SMPLPP_OK;

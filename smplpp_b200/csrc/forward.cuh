@@ -40,7 +40,11 @@ int launch_lbs(const ModelDev & d, cudaStream_t st, int B, const float * rest, c
 bool lbs_tma_usable(const ModelDev & d, const float * rest, const float * out, const float * xforms);
 int launch_lbs_tma(const ModelDev & d, cudaStream_t st, int B, const float * rest, const float * xforms, const float * root,
                    int root_stride, float * out);
-extern int g_lbs_variant; // 0: TMA pipeline when usable, 1: register-pipelined kernel (default)
+// K3'' (lbs_tc.cu): skinning matrices on tcgen05; needs the tc2 model data, even V >= 128, 16-byte aligned tensors
+bool lbs_tc_usable(const ModelDev & d, const float * rest, const float * out, const float * xforms);
+int launch_lbs_tc(const ModelDev & d, cudaStream_t st, int B, const float * rest, const float * xforms, int xf_floats,
+                  const float * root, int root_stride, float * out);
+extern int g_lbs_variant; // 0: FFMA TMA pipeline when usable, 1: FFMA register-pipelined kernel, 2: tcgen05 (default)
 // frees the streams, events and buffers of smplpp_forward_host (host_pipe.cu)
 void release_host_pipe(smplpp_model * m);
 

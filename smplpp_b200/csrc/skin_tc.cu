@@ -37,6 +37,7 @@
 #include <vector>
 
 #include "forward.cuh"
+#include "skin_common.cuh"
 #include "tc_ptx.cuh"
 
 using namespace sb;
@@ -75,8 +76,8 @@ constexpr int SMEM_BYTES = 1024 + OFF_BAR + 512;
 constexpr int TMEM_COLS = 512;
 constexpr int COL_M = 3 * NF;                    // 288
 constexpr int COL_W = COL_M + 2 * SUBN;          // 480
-// power-of-two operand scales (exact; undone in the epilogue)
-constexpr int COEF_EXP = 6, W_EXP = 10, G_EXP = 4;
+// power-of-two operand scales (exact; undone in the epilogue); W_EXP / G_EXP live in skin_common.cuh
+constexpr int COEF_EXP = 6, W_EXP = skin::W_EXP, G_EXP = skin::G_EXP;
 static_assert(COL_W + 2 * (KJ / 2) == TMEM_COLS, "TMEM column map");
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
@@ -93,11 +94,6 @@ struct Params
 };
 } // namespace tc2
 
-__device__ __forceinline__ uint32_t pack_half2(float lo16, float hi16)
-{
-  const __half2 h = __floats2half2_rn(lo16, hi16);
-  return *reinterpret_cast<const uint32_t *>(&h);
-}
 
 // ------------------------------------------------------------------------------------------------------------
 // operand preparation
@@ -317,28 +313,7 @@ __global__ void __launch_bounds__(tc2::THREADS, 1)
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     if(ew < 4)
     {
-      // this vertex's row of W as the fp16 hi | lo A operand of GEMM 2: 32 joints = 16 packed columns per part
-      float w[KJ];
-      const float4 * wp = reinterpret_cast<const float4 *>(p.weights + static_cast<size_t>(vc) * kJoints);
-#pragma unroll
-      for(int i = 0; i < kJoints / 4; i++)
-      {
-        const float4 t = __ldg(wp + i);
-        w[4 * i] = t.x, w[4 * i + 1] = t.y, w[4 * i + 2] = t.z, w[4 * i + 3] = t.w;
-      }
-#pragma unroll
-      for(int j = kJoints; j < KJ; j++) w[j] = 0.f;
-      uint32_t hi[KJ / 2], lo[KJ / 2];
-#pragma unroll
-      for(int i = 0; i < KJ / 2; i++)
-      {
-        const float a = w[2 * i] * static_cast<float>(1 << W_EXP), b = w[2 * i + 1] * static_cast<float>(1 << W_EXP);
-        const float ah = __half2float(__float2half_rn(a)), bh = __half2float(__float2half_rn(b));
-        hi[i] = pack_half2(ah, bh);
-        lo[i] = pack_half2(a - ah, b - bh);
-      }
-      ptx::tmem_st_x16(lane_taddr + COL_W, hi);
-      ptx::tmem_st_x16(lane_taddr + COL_W + KJ / 2, lo);
+      skin::store_w_row_tmem(p.weights + static_cast<size_t>(vc) * kJoints, lane_taddr + COL_W);
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
       __syncwarp();

@@ -191,7 +191,7 @@ def test_model_skinning_vs_oracle(smpl_gpu, oracle_model, params):
     assert np.abs(out34.cpu().numpy() - r.vertices.numpy()).max() <= TOL_VERTEX_M
 
 
-@pytest.mark.parametrize("batch", [1, 2, 19, 50])
+@pytest.mark.parametrize("batch", [1, 2, 19, 50, 700])
 def test_skinning_tma_pipeline(smpl_gpu, oracle_model, batch):
     """K3' (per-warp TMA pipelines, lbs_tma.cu) against LinearBlendSkinning (oracle) and against the
     register-pipelined kernel bit for bit: odd frames start 8 bytes off a 16-byte boundary, the last slice is short
@@ -209,7 +209,7 @@ def test_skinning_tma_pipeline(smpl_gpu, oracle_model, batch):
     rest = dev(r.rest_shape.numpy())
     guard = torch.full((batch * V * 3 + 64,), 7.0, dtype=torch.float32, device="cuda:0")
     outs = {}
-    for var in (201, 200):  # register kernel, then TMA pipeline (auto)
+    for var in (201, 200, 202):  # FFMA register kernel, FFMA TMA pipeline, tcgen05 skinning matrices
         capi.check(capi.lib().smplpp_set_forward_variant(var))
         guard.fill_(7.0)
         out = guard[:batch * V * 3].view(batch, V, 3)
@@ -218,11 +218,13 @@ def test_skinning_tma_pipeline(smpl_gpu, oracle_model, batch):
                                                           api._ptr(xf34), api._ptr(root), api._ptr(out)))
             torch.cuda.synchronize()
         finally:
-            capi.check(capi.lib().smplpp_set_forward_variant(201))
+            capi.check(capi.lib().smplpp_set_forward_variant(202))
         assert (guard[batch * V * 3:] == 7.0).all()
         outs[var] = out.cpu().numpy().copy()
-    assert np.abs(outs[200] - r.vertices.numpy()).max() <= TOL_VERTEX_M
+    for var in outs:
+        assert np.abs(outs[var] - r.vertices.numpy()).max() <= TOL_VERTEX_M
     assert np.array_equal(outs[200], outs[201])
+    assert np.abs(outs[202] - outs[201]).max() < 1.5e-6  # fp16x3 split of W and G' (2^-22 relative on ~1 m terms)
     # no root translation
     out = torch.empty_like(rest)
     capi.check(capi.lib().smplpp_model_skinning34(smpl_gpu.handle, None, C.c_int64(batch), api._ptr(rest), api._ptr(xf34),
