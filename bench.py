@@ -46,6 +46,21 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the newest committed ncu capture
+    (profiles/*_traffic.json, written by scripts/ncu_summary.py); None when no capture names the kernel."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")), reverse=True):
+        try:
+            with open(path) as f:
+                t = json.load(f)
+            if kernel in t.get("bytes_per_launch", {}):
+                return {"bytes_per_launch": t["bytes_per_launch"][kernel], "source": os.path.basename(path)}
+        except Exception:
+            continue
+    return None
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons during the timed region."""
 
@@ -253,7 +268,8 @@ def main():
     peak, peak_src = measured_peaks()
     ach = BYTES_FUSED * B / (ms_k2 * 1e-3) / 1e9
     roofline = {"kernel": "blend_skin (fused pose/shape blend contraction + linear blend skinning)", "bound": "hbm",
-                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": ncu_traffic("blend_skin_tc2_kernel"),
+                "algorithmic_bytes_per_launch": BYTES_FUSED * B,
                 "peak_source": peak_src, "ms_per_launch": ms_k2,
                 "fp32_tflops_algorithmic": FLOPS_BLEND * B / (ms_k2 * 1e-3) / 1e12}
 
@@ -286,7 +302,8 @@ def main():
     capi.check(lib.smplpp_set_forward_variant(202))
     ach_lbs = BYTES_LBS * B / (ms_lbs * 1e-3) / 1e9
     roofline["lbs"] = {"kernel": "lbs_tc_kernel (standalone skinning, skinning matrices on tcgen05)", "bound": "hbm", "achieved": ach_lbs, "peak": peak,
-                       "unit": "GB/s", "frac": ach_lbs / peak, "ms_per_launch": ms_lbs,
+                       "unit": "GB/s", "frac": ach_lbs / peak, "ms_per_launch": ms_lbs, "traffic": ncu_traffic("lbs_tc_kernel"),
+                       "algorithmic_bytes_per_launch": BYTES_LBS * B,
                        "meshes_per_s": B / (ms_lbs * 1e-3), "ms_per_launch_other_variants": ms_lbs_var,
                        "ms_per_launch_4x4_transforms": time_kernel(lbs_only44, 20)}
     del rest, xf, xf34

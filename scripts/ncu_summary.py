@@ -85,6 +85,19 @@ def rep_md(path: str, tag: str) -> str:
     return "\n".join(out) + "\n"
 
 
+def rep_traffic(path: str) -> dict:
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = [r for r in csv.reader(io.StringIO(raw)) if r and not r[0].startswith("==")]
+    hdr, units, body = rows[0], rows[1], rows[2:]
+    out = {}
+    for r in body:
+        name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").split("<")[0]
+        rd = float(r[hdr.index("dram__bytes_read.sum")]) * unit_scale(units[hdr.index("dram__bytes_read.sum")])
+        wr = float(r[hdr.index("dram__bytes_write.sum")]) * unit_scale(units[hdr.index("dram__bytes_write.sum")])
+        out[name] = rd + wr
+    return out
+
+
 def unit_scale(u: str) -> float:
     u = u.lower()
     return {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1.0)
@@ -108,10 +121,17 @@ def main():
     if reps is None:
         d = os.path.join(ROOT, "gpurun_out")
         reps = [os.path.join(d, f) for f in sorted(os.listdir(d)) if f.endswith(".ncu-rep")]
+    traffic = {}
     for rep in reps:
         name = os.path.splitext(os.path.basename(rep))[0]
         with open(os.path.join(ROOT, "profiles", "%s_%s.md" % (a.tag, name)), "w") as f:
             f.write(rep_md(rep, a.tag))
+        traffic.update(rep_traffic(rep))
+    if traffic:
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch: what bench.py reports as roofline.traffic
+        import json
+        with open(os.path.join(ROOT, "profiles", "%s_traffic.json" % a.tag), "w") as f:
+            json.dump({"source": "ncu --set full --clock-control none, %s" % a.tag, "bytes_per_launch": traffic}, f, indent=1)
     print("wrote profiles/%s_*" % a.tag)
 
 
