@@ -131,7 +131,7 @@ def cpu_reference_forward(batch_total: int, threads: int | None = None, chunk: i
     return chunk / best, cores, sample
 
 
-def run_reference(args):
+def run_reference(args, json_out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -161,7 +161,8 @@ def run_reference(args):
                                    "%d meshes per step" % per_step},
         "e2e": {"value": value, "unit": "meshes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    json_out.write(json.dumps(line) + "\n")
+    json_out.flush()
     return 0
 
 
@@ -176,8 +177,12 @@ def main():
     ap.add_argument("--no-ik", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # rank 0 prints ONE JSON line on stdout: libraries that write to fd 1 (NCCL's version banner) go to stderr instead
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, json_out)
 
     import torch
     import torch.distributed as dist
@@ -365,7 +370,8 @@ def main():
             line["cpu_baseline"] = {"value": None, "unit": "meshes/s", "cores": 0, "kind": "reference",
                                     "sample": "unavailable: %s" % ex}
     if rank == 0:
-        print(json.dumps(line))
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     if world > 1:
         dist.destroy_process_group()
     return 0
