@@ -103,6 +103,10 @@ struct ModelDev
   int tc2_basis_exp = 0;
   int tc2_tiles = 0;
   bool tc2_ready = false;
+  // persistent pipelined variant (skin_tc3.cu): shares the tc2 model data
+  void * basis_img16 = nullptr; // [tile][K-block][hi | lo][plane][128][32 fp16]: SWIZZLE_64B stage images
+  bool tc3_ready = false;
+  int sm_count = 0;
 };
 } // namespace sb
 

@@ -860,7 +860,7 @@ extern "C" int smplpp_set_forward_variant(int variant)
     g_lbs_variant = variant - 200;
     return SMPLPP_OK;
   }
-  if(variant < 0 || variant > 5) return fail(SMPLPP_ERR_INVALID, "SMPL", "unknown forward variant");
+  if(variant < 0 || variant > 6) return fail(SMPLPP_ERR_INVALID, "SMPL", "unknown forward variant");
   g_forward_variant = variant;
   return SMPLPP_OK;
 }
@@ -873,7 +873,7 @@ extern "C" size_t smplpp_forward_workspace_bytes(const smplpp_model_t * model, i
   bytes += align_up(bpad * kBlendK * sizeof(float));         // coefficients (A operand)
   bytes += align_up(bpad * kJoints * 12 * sizeof(float));    // relative transforms 3x4
   bytes += tc_coef_split_bytes(batch);                      // hi / lo coefficient parts (tcgen05 variants)
-  bytes += tc2_frame_operand_bytes(batch);                  // fp16 hi / lo coefficients + transforms (variant 5)
+  bytes += std::max(tc2_frame_operand_bytes(batch), tc3_frame_operand_bytes(batch));                  // fp16 hi / lo coefficients + transforms (variant 5)
   bytes += align_up(static_cast<size_t>(batch) * model->d.V * 3 * sizeof(float)); // rest shape (unfused variant)
   return bytes;
 }
@@ -898,7 +898,7 @@ extern "C" int smplpp_forward(const smplpp_model_t * model, void * stream, int64
   void * coef_split = ws;
   ws += tc_coef_split_bytes(batch);
   void * tc2_scratch = ws;
-  ws += tc2_frame_operand_bytes(batch);
+  ws += std::max(tc2_frame_operand_bytes(batch), tc3_frame_operand_bytes(batch));
   float * rest_ws = reinterpret_cast<float *>(ws);
 
   const bool need_verts = vertices != nullptr;
@@ -907,8 +907,9 @@ extern "C" int smplpp_forward(const smplpp_model_t * model, void * stream, int64
                              joints, transforms);
   if(rc != SMPLPP_OK) return rc;
   int variant = g_forward_variant;
-  if(variant == 0) variant = model->d.tc2_ready ? 5 : (model->d.tc_ready ? 2 : 1);
-  if(((variant == 2 || variant == 4) && !model->d.tc_ready) || (variant == 5 && !model->d.tc2_ready))
+  if(variant == 0) variant = model->d.tc3_ready ? 6 : (model->d.tc2_ready ? 5 : (model->d.tc_ready ? 2 : 1));
+  if(((variant == 2 || variant == 4) && !model->d.tc_ready) || (variant == 5 && !model->d.tc2_ready)
+     || (variant == 6 && !model->d.tc3_ready))
     return fail(SMPLPP_ERR_INVALID, "SMPL", "tcgen05 blend variant is not available for this model");
   if(need_rest || (need_verts && variant == 3))
   {
@@ -920,7 +921,9 @@ extern "C" int smplpp_forward(const smplpp_model_t * model, void * stream, int64
   }
   if(need_verts)
   {
-    if(variant == 5)
+    if(variant == 6)
+      rc = launch_blend_skin_tc3(d, st, B, coef, xforms, tc2_scratch, theta, vertices);
+    else if(variant == 5)
       rc = launch_blend_skin_tc2(d, st, B, coef, xforms, tc2_scratch, theta, vertices);
     else if(variant == 2 || variant == 4)
       rc = launch_blend_skin_tc(d, st, B, coef, coef_split, xforms, theta, vertices, variant == 2);

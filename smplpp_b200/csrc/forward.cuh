@@ -32,6 +32,13 @@ void tc2_release_model(ModelDev & d);
 size_t tc2_frame_operand_bytes(int64_t batch);
 int launch_blend_skin_tc2(const ModelDev & d, cudaStream_t st, int B, const float * coef, const float * xforms, void * scratch,
                           const float * theta, float * out);
+// K2''' (skin_tc3.cu): the same two GEMMs in a persistent CTA per SM; GEMM 1 of item i+1 runs under GEMM 2 + epilogue of item i
+int tc3_prepare_model(ModelDev & d);
+void tc3_release_model(ModelDev & d);
+size_t tc3_frame_operand_bytes(int64_t batch);
+int launch_blend_skin_tc3(const ModelDev & d, cudaStream_t st, int B, const float * coef, const float * xforms, void * scratch,
+                          const float * theta, float * out);
+bool tc_encode_f16(void * out_map, void * base, uint64_t rows, uint64_t cols, uint32_t box_rows);
 // K3: standalone skinning; affine: xforms are (B,24,3,4) else (B,24,4,4)
 int launch_lbs(const ModelDev & d, cudaStream_t st, int B, const float * rest, const float * xforms, bool affine,
                const float * root, int root_stride, float * out);

@@ -237,6 +237,7 @@ extern "C" int smplpp_model_create(const smplpp_model_desc * desc, smplpp_model_
     for(size_t r = 0; r < static_cast<size_t>(3) * V; r++)
       for(int k = 0; k < kPoseDim + kShapeDim; k++) mx = std::max(mx, std::fabs(m->h_basis[r * kBlendK + k]));
     if(tc2_prepare_model(d, mx) != SMPLPP_OK) return SMPLPP_ERR_CUDA;
+    if(tc3_prepare_model(d) != SMPLPP_OK) return SMPLPP_ERR_CUDA;
   }
   *out = m;
   return SMPLPP_OK;
@@ -260,6 +261,7 @@ extern "C" void smplpp_model_destroy(smplpp_model_t * m)
   cudaFree(d.adj_faces);
   cudaFree(d.weights_dense);
   tc_release_model(d);
+  tc3_release_model(d);
   tc2_release_model(d);
   release_host_pipe(m);
   delete m;

@@ -437,6 +437,11 @@ bool encode_f16(CUtensorMap * out, void * base, uint64_t rows, uint64_t cols, ui
 
 namespace sb
 {
+bool tc_encode_f16(void * out_map, void * base, uint64_t rows, uint64_t cols, uint32_t box_rows)
+{
+  return encode_f16(static_cast<CUtensorMap *>(out_map), base, rows, cols, box_rows);
+}
+
 size_t tc2_frame_operand_bytes(int64_t batch)
 {
   const size_t bpad = align_up(static_cast<size_t>(batch), tc2::NF);

@@ -1,0 +1,633 @@
+// K2''' (tcgen05, persistent + pipelined): fused blend-shape contraction + linear blend skinning, both products on the
+// tensor cores, with the contraction of work item i+1 running UNDER the skinning GEMM + epilogue of work item i.
+//
+// Reference semantics: BlendShape::poseBlend / shapeBlend (src/BlendShape.cpp:764, 670-683), the rest shape
+// T + S + P (src/JointRegression.cpp:551-565) and LinearBlendSkinning::skinning (src/LinearBlendSkinning.cpp:445-553).
+//
+//   rest[v,f]   = T[v] + sum_k basis[v,k] coef[f,k]                 GEMM 1: (128 vertices x 3 planes) x 96 frames, K = 224
+//   M[v,f]      = sum_j W[v,j] G'[f,j]  (3x4 per vertex and frame)  GEMM 2: 128 vertices x (8 frames x 12), K = 24 -> 32
+//   vert[v,f]   = M[v,f] [rest; 1] / sum_j W[v,j] + trans[f]        epilogue: 12 FMA per vertex and frame
+//
+// What changed against K2'' (skin_tc.cu), whose CTA ran wait(3.2 k) -> GEMM 1 (8.6 k) -> GEMM 2 + epilogue (11 k cycles)
+// back to back with the tensor pipe idle for two thirds of the time:
+//   * one persistent CTA per SM walks a contiguous range of (vertex tile, frame block) work items;
+//   * when GEMM 1 of an item completes, the sixteen epilogue warps DRAIN its 288 accumulator columns into registers
+//     (72 per thread, pre-scaled by 1 / sum_j W), which frees the TMEM columns: the MMA thread then interleaves the
+//     126 MMAs of the NEXT item's GEMM 1 with the 12 sub-batches of this item's GEMM 2 (3-4 MMA triples per sub-batch);
+//   * two TMA producer threads, one per ring (2 x 60 KB GEMM 1 stages, 6 x 12 KB transform sub-batches), so neither
+//     ring can starve the other;
+//   * the frames of a 96-frame block are permuted in the fp16 coefficient operand so that the 24 frames an epilogue
+//     warp owns are 24 adjacent accumulator columns (6 tcgen05.ld per drain instead of 36).
+//   * every operand tile is stored in global memory as the exact (SWIZZLE_64B) shared-memory image of its pipeline
+//     stage, so a stage is two contiguous cp.async.bulk copies (48 KB basis + 12 KB coefficients) and a transform
+//     sub-batch is one (12 KB).  Tiled TMA loads with a 64-byte inner box (K2'') delivered ~21 B/cycle per SM - one L2
+//     request per 64-byte row - and bounded that kernel and the first version of this one (20.5 k cycles per item,
+//     whatever the number of CTAs).
+// Precision is that of K2'': fp16 hi + lo split of every operand, hi.hi + lo.hi + hi.lo in fp32 TMEM.
+//
+// TMEM (512 columns): [0,288) rest accumulators (x | y | z planes x 96 frames), [288,480) two 96-column buffers of
+// skinning matrices (8 frames x 12), [480,512) the W tile (A operand of GEMM 2, fp16 hi | lo).
+// warp 0: TMA producer of the GEMM 1 stages | warp 1: TMEM allocator + MMA issuer | warp 2: TMA producer of the transform
+// sub-batches | warp 3: idle (the first warpgroup hands its registers back with setmaxnreg) | warps 4-19: epilogue, 112 registers each (four per TMEM lane quadrant, one
+// per frame pair of an 8-frame sub-batch).
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "forward.cuh"
+#include "skin_common.cuh"
+#include "tc_ptx.cuh"
+
+using namespace sb;
+
+namespace tc3
+{
+constexpr int MV = 128;                          // vertices per tile (UMMA M)
+constexpr int NF = 96;                           // frames per block (UMMA N of GEMM 1)
+constexpr int ROWB = 64;                         // bytes of K per shared-memory row (one SWIZZLE_64B span = 32 fp16)
+constexpr int KP = kBlendK;                      // 224
+constexpr int KUSED = kPoseDim + kShapeDim;      // 217: the template column is excluded
+constexpr int NKB = KP * 2 / ROWB;               // 7 K-blocks of 32
+constexpr int A_PART = 3 * MV * ROWB;            // 24576: one part (hi or lo) of the basis tile, 3 planes
+constexpr int B_PART = NF * ROWB;                // 6144
+constexpr int STAGE = 2 * A_PART + 2 * B_PART;   // 61440
+constexpr int SUBF = 8;                          // frames per skinning sub-batch
+constexpr int SUBN = SUBF * kXformFloats;        // 96 = UMMA N of GEMM 2
+constexpr int KJ = skin::KJ;                     // joints padded to two K = 16 steps
+constexpr int G_PART = SUBN * ROWB;              // 6144
+constexpr int G_STAGE = 2 * G_PART;              // 12288
+constexpr int NSUB = NF / SUBF;                  // 12 sub-batches per item
+constexpr int EPI_WARPS = 16;
+constexpr int EPI_FR = 2;                        // frames of a sub-batch handled by one epilogue warp
+constexpr int FR_WARP = NSUB * EPI_FR;           // 24 frames of an item per epilogue warp
+constexpr int CTRL_WARPS = 4;                     // one warpgroup: producer, MMA issuer, two idle
+constexpr int THREADS = 32 * (CTRL_WARPS + EPI_WARPS);
+constexpr int STG_FLOATS = EPI_FR * 32 * 3;      // per warp: 2 frames x 32 vertices x 3
+constexpr int STG_BYTES = EPI_WARPS * STG_FLOATS * 4;
+// shared memory: [ST GEMM 1 stages][GS transform sub-batch slots][output staging][barriers]
+template<int ST, int GS>
+struct Layout
+{
+  static constexpr int OFF_G = ST * STAGE;
+  static constexpr int OFF_STG = OFF_G + GS * G_STAGE;
+  static constexpr int OFF_BAR = OFF_STG + STG_BYTES;
+  static constexpr int SMEM_BYTES = 1024 + OFF_BAR + 512;
+  static_assert(OFF_STG % 1024 == 0, "swizzle atoms stay aligned");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+constexpr int TMEM_COLS = 512;
+constexpr int COL_M = 3 * NF;                    // 288
+constexpr int COL_W = COL_M + 2 * SUBN;          // 480
+constexpr int TRIPLES = NKB * 6;                 // GEMM 1 = 42 (K-block, product, K-step) triples of 3 MMAs (planes)
+constexpr int COEF_EXP = 6, W_EXP = skin::W_EXP, G_EXP = skin::G_EXP;
+static_assert(COL_W + 2 * (KJ / 2) == TMEM_COLS, "TMEM column map");
+static_assert(STAGE % 1024 == 0 && G_STAGE % 1024 == 0, "swizzle atoms stay aligned");
+
+struct Params
+{
+  int V, B, Bpad, ntiles, nfb, nitems;
+  float scale_p, scale_m;       // 2^-(basis_exp + COEF_EXP), 2^-(W_EXP + G_EXP)
+  const uint8_t * img_a;        // [tile][K-block][part][plane][128][64 B]   stage image of the fp16 basis
+  const uint8_t * img_b;        // [frame block][K-block][part][96][64 B]   stage image of the fp16 coefficients
+  const uint8_t * img_g;        // [frame block][sub-batch][part][96][64 B] stage image of the fp16 transforms
+  const float * basis;          // (3 Vpad, 224): column 217 = template
+  const float * weights;        // (V, 24) dense
+  const float * wsum;           // (Vpad)
+  const float * theta;          // (B, 25, 3): row 0 = root translation
+  float * out;                  // (B, V, 3)
+  long long * dbg;              // optional per-CTA timestamps (SMPLPP_TC3_DBG)
+};
+
+// frame n of a 96-frame block -> row of the block in the fp16 coefficient operand (= accumulator column of GEMM 1):
+// the 24 frames epilogue warp group fp owns (frame pair fp of every 8-frame sub-batch) become adjacent columns
+__host__ __device__ constexpr int coef_row(int n)
+{
+  return ((n % SUBF) / EPI_FR) * FR_WARP + (n / SUBF) * EPI_FR + (n % EPI_FR);
+}
+
+
+// byte offset inside a 1024-byte aligned stage region -> SWIZZLE_64B position (16-byte chunk index XOR bits [7,9) of the
+// offset: what a tiled TMA load with CU_TENSOR_MAP_SWIZZLE_64B writes and what the UMMA descriptor expects)
+__host__ __device__ constexpr uint32_t swz64(uint32_t o)
+{
+  return o ^ (((o >> 7) & 3u) << 4);
+}
+} // namespace tc3
+
+// basis (3 Vpad, 224) fp32 -> stage images [tile][K-block][part hi | lo][plane][128 rows][32 fp16], scaled by 2^e
+__global__ void basis_image_f16_kernel(const float * __restrict__ basis, int V, int ntiles, float scale, uint8_t * __restrict__ img)
+{
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long n = static_cast<long long>(ntiles) * 3 * tc3::MV * tc3::KP;
+  if(i >= n) return;
+  const int k = static_cast<int>(i % tc3::KP);
+  const long long row = i / tc3::KP;
+  const int r = static_cast<int>(row % tc3::MV);
+  const int plane = static_cast<int>((row / tc3::MV) % 3);
+  const int tile = static_cast<int>(row / (3 * tc3::MV));
+  const int v = tile * tc3::MV + r;
+  const float x = (v < V && k < tc3::KUSED) ? basis[(static_cast<size_t>(3) * v + plane) * kBlendK + k] * scale : 0.f;
+  const __half hi = __float2half_rn(x);
+  const __half lo = __float2half_rn(x - __half2float(hi));
+  uint8_t * blk = img + (static_cast<size_t>(tile) * tc3::NKB + k / 32) * (2 * tc3::A_PART);
+  const uint32_t o = static_cast<uint32_t>(plane * tc3::MV * tc3::ROWB + r * tc3::ROWB + (k % 32) * 2);
+  *reinterpret_cast<__half *>(blk + tc3::swz64(o)) = hi;
+  *reinterpret_cast<__half *>(blk + tc3::swz64(tc3::A_PART + o)) = lo;
+}
+
+// per-call operands: coef (B,224) fp32 -> img_b (rows of every 96-frame block permuted by coef_row, x 2^6);
+// xforms (B,24,12) fp32 -> img_g (row = frame in sub-batch * 12 + element of the 3x4, column = joint, x 2^4).
+// Padding (frames >= B, K >= 217, joints >= 24) is zero-filled.
+__global__ void frame_images3_kernel(const float * __restrict__ coef, const float * __restrict__ xforms, int B, int Bpad,
+                                     uint8_t * __restrict__ img_b, uint8_t * __restrict__ img_g)
+{
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long n_coef = static_cast<long long>(Bpad) * tc3::KP;
+  const long long n_xf = static_cast<long long>(Bpad) * kXformFloats * tc3::KJ;
+  if(i < n_coef)
+  {
+    const int k = static_cast<int>(i % tc3::KP);
+    const long long f = i / tc3::KP;
+    const float x = (f < B && k < tc3::KUSED) ? coef[i] * static_cast<float>(1 << tc3::COEF_EXP) : 0.f;
+    const __half hi = __float2half_rn(x);
+    const __half lo = __float2half_rn(x - __half2float(hi));
+    const long long fb = f / tc3::NF;
+    const int r = tc3::coef_row(static_cast<int>(f - fb * tc3::NF));
+    uint8_t * blk = img_b + (static_cast<size_t>(fb) * tc3::NKB + k / 32) * (2 * tc3::B_PART);
+    const uint32_t o = static_cast<uint32_t>(r * tc3::ROWB + (k % 32) * 2);
+    *reinterpret_cast<__half *>(blk + tc3::swz64(o)) = hi;
+    *reinterpret_cast<__half *>(blk + tc3::swz64(tc3::B_PART + o)) = lo;
+  }
+  else if(i < n_coef + n_xf)
+  {
+    const long long q = i - n_coef;
+    const int j = static_cast<int>(q % tc3::KJ);
+    const long long row = q / tc3::KJ;
+    const int e = static_cast<int>(row % kXformFloats);
+    const long long f = row / kXformFloats;
+    const float x = (f < B && j < kJoints) ? xforms[(f * kJoints + j) * kXformFloats + e] * static_cast<float>(1 << tc3::G_EXP) : 0.f;
+    const __half hi = __float2half_rn(x);
+    const __half lo = __float2half_rn(x - __half2float(hi));
+    const long long fb = f / tc3::NF;
+    const int nf = static_cast<int>(f - fb * tc3::NF);
+    uint8_t * blk = img_g + (static_cast<size_t>(fb) * tc3::NSUB + nf / tc3::SUBF) * tc3::G_STAGE;
+    const uint32_t o = static_cast<uint32_t>(((nf % tc3::SUBF) * kXformFloats + e) * tc3::ROWB + j * 2);
+    *reinterpret_cast<__half *>(blk + tc3::swz64(o)) = hi;
+    *reinterpret_cast<__half *>(blk + tc3::swz64(tc3::G_PART + o)) = lo;
+  }
+}
+
+template<int STAGES, int GSLOTS, int ACHUNKS>
+__global__ void __launch_bounds__(tc3::THREADS, 1)
+    blend_skin_tc3_kernel(const tc3::Params p)
+{
+  using namespace tc3;
+  using L = Layout<STAGES, GSLOTS>;
+  constexpr int OFF_G = L::OFF_G, OFF_STG = L::OFF_STG, OFF_BAR = L::OFF_BAR;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t * smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t * bars = reinterpret_cast<uint64_t *>(smem + OFF_BAR);
+  uint64_t * full = bars;                // [STAGES]  TMA -> MMA (GEMM 1 stages)
+  uint64_t * empty = full + STAGES;      // [STAGES]  MMA -> TMA
+  uint64_t * g_full = empty + STAGES;    // [GSLOTS]  TMA -> MMA (transform sub-batches)
+  uint64_t * g_empty = g_full + GSLOTS;  // [GSLOTS]  MMA -> TMA
+  uint64_t * m_full = g_empty + GSLOTS;  // [2]       MMA -> epilogue (skinning matrices of a sub-batch)
+  uint64_t * m_empty = m_full + 2;       // [2]       epilogue -> MMA
+  uint64_t * p_full = m_empty + 2;       //           MMA -> epilogue (rest accumulators of an item complete)
+  uint64_t * rest_free = p_full + 1;     //           epilogue -> MMA (accumulators drained into registers)
+  uint64_t * w_ready = rest_free + 1;    //           epilogue -> MMA (W tile stored in TMEM)
+  uint32_t * tmem_slot = reinterpret_cast<uint32_t *>(w_ready + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // contiguous range of work items, vertex tile major / frame block minor: a CTA changes its vertex tile (W tile,
+  // template, 1 / sum w) at most a couple of times
+  const int it0 = static_cast<int>(static_cast<long long>(blockIdx.x) * p.nitems / gridDim.x);
+  const int it1 = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * p.nitems / gridDim.x);
+  const int nit = it1 - it0;
+
+  if(warp == 0 && lane == 0)
+  {
+    for(int s = 0; s < STAGES; s++)
+    {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for(int s = 0; s < GSLOTS; s++)
+    {
+      ptx::mbar_init(&g_full[s], 1);
+      ptx::mbar_init(&g_empty[s], 1);
+    }
+    for(int i = 0; i < 2; i++)
+    {
+      ptx::mbar_init(&m_full[i], 1);
+      ptx::mbar_init(&m_empty[i], EPI_WARPS);
+    }
+    ptx::mbar_init(p_full, 1);
+    ptx::mbar_init(rest_free, EPI_WARPS);
+    ptx::mbar_init(w_ready, 4);
+    ptx::fence_barrier_init();
+  }
+  if(warp == 1) ptx::tmem_alloc<TMEM_COLS>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  long long * dbg = p.dbg ? p.dbg + static_cast<size_t>(blockIdx.x) * 256 : nullptr;
+
+  if(warp < CTRL_WARPS)
+  {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+  if(warp == 0)
+  {
+    // ---- producer of the GEMM 1 stage ring ----
+    // (Measured, scripts/ubench/ubench_tma.cu: the [expect_tx, copy] groups issued by ONE thread retire one at a time,
+    // ~410 cycles apart from L2 whatever their size, so groups are as large as a stage and the two rings have a
+    // producer thread each: a single thread feeding both rings left the kernel at 17.5 k cycles per item.)
+    if(ptx::elect_one())
+    {
+      const int total_kb = nit * NKB;
+      for(int kbn = 0; kbn < total_kb; kbn++)
+      {
+        const int item = it0 + kbn / NKB, kb = kbn % NKB, s = kbn % STAGES;
+        const int tile = item / p.nfb, fb = item % p.nfb;
+        ptx::mbar_wait(&empty[s], ((kbn / STAGES) & 1) ^ 1);
+        ptx::mbar_expect_tx(&full[s], STAGE);
+        uint8_t * dst = smem + s * STAGE;
+        const uint8_t * srca = p.img_a + (static_cast<size_t>(tile) * NKB + kb) * (2 * A_PART);
+#pragma unroll
+        for(int c = 0; c < ACHUNKS; c++)
+          ptx::bulk_load_1d(dst + c * (2 * A_PART / ACHUNKS), srca + c * (2 * A_PART / ACHUNKS), 2 * A_PART / ACHUNKS, &full[s]);
+        ptx::bulk_load_1d(dst + 2 * A_PART, p.img_b + (static_cast<size_t>(fb) * NKB + kb) * (2 * B_PART), 2 * B_PART, &full[s]);
+        if(dbg && kbn < 14) dbg[34 + kbn] = clock64();
+      }
+    }
+  }
+  else if(warp == 2)
+  {
+    // ---- producer of the transform sub-batch ring ----
+    if(ptx::elect_one())
+    {
+      const int total_g = nit * NSUB;
+      for(int gn = 0; gn < total_g; gn++)
+      {
+        const int item = it0 + gn / NSUB, sb = gn % NSUB, s = gn % GSLOTS;
+        ptx::mbar_wait(&g_empty[s], ((gn / GSLOTS) & 1) ^ 1);
+        ptx::mbar_expect_tx(&g_full[s], G_STAGE);
+        ptx::bulk_load_1d(smem + OFF_G + s * G_STAGE, p.img_g + (static_cast<size_t>(item % p.nfb) * NSUB + sb) * G_STAGE, G_STAGE,
+                          &g_full[s]);
+      }
+    }
+  }
+  else if(warp == 1)
+  {
+    if(ptx::elect_one())
+    {
+      constexpr uint32_t idesc1 = ptx::make_idesc_f16(MV, NF);
+      constexpr uint32_t idesc2 = ptx::make_idesc_f16(MV, SUBN);
+      // Single-thread issue: every instruction between two tcgen05.mma is on the critical path (a first version that
+      // derived (K-block, product, K-step) from a running triple index spent ~16 instructions per MMA and issued one
+      // every ~105 cycles).  GEMM 1 is issued in HALF K-blocks of 9 MMAs with compile-time operand offsets; only the
+      // stage base is a run-time value.  Descriptor = constant high word | (shared address >> 4).
+      constexpr uint32_t DHI = ptx::smem_desc_hi<ROWB>();
+      const uint32_t smem16 = ptx::smem_u32(smem) >> 4;
+      int kbn = 0;   // K-blocks of GEMM 1 consumed so far (over all items): ring position
+      int half = 0;  // half K-blocks of the GEMM 1 being issued (0 .. 2 NKB)
+      // MMA i (0..8) of a half K-block: triple i / 3 (operand parts and K step), plane i % 3.
+      //   half 0: (hi.hi, ks 0), (hi.hi, ks 1), (lo.hi, ks 0)      half 1: (lo.hi, ks 1), (hi.lo, ks 0), (hi.lo, ks 1)
+      auto g1_mma = [&](uint32_t st16, int hpar, int i, uint32_t acc) {
+        const int t = i / 3, c = i % 3;
+        const int a_part = hpar == 0 ? (t == 2 ? 1 : 0) : (t == 0 ? 1 : 0);
+        const int b_part = hpar == 0 ? 0 : (t == 0 ? 0 : 1);
+        const int ks = hpar == 0 ? (t == 1 ? 1 : 0) : (t == 1 ? 0 : 1);
+        ptx::umma_f16_ss_lo(tmem_base + c * NF, st16 + ((a_part * A_PART + c * MV * ROWB + ks * 32) >> 4),
+                            st16 + ((2 * A_PART + b_part * B_PART + ks * 32) >> 4), DHI, idesc1, acc);
+      };
+      // GEMM 2 MMA j (0..5) of a sub-batch: hi.hi, lo.hi, hi.lo with two K = 16 steps each
+      auto g2_mma = [&](uint32_t dm, uint32_t aw, uint32_t sg16, int j) {
+        const int prod = j >> 1, ks = j & 1;
+        const int pa = prod == 1 ? 1 : 0, pb = prod == 2 ? 1 : 0;
+        ptx::umma_f16_ts_lo(dm, aw + pa * (KJ / 2) + ks * 8, sg16 + ((pb * G_PART + ks * 32) >> 4), DHI, idesc2, j != 0 ? 1u : 0u);
+      };
+      // stage of the current half K-block (waits for the TMA data when the half opens a K-block)
+      auto g1_open = [&]() -> uint32_t {
+        const int s = kbn % STAGES;
+        if((half & 1) == 0)
+        {
+          ptx::mbar_wait(&full[s], (kbn / STAGES) & 1);
+          ptx::tc_fence_after();
+          if(dbg && kbn < 14) dbg[48 + kbn] = clock64();
+        }
+        return smem16 + s * (STAGE >> 4);
+      };
+      auto g1_close = [&]() {
+        if(half & 1)
+        {
+          ptx::tc_commit(&empty[kbn % STAGES]);
+          kbn++;
+        }
+        half++;
+      };
+      auto g1_half_alone = [&]() {
+        const uint32_t st16 = g1_open();
+        const uint32_t acc0 = half != 0 ? 1u : 0u;
+        if((half & 1) == 0)
+        {
+#pragma unroll
+          for(int i = 0; i < 9; i++) g1_mma(st16, 0, i, i < 3 ? acc0 : 1u);
+        }
+        else
+        {
+#pragma unroll
+          for(int i = 0; i < 9; i++) g1_mma(st16, 1, i, 1u);
+        }
+        g1_close();
+      };
+      if(dbg) dbg[0] = clock64();
+      if(nit > 0)
+      {
+        for(int h = 0; h < 2 * NKB; h++) g1_half_alone();
+        ptx::tc_commit(p_full);
+      }
+      if(dbg) dbg[1] = clock64();
+      int wcount = 0, prev_tile = -1;
+      for(int k = 0; k < nit; k++)
+      {
+        const int tile = (it0 + k) / p.nfb;
+        if(tile != prev_tile)
+        {
+          ptx::mbar_wait(w_ready, wcount & 1);
+          ptx::tc_fence_after();
+          wcount++;
+          prev_tile = tile;
+        }
+        const bool more = k + 1 < nit;
+        half = 0;
+        for(int sb = 0; sb < NSUB; sb++)
+        {
+          const int m = k * NSUB + sb, b = sb & 1, gs = m % GSLOTS;
+          ptx::mbar_wait(&g_full[gs], (m / GSLOTS) & 1);
+          ptx::mbar_wait(&m_empty[b], ((m >> 1) & 1) ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t sg16 = smem16 + ((OFF_G + gs * G_STAGE) >> 4);
+          const uint32_t dm = tmem_base + COL_M + b * SUBN, aw = tmem_base + COL_W;
+#pragma unroll
+          for(int j = 0; j < 6; j++) g2_mma(dm, aw, sg16, j);
+          ptx::tc_commit(&m_full[b]);
+          ptx::tc_commit(&g_empty[gs]);
+          if(more)
+          {
+            if(sb == 0)
+            {
+              ptx::mbar_wait(rest_free, k & 1); // item k's accumulators now live in the epilogue warps' registers
+              ptx::tc_fence_after();
+            }
+            // 14 half K-blocks of the next item's GEMM 1 over the 12 sub-batches.  (Interleaving the 9 MMAs of a half
+            // with the 6 GEMM 2 MMAs, to avoid chaining on one accumulator, was measured and is SLOWER: 23 k instead of
+            // 17.5 k cycles per item - alternating between the shared-memory-A and TMEM-A forms costs more than the chain.)
+            g1_half_alone();
+            if(sb == 0 || sb == NSUB / 2) g1_half_alone();
+          }
+        }
+        if(more) ptx::tc_commit(p_full);
+        if(dbg && k < 30) dbg[2 + k] = clock64();
+      }
+    }
+  }
+  }
+  else
+  {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    const int ew = warp - CTRL_WARPS;
+    const int q = warp & 3;        // TMEM lane quadrant this warp may access (hardware rule: warp id % 4)
+    const int fp = ew >> 2;        // which frame pair of every 8-frame sub-batch
+    const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t my_stg = ptx::smem_u32(smem + OFF_STG) + ew * STG_FLOATS * 4;
+    const float sp = p.scale_p;
+    int prev_tile = -1;
+    int wv0 = 0, nvalid = 0;
+    float T0 = 0.f, T1 = 0.f, T2 = 0.f, sm = 0.f;
+    if(dbg && ew == 0 && lane == 0) dbg[32] = clock64();
+    for(int k = 0; k < nit; k++)
+    {
+      const int item = it0 + k;
+      const int tile = item / p.nfb, f0 = (item - tile * p.nfb) * NF;
+      if(tile != prev_tile)
+      {
+        prev_tile = tile;
+        wv0 = tile * MV + q * 32;
+        const int vc = min(wv0 + lane, p.V - 1);
+        nvalid = max(0, min(32, p.V - wv0));
+        if(ew < 4)
+        {
+          // every MMA that read the previous W tile has completed: this warp has seen m_full of the item's last sub-batch
+          skin::store_w_row_tmem(p.weights + static_cast<size_t>(vc) * kJoints, lane_taddr + COL_W);
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if(lane == 0) ptx::mbar_arrive(w_ready);
+        }
+        sm = p.scale_m / p.wsum[vc]; // homogeneous divide (LinearBlendSkinning.cpp:545-550) folded into the scale
+        const float * tp = p.basis + static_cast<size_t>(3) * vc * kBlendK + KUSED;
+        T0 = __ldg(tp) * sm, T1 = __ldg(tp + kBlendK) * sm, T2 = __ldg(tp + 2 * kBlendK) * sm;
+      }
+      // root translations (theta row 0, SMPL.cpp:726-727) of this warp's 24 frames: lane l holds frame pair l / 2, frame
+      // l % 2; fetched once per item (in flight during the p_full wait) and broadcast by shuffles in the sub-batch loop
+      float trx = 0.f, try_ = 0.f, trz = 0.f;
+      if(lane < FR_WARP)
+      {
+        const int f = min(f0 + (lane >> 1) * SUBF + fp * EPI_FR + (lane & 1), p.B - 1);
+        const float * tq = p.theta + static_cast<size_t>(f) * ((kJoints + 1) * 3);
+        trx = __ldg(tq), try_ = __ldg(tq + 1), trz = __ldg(tq + 2);
+      }
+      // ---- drain the rest accumulators of this item: 24 frames x (x, y, z), pre-multiplied by scale / sum w ----
+      float R[3][FR_WARP];
+      ptx::mbar_wait(p_full, k & 1);
+      ptx::tc_fence_after();
+#pragma unroll
+      for(int c = 0; c < 3; c++)
+      {
+        ptx::tmem_ld_x16(lane_taddr + c * NF + fp * FR_WARP, R[c]);
+        ptx::tmem_ld_x8p(lane_taddr + c * NF + fp * FR_WARP + 16, R[c] + 16);
+      }
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if(lane == 0) ptx::mbar_arrive(rest_free);
+      {
+        const float s = sp * sm;
+#pragma unroll
+        for(int i = 0; i < FR_WARP; i++)
+        {
+          R[0][i] = fmaf(R[0][i], s, T0);
+          R[1][i] = fmaf(R[1][i], s, T1);
+          R[2][i] = fmaf(R[2][i], s, T2);
+        }
+      }
+      float * outp = p.out + (static_cast<size_t>(f0 + fp * EPI_FR) * p.V + wv0) * 3;
+#pragma unroll
+      for(int sb = 0; sb < NSUB; sb++)
+      {
+        const int h = sb & 1; // matrix buffer of this sub-batch (NSUB is even: the same for every item)
+        float tr[EPI_FR][3];
+#pragma unroll
+        for(int t = 0; t < EPI_FR; t++)
+        {
+          tr[t][0] = __shfl_sync(0xffffffffu, trx, sb * EPI_FR + t);
+          tr[t][1] = __shfl_sync(0xffffffffu, try_, sb * EPI_FR + t);
+          tr[t][2] = __shfl_sync(0xffffffffu, trz, sb * EPI_FR + t);
+        }
+        ptx::mbar_wait(&m_full[h], (sb >> 1) & 1); // 6 ring rounds per item: the parity does not depend on the item
+        ptx::tc_fence_after();
+        float M[EPI_FR * kXformFloats];
+        const uint32_t mcol = lane_taddr + COL_M + h * SUBN + fp * (EPI_FR * kXformFloats);
+        ptx::tmem_ld_x16(mcol, M);
+        ptx::tmem_ld_x8p(mcol + 16, M + 16);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if(lane == 0) ptx::mbar_arrive(&m_empty[h]); // the MMA warp may overwrite this matrix buffer
+#pragma unroll
+        for(int t = 0; t < EPI_FR; t++)
+        {
+          const float rx = R[0][sb * EPI_FR + t], ry = R[1][sb * EPI_FR + t], rz = R[2][sb * EPI_FR + t];
+          const float * m = M + kXformFloats * t;
+          const float ox = fmaf(m[0], rx, fmaf(m[1], ry, fmaf(m[2], rz, fmaf(m[3], sm, tr[t][0]))));
+          const float oy = fmaf(m[4], rx, fmaf(m[5], ry, fmaf(m[6], rz, fmaf(m[7], sm, tr[t][1]))));
+          const float oz = fmaf(m[8], rx, fmaf(m[9], ry, fmaf(m[10], rz, fmaf(m[11], sm, tr[t][2]))));
+          const uint32_t sa = my_stg + (t * 96 + lane * 3) * 4;
+          ptx::sts32(sa, ox);
+          ptx::sts32(sa + 4, oy);
+          ptx::sts32(sa + 8, oz);
+        }
+        __syncwarp();
+        // each frame's 32 vertices are 384 contiguous bytes: 8-byte coalesced streaming stores
+#pragma unroll
+        for(int i = 0; i < EPI_FR * 48 / 32; i++)
+        {
+          const int idx = 32 * i + lane; // float2 index over EPI_FR frames x 48
+          const int t = idx / 48;
+          const int w2 = idx - 48 * t;
+          const int f = f0 + sb * SUBF + fp * EPI_FR + t;
+          const float2 val = ptx::lds64(my_stg + idx * 8);
+          if(f < p.B && 2 * w2 < 3 * nvalid)
+            __stcs(reinterpret_cast<float2 *>(outp + (static_cast<size_t>(sb * SUBF + t) * p.V) * 3) + w2, val);
+        }
+        __syncwarp();
+      }
+    }
+    if(dbg && ew == 0 && lane == 0) dbg[33] = clock64();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if(warp == 1) ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+namespace sb
+{
+size_t tc3_frame_operand_bytes(int64_t batch)
+{
+  const size_t bpad = align_up(static_cast<size_t>(batch), tc3::NF);
+  return align_up(2 * bpad * tc3::KP * sizeof(__half)) + align_up(2 * bpad * kXformFloats * tc3::KJ * sizeof(__half));
+}
+
+// builds the stage images of the fp16 split basis (scaled like the tc2 copy); called once from smplpp_model_create
+int tc3_prepare_model(ModelDev & d)
+{
+  d.tc3_ready = false;
+  if(!d.tc2_ready) return SMPLPP_OK;
+  const long long n = static_cast<long long>(d.tc2_tiles) * 3 * tc3::MV * tc3::KP;
+  SB_CUDA(cudaMalloc(&d.basis_img16, static_cast<size_t>(2) * n * sizeof(__half)));
+  basis_image_f16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(d.basis, d.V, d.tc2_tiles, ldexpf(1.f, d.tc2_basis_exp),
+                                                                         static_cast<uint8_t *>(d.basis_img16));
+  SB_LAUNCHED();
+  SB_CUDA(cudaDeviceSynchronize());
+  SB_CUDA(cudaFuncSetAttribute(blend_skin_tc3_kernel<2, 6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::Layout<2, 6>::SMEM_BYTES));
+  SB_CUDA(cudaFuncSetAttribute(blend_skin_tc3_kernel<3, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::Layout<3, 2>::SMEM_BYTES));
+  int dev = 0;
+  SB_CUDA(cudaGetDevice(&dev));
+  SB_CUDA(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev));
+  d.tc3_ready = d.sm_count > 0;
+  return SMPLPP_OK;
+}
+
+void tc3_release_model(ModelDev & d)
+{
+  if(d.basis_img16) cudaFree(d.basis_img16);
+  d.basis_img16 = nullptr;
+  d.tc3_ready = false;
+}
+
+// coef (B,224) and xforms (B,24,12) fp32 from K1; scratch: tc3_frame_operand_bytes(B)
+int launch_blend_skin_tc3(const ModelDev & d, cudaStream_t st, int B, const float * coef, const float * xforms, void * scratch,
+                          const float * theta, float * out)
+{
+  if(!d.tc3_ready) return fail(SMPLPP_ERR_INVALID, "SMPL", "pipelined tcgen05 skinning variant is not available for this model");
+  if(reinterpret_cast<uintptr_t>(out) & 7) return fail(SMPLPP_ERR_INVALID, "SMPL", "tcgen05 variants need 8-byte aligned vertices");
+  if(reinterpret_cast<uintptr_t>(scratch) & 127) return fail(SMPLPP_ERR_INVALID, "SMPL", "tcgen05 variants need a 128-byte aligned workspace");
+  const int Bpad = static_cast<int>(align_up(static_cast<size_t>(B), tc3::NF));
+  uint8_t * img_b = static_cast<uint8_t *>(scratch);
+  uint8_t * img_g = img_b + align_up(static_cast<size_t>(2) * Bpad * tc3::KP * sizeof(__half));
+  const long long n = static_cast<long long>(Bpad) * (tc3::KP + kXformFloats * tc3::KJ);
+  frame_images3_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(coef, xforms, B, Bpad, img_b, img_g);
+  SB_LAUNCHED();
+  tc3::Params p;
+  p.V = d.V;
+  p.B = B;
+  p.Bpad = Bpad;
+  p.ntiles = d.tc2_tiles;
+  p.nfb = Bpad / tc3::NF;
+  p.nitems = p.ntiles * p.nfb;
+  p.scale_p = ldexpf(1.f, -(d.tc2_basis_exp + tc3::COEF_EXP));
+  p.scale_m = ldexpf(1.f, -(tc3::W_EXP + tc3::G_EXP));
+  p.img_a = static_cast<const uint8_t *>(d.basis_img16);
+  p.img_b = img_b;
+  p.img_g = img_g;
+  p.basis = d.basis;
+  p.weights = d.weights_dense;
+  p.wsum = d.lbs_wsum;
+  p.theta = theta;
+  p.out = out;
+  int grid = p.nitems < d.sm_count ? p.nitems : d.sm_count;
+  static const int grid_env = getenv("SMPLPP_TC3_GRID") ? atoi(getenv("SMPLPP_TC3_GRID")) : 0;
+  static const int ring_env = getenv("SMPLPP_TC3_RING") ? atoi(getenv("SMPLPP_TC3_RING")) : 0;
+  if(grid_env > 0 && grid_env < grid) grid = grid_env;
+  static const bool dbg_on = getenv("SMPLPP_TC3_DBG") != nullptr;
+  p.dbg = nullptr;
+  if(dbg_on)
+  {
+    SB_CUDA(cudaMalloc(&p.dbg, static_cast<size_t>(grid) * 256 * sizeof(long long)));
+    SB_CUDA(cudaMemsetAsync(p.dbg, 0, static_cast<size_t>(grid) * 256 * sizeof(long long), st));
+  }
+  if(ring_env == 1)
+    blend_skin_tc3_kernel<3, 2, 1><<<grid, tc3::THREADS, tc3::Layout<3, 2>::SMEM_BYTES, st>>>(p);
+  else
+    blend_skin_tc3_kernel<2, 6, 1><<<grid, tc3::THREADS, tc3::Layout<2, 6>::SMEM_BYTES, st>>>(p);
+  SB_LAUNCHED();
+  if(dbg_on)
+  {
+    SB_CUDA(cudaStreamSynchronize(st));
+    std::vector<long long> h(static_cast<size_t>(grid) * 256);
+    SB_CUDA(cudaMemcpy(h.data(), p.dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(p.dbg);
+    for(int cta : {0, grid / 2})
+    {
+      const long long * t = h.data() + static_cast<size_t>(cta) * 256;
+      fprintf(stderr, "[tc3 dbg] cta %d: first GEMM 1 issued +%lld | items", cta, t[1] - t[0]);
+      for(int k = 0; k < 30 && t[2 + k]; k++) fprintf(stderr, " %lld", t[2 + k] - (k ? t[1 + k] : t[1]));
+      fprintf(stderr, " | epilogue %lld .. %lld\n", t[32] - t[0], t[33] - t[0]);
+      fprintf(stderr, "   stage loads issued (K-block 0..13):");
+      for(int i = 0; i < 14; i++) fprintf(stderr, " %lld", t[34 + i] - t[0]);
+      fprintf(stderr, "\n   stage seen full by the MMA thread:  ");
+      for(int i = 0; i < 14; i++) fprintf(stderr, " %lld", t[48 + i] - t[0]);
+      fprintf(stderr, "\n");
+    }
+  }
+  return SMPLPP_OK;
+}
+} // namespace sb

@@ -95,6 +95,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t * bar, uint32_t parity)
       : "memory");
   return ok != 0;
 }
+// non-blocking test (try_wait may suspend the thread for a system-dependent time when the phase is not complete -
+// thousands of cycles when measured on B200 - so a thread that polls several barriers must use this one)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t * bar, uint32_t parity)
+{
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol error becomes a trap (cudaErrorLaunchFailure) instead of a hung GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t * bar, uint32_t parity)
 {
@@ -284,6 +300,43 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, ui
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// the same two instructions with the shared-memory descriptors given as (constant high word, address >> 4): the
+// single issuing thread then spends one integer add per operand instead of rebuilding 64-bit descriptors
+template<int kRowBytes>
+__host__ __device__ constexpr uint32_t smem_desc_hi()
+{
+  static_assert(kRowBytes == 64 || kRowBytes == 128, "row = one swizzle span");
+  return static_cast<uint32_t>((8 * kRowBytes) >> 4) | (1u << 14) | ((kRowBytes == 128 ? 2u : 4u) << 29);
+}
+__device__ __forceinline__ void umma_f16_ss_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                               uint32_t accumulate)
+{
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_ts_lo(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                               uint32_t accumulate)
+{
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // instruction descriptor for kind::f16 with FP16 inputs (a/b format 0), fp32 accumulate, K-major A and B

@@ -71,7 +71,7 @@ def test_kat_linear_blend_skinning(kat):
 
 # ---- full model: golden vectors of the compiled reference ----
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
 def test_forward_vs_reference_golden(smpl_gpu, golden_forward, variant):
     from smplpp_b200 import capi
     g = golden_forward
@@ -91,7 +91,7 @@ def test_forward_vs_reference_golden(smpl_gpu, golden_forward, variant):
     assert np.abs(v - g["vertices"]).max() < (5e-6 if variant == 4 else 2e-6)
 
 
-@pytest.mark.parametrize("variant", [2, 4, 5])
+@pytest.mark.parametrize("variant", [2, 4, 5, 6])
 @pytest.mark.parametrize("batch", [1, 127, 300])
 def test_forward_tensor_core_variants_match_ffma(smpl_gpu, variant, batch):
     """Ragged frame counts through the tcgen05 kernel (128-frame tiles, 32-frame transform windows) against the
@@ -108,6 +108,24 @@ def test_forward_tensor_core_variants_match_ffma(smpl_gpu, variant, batch):
             capi.check(capi.lib().smplpp_set_forward_variant(0))
     assert np.isfinite(out[variant]).all()
     assert np.abs(out[variant] - out[1]).max() < (5e-6 if variant == 4 else 1e-6)
+
+
+@pytest.mark.parametrize("batch", [2000, 4096 + 37])
+def test_forward_pipelined_kernel_many_items_per_cta(smpl_gpu, batch):
+    """The persistent tcgen05 kernel (variant 6, skin_tc3.cu) with many work items per CTA: ring wrap-around, vertex-tile
+    changes inside a CTA's range and a ragged last frame block, against the FFMA kernel on every frame and vertex."""
+    from smplpp_b200 import capi, synth
+    beta, theta = synth.make_forward_inputs(batch, 5 + batch)
+    out = {}
+    for var in (1, 6):
+        capi.check(capi.lib().smplpp_set_forward_variant(var))
+        try:
+            smpl_gpu.launch(beta, theta)
+            out[var] = smpl_gpu.getVertex()
+        finally:
+            capi.check(capi.lib().smplpp_set_forward_variant(0))
+    assert bool(torch.isfinite(out[6]).all())
+    assert float((out[6] - out[1]).abs().max()) < 1e-6
 
 
 def test_normals_vs_reference_golden(smpl_gpu, golden_forward, oracle_model):
