@@ -273,7 +273,7 @@ def main():
     peak, peak_src = measured_peaks()
     ach = BYTES_FUSED * B / (ms_k2 * 1e-3) / 1e9
     roofline = {"kernel": "blend_skin (fused pose/shape blend contraction + linear blend skinning)", "bound": "hbm",
-                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": ncu_traffic("blend_skin_tc2_kernel"),
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": ncu_traffic("blend_skin_tc3_kernel") or ncu_traffic("blend_skin_tc2_kernel"),
                 "algorithmic_bytes_per_launch": BYTES_FUSED * B,
                 "peak_source": peak_src, "ms_per_launch": ms_k2,
                 "fp32_tflops_algorithmic": FLOPS_BLEND * B / (ms_k2 * 1e-3) / 1e12}
