@@ -228,6 +228,19 @@ int smplpp_task_positions(const smplpp_model_t * model, const smplpp_tasks_t * t
                           const float * vertices_dev, const float * vertex_weights_dev, float normal_offset,
                           float * positions_dev, float * normals_dev);
 
+/* Projection of the task points onto the posed mesh and the re-seated attachment (replaces the
+ * igl::point_mesh_squared_distance call and the faceIdx_ / calcVertexWeights update of node/node.cpp:970-1001):
+ *   vertices        (B, V, 3)   posed mesh of every frame (smplpp_forward)
+ *   points          (B, n, 3)   actualPos + tangents * phi of every task (node.cpp:957-959); n <= 512
+ *   face_idx        (B, n)      out: closest face, 0-BASED like igl's closestFaceIndices (ties: lowest face index)
+ *   closest         (B, n, 3)   out (optional): closest point on that face
+ *   sq_dist         (B, n)      out (optional): squared distance
+ *   vertex_weights  (B, n, 3)   out (optional): calcTriangleVertexWeights(closest, face) (GeometryUtils.h:42-52)
+ * All pointers are device pointers. */
+int smplpp_closest_points(const smplpp_model_t * model, void * stream, int64_t batch, int64_t n_points,
+                          const float * vertices_dev, const float * points_dev, int32_t * face_idx_dev,
+                          float * closest_dev, float * sq_dist_dev, float * vertex_weights_dev);
+
 /* One IK iteration for B independent frames (replaces node/node.cpp:753-968 per frame):
  *   theta assembly (+VPoser) -> sparse forward on the task vertices -> tangents + re-weighting (:803-804) ->
  *   residual e (:807-820) -> analytic Jacobian J (what the one-hot backward rows of :823-873 yield) ->

@@ -219,6 +219,28 @@ class SMPL:
         self._launched("LinearBlendSknning Error: Failed to get vertices of new pose!")  # LinearBlendSkinning.cpp:409
         return self._vertices.clone()
 
+    def projectPoints(self, points, vertices: Optional[torch.Tensor] = None, want_weights: bool = True):
+        """Closest point on the posed mesh for (B, n, 3) points: the igl::point_mesh_squared_distance call and the
+        faceIdx_ / calcVertexWeights re-seat of node/node.cpp:970-1001, batched over frames.  `vertices` defaults to
+        the last launch.  Returns (face_idx (B,n) int32 0-based, closest (B,n,3), sq_dist (B,n), weights (B,n,3))."""
+        dev = self.m__device
+        if vertices is None:
+            self._launched("LinearBlendSknning Error: Failed to get vertices of new pose!")
+            vertices = self._vertices
+        v = _dev_f32(vertices, dev)
+        pts = _dev_f32(points, dev)
+        if pts.dim() != 3 or pts.shape[0] != v.shape[0] or pts.shape[2] != 3:
+            raise SmplppError("IkTask Error: Failed to project points onto the mesh!")
+        b, n = pts.shape[0], pts.shape[1]
+        face = torch.empty((b, n), dtype=torch.int32, device=dev)
+        closest = torch.empty((b, n, 3), dtype=torch.float32, device=dev)
+        sq = torch.empty((b, n), dtype=torch.float32, device=dev)
+        w = torch.empty((b, n, 3), dtype=torch.float32, device=dev) if want_weights else None
+        with torch.cuda.device(dev):
+            check(lib().smplpp_closest_points(self.handle, _stream(dev), C.c_int64(b), C.c_int64(n), _ptr(v), _ptr(pts),
+                                              C.c_void_p(face.data_ptr()), _ptr(closest), _ptr(sq), _ptr(w)))
+        return face, closest, sq, w
+
     def getVertexRaw(self, idx):
         """Batch element 0 only, like the reference (LinearBlendSkinning.cpp:419-427)."""
         self._launched("LinearBlendSknning Error: Failed to get vertices of new pose!")

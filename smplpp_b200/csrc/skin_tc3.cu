@@ -140,43 +140,68 @@ __global__ void basis_image_f16_kernel(const float * __restrict__ basis, int V, 
 
 // per-call operands: coef (B,224) fp32 -> img_b (rows of every 96-frame block permuted by coef_row, x 2^6);
 // xforms (B,24,12) fp32 -> img_g (row = frame in sub-batch * 12 + element of the 3x4, column = joint, x 2^4).
-// Padding (frames >= B, K >= 217, joints >= 24) is zero-filled.
+// Padding (frames >= B, K >= 217, joints >= 24) is zero-filled.  One thread per 16-byte chunk (8 fp16 of one row:
+// the swizzle moves whole chunks), hi and lo written as one 16-byte store each.
+__device__ __forceinline__ void split8_store(const float (&x)[8], uint8_t * hi_dst, uint8_t * lo_dst)
+{
+  uint32_t h[4], l[4];
+#pragma unroll
+  for(int i = 0; i < 4; i++)
+  {
+    const float a = x[2 * i], b = x[2 * i + 1];
+    const float ah = __half2float(__float2half_rn(a)), bh = __half2float(__float2half_rn(b));
+    h[i] = skin::pack_half2(ah, bh);
+    l[i] = skin::pack_half2(a - ah, b - bh);
+  }
+  *reinterpret_cast<uint4 *>(hi_dst) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4 *>(lo_dst) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 __global__ void frame_images3_kernel(const float * __restrict__ coef, const float * __restrict__ xforms, int B, int Bpad,
                                      uint8_t * __restrict__ img_b, uint8_t * __restrict__ img_g)
 {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long n_coef = static_cast<long long>(Bpad) * tc3::KP;
-  const long long n_xf = static_cast<long long>(Bpad) * kXformFloats * tc3::KJ;
+  constexpr int CK = tc3::KP / 8;   // 28 chunks per coefficient row
+  constexpr int CJ = tc3::KJ / 8;   // 4 chunks per transform row
+  const long long n_coef = static_cast<long long>(Bpad) * CK;
+  const long long n_xf = static_cast<long long>(Bpad) * kXformFloats * CJ;
+  float x[8];
   if(i < n_coef)
   {
-    const int k = static_cast<int>(i % tc3::KP);
-    const long long f = i / tc3::KP;
-    const float x = (f < B && k < tc3::KUSED) ? coef[i] * static_cast<float>(1 << tc3::COEF_EXP) : 0.f;
-    const __half hi = __float2half_rn(x);
-    const __half lo = __float2half_rn(x - __half2float(hi));
+    const int ck = static_cast<int>(i % CK);
+    const long long f = i / CK;
+    if(f < B)
+    {
+      const float4 a = __ldg(reinterpret_cast<const float4 *>(coef + f * tc3::KP + ck * 8));
+      const float4 b = __ldg(reinterpret_cast<const float4 *>(coef + f * tc3::KP + ck * 8 + 4));
+      x[0] = a.x, x[1] = a.y, x[2] = a.z, x[3] = a.w, x[4] = b.x, x[5] = b.y, x[6] = b.z, x[7] = b.w;
+    }
+#pragma unroll
+    for(int e = 0; e < 8; e++) x[e] = (f < B && ck * 8 + e < tc3::KUSED) ? x[e] * static_cast<float>(1 << tc3::COEF_EXP) : 0.f;
     const long long fb = f / tc3::NF;
     const int r = tc3::coef_row(static_cast<int>(f - fb * tc3::NF));
-    uint8_t * blk = img_b + (static_cast<size_t>(fb) * tc3::NKB + k / 32) * (2 * tc3::B_PART);
-    const uint32_t o = static_cast<uint32_t>(r * tc3::ROWB + (k % 32) * 2);
-    *reinterpret_cast<__half *>(blk + tc3::swz64(o)) = hi;
-    *reinterpret_cast<__half *>(blk + tc3::swz64(tc3::B_PART + o)) = lo;
+    uint8_t * blk = img_b + (static_cast<size_t>(fb) * tc3::NKB + ck / 4) * (2 * tc3::B_PART);
+    const uint32_t o = static_cast<uint32_t>(r * tc3::ROWB + (ck % 4) * 16);
+    split8_store(x, blk + tc3::swz64(o), blk + tc3::swz64(tc3::B_PART + o));
   }
   else if(i < n_coef + n_xf)
   {
     const long long q = i - n_coef;
-    const int j = static_cast<int>(q % tc3::KJ);
-    const long long row = q / tc3::KJ;
+    const int cj = static_cast<int>(q % CJ);
+    const long long row = q / CJ;
     const int e = static_cast<int>(row % kXformFloats);
     const long long f = row / kXformFloats;
-    const float x = (f < B && j < kJoints) ? xforms[(f * kJoints + j) * kXformFloats + e] * static_cast<float>(1 << tc3::G_EXP) : 0.f;
-    const __half hi = __float2half_rn(x);
-    const __half lo = __float2half_rn(x - __half2float(hi));
+#pragma unroll
+    for(int jj = 0; jj < 8; jj++)
+    {
+      const int j = cj * 8 + jj;
+      x[jj] = (f < B && j < kJoints) ? __ldg(xforms + (f * kJoints + j) * kXformFloats + e) * static_cast<float>(1 << tc3::G_EXP) : 0.f;
+    }
     const long long fb = f / tc3::NF;
     const int nf = static_cast<int>(f - fb * tc3::NF);
     uint8_t * blk = img_g + (static_cast<size_t>(fb) * tc3::NSUB + nf / tc3::SUBF) * tc3::G_STAGE;
-    const uint32_t o = static_cast<uint32_t>(((nf % tc3::SUBF) * kXformFloats + e) * tc3::ROWB + j * 2);
-    *reinterpret_cast<__half *>(blk + tc3::swz64(o)) = hi;
-    *reinterpret_cast<__half *>(blk + tc3::swz64(tc3::G_PART + o)) = lo;
+    const uint32_t o = static_cast<uint32_t>(((nf % tc3::SUBF) * kXformFloats + e) * tc3::ROWB + cj * 16);
+    split8_store(x, blk + tc3::swz64(o), blk + tc3::swz64(tc3::G_PART + o));
   }
 }
 
@@ -589,7 +614,7 @@ int launch_blend_skin_tc3(const ModelDev & d, cudaStream_t st, int B, const floa
   const int Bpad = static_cast<int>(align_up(static_cast<size_t>(B), tc3::NF));
   uint8_t * img_b = static_cast<uint8_t *>(scratch);
   uint8_t * img_g = img_b + align_up(static_cast<size_t>(2) * Bpad * tc3::KP * sizeof(__half));
-  const long long n = static_cast<long long>(Bpad) * (tc3::KP + kXformFloats * tc3::KJ);
+  const long long n = static_cast<long long>(Bpad) * (tc3::KP + kXformFloats * tc3::KJ) / 8; // 16-byte chunks
   frame_images3_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(coef, xforms, B, Bpad, img_b, img_g);
   SB_LAUNCHED();
   tc3::Params p;

@@ -39,17 +39,23 @@ def test_task_positions_vs_oracle(smpl_gpu, task_set, oracle_model, marker_tasks
     beta, theta = synth.make_forward_inputs(3, 40)
     smpl_gpu.launch(beta, theta)
     w = cu(np.repeat(vw[None], 3, axis=0))
+    with torch.no_grad():
+        r = so.smpl_launch(oracle_model, torch.as_tensor(beta), torch.as_tensor(theta))
     for off in (0.0, 0.015):
-        pos, nrm = task_set.positions(smpl_gpu.getVertex(), w, off, want_normals=True)
+        # end to end: positions from the GPU forward pass (vertex tolerance)
+        pos, _ = task_set.positions(smpl_gpu.getVertex(), w, off, want_normals=True)
+        # kernel parity: the SAME vertices as the oracle.  A normal amplifies a vertex difference by 1 / edge length
+        # (edges of the synthetic mesh go down to a few mm), so normals are only compared on identical inputs.
+        pos_o, nrm_o = task_set.positions(cu(r.vertices.numpy()), w, off, want_normals=True)
         with torch.no_grad():
-            r = so.smpl_launch(oracle_model, torch.as_tensor(beta), torch.as_tensor(theta))
             for b in range(3):
                 for m in (0, 7, 40):
                     t = so.IkTask(int(face_idx[m]), normal_offset=off, vertex_weights=torch.as_tensor(vw[m]))
-                    assert np.abs(pos[b, m].cpu().numpy() - t.calc_actual_pos(oracle_model, r.vertices[b]).numpy()).max() \
-                        <= TOL_VERTEX_M
-                    assert np.abs(nrm[b, m].cpu().numpy()
-                                  - t.calc_actual_normal(oracle_model, r.vertices[b]).numpy()).max() < 5e-5
+                    ref_pos = t.calc_actual_pos(oracle_model, r.vertices[b]).numpy()
+                    assert np.abs(pos[b, m].cpu().numpy() - ref_pos).max() <= TOL_VERTEX_M
+                    assert np.abs(pos_o[b, m].cpu().numpy() - ref_pos).max() <= 2e-6
+                    assert np.abs(nrm_o[b, m].cpu().numpy()
+                                  - t.calc_actual_normal(oracle_model, r.vertices[b]).numpy()).max() < 2e-5
 
 
 def test_triangle_vertex_weights_property():

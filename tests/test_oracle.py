@@ -181,3 +181,47 @@ def test_box_qp_kkt():
         at_lo = (np.abs(x - lo) <= 1e-12) & (lo != hi)
         at_hi = (np.abs(x - hi) <= 1e-12) & (lo != hi)
         assert (g[at_lo] >= -1e-8).all() and (g[at_hi] <= 1e-8).all()
+
+
+# ---- projection onto the mesh (node/node.cpp:970-1001; libigl is un-vendored: property checks pin the restatement) ----
+
+def test_oracle_mesh_projection_properties(params):
+    """The restated point-mesh projection: (1) a point lifted off a face along its normal by less than the local
+    feature size projects back to its foot with the barycentric weights it was built from; (2) no sampled point of
+    any face is closer than the reported minimum; (3) a point at a vertex returns that vertex, the lowest incident
+    face index, and weights that reproduce it."""
+    model = so.SmplModel.from_params(params)
+    faces0 = (model.face_indices.numpy() - 1)
+    verts = np.asarray(params.vertices_template, dtype=np.float64)
+    rng = np.random.default_rng(5)
+    fidx = rng.choice(len(faces0), size=24, replace=False)
+    bary = rng.dirichlet(np.ones(3) * 2.0, size=24)
+    tri = verts[faces0[fidx]]                                  # (24,3,3)
+    foot = (bary[:, :, None] * tri).sum(1)
+    nrm = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    pts = foot + 1e-4 * nrm                                    # 0.1 mm above the face
+    face, closest, sq, w = so.project_points_on_mesh(verts, faces0, pts)
+    # (2) brute-force sampling of EVERY face on a barycentric grid never beats the reported distance
+    g = np.array([[i, j, 8 - i - j] for i in range(9) for j in range(9 - i)], dtype=np.float64) / 8.0
+    samples = np.einsum("gk,fkd->fgd", g, verts[faces0])      # (F, 45, 3)
+    for i in range(len(pts)):
+        d2 = ((samples - pts[i]) ** 2).sum(-1).min()
+        assert sq[i] <= d2 + 1e-15
+        # the reported closest point lies on the reported face and reproduces the distance
+        t = verts[faces0[face[i]]]
+        assert np.abs((w[i][:, None] * t).sum(0) - closest[i]).max() < 1e-9
+        assert abs(((closest[i] - pts[i]) ** 2).sum() - sq[i]) < 1e-15
+    # (1) convex-ish neighbourhoods: whenever the own face is the answer the foot and the weights come back exactly
+    own = face == fidx
+    assert own.sum() >= 12
+    assert np.abs(closest[own] - foot[own]).max() < 1e-9
+    assert np.abs(w[own] - bary[own]).max() < 1e-6
+    assert np.all(sq <= 1e-8 + 1e-12)                          # never farther than the 0.1 mm lift
+    # (3) exactly at a vertex
+    vid = int(faces0[fidx[0], 1])
+    face_v, closest_v, sq_v, w_v = so.project_points_on_mesh(verts, faces0, verts[vid][None])
+    incident = np.nonzero((faces0 == vid).any(1))[0]
+    assert face_v[0] == incident.min() and sq_v[0] == 0.0
+    assert np.abs(closest_v[0] - verts[vid]).max() == 0.0
+    assert np.abs((w_v[0][:, None] * verts[faces0[face_v[0]]]).sum(0) - verts[vid]).max() < 1e-12
