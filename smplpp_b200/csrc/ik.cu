@@ -261,13 +261,13 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
   float * s_JS = s_M + 648;              // 24*30 (beta only)
   float * s_dTg = s_JS + (p.beta_cols ? 720 : 0);
   float * s_dTp = s_dTg + (p.beta_cols ? 720 : 0);
-  float * s_verts = s_dTp + (p.beta_cols ? 720 : 0);
+  float * s_C4 = s_dTp + (p.beta_cols ? 720 : 0);                // nPairs*12, 16-byte aligned (read as float4 in P5d)
+  float * s_verts = s_C4 + 12 * t.nPairs;
   float * s_rest = s_verts + 3 * p.nUse;
   float * s_itemN = s_rest + 3 * p.nUse;                   // nItems*4
   float * s_cornN = s_itemN + (p.use_ring ? 4 * t.nItems : 0); // 3n*4
   float * s_task = s_cornN + (p.use_ring ? 12 * n : 0);        // n*TS
-  float * s_C4 = s_task + TS * n;                              // nPairs*12
-  float * s_sw = s_C4 + 12 * t.nPairs;                         // nUse*kmax   normalised skinning weights w_j / sum w
+  float * s_sw = s_task + TS * n;                              // nUse*kmax   normalised skinning weights w_j / sum w
   float * s_xw = s_sw + p.nUse * t.kmax;                       // nUse*kmax*3 wn_j * x_uj (vertex carried by bone j)
   uint8_t * s_sj = reinterpret_cast<uint8_t *>(s_xw + 3 * p.nUse * t.kmax); // nUse*kmax joint ids
   __shared__ int s_valid, s_bad;
@@ -739,9 +739,44 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
         for(int r = 0; r < ROWS; r++) q4[r] = 0.f;
         const int p0 = t.pair_off[m];
         const int np = p.use_ring ? t.pair_off[m + 1] - p0 : 3;
+        // the rigid part of these entries was written by an earlier phase: fetch it now so that the global round trip
+        // overlaps the contraction (ncu: the dependent read-modify-write at the end of every task was 30 % of the samples)
+        float jprev[ROWS][3];
+        if(joint_lane && e == 0)
+        {
+#pragma unroll
+          for(int r = 0; r < ROWS; r++)
+#pragma unroll
+            for(int c = 0; c < 3; c++) jprev[r][c] = Jf[(4 * m + r) * p.ldfull + 3 + 3 * k + c];
+        }
         if(d >= 0)
         {
-          for(int q = 0; q < np; q++)
+          // basis rows come from L2 (~300 cycles): four pairs per trip keep 12 loads in flight instead of 3
+          // (ncu: this loop was 28 % of the samples, latency-bound with 4 warps per scheduler)
+          constexpr int UQ = 4;
+          int q = 0;
+          for(; q + UQ <= np; q += UQ)
+          {
+            float b0[UQ], b1[UQ], b2[UQ];
+#pragma unroll
+            for(int i = 0; i < UQ; i++)
+            {
+              const int u = t.pair_vert[p0 + q + i];
+              const float * bu = t.basis + static_cast<size_t>(3 * u) * kBlendK + d;
+              b0[i] = __ldg(bu), b1[i] = __ldg(bu + kBlendK), b2[i] = __ldg(bu + 2 * kBlendK);
+            }
+#pragma unroll
+            for(int i = 0; i < UQ; i++)
+            {
+              // the 12 floats of a pair are warp-uniform: three 16-byte broadcast loads instead of nine / twelve scalar ones
+              const float4 * C4 = reinterpret_cast<const float4 *>(s_C4 + 12 * (p0 + q + i));
+              const float4 c0 = C4[0], c1 = C4[1], c2 = C4[2];
+              const float C[12] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w};
+#pragma unroll
+              for(int r = 0; r < ROWS; r++) q4[r] = fmaf(C[3 * r], b0[i], fmaf(C[3 * r + 1], b1[i], fmaf(C[3 * r + 2], b2[i], q4[r])));
+            }
+          }
+          for(; q < np; q++)
           {
             const int u = t.pair_vert[p0 + q];
             const float * bu = t.basis + static_cast<size_t>(3 * u) * kBlendK + d;
@@ -771,7 +806,7 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
 #pragma unroll
           for(int r = 0; r < ROWS; r++)
 #pragma unroll
-            for(int c = 0; c < 3; c++) Jf[(4 * m + r) * p.ldfull + 3 + 3 * k + c] += val[r][c];
+            for(int c = 0; c < 3; c++) Jf[(4 * m + r) * p.ldfull + 3 + 3 * k + c] = jprev[r][c] + val[r][c];
         }
         if(ib >= 0)
         {
