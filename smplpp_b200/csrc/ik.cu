@@ -892,8 +892,13 @@ __device__ __forceinline__ int tri_idx(int i, int j) // i >= j
 // Right-looking Cholesky of the leading `npiv` pivots of the packed lower-triangular (N x N) matrix in shared
 // memory.  Returns false (in *ok) on a non-positive pivot (Eigen::LLT NumericalIssue, node.cpp:934-937).
 // With npiv < N the trailing block is left holding the Schur complement.
-__device__ void block_cholesky(double * L, int N, int npiv, int tid, int nthreads, int * ok)
+// `col` (N doubles of shared memory) receives the scaled pivot column, so the trailing update reads it with unit
+// stride; rows of the trailing triangle go to warps round-robin, lanes along the row.  (The first version mapped a
+// flat element index to (row, column) with a double-precision sqrt per element and pivot: 65 % of the kernel's
+// instructions, ncu source page of r01e.)
+__device__ void block_cholesky(double * L, double * col, int N, int npiv, int tid, int nthreads, int * ok)
 {
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
   for(int j = 0; j < npiv; j++)
   {
     __syncthreads();
@@ -906,20 +911,19 @@ __device__ void block_cholesky(double * L, int N, int npiv, int tid, int nthread
     }
     const double inv = 1.0 / sqrt(d);
     __syncthreads();
-    for(int i = j + tid; i < N; i += nthreads) L[tri_idx(i, j)] = i == j ? sqrt(d) : L[tri_idx(i, j)] * inv;
+    for(int i = j + tid; i < N; i += nthreads)
+    {
+      const double v = i == j ? sqrt(d) : L[tri_idx(i, j)] * inv;
+      L[tri_idx(i, j)] = v;
+      col[i] = v;
+    }
     __syncthreads();
     // trailing update: L[i][k] -= L[i][j] L[k][j] for j < k <= i
-    const int rem = N - j - 1;
-    const int total = rem * (rem + 1) / 2;
-    for(int e = tid; e < total; e += nthreads)
+    for(int i = j + 1 + warp; i < N; i += nwarps)
     {
-      // e -> (ii, kk) with ii >= kk in the (rem x rem) lower triangle
-      int ii = static_cast<int>((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-      while((ii + 1) * (ii + 2) / 2 <= e) ii++;
-      while(ii * (ii + 1) / 2 > e) ii--;
-      const int kk = e - ii * (ii + 1) / 2;
-      const int i = j + 1 + ii, k = j + 1 + kk;
-      L[tri_idx(i, k)] -= L[tri_idx(i, j)] * L[tri_idx(k, j)];
+      const double lij = col[i];
+      double * row = L + tri_idx(i, 0);
+      for(int k = j + 1 + lane; k <= i; k += 32) row[k] -= lij * col[k];
     }
   }
   __syncthreads();
@@ -949,7 +953,7 @@ __device__ void warp_chol_solve(const double * L, int n, double * x, int tid)
   }
 }
 
-__global__ void __launch_bounds__(c2::THREADS) ik_solve_kernel(const IkSolveParams p)
+__global__ void __launch_bounds__(c2::THREADS, 4) ik_solve_kernel(const IkSolveParams p)
 {
   using namespace c2;
   extern __shared__ __align__(16) double smd[];
@@ -962,7 +966,8 @@ __global__ void __launch_bounds__(c2::THREADS) ik_solve_kernel(const IkSolvePara
   double * x = bvec + D;       // D
   double * g = x + D;          // D
   double * dstep = g + D;      // D
-  int * state = reinterpret_cast<int *>(dstep + D); // D: 0 free, -1 at lower, +1 at upper, 2 pinned
+  double * colbuf = dstep + D; // D + 2: pivot column of block_cholesky
+  int * state = reinterpret_cast<int *>(colbuf + D + 2); // D: 0 free, -1 at lower, +1 at upper, 2 pinned
   __shared__ double s_esq;
   __shared__ int s_ok, s_flag, s_iter;
   __shared__ double s_red[THREADS / 32];
@@ -1002,17 +1007,29 @@ __global__ void __launch_bounds__(c2::THREADS) ik_solve_kernel(const IkSolvePara
     for(int a = 0; a < 4; a++)
 #pragma unroll
       for(int b = 0; b < 4; b++) acc[a][b] = 0.0;
-    for(int r = 0; r < rows; r++)
+    // one task (4 rows, rows_per_task of them live) per trip: its 6-8 row loads are issued together (the row-by-row
+    // loop with a `continue` kept two L2 loads in flight and was 17 % of the samples)
+    for(int m = 0; m < p.n; m++)
     {
-      if((r & 3) >= p.rows_per_task) continue;
-      const float4 ja = *reinterpret_cast<const float4 *>(J + static_cast<size_t>(r) * p.ld + 4 * bi);
-      const float4 jb = *reinterpret_cast<const float4 *>(J + static_cast<size_t>(r) * p.ld + 4 * bj);
-      const double a4[4] = {ja.x, ja.y, ja.z, ja.w};
-      const double b4[4] = {jb.x, jb.y, jb.z, jb.w};
+      float4 ja[4], jb[4];
 #pragma unroll
-      for(int a = 0; a < 4; a++)
+      for(int q = 0; q < 4; q++)
+        if(q < p.rows_per_task)
+        {
+          ja[q] = *reinterpret_cast<const float4 *>(J + static_cast<size_t>(4 * m + q) * p.ld + 4 * bi);
+          jb[q] = *reinterpret_cast<const float4 *>(J + static_cast<size_t>(4 * m + q) * p.ld + 4 * bj);
+        }
 #pragma unroll
-        for(int b = 0; b < 4; b++) acc[a][b] = fma(a4[a], b4[b], acc[a][b]);
+      for(int q = 0; q < 4; q++)
+        if(q < p.rows_per_task)
+        {
+          const double a4[4] = {ja[q].x, ja[q].y, ja[q].z, ja[q].w};
+          const double b4[4] = {jb[q].x, jb[q].y, jb[q].z, jb[q].w};
+#pragma unroll
+          for(int a = 0; a < 4; a++)
+#pragma unroll
+            for(int b = 0; b < 4; b++) acc[a][b] = fma(a4[a], b4[b], acc[a][b]);
+        }
     }
 #pragma unroll
     for(int a = 0; a < 4; a++)
@@ -1092,7 +1109,7 @@ __global__ void __launch_bounds__(c2::THREADS) ik_solve_kernel(const IkSolvePara
     // bvec already sits at L + NT .. L + NT + D - 1 = packed row D, columns 0..D-1; set the corner
     if(tid == 0) aug[D] = 0.0;
     __syncthreads();
-    block_cholesky(L, D + 1, npiv, tid, THREADS, &s_ok);
+    block_cholesky(L, colbuf, D + 1, npiv, tid, THREADS, &s_ok);
     double * out = p.schur_out + static_cast<size_t>(f) * 111;
     const bool good = s_ok && !bad && !too_few;
     for(int i = tid; i < 111; i += THREADS)
@@ -1134,7 +1151,7 @@ __global__ void __launch_bounds__(c2::THREADS) ik_solve_kernel(const IkSolvePara
   if(!qp)
   {
     // plain LLT: delta = -A^-1 b
-    block_cholesky(L, D, D, tid, THREADS, &s_ok);
+    block_cholesky(L, colbuf, D, D, tid, THREADS, &s_ok);
     for(int i = tid; i < D; i += THREADS) x[i] = -bvec[i];
     __syncthreads();
     if(s_ok) warp_chol_solve(L, D, x, tid);
@@ -1179,7 +1196,7 @@ __global__ void __launch_bounds__(c2::THREADS) ik_solve_kernel(const IkSolvePara
         L[i] = fixed ? (r == c ? 1.0 : 0.0) : A0[i];
       }
       __syncthreads();
-      block_cholesky(L, D, D, tid, THREADS, &s_ok);
+      block_cholesky(L, colbuf, D, D, tid, THREADS, &s_ok);
       if(!s_ok)
       {
         status = 2;
@@ -1783,7 +1800,7 @@ size_t jac_smem_bytes(const TasksDev & t, const IkLayout & L)
 size_t solve_smem_bytes(const IkLayout & L, bool schur)
 {
   const size_t D = L.D;
-  size_t dbl = D * (D + 1) / 2 + 4 * D + 2 + (schur ? D + 2 : 0);
+  size_t dbl = D * (D + 1) / 2 + 5 * D + 4 + (schur ? D + 2 : 0);
   return dbl * sizeof(double) + D * sizeof(int) + 64;
 }
 
