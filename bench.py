@@ -235,13 +235,17 @@ def main():
     barrier()
     launches0 = lib.smplpp_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
-        barrier()
-        ev0.record(stream)
-        for _ in range(args.steps):
-            step()
-        ev1.record(stream)
-        barrier()
+    # nvidia-smi is sampled every 100 ms from here to the end of the last measurement leg; the headline region is a
+    # few milliseconds long, so the samples taken during the kernel-timing, e2e and IK legs (same process, same clocks,
+    # seconds of load) are what the median is made of
+    clocks = ClockSampler(local)
+    clocks.__enter__()
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     launches = int(lib.smplpp_launch_count() - launches0)
     ms_step = ms_total / args.steps
@@ -349,6 +353,7 @@ def main():
         except ImportError:
             ik = None
 
+    clocks.__exit__(None, None, None)
     line = {
         "metric": "SMPL FK+LBS meshes/s", "value": value, "unit": "meshes/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",

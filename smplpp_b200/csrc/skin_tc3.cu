@@ -20,9 +20,7 @@
 //     warp owns are 24 adjacent accumulator columns (6 tcgen05.ld per drain instead of 36).
 //   * every operand tile is stored in global memory as the exact (SWIZZLE_64B) shared-memory image of its pipeline
 //     stage, so a stage is two contiguous cp.async.bulk copies (48 KB basis + 12 KB coefficients) and a transform
-//     sub-batch is one (12 KB).  Tiled TMA loads with a 64-byte inner box (K2'') delivered ~21 B/cycle per SM - one L2
-//     request per 64-byte row - and bounded that kernel and the first version of this one (20.5 k cycles per item,
-//     whatever the number of CTAs).
+//     sub-batch is one (12 KB): no tensor maps, a handful of large copies per item (DESIGN.md 4.1 has the measurements).
 // Precision is that of K2'': fp16 hi + lo split of every operand, hi.hi + lo.hi + hi.lo in fp32 TMEM.
 //
 // TMEM (512 columns): [0,288) rest accumulators (x | y | z planes x 96 frames), [288,480) two 96-column buffers of
@@ -268,9 +266,9 @@ __global__ void __launch_bounds__(tc3::THREADS, 1)
   if(warp == 0)
   {
     // ---- producer of the GEMM 1 stage ring ----
-    // (Measured, scripts/ubench/ubench_tma.cu: the [expect_tx, copy] groups issued by ONE thread retire one at a time,
-    // ~410 cycles apart from L2 whatever their size, so groups are as large as a stage and the two rings have a
-    // producer thread each: a single thread feeding both rings left the kernel at 17.5 k cycles per item.)
+    // (Measured, scripts/ubench/ubench_tma.cu: [expect_tx, copy] groups issued back to back by ONE thread onto different
+    // barriers retire ~410 cycles apart whatever their size, so a group is as large as a stage, and each ring has its own
+    // producer thread with plain blocking waits.  A single polling producer over both rings performed the same.)
     if(ptx::elect_one())
     {
       const int total_kb = nit * NKB;

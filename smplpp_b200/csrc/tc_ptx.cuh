@@ -95,8 +95,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t * bar, uint32_t parity)
       : "memory");
   return ok != 0;
 }
-// non-blocking test (try_wait may suspend the thread for a system-dependent time when the phase is not complete -
-// thousands of cycles when measured on B200 - so a thread that polls several barriers must use this one)
+// non-blocking test (try_wait may suspend the thread for a system-dependent time when the phase is not complete, so a
+// thread that polls several barriers uses this one)
 __device__ __forceinline__ bool mbar_test_wait(uint64_t * bar, uint32_t parity)
 {
   uint32_t ok;

@@ -98,6 +98,20 @@ def run(dev, rank, world, max_over_ranks, barrier, frames: int = 16384, iters: i
     ms = time_steps(step_shared, max(3, iters // 2), 2, barrier, max_over_ranks, dev)
     out["shared_beta"] = {"value": world * frames / (ms * 1e-3), "ms_per_iter": ms,
                           "collective": "all_reduce(sum) of 111 float64 per iteration" if world > 1 else "none (1 GPU)"}
+    # (4) projection of the task points onto the posed mesh + re-seated face / weights (node.cpp:970-1001):
+    # full forward pass of a block of frames, then smplpp_closest_points (41 points x 13776 faces per frame)
+    rb = min(frames, 4096)
+    smpl.launch(prob["beta"].cpu().numpy(), prob["gt"][:rb])
+    verts = smpl._vertices
+    pts = tasks.positions(verts, prob["w0"][:rb], 0.015)
+
+    def reproject():
+        smpl.projectPoints(pts, verts, want_weights=True)
+
+    ms = time_steps(reproject, 5, 2, barrier, max_over_ranks, dev)
+    out["reproject"] = {"value": world * rb / (ms * 1e-3), "unit": "frames/s", "ms_per_call": ms, "frames": rb,
+                        "points_per_frame": tasks.n, "faces": int(params.face_indices.shape[0]),
+                        "vertex_bytes_read_gbs": rb * 82680 / (ms * 1e-3) / 1e9}
     out["value"] = out["mosh_direct"]["value"]
     return out
 
