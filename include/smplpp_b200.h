@@ -30,6 +30,7 @@ extern "C" {
 #define SMPLPP_ERR_INVALID (-1) /* bad argument / shape (the reference throws smpl_error) */
 #define SMPLPP_ERR_CUDA (-2)    /* CUDA runtime failure, or no device */
 #define SMPLPP_ERR_ALLOC (-3)
+#define SMPLPP_ERR_IO (-4)      /* missing / malformed parameter or mocap file */
 
 /* shape constants of include/smplpp/definition/def.h:8-14 */
 #define SMPLPP_VERTEX_NUM 6890
@@ -44,6 +45,8 @@ extern "C" {
 typedef struct smplpp_model smplpp_model_t;
 typedef struct smplpp_vposer smplpp_vposer_t;
 typedef struct smplpp_tasks smplpp_tasks_t;
+typedef struct smplpp_json smplpp_json_t;
+typedef struct smplpp_c3d smplpp_c3d_t;
 
 const char * smplpp_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches evidence) */
@@ -288,6 +291,36 @@ int smplpp_ik_shared_beta_apply(const smplpp_tasks_t * tasks, const smplpp_ik_op
                                 int64_t batch, float * theta_state_dev, float * shared_beta_dev,
                                 const int32_t * status_dev, const double * reduced_dev, void * workspace_dev,
                                 size_t workspace_bytes);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Data formats on either side of the path (host only)
+ * ------------------------------------------------------------------------------------------------------- */
+/* A parameter file = one JSON object of nested numeric arrays (what nlohmann::json + xt::from_json read in
+ * src/SMPL.cpp:566-611 and src/VPoser.cpp:173-237).  shape8 receives up to 8 extents, data points into the handle. */
+int smplpp_json_open(const char * path, smplpp_json_t ** out);
+void smplpp_json_close(smplpp_json_t * json);
+int smplpp_json_array(const smplpp_json_t * json, const char * key, int32_t * ndim, int64_t * shape8,
+                      const double ** data);
+/* SMPL::setModelPath + SMPL::init (src/SMPL.cpp:560-643): keys face_indices, shape_blend_shapes, pose_blend_shapes,
+ * vertices_template, joint_regressor, kinematic_tree, weights; the reference's messages ("Cannot initialize a SMPL
+ * model!", "Shape parameter dimensions are invalid: 9 != 10", ...) come back through smplpp_last_error(). */
+int smplpp_model_load_json(const char * path, smplpp_model_t ** out);
+/* VPoserDecoderImpl::loadParamsFromJson (src/VPoser.cpp:169-238): keys decoder_net.{0,3,5}.{weight,bias} */
+int smplpp_vposer_load_json(const char * path, smplpp_vposer_t ** out);
+
+/* C3D motion capture file as the node reads it through ezc3d (node/node.cpp:572-595, 667-691) */
+int smplpp_c3d_open(const char * path, smplpp_c3d_t ** out);
+void smplpp_c3d_close(smplpp_c3d_t * c3d);
+int64_t smplpp_c3d_frame_count(const smplpp_c3d_t * c3d);   /* header().nbFrames() */
+int64_t smplpp_c3d_point_count(const smplpp_c3d_t * c3d);   /* POINT:USED */
+double smplpp_c3d_frame_rate(const smplpp_c3d_t * c3d);     /* header().frameRate() */
+const char * smplpp_c3d_label(const smplpp_c3d_t * c3d, int64_t point); /* POINT:LABELS[point] */
+const char * smplpp_c3d_units(const smplpp_c3d_t * c3d);    /* POINT:UNITS */
+/* index of the first label that ends with `name` (node.cpp:580-594); the point count when there is none */
+int64_t smplpp_c3d_find_label(const smplpp_c3d_t * c3d, const char * name);
+/* frames [first, first + count) -> xyz_host (count, points, 3), valid_host (count, points): 0 = point.isEmpty(),
+ * whose coordinates are returned as 0 (node.cpp:682-683 zeroes the target of a missing marker) */
+int smplpp_c3d_read(const smplpp_c3d_t * c3d, int64_t first, int64_t count, float * xyz_host, uint8_t * valid_host);
 
 #ifdef __cplusplus
 }

@@ -83,7 +83,38 @@ public:
     if(m__model) smplpp_model_destroy(m__model);
   }
 
-  /// SMPL::init (SMPL.cpp:560-643) from already-parsed arrays (JSON / npz parsing is the caller's).
+  /// SMPL::setModelPath (SMPL.cpp:325-339) + SMPL::init() (SMPL.cpp:560-643): the model JSON is read by the library
+  /// (smplpp_model_load_json); the messages are the reference's.
+  void setModelPath(const std::string & modelPath)
+  {
+    if(FILE * f = fopen(modelPath.c_str(), "rb"))
+      fclose(f);
+    else
+      throw Exception("SMPL Error: Failed to initialize model path!"); // SMPL.cpp:337
+    m__modelPath = modelPath;
+  }
+  void init()
+  {
+    if(m__model) smplpp_model_destroy(m__model);
+    m__model = nullptr;
+    check(smplpp_model_load_json(m__modelPath.c_str(), &m__model));
+    m__vertexNum = smplpp_model_vertex_num(m__model);
+    smplpp_json_t * j = nullptr;
+    check(smplpp_json_open(m__modelPath.c_str(), &j));
+    int32_t ndim = 0;
+    int64_t shape[8];
+    const double * data = nullptr;
+    const int rc = smplpp_json_array(j, "face_indices", &ndim, shape, &data);
+    if(rc == SMPLPP_OK && ndim == 2)
+    {
+      m__faceIndices.resize(static_cast<size_t>(shape[0] * shape[1]));
+      for(size_t i = 0; i < m__faceIndices.size(); i++) m__faceIndices[i] = static_cast<int32_t>(data[i]);
+    }
+    smplpp_json_close(j);
+    check(rc);
+  }
+
+  /// SMPL::init from already-parsed arrays
   void init(const ModelParams & p)
   {
     const size_t V = static_cast<size_t>(p.vertex_num);
@@ -146,6 +177,7 @@ public:
 
 private:
   smplpp_model_t * m__model = nullptr;
+  std::string m__modelPath;
   std::vector<int32_t> m__faceIndices;
   int64_t m__vertexNum = 0;
   Array m__vertices, m__joints;
@@ -165,6 +197,14 @@ public:
     smplpp_vposer_desc d{w0.data(), b0.data(), w3.data(), b3.data(), w5.data(), b5.data()};
     check(smplpp_vposer_create(&d, &vposer_));
   }
+  /// VPoserDecoderImpl::loadParamsFromJson (VPoser.cpp:169-238)
+  VPoserDecoder() = default;
+  void loadParamsFromJson(const std::string & jsonPath)
+  {
+    if(vposer_) smplpp_vposer_destroy(vposer_);
+    vposer_ = nullptr;
+    check(smplpp_vposer_load_json(jsonPath.c_str(), &vposer_));
+  }
   VPoserDecoder(const VPoserDecoder &) = delete;
   VPoserDecoder & operator=(const VPoserDecoder &) = delete;
   ~VPoserDecoder()
@@ -175,6 +215,35 @@ public:
 
 private:
   smplpp_vposer_t * vposer_ = nullptr;
+};
+
+/// The C3D file of the mocap modes as node/node.cpp:572-595, 667-691 uses it (there: ezc3d::c3d).
+class C3d
+{
+public:
+  explicit C3d(const std::string & path) { check(smplpp_c3d_open(path.c_str(), &c3d_)); }
+  C3d(const C3d &) = delete;
+  C3d & operator=(const C3d &) = delete;
+  ~C3d()
+  {
+    if(c3d_) smplpp_c3d_close(c3d_);
+  }
+  int64_t nbFrames() const { return smplpp_c3d_frame_count(c3d_); }
+  int64_t nbPoints() const { return smplpp_c3d_point_count(c3d_); }
+  double frameRate() const { return smplpp_c3d_frame_rate(c3d_); }
+  std::string label(int64_t i) const { return smplpp_c3d_label(c3d_, i); }
+  /// first label ending with the task name (node.cpp:580-594); nbPoints() when there is none
+  int64_t findLabel(const std::string & taskName) const { return smplpp_c3d_find_label(c3d_, taskName.c_str()); }
+  /// frames [first, first + count): xyz (count, points, 3), valid (count, points); a missing point is zero / 0
+  void read(int64_t first, int64_t count, std::vector<float> & xyz, std::vector<uint8_t> & valid) const
+  {
+    xyz.resize(static_cast<size_t>(count * nbPoints() * 3));
+    valid.resize(static_cast<size_t>(count * nbPoints()));
+    check(smplpp_c3d_read(c3d_, first, count, xyz.data(), valid.data()));
+  }
+
+private:
+  smplpp_c3d_t * c3d_ = nullptr;
 };
 
 /// n smplpp::IkTask objects (IkTask.h:13-85) handled as one batch: the attachment faces are fixed here, the per-frame

@@ -142,10 +142,30 @@ class SMPL:
         self._face_dev = None
         self._adjacent = None
 
+    @classmethod
+    def from_json_native(cls, path: str, device="cuda:0") -> "SMPL":
+        """setModelPath + init through the C-ABI loader smplpp_model_load_json (the C++ twin of load_model_file):
+        what the header-only facade's SMPL::init() calls."""
+        self = cls(None, device)
+        _require_cuda(self.m__device)
+        self.m__modelPath = path
+        h = C.c_void_p()
+        with torch.cuda.device(self.m__device):
+            check(lib().smplpp_model_load_json(path.encode(), C.byref(h)))
+        self._h = h
+        self.vertex_num = int(lib().smplpp_model_vertex_num(h))
+        self._faces_host = np.ascontiguousarray(read_json_arrays(path, ["face_indices"])["face_indices"], dtype=np.int32)
+        self._face_dev = None
+        self._adjacent = None
+        return self
+
     def __del__(self):
-        if getattr(self, "_h", None) is not None and capi._lib is not None:
-            capi._lib.smplpp_model_destroy(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None) is not None and capi is not None and capi._lib is not None:
+                capi._lib.smplpp_model_destroy(self._h)
+                self._h = None
+        except Exception:  # interpreter shutdown: module globals may already be gone
+            pass
 
     @property
     def handle(self):
@@ -330,6 +350,72 @@ def load_model_file(path: str):
         joint_regressor=np.asarray(get("joint_regressor"), dtype=np.float32),
         kinematic_tree=np.asarray(get("kinematic_tree"), dtype=np.int64),
         weights=np.asarray(get("weights"), dtype=np.float32))
+
+
+def read_json_arrays(path: str, keys):
+    """Numeric arrays of a parameter file through the C-ABI reader (smplpp_json_*): {key: float64 ndarray}."""
+    h = C.c_void_p()
+    check(lib().smplpp_json_open(path.encode(), C.byref(h)))
+    try:
+        out = {}
+        for k in keys:
+            ndim, shape, data = C.c_int32(), (C.c_int64 * 8)(), C.POINTER(C.c_double)()
+            check(lib().smplpp_json_array(h, k.encode(), C.byref(ndim), shape, C.byref(data)))
+            shp = tuple(int(shape[i]) for i in range(ndim.value))
+            n = int(np.prod(shp)) if shp else 1
+            out[k] = (np.ctypeslib.as_array(data, shape=(n,)).copy() if n else np.zeros(0)).reshape(shp)
+        return out
+    finally:
+        lib().smplpp_json_close(h)
+
+
+class C3D:
+    """A C3D motion-capture file as node/node.cpp:572-595, 667-691 reads it through ezc3d: labels, frame rate, frame
+    count and, per frame and point, x / y / z / isEmpty (C-ABI reader smplpp_c3d_*, host only)."""
+
+    def __init__(self, path: str):
+        self._h = C.c_void_p()
+        self._lib = lib()
+        check(self._lib.smplpp_c3d_open(path.encode(), C.byref(self._h)))
+        self.frames = int(self._lib.smplpp_c3d_frame_count(self._h))
+        self.points = int(self._lib.smplpp_c3d_point_count(self._h))
+        self.frame_rate = float(self._lib.smplpp_c3d_frame_rate(self._h))
+        self.units = self._lib.smplpp_c3d_units(self._h).decode()
+        self.labels = [self._lib.smplpp_c3d_label(self._h, C.c_int64(i)).decode() for i in range(self.points)]
+
+    def find_label(self, name: str) -> int:
+        """Index of the first label ending with `name` (node.cpp:580-594); `points` when there is none."""
+        return int(self._lib.smplpp_c3d_find_label(self._h, name.encode()))
+
+    def read(self, first: int = 0, count: Optional[int] = None):
+        """(xyz (count, points, 3) float32, valid (count, points) bool); missing points are returned as zeros."""
+        count = self.frames - first if count is None else count
+        xyz = np.empty((count, self.points, 3), np.float32)
+        valid = np.empty((count, self.points), np.uint8)
+        check(self._lib.smplpp_c3d_read(self._h, C.c_int64(first), C.c_int64(count), xyz.ctypes.data_as(C.c_void_p),
+                                        valid.ctypes.data_as(C.c_void_p)))
+        return xyz, valid.astype(bool)
+
+    def marker_targets(self, task_names, first: int = 0, count: Optional[int] = None):
+        """Targets of the IK tasks for a block of frames: (target_pos (count, n, 3), pos_task_weight (count, n)) with
+        weight 0 and a zero target for a missing marker (node.cpp:667-691)."""
+        idx = [self.find_label(n) for n in task_names]
+        missing = [n for n, i in zip(task_names, idx) if i >= self.points]
+        if missing:
+            raise SmplppError("node Error: mocap markers not found in the C3D file: %s" % ", ".join(missing))
+        xyz, valid = self.read(first, count)
+        return np.ascontiguousarray(xyz[:, idx]), np.ascontiguousarray(valid[:, idx].astype(np.float32))
+
+    def close(self):
+        if self._h:
+            self._lib.smplpp_c3d_close(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -519,6 +605,14 @@ class VPoserDecoder:
             j = json.load(f)
         self.loadParams({k: np.asarray(j[k], dtype=np.float32) for k in _VPOSER_KEYS})
 
+    def loadParamsFromJsonNative(self, jsonPath: str):
+        """The same through the C-ABI loader smplpp_vposer_load_json (what the C++ facade calls)."""
+        _require_cuda(self.m__device)
+        h = C.c_void_p()
+        with torch.cuda.device(self.m__device):
+            check(lib().smplpp_vposer_load_json(jsonPath.encode(), C.byref(h)))
+        self._h = h
+
     def loadParams(self, params: dict):
         _require_cuda(self.m__device)
         arrs = []
@@ -534,9 +628,12 @@ class VPoserDecoder:
         self._h = h
 
     def __del__(self):
-        if getattr(self, "_h", None) is not None and capi._lib is not None:
-            capi._lib.smplpp_vposer_destroy(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None) is not None and capi is not None and capi._lib is not None:
+                capi._lib.smplpp_vposer_destroy(self._h)
+                self._h = None
+        except Exception:  # interpreter shutdown
+            pass
 
     @property
     def handle(self):

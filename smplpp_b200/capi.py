@@ -50,6 +50,9 @@ EXPORTS = [
     "smplpp_triangle_vertex_weights", "smplpp_ik_options_default", "smplpp_ik_theta_dim", "smplpp_ik_dim",
     "smplpp_task_positions", "smplpp_closest_points", "smplpp_ik_workspace_bytes", "smplpp_ik_step",
     "smplpp_ik_shared_beta_workspace_bytes", "smplpp_ik_shared_beta_reduce", "smplpp_ik_shared_beta_apply",
+    "smplpp_json_open", "smplpp_json_close", "smplpp_json_array", "smplpp_model_load_json", "smplpp_vposer_load_json",
+    "smplpp_c3d_open", "smplpp_c3d_close", "smplpp_c3d_frame_count", "smplpp_c3d_point_count", "smplpp_c3d_frame_rate",
+    "smplpp_c3d_label", "smplpp_c3d_units", "smplpp_c3d_find_label", "smplpp_c3d_read",
 ]
 
 _lib = None
@@ -70,6 +73,11 @@ def lib() -> C.CDLL:
         _lib.smplpp_last_error.restype = C.c_char_p
         _lib.smplpp_launch_count.restype = C.c_uint64
         _lib.smplpp_model_vertex_num.restype = C.c_int64
+        for name in ("smplpp_c3d_frame_count", "smplpp_c3d_point_count", "smplpp_c3d_find_label"):
+            getattr(_lib, name).restype = C.c_int64
+        _lib.smplpp_c3d_frame_rate.restype = C.c_double
+        _lib.smplpp_c3d_label.restype = C.c_char_p
+        _lib.smplpp_c3d_units.restype = C.c_char_p
         for name in ("smplpp_forward_workspace_bytes", "smplpp_ik_workspace_bytes",
                      "smplpp_ik_shared_beta_workspace_bytes"):
             if hasattr(_lib, name):

@@ -1,0 +1,588 @@
+// Host-side data formats on either side of the hot path; no CUDA in this file except the
+// model / decoder creation calls the loaders end with.
+//
+//   * JSON parameter files: the SMPL model (keys of src/SMPL.cpp:572-612, written by scripts/preprocess.py:109-117) and
+//     the VPoser decoder (keys of src/VPoser.cpp:185-237).  The reference parses them with nlohmann::json +
+//     xt::from_json (both un-vendored); a parameter file is one flat object of nested numeric arrays, so a 100-line
+//     recursive-descent reader that keeps only numbers and shapes replaces both.
+//   * C3D motion capture files: what the node reads through ezc3d (un-vendored; node/node.cpp:572-595, 667-691):
+//     POINT:LABELS (suffix match against the task names), header().frameRate() / nbFrames(), and per frame and point
+//     x, y, z, isEmpty().  Layout per the public C3D specification (c3d.org): 512-byte header block, parameter section,
+//     frame-major point data as 4 x float32 (scale < 0) or 4 x int16 (scaled by POINT:SCALE), Intel byte order.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace sb;
+
+// ------------------------------------------------------------------------------------------------------------
+// JSON: one object of (nested) numeric arrays
+// ------------------------------------------------------------------------------------------------------------
+struct smplpp_json
+{
+  struct Array
+  {
+    std::vector<int64_t> shape;
+    std::vector<double> data;
+    bool ragged = false;
+  };
+  std::map<std::string, Array> arrays;
+};
+
+namespace
+{
+struct JsonReader
+{
+  const char * p;
+  const char * end;
+  std::string err;
+
+  void ws()
+  {
+    while(p < end && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) p++;
+  }
+  bool fail_at(const char * what)
+  {
+    if(err.empty()) err = what;
+    return false;
+  }
+  bool string(std::string & out)
+  {
+    if(p >= end || *p != '"') return fail_at("expected a string");
+    p++;
+    out.clear();
+    while(p < end && *p != '"')
+    {
+      if(*p == '\\' && p + 1 < end) p++;
+      out.push_back(*p++);
+    }
+    if(p >= end) return fail_at("unterminated string");
+    p++;
+    return true;
+  }
+  // numeric array of any depth -> shape + flat row-major data; depth = nesting level of this '['
+  bool array(smplpp_json::Array & a, size_t depth)
+  {
+    p++; // '['
+    int64_t count = 0;
+    ws();
+    if(p < end && *p == ']')
+    {
+      p++;
+    }
+    else
+    {
+      for(;;)
+      {
+        ws();
+        if(p >= end) return fail_at("unterminated array");
+        if(*p == '[')
+        {
+          if(!array(a, depth + 1)) return false;
+        }
+        else
+        {
+          char * stop = nullptr;
+          const double v = strtod(p, &stop);
+          if(stop == p) return fail_at("expected a number");
+          p = stop;
+          a.data.push_back(v);
+          if(a.shape.size() < depth + 1) a.shape.resize(depth + 1, -1);
+        }
+        count++;
+        ws();
+        if(p < end && *p == ',')
+        {
+          p++;
+          continue;
+        }
+        if(p < end && *p == ']')
+        {
+          p++;
+          break;
+        }
+        return fail_at("expected ',' or ']'");
+      }
+    }
+    if(a.shape.size() < depth + 1) a.shape.resize(depth + 1, -1);
+    if(a.shape[depth] == -1)
+      a.shape[depth] = count;
+    else if(a.shape[depth] != count)
+      a.ragged = true;
+    return true;
+  }
+  // any value we do not keep (strings, literals, nested objects)
+  bool skip_value()
+  {
+    ws();
+    if(p >= end) return fail_at("unexpected end");
+    if(*p == '"')
+    {
+      std::string s;
+      return string(s);
+    }
+    if(*p == '{')
+    {
+      p++;
+      ws();
+      if(p < end && *p == '}')
+      {
+        p++;
+        return true;
+      }
+      for(;;)
+      {
+        ws();
+        std::string k;
+        if(!string(k)) return false;
+        ws();
+        if(p >= end || *p != ':') return fail_at("expected ':'");
+        p++;
+        if(!skip_value()) return false;
+        ws();
+        if(p < end && *p == ',')
+        {
+          p++;
+          continue;
+        }
+        if(p < end && *p == '}')
+        {
+          p++;
+          return true;
+        }
+        return fail_at("expected ',' or '}'");
+      }
+    }
+    if(*p == '[')
+    {
+      smplpp_json::Array tmp;
+      return array(tmp, 0);
+    }
+    while(p < end && *p != ',' && *p != '}' && *p != ']') p++; // number / true / false / null
+    return true;
+  }
+  bool object(smplpp_json & out)
+  {
+    ws();
+    if(p >= end || *p != '{') return fail_at("a parameter file is one JSON object");
+    p++;
+    ws();
+    if(p < end && *p == '}') return true;
+    for(;;)
+    {
+      ws();
+      std::string key;
+      if(!string(key)) return false;
+      ws();
+      if(p >= end || *p != ':') return fail_at("expected ':'");
+      p++;
+      ws();
+      if(p < end && *p == '[')
+      {
+        smplpp_json::Array a;
+        if(!array(a, 0)) return false;
+        out.arrays[key] = std::move(a);
+      }
+      else if(p < end && (*p == '-' || (*p >= '0' && *p <= '9')))
+      {
+        char * stop = nullptr;
+        smplpp_json::Array a;
+        a.data.push_back(strtod(p, &stop)); // scalar: shape ()
+        p = stop;
+        out.arrays[key] = std::move(a);
+      }
+      else if(!skip_value())
+        return false;
+      ws();
+      if(p < end && *p == ',')
+      {
+        p++;
+        continue;
+      }
+      if(p < end && *p == '}') return true;
+      return fail_at("expected ',' or '}'");
+    }
+  }
+};
+
+bool read_file(const char * path, std::string & out)
+{
+  std::ifstream f(path, std::ios::binary);
+  if(!f) return false;
+  std::ostringstream ss;
+  ss << f.rdbuf();
+  out = ss.str();
+  return true;
+}
+
+int load_json(const char * path, const char * module, const char * missing_msg, std::unique_ptr<smplpp_json> & out)
+{
+  std::string text;
+  if(!path || !read_file(path, text)) return fail(SMPLPP_ERR_IO, module, missing_msg);
+  out.reset(new smplpp_json());
+  JsonReader r{text.data(), text.data() + text.size(), {}};
+  if(!r.object(*out)) return fail(SMPLPP_ERR_IO, module, std::string("Cannot parse the JSON file: ") + r.err);
+  return SMPLPP_OK;
+}
+
+template<typename T>
+std::vector<T> cast_to(const std::vector<double> & v)
+{
+  std::vector<T> o(v.size());
+  for(size_t i = 0; i < v.size(); i++) o[i] = static_cast<T>(v[i]);
+  return o;
+}
+
+const smplpp_json::Array * find(const smplpp_json & j, const char * key)
+{
+  auto it = j.arrays.find(key);
+  return it == j.arrays.end() || it->second.ragged ? nullptr : &it->second;
+}
+} // namespace
+
+extern "C" int smplpp_json_open(const char * path, smplpp_json_t ** out)
+{
+  if(!out) return fail(SMPLPP_ERR_INVALID, "JSON", "null output");
+  std::unique_ptr<smplpp_json> j;
+  const int rc = load_json(path, "JSON", "Cannot find a JSON file!", j);
+  if(rc != SMPLPP_OK) return rc;
+  *out = j.release();
+  return SMPLPP_OK;
+}
+
+extern "C" void smplpp_json_close(smplpp_json_t * j)
+{
+  delete j;
+}
+
+extern "C" int smplpp_json_array(const smplpp_json_t * j, const char * key, int32_t * ndim, int64_t * shape8,
+                                 const double ** data)
+{
+  if(!j || !key || !ndim || !shape8 || !data) return fail(SMPLPP_ERR_INVALID, "JSON", "null argument");
+  const smplpp_json::Array * a = find(*j, key);
+  if(!a) return fail(SMPLPP_ERR_IO, "JSON", std::string("no rectangular numeric array under key ") + key);
+  if(a->shape.size() > 8) return fail(SMPLPP_ERR_IO, "JSON", "more than 8 dimensions");
+  *ndim = static_cast<int32_t>(a->shape.size());
+  for(size_t i = 0; i < a->shape.size(); i++) shape8[i] = a->shape[i];
+  *data = a->data.data();
+  return SMPLPP_OK;
+}
+
+// SMPL::init (src/SMPL.cpp:560-617): same keys, same shape checks, same messages
+extern "C" int smplpp_model_load_json(const char * path, smplpp_model_t ** out)
+{
+  if(!out) return fail(SMPLPP_ERR_INVALID, "SMPL", "Cannot initialize a SMPL model!");
+  std::unique_ptr<smplpp_json> j;
+  int rc = load_json(path, "SMPL", "Cannot initialize a SMPL model!", j); // SMPL.cpp:614-617: the file does not exist
+  if(rc != SMPLPP_OK) return rc;
+  const char * keys[] = {"face_indices", "shape_blend_shapes", "pose_blend_shapes", "vertices_template", "joint_regressor",
+                         "kinematic_tree", "weights"};
+  const smplpp_json::Array * a[7];
+  for(int i = 0; i < 7; i++)
+  {
+    a[i] = find(*j, keys[i]);
+    if(!a[i]) return fail(SMPLPP_ERR_IO, "SMPL", std::string("Cannot initialize a SMPL model! (key ") + keys[i] + " is missing)");
+  }
+  const smplpp_json::Array &faces = *a[0], &sbs = *a[1], &pbs = *a[2], &templ = *a[3], &jreg = *a[4], &tree = *a[5], &w = *a[6];
+  if(sbs.shape.size() != 3 || sbs.shape[2] != kShapeDim)
+    return fail(SMPLPP_ERR_IO, "SMPL",
+                "Shape parameter dimensions are invalid: " + std::to_string(sbs.shape.size() == 3 ? sbs.shape[2] : -1) + " != "
+                    + std::to_string(kShapeDim)); // SMPL.cpp:579-583
+  if(pbs.shape.size() != 3 || pbs.shape[2] != kPoseDim)
+    return fail(SMPLPP_ERR_IO, "SMPL",
+                "Pose parameter dimensions are invalid: " + std::to_string(pbs.shape.size() == 3 ? pbs.shape[2] : -1) + " != "
+                    + std::to_string(kPoseDim)); // SMPL.cpp:586-590
+  const int64_t V = templ.shape.empty() ? 0 : templ.shape[0];
+  const bool ok = V >= 1 && templ.shape.size() == 2 && templ.shape[1] == 3 && sbs.shape[0] == V && sbs.shape[1] == 3
+                  && pbs.shape[0] == V && pbs.shape[1] == 3 && jreg.shape.size() == 2 && jreg.shape[0] == kJoints
+                  && jreg.shape[1] == V && tree.shape.size() == 2 && tree.shape[0] == 2 && tree.shape[1] == kJoints
+                  && w.shape.size() == 2 && w.shape[0] == V && w.shape[1] == kJoints && faces.shape.size() == 2
+                  && faces.shape[1] == 3;
+  if(!ok) return fail(SMPLPP_ERR_IO, "SMPL", "Cannot initialize a SMPL model! (array shapes do not match)");
+  const std::vector<int32_t> h_faces = cast_to<int32_t>(faces.data);
+  const std::vector<float> h_sbs = cast_to<float>(sbs.data), h_pbs = cast_to<float>(pbs.data), h_templ = cast_to<float>(templ.data),
+                           h_jreg = cast_to<float>(jreg.data), h_w = cast_to<float>(w.data);
+  const std::vector<int64_t> h_tree = cast_to<int64_t>(tree.data); // the root's parent 4294967295 survives the double round trip
+  smplpp_model_desc d;
+  d.vertex_num = V;
+  d.face_num = faces.shape[0];
+  d.face_indices = h_faces.data();
+  d.shape_blend_shapes = h_sbs.data();
+  d.pose_blend_shapes = h_pbs.data();
+  d.vertices_template = h_templ.data();
+  d.joint_regressor = h_jreg.data();
+  d.kinematic_tree = h_tree.data();
+  d.weights = h_w.data();
+  return smplpp_model_create(&d, out);
+}
+
+// VPoserDecoderImpl::loadParamsFromJson (src/VPoser.cpp:169-238): same keys, same shape checks, same messages
+extern "C" int smplpp_vposer_load_json(const char * path, smplpp_vposer_t ** out)
+{
+  if(!out) return fail(SMPLPP_ERR_INVALID, "VPoser", "Cannot find a JSON file!");
+  std::unique_ptr<smplpp_json> j;
+  int rc = load_json(path, "VPoser", "Cannot find a JSON file!", j); // VPoser.cpp:181-184
+  if(rc != SMPLPP_OK) return rc;
+  struct Want
+  {
+    const char * key;
+    int64_t d0, d1; // d1 = 0: one-dimensional
+  };
+  const int64_t hidden = 512, latent = 32, outd = 126;
+  const Want want[6] = {{"decoder_net.0.weight", hidden, latent}, {"decoder_net.0.bias", hidden, 0},
+                        {"decoder_net.3.weight", hidden, hidden}, {"decoder_net.3.bias", hidden, 0},
+                        {"decoder_net.5.weight", outd, hidden},   {"decoder_net.5.bias", outd, 0}};
+  std::vector<float> host[6];
+  for(int i = 0; i < 6; i++)
+  {
+    const smplpp_json::Array * a = find(*j, want[i].key);
+    const bool ok = a
+                    && (want[i].d1 ? (a->shape.size() == 2 && a->shape[0] == want[i].d0 && a->shape[1] == want[i].d1)
+                                   : (a->shape.size() == 1 && a->shape[0] == want[i].d0));
+    if(!ok) return fail(SMPLPP_ERR_IO, "VPoser", std::string("invalid dimension of ") + want[i].key + " from JSON file!");
+    host[i] = cast_to<float>(a->data);
+  }
+  smplpp_vposer_desc d;
+  d.w0 = host[0].data(), d.b0 = host[1].data(), d.w3 = host[2].data(), d.b3 = host[3].data(), d.w5 = host[4].data(),
+  d.b5 = host[5].data();
+  return smplpp_vposer_create(&d, out);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// C3D
+// ------------------------------------------------------------------------------------------------------------
+struct smplpp_c3d
+{
+  std::string bytes;      // the whole file
+  int points = 0;         // 3D points per frame
+  int analog_per_frame = 0; // analog words per frame (samples x channels)
+  int64_t frames = 0;
+  int first_frame = 1;
+  float scale = 0.f;      // < 0: float32 data, else int16 * scale
+  float rate = 0.f;
+  size_t data_offset = 0;
+  std::vector<std::string> labels;
+  std::string units;
+};
+
+namespace
+{
+template<typename T>
+T rd(const std::string & b, size_t off)
+{
+  T v;
+  memcpy(&v, b.data() + off, sizeof(T));
+  return v;
+}
+
+struct C3dParam
+{
+  int type = 0; // -1 char, 1 byte, 2 int16, 4 float
+  std::vector<int> dims;
+  size_t data_off = 0;
+};
+
+// walks the parameter section and returns the parameters of groups POINT and TRIAL, keyed "GROUP:NAME"
+bool c3d_parameters(const std::string & b, size_t start, std::map<std::string, C3dParam> & out, std::string & err)
+{
+  if(start + 4 > b.size()) return err = "parameter section is outside the file", false;
+  const int proc = static_cast<uint8_t>(b[start + 3]);
+  if(proc != 84) return err = "only Intel (little-endian IEEE) C3D files are supported, processor type " + std::to_string(proc), false;
+  std::map<int, std::string> groups;
+  struct Pending
+  {
+    int gid;
+    std::string name;
+    C3dParam prm;
+  };
+  std::vector<Pending> params;
+  size_t pos = start + 4;
+  while(pos + 2 <= b.size())
+  {
+    const int nlen = std::abs(static_cast<int>(static_cast<int8_t>(b[pos])));
+    const int gid = static_cast<int8_t>(b[pos + 1]);
+    if(nlen == 0) break;
+    if(pos + 2 + nlen + 2 > b.size()) return err = "truncated parameter record", false;
+    std::string name(b.data() + pos + 2, nlen);
+    for(auto & c : name) c = static_cast<char>(toupper(static_cast<unsigned char>(c)));
+    const size_t off_field = pos + 2 + nlen;
+    const int next = rd<int16_t>(b, off_field);
+    if(gid < 0)
+      groups[-gid] = name;
+    else
+    {
+      size_t q = off_field + 2;
+      if(q + 2 > b.size()) return err = "truncated parameter record", false;
+      C3dParam prm;
+      prm.type = static_cast<int8_t>(b[q]);
+      const int nd = static_cast<uint8_t>(b[q + 1]);
+      q += 2;
+      if(q + nd > b.size()) return err = "truncated parameter record", false;
+      for(int i = 0; i < nd; i++) prm.dims.push_back(static_cast<uint8_t>(b[q + i]));
+      prm.data_off = q + nd;
+      params.push_back({gid, name, prm});
+    }
+    if(next <= 0) break;
+    pos = off_field + next;
+  }
+  for(auto & pp : params)
+  {
+    auto g = groups.find(pp.gid);
+    if(g != groups.end()) out[g->second + ":" + pp.name] = pp.prm;
+  }
+  return true;
+}
+
+double c3d_scalar(const std::string & b, const C3dParam & prm)
+{
+  if(prm.type == 4) return rd<float>(b, prm.data_off);
+  if(prm.type == 2) return static_cast<uint16_t>(rd<int16_t>(b, prm.data_off)); // counts are stored unsigned
+  if(prm.type == 1) return static_cast<uint8_t>(b[prm.data_off]);
+  return 0.0;
+}
+
+void c3d_strings(const std::string & b, const C3dParam & prm, std::vector<std::string> & out)
+{
+  if(prm.type != -1 || prm.dims.empty()) return;
+  const int len = prm.dims[0];
+  int count = 1;
+  for(size_t i = 1; i < prm.dims.size(); i++) count *= prm.dims[i];
+  for(int i = 0; i < count; i++)
+  {
+    if(prm.data_off + static_cast<size_t>(i + 1) * len > b.size()) break;
+    std::string s(b.data() + prm.data_off + static_cast<size_t>(i) * len, len);
+    while(!s.empty() && (s.back() == ' ' || s.back() == '\0')) s.pop_back();
+    out.push_back(s);
+  }
+}
+} // namespace
+
+extern "C" int smplpp_c3d_open(const char * path, smplpp_c3d_t ** out)
+{
+  if(!out) return fail(SMPLPP_ERR_INVALID, "C3D", "null output");
+  std::unique_ptr<smplpp_c3d> c(new smplpp_c3d());
+  if(!path || !read_file(path, c->bytes)) return fail(SMPLPP_ERR_IO, "C3D", std::string("Cannot open the C3D file ") + (path ? path : ""));
+  const std::string & b = c->bytes;
+  if(b.size() < 512 || static_cast<uint8_t>(b[1]) != 0x50) return fail(SMPLPP_ERR_IO, "C3D", "not a C3D file (key byte 0x50 missing)");
+  const int param_block = static_cast<uint8_t>(b[0]);
+  c->points = rd<uint16_t>(b, 2);
+  c->analog_per_frame = rd<uint16_t>(b, 4);
+  const int first = rd<uint16_t>(b, 6), last = rd<uint16_t>(b, 8);
+  c->first_frame = first;
+  c->scale = rd<float>(b, 12);
+  int data_block = rd<uint16_t>(b, 16);
+  c->rate = rd<float>(b, 20);
+  c->frames = static_cast<int64_t>(last) - first + 1;
+  std::map<std::string, C3dParam> prm;
+  std::string err;
+  if(!c3d_parameters(b, static_cast<size_t>(param_block - 1) * 512, prm, err)) return fail(SMPLPP_ERR_IO, "C3D", err);
+  // the parameter section is authoritative where the 16-bit header fields overflow (long captures)
+  auto it = prm.find("POINT:FRAMES");
+  if(it != prm.end())
+  {
+    const double n = c3d_scalar(b, it->second);
+    if(n > 0 && it->second.type == 4) c->frames = static_cast<int64_t>(n);
+    else if(n > 0 && c->frames <= 0) c->frames = static_cast<int64_t>(n);
+  }
+  if((it = prm.find("POINT:DATA_START")) != prm.end() && data_block == 0) data_block = static_cast<int>(c3d_scalar(b, it->second));
+  if((it = prm.find("POINT:RATE")) != prm.end() && !(c->rate > 0.f)) c->rate = static_cast<float>(c3d_scalar(b, it->second));
+  if((it = prm.find("POINT:SCALE")) != prm.end() && c->scale == 0.f) c->scale = static_cast<float>(c3d_scalar(b, it->second));
+  if((it = prm.find("POINT:LABELS")) != prm.end()) c3d_strings(b, it->second, c->labels);
+  for(int k = 2; k < 10; k++) // POINT:LABELS2 ... for more than 255 points
+    if((it = prm.find("POINT:LABELS" + std::to_string(k))) != prm.end()) c3d_strings(b, it->second, c->labels);
+  if((it = prm.find("POINT:UNITS")) != prm.end())
+  {
+    std::vector<std::string> u;
+    c3d_strings(b, it->second, u);
+    if(!u.empty()) c->units = u[0];
+  }
+  c->labels.resize(static_cast<size_t>(c->points)); // unnamed points keep an empty label
+  if(data_block < 1 || c->points < 0 || c->frames < 0) return fail(SMPLPP_ERR_IO, "C3D", "inconsistent C3D header");
+  c->data_offset = static_cast<size_t>(data_block - 1) * 512;
+  const size_t word = c->scale < 0.f ? 4 : 2;
+  const size_t frame_bytes = (static_cast<size_t>(c->points) * 4 + c->analog_per_frame) * word;
+  if(c->data_offset + static_cast<size_t>(c->frames) * frame_bytes > b.size())
+    return fail(SMPLPP_ERR_IO, "C3D", "the C3D file is shorter than its header says");
+  *out = c.release();
+  return SMPLPP_OK;
+}
+
+extern "C" void smplpp_c3d_close(smplpp_c3d_t * c)
+{
+  delete c;
+}
+extern "C" int64_t smplpp_c3d_frame_count(const smplpp_c3d_t * c)
+{
+  return c ? c->frames : 0;
+}
+extern "C" int64_t smplpp_c3d_point_count(const smplpp_c3d_t * c)
+{
+  return c ? c->points : 0;
+}
+extern "C" double smplpp_c3d_frame_rate(const smplpp_c3d_t * c)
+{
+  return c ? c->rate : 0.0;
+}
+extern "C" const char * smplpp_c3d_label(const smplpp_c3d_t * c, int64_t i)
+{
+  return (c && i >= 0 && i < static_cast<int64_t>(c->labels.size())) ? c->labels[static_cast<size_t>(i)].c_str() : "";
+}
+extern "C" const char * smplpp_c3d_units(const smplpp_c3d_t * c)
+{
+  return c ? c->units.c_str() : "";
+}
+
+// node/node.cpp:580-594: index of the first label that ENDS with `name` (std::find_if + std::distance: the point
+// count when there is none)
+extern "C" int64_t smplpp_c3d_find_label(const smplpp_c3d_t * c, const char * name)
+{
+  if(!c || !name) return 0;
+  const size_t n = strlen(name);
+  for(size_t i = 0; i < c->labels.size(); i++)
+  {
+    const std::string & s = c->labels[i];
+    if(s.size() >= n && s.compare(s.size() - n, n, name) == 0) return static_cast<int64_t>(i);
+  }
+  return static_cast<int64_t>(c->labels.size());
+}
+
+// frames [first, first + count) -> xyz (count, points, 3) and valid (count, points): 1 when the point exists
+// (ezc3d isEmpty(): negative residual word), else 0 with xyz = 0 like the node's targetPos_.zero_() (node.cpp:682-683)
+extern "C" int smplpp_c3d_read(const smplpp_c3d_t * c, int64_t first, int64_t count, float * xyz, uint8_t * valid)
+{
+  if(!c || !xyz || !valid || first < 0 || count < 0 || first + count > c->frames)
+    return fail(SMPLPP_ERR_INVALID, "C3D", "frame range outside the C3D file");
+  const bool is_float = c->scale < 0.f;
+  const size_t word = is_float ? 4 : 2;
+  const size_t frame_bytes = (static_cast<size_t>(c->points) * 4 + c->analog_per_frame) * word;
+  const float s = std::fabs(c->scale);
+  for(int64_t f = 0; f < count; f++)
+  {
+    const size_t base = c->data_offset + static_cast<size_t>(first + f) * frame_bytes;
+    for(int k = 0; k < c->points; k++)
+    {
+      float v[4];
+      if(is_float)
+        memcpy(v, c->bytes.data() + base + static_cast<size_t>(k) * 16, 16);
+      else
+      {
+        int16_t w[4];
+        memcpy(w, c->bytes.data() + base + static_cast<size_t>(k) * 8, 8);
+        v[0] = w[0] * s, v[1] = w[1] * s, v[2] = w[2] * s, v[3] = w[3];
+      }
+      const bool ok = v[3] >= 0.f;
+      const size_t o = (static_cast<size_t>(f) * c->points + k);
+      valid[o] = ok ? 1 : 0;
+      xyz[3 * o] = ok ? v[0] : 0.f, xyz[3 * o + 1] = ok ? v[1] : 0.f, xyz[3 * o + 2] = ok ? v[2] : 0.f;
+    }
+  }
+  return SMPLPP_OK;
+}

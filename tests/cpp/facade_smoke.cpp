@@ -15,7 +15,7 @@ static float frand()
   return static_cast<float>((g_seed >> 8) & 0xFFFFFF) / 16777216.f - 0.5f;
 }
 
-int main()
+int main(int argc, char ** argv)
 {
   using namespace smplpp;
   const int64_t V = 300; // even, >= 128: exercises the tcgen05 path
@@ -59,7 +59,52 @@ int main()
     {
       if(!std::strstr(e.what(), "Cannot launch a SMPL model!")) return 1;
     }
+    try
+    {
+      smpl.setModelPath("/nonexistent/smpl_male.json");
+      std::puts("FAIL: setModelPath on a missing file did not throw");
+      return 1;
+    }
+    catch(const Exception & e)
+    {
+      if(!std::strstr(e.what(), "SMPL Error: Failed to initialize model path!")) return 1;
+    }
+    try
+    {
+      VPoserDecoder missing;
+      missing.loadParamsFromJson("/nonexistent/vposer.json");
+      return 1;
+    }
+    catch(const Exception & e)
+    {
+      if(!std::strstr(e.what(), "VPoser Error: Cannot find a JSON file!")) return 1;
+    }
+    if(argc > 3)
+    {
+      // C3D reader (node.cpp:572-595): host only
+      C3d c3d(argv[3]);
+      std::vector<float> xyz;
+      std::vector<uint8_t> valid;
+      c3d.read(0, c3d.nbFrames(), xyz, valid);
+      std::printf("facade smoke: c3d %lld frames x %lld points at %.0f Hz, first label %s\n", (long long)c3d.nbFrames(),
+                  (long long)c3d.nbPoints(), c3d.frameRate(), c3d.label(0).c_str());
+      if(c3d.findLabel("no such marker") != c3d.nbPoints()) return 1;
+    }
     smpl.init(p);
+    if(argc > 2)
+    {
+      // setModelPath + init() and VPoserDecoder::loadParamsFromJson through the library's JSON reader
+      SMPL fromJson;
+      fromJson.setModelPath(argv[1]);
+      fromJson.init();
+      VPoserDecoder vposer;
+      vposer.loadParamsFromJson(argv[2]);
+      Array b1({1, 10}), t1({1, 25, 3});
+      fromJson.launch(b1, t1);
+      std::printf("facade smoke: model from %s: V=%lld, %zu faces\n", argv[1], (long long)fromJson.getVertexNum(),
+                  fromJson.getFaceIndex().size() / 3);
+      if(fromJson.getVertex().size(1) != fromJson.getVertexNum() || !vposer.handle()) return 1;
+    }
     const int64_t N = 37;
     Array beta({N, 10}), theta({N, 25, 3});
     for(auto & x : beta.data) x = 2.f * frand();

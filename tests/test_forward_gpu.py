@@ -364,13 +364,46 @@ def test_error_messages(smpl_gpu):
         fresh.init()
 
 
-def test_cpp_facade_smoke():
-    """The header-only C++ facade (smplpp::SMPL over the C ABI) end to end on the GPU: tests/cpp/facade_smoke.cpp."""
+def test_cpp_facade_smoke(tmp_path, params, vposer_params):
+    """The header-only C++ facade (smplpp::SMPL / VPoserDecoder / C3d over the C ABI) end to end on the GPU:
+    tests/cpp/facade_smoke.cpp, including setModelPath + init() and loadParamsFromJson on JSON files and the C3D reader."""
     import os
     import subprocess
+    import sys
+    from smplpp_b200 import synth
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tests"))
+    from c3d_writer import write_c3d
     exe = os.path.join(root, "tests", "cpp", "facade_smoke")
     if not os.path.exists(exe):
         subprocess.check_call(["make", "-s", "-C", os.path.join(root, "tests", "cpp")])
-    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    mpath, vpath, cpath = str(tmp_path / "model.json"), str(tmp_path / "vposer.json"), str(tmp_path / "walk.c3d")
+    params.to_json(mpath)
+    synth.vposer_to_json(vposer_params, vpath)
+    rng = np.random.default_rng(0)
+    write_c3d(cpath, rng.normal(size=(12, 5, 3)).astype(np.float32), rng.random((12, 5)) > 0.2, ["A", "B", "C", "D", "E"])
+    r = subprocess.run([exe, mpath, vpath, cpath], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "facade smoke: OK" in r.stdout, r.stdout + r.stderr
+    assert "c3d 12 frames x 5 points at 120 Hz, first label A" in r.stdout
+    assert "V=6890, 13776 faces" in r.stdout
+
+
+def test_native_json_loaders_match_python_loaders(tmp_path, params, vposer_params):
+    """smplpp_model_load_json / smplpp_vposer_load_json (SMPL::init, VPoserDecoder::loadParamsFromJson through the
+    C-ABI JSON reader) build the same device models as the arrays handed over by the Python mirror."""
+    from smplpp_b200 import api, synth
+    mpath, vpath = str(tmp_path / "model.json"), str(tmp_path / "vposer.json")
+    params.to_json(mpath)
+    synth.vposer_to_json(vposer_params, vpath)
+    a = api.SMPL(params, device="cuda:0")
+    b = api.SMPL.from_json_native(mpath, device="cuda:0")
+    beta, theta = synth.make_forward_inputs(7, 3)
+    a.launch(beta, theta)
+    b.launch(beta, theta)
+    assert torch.equal(a.getVertex(), b.getVertex()) and torch.equal(a.getRestJoint(), b.getRestJoint())
+    assert torch.equal(a.getFaceIndex(), b.getFaceIndex())
+    va = api.VPoserDecoder(vposer_params, device="cuda:0")
+    vb = api.VPoserDecoder(device="cuda:0")
+    vb.loadParamsFromJsonNative(vpath)
+    z = np.random.default_rng(0).normal(size=(5, 32)).astype(np.float32)
+    assert torch.equal(va.forward(z), vb.forward(z))
