@@ -1,4 +1,4 @@
-timeout 600 python -m pytest tests/test_ik_gpu.py -m gpu -x -q 2>&1 | tail -5
+timeout 600 python -m pytest tests/test_ik_gpu.py tests/test_vposer_gpu.py -m gpu -x -q 2>&1 | tail -5
 python - <<'PY'
 import sys, json, torch
 sys.path.insert(0, '.')

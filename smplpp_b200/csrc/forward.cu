@@ -10,6 +10,7 @@
 //   skinning            src/LinearBlendSkinning.cpp:445-553 (homogeneous divide kept, root translation added)
 #include "common.cuh"
 #include "forward.cuh"
+#include "vposer.cuh"
 
 using namespace sb;
 
@@ -855,6 +856,11 @@ extern "C" int smplpp_set_forward_variant(int variant)
   }
   // 200 / 201 / 202: standalone skinning kernel (FFMA per-warp TMA pipelines / FFMA register-pipelined kernel / skinning
   // matrices on tcgen05, the default; the FFMA kernels are bound by FFMA issue at ~3.2 TB/s)
+  if(variant == 300 || variant == 301) // VPoser Jacobian: 300 tensor cores (default), 301 FFMA kernel
+  {
+    g_vposer_jac_variant = variant - 300;
+    return SMPLPP_OK;
+  }
   if(variant >= 200 && variant <= 202)
   {
     g_lbs_variant = variant - 200;

@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(vp::THREADS, 1)
     vposer_decode_kernel(const float * __restrict__ w0, const float * __restrict__ b0, const float * __restrict__ w3t,
                          const float * __restrict__ b3, const float * __restrict__ w5t, const float * __restrict__ b5,
                          int B, const float * __restrict__ latent, long long latent_stride, float * __restrict__ aa_out,
-                         long long aa_stride, float * __restrict__ jac_out)
+                         long long aa_stride, float * __restrict__ jac_out, float * __restrict__ aux_out, int aux_ld)
 {
   using namespace vp;
   using S = typename std::conditional<kJac, Smem, SmemFwd>::type;
@@ -308,6 +308,7 @@ __global__ void __launch_bounds__(vp::THREADS, 1)
         bool pos = acc[f] > 0.f;
         s.h1[f][tid] = pos ? acc[f] : 0.01f * acc[f];
         s.d1[f][tid] = pos ? 1.f : 0.01f;
+        if(aux_out && f0 + f < B) aux_out[static_cast<size_t>(f0 + f) * aux_ld + tid] = pos ? 1.f : 0.01f;
       }
     }
     __syncthreads();
@@ -329,6 +330,7 @@ __global__ void __launch_bounds__(vp::THREADS, 1)
         bool pos = acc[f] > 0.f;
         s.h2[f][tid] = pos ? acc[f] : 0.01f * acc[f];
         s.d2[f][tid] = pos ? 1.f : 0.01f;
+        if(aux_out && f0 + f < B) aux_out[static_cast<size_t>(f0 + f) * aux_ld + H + tid] = pos ? 1.f : 0.01f;
       }
     }
     __syncthreads();
@@ -352,9 +354,15 @@ __global__ void __launch_bounds__(vp::THREADS, 1)
       if(f0 + f < B)
       {
         float aa[3];
-        decode_joint(&s.y[f][6 * j], aa, kJac ? s.daa[f][j] : nullptr);
+        decode_joint(&s.y[f][6 * j], aa, (kJac || aux_out) ? s.daa[f][j] : nullptr);
         float * dst = aa_out + static_cast<size_t>(f0 + f) * aa_stride + 3 * j;
         dst[0] = aa[0], dst[1] = aa[1], dst[2] = aa[2];
+        if(aux_out)
+        {
+          float * da = aux_out + static_cast<size_t>(f0 + f) * aux_ld + 2 * H + 18 * j;
+#pragma unroll
+          for(int e = 0; e < 18; e++) da[e] = s.daa[f][j][e];
+        }
       }
     }
     if(kJac)
@@ -456,6 +464,8 @@ __global__ void __launch_bounds__(vp::THREADS, 1)
 // ------------------------------------------------------------------------------------------------------------
 namespace sb
 {
+int g_vposer_jac_variant = 0;
+
 int launch_vposer_decode(const smplpp_vposer * vposer, cudaStream_t st, int B, const float * latent,
                          long long latent_stride, float * aa, long long aa_stride, float * jac)
 {
@@ -473,19 +483,35 @@ int launch_vposer_decode(const smplpp_vposer * vposer, cudaStream_t st, int B, c
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int passes = (B + vp::FB - 1) / vp::FB;
+  if(jac && vposer->tc_ready && g_vposer_jac_variant == 0)
+  {
+    // forward pass (FFMA, 0.7 MFLOP per frame) leaves LeakyReLU'(h1), LeakyReLU'(h2) and d aa / d y6 of every frame in a
+    // stream-ordered scratch buffer; the 21 MFLOP per frame of the Jacobian chain run on the tensor cores (vposer_tc.cu)
+    const int aux_ld = static_cast<int>(vposer_tc_aux_floats());
+    float * aux = nullptr;
+    SB_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&aux), static_cast<size_t>(B) * aux_ld * sizeof(float), st));
+    int grid = passes < 2 * sms ? passes : 2 * sms;
+    vposer_decode_kernel<false><<<grid, vp::THREADS, sizeof(vp::SmemFwd), st>>>(
+        vposer->w0, vposer->b0, vposer->w3t, vposer->b3, vposer->w5t, vposer->b5, B, latent, latent_stride, aa,
+        aa_stride, nullptr, aux, aux_ld);
+    SB_LAUNCHED();
+    const int rc = launch_vposer_jac_tc(*vposer, st, B, aux, jac);
+    SB_CUDA(cudaFreeAsync(aux, st));
+    return rc;
+  }
   if(jac)
   {
     int grid = passes < sms ? passes : sms;
     vposer_decode_kernel<true><<<grid, vp::THREADS, sizeof(vp::Smem), st>>>(
         vposer->w0, vposer->b0, vposer->w3t, vposer->b3, vposer->w5t, vposer->b5, B, latent, latent_stride, aa,
-        aa_stride, jac);
+        aa_stride, jac, nullptr, 0);
   }
   else
   {
     int grid = passes < 2 * sms ? passes : 2 * sms;
     vposer_decode_kernel<false><<<grid, vp::THREADS, sizeof(vp::SmemFwd), st>>>(
         vposer->w0, vposer->b0, vposer->w3t, vposer->b3, vposer->w5t, vposer->b5, B, latent, latent_stride, aa,
-        aa_stride, nullptr);
+        aa_stride, nullptr, nullptr, 0);
   }
   SB_LAUNCHED();
   return SMPLPP_OK;
@@ -515,6 +541,7 @@ extern "C" int smplpp_vposer_create(const smplpp_vposer_desc * desc, smplpp_vpos
   if(rc == SMPLPP_OK) rc = up(&v->b3, desc->b3, H);
   if(rc == SMPLPP_OK) rc = up(&v->w5t, w5t.data(), w5t.size());
   if(rc == SMPLPP_OK) rc = up(&v->b5, desc->b5, OUT);
+  if(rc == SMPLPP_OK) rc = vposer_tc_prepare(*v, desc->w0, desc->w3, desc->w5);
   if(rc != SMPLPP_OK)
   {
     smplpp_vposer_destroy(v);
@@ -533,6 +560,7 @@ extern "C" void smplpp_vposer_destroy(smplpp_vposer_t * v)
   cudaFree(v->b3);
   cudaFree(v->w5t);
   cudaFree(v->b5);
+  vposer_tc_release(*v);
   delete v;
 }
 

@@ -100,3 +100,26 @@ def test_vposer_errors(vposer_params):
         api.VPoserDecoder(bad)
     with pytest.raises(api.SmplppError, match="Cannot find a JSON file!"):
         api.VPoserDecoder().loadParamsFromJson("/nonexistent/vposer_parameters.json")
+
+
+@pytest.mark.parametrize("batch", [1, 3, 4, 257, 2048])
+def test_tensor_core_jacobian_matches_ffma_kernel(vposer_gpu, batch):
+    """The tcgen05 Jacobian (vposer_tc.cu: four frames per 128-lane tile, fp16 x 3 split precision) against the FFMA
+    forward-mode kernel on the same latents, every frame and entry; ragged batches (not a multiple of 4) included.
+    Tolerance: 1e-4 of the frame's largest entry, the north-star Jacobian bound; in practice ~6e-6."""
+    from smplpp_b200 import capi
+    z = np.random.default_rng(100 + batch).normal(size=(batch, 32)).astype(np.float32)
+    out = {}
+    for var in (301, 300):
+        capi.check(capi.lib().smplpp_set_forward_variant(var))
+        try:
+            aa, jac = vposer_gpu.forward(z, jacobian=True)
+            out[var] = (aa.clone(), jac.clone())
+        finally:
+            capi.check(capi.lib().smplpp_set_forward_variant(300))
+    assert torch.equal(out[300][0], out[301][0])  # the forward pass is the same kernel
+    assert bool(torch.isfinite(out[300][1]).all())
+    scale = out[301][1].abs().amax(dim=(1, 2), keepdim=True)
+    rel = ((out[300][1] - out[301][1]).abs() / scale).max()
+    assert float(rel) < 1e-4
+    assert float(rel) < 2e-5
