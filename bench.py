@@ -46,6 +46,18 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_tensor_peak():
+    """Dense bf16/fp16 tensor peak in TFLOP/s: the burst figure of MEASURED_PEAKS.json (a kernel timed alone), else the
+    fallback of B200_PROFILING.md."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        if "bf16_tflops" in p:
+            return float(p["bf16_tflops"]), "measured burst (MEASURED_PEAKS.json)"
+    return 1590.0, "fallback (B200_PROFILING.md)"
+
+
 def ncu_traffic(kernel: str):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the newest committed ncu capture
     (profiles/*_traffic.json, written by scripts/ncu_summary.py); None when no capture names the kernel."""
@@ -281,6 +293,18 @@ def main():
                 "algorithmic_bytes_per_launch": BYTES_FUSED * B,
                 "peak_source": peak_src, "ms_per_launch": ms_k2,
                 "fp32_tflops_algorithmic": FLOPS_BLEND * B / (ms_k2 * 1e-3) / 1e12}
+    # the same kernel against the tensor pipe: its two products are computed as 3 fp16 passes each (hi.hi + lo.hi +
+    # hi.lo, fp32 accumulation).  "split_algorithmic" counts 3 x the unpadded fp32 products (217 blend columns, 24
+    # joints x 12 matrix entries), "executed" the padded tiles the MMAs really run (128 x 96 x 16 per instruction).
+    tpeak, tpeak_src = measured_tensor_peak()
+    flops_split = 3 * (2 * 217 * VERTS * 3 + 2 * 24 * 12 * VERTS) * B
+    tiles, fblocks = (VERTS + 127) // 128, (B + 95) // 96
+    flops_exec = tiles * fblocks * (126 + 72) * (2 * 128 * 96 * 16)
+    roofline["tensor"] = {"unit": "TFLOP/s", "peak": tpeak, "peak_source": tpeak_src,
+                          "split_algorithmic": flops_split / (ms_k2 * 1e-3) / 1e12,
+                          "executed": flops_exec / (ms_k2 * 1e-3) / 1e12,
+                          "frac": flops_split / (ms_k2 * 1e-3) / 1e12 / tpeak,
+                          "note": "fp32 products as 3 fp16 tensor-core passes; ncu: sm__pipe_tensor_cycles_active in profiles/"}
 
     # standalone skinning kernel (the HBM-bound row): rest shape + 4x4 transforms -> vertices
     rest = torch.empty((B, VERTS, 3), dtype=torch.float32, device=dev)
