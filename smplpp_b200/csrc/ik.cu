@@ -762,8 +762,8 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
             for(int i = 0; i < UQ; i++)
             {
               const int u = t.pair_vert[p0 + q + i];
-              const float * bu = t.basis + static_cast<size_t>(3 * u) * kBlendK + d;
-              b0[i] = __ldg(bu), b1[i] = __ldg(bu + kBlendK), b2[i] = __ldg(bu + 2 * kBlendK);
+              const float4 bb = __ldg(t.basis4 + static_cast<size_t>(u) * kBlendK + d); // x, y, z rows in one load
+              b0[i] = bb.x, b1[i] = bb.y, b2[i] = bb.z;
             }
 #pragma unroll
             for(int i = 0; i < UQ; i++)
@@ -779,8 +779,8 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
           for(; q < np; q++)
           {
             const int u = t.pair_vert[p0 + q];
-            const float * bu = t.basis + static_cast<size_t>(3 * u) * kBlendK + d;
-            const float b0 = __ldg(bu), b1 = __ldg(bu + kBlendK), b2 = __ldg(bu + 2 * kBlendK);
+            const float4 bb = __ldg(t.basis4 + static_cast<size_t>(u) * kBlendK + d);
+            const float b0 = bb.x, b1 = bb.y, b2 = bb.z;
             const float * C = s_C4 + 12 * (p0 + q);
 #pragma unroll
             for(int r = 0; r < ROWS; r++) q4[r] = fmaf(C[3 * r], b0, fmaf(C[3 * r + 1], b1, fmaf(C[3 * r + 2], b2, q4[r])));
@@ -1616,6 +1616,16 @@ extern "C" int smplpp_tasks_create(const smplpp_model_t * model, int32_t n, cons
   if(rc == SMPLPP_OK) rc = upload_vec(t, &d.task_joint_mask, mask_all);
   if(rc == SMPLPP_OK) rc = upload_vec(t, &d.task_joint_mask_corner, mask_corner);
   if(rc == SMPLPP_OK) rc = upload_vec(t, &d.basis, basis);
+  if(rc == SMPLPP_OK)
+  {
+    std::vector<float4> basis4(static_cast<size_t>(nUpad) * kBlendK);
+    for(int u = 0; u < nUpad; u++)
+      for(int k = 0; k < kBlendK; k++)
+        basis4[static_cast<size_t>(u) * kBlendK + k] =
+            make_float4(basis[(static_cast<size_t>(3) * u) * kBlendK + k], basis[(static_cast<size_t>(3) * u + 1) * kBlendK + k],
+                        basis[(static_cast<size_t>(3) * u + 2) * kBlendK + k], 0.f);
+    rc = upload_vec(t, &d.basis4, basis4);
+  }
   if(rc == SMPLPP_OK) rc = upload_vec(t, &d.lbs_joint, lj);
   if(rc == SMPLPP_OK) rc = upload_vec(t, &d.lbs_weight, lw);
   if(rc == SMPLPP_OK) rc = upload_vec(t, &d.lbs_wsum, ws);

@@ -29,6 +29,7 @@ struct TasksDev
   const uint32_t * task_joint_mask_corner = nullptr; // (n) same, restricted to the three corners
   // compact model rows of the nU vertices (same layouts as ModelDev, V -> nU)
   const float * basis = nullptr;       // (3 nUpad, 224)
+  const float4 * basis4 = nullptr;     // (nUpad, 224): (x, y, z, 0) of every basis column, one 16-byte load in the IK Jacobian
   const uint8_t * lbs_joint = nullptr; // [kmax][nUpad]
   const float * lbs_weight = nullptr;  // [kmax][nUpad]
   const float * lbs_wsum = nullptr;    // (nUpad)
