@@ -899,10 +899,14 @@ __device__ __forceinline__ int tri_idx(int i, int j) // i >= j
 __device__ void block_cholesky(double * L, double * col, int N, int npiv, int tid, int nthreads, int * ok)
 {
   const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
+  // two block barriers per pivot: the next pivot's diagonal is also published in col[N] by the thread that updates it,
+  // so every thread can read it without racing the scaling step that overwrites L[j][j]
+  __syncthreads();
+  if(tid == 0) col[N] = L[0];
+  __syncthreads();
   for(int j = 0; j < npiv; j++)
   {
-    __syncthreads();
-    const double d = L[tri_idx(j, j)];
+    const double d = col[N];
     if(!(d > 0.0))
     {
       if(tid == 0) *ok = 0;
@@ -910,7 +914,6 @@ __device__ void block_cholesky(double * L, double * col, int N, int npiv, int ti
       return;
     }
     const double inv = 1.0 / sqrt(d);
-    __syncthreads();
     for(int i = j + tid; i < N; i += nthreads)
     {
       const double v = i == j ? sqrt(d) : L[tri_idx(i, j)] * inv;
@@ -923,10 +926,15 @@ __device__ void block_cholesky(double * L, double * col, int N, int npiv, int ti
     {
       const double lij = col[i];
       double * row = L + tri_idx(i, 0);
-      for(int k = j + 1 + lane; k <= i; k += 32) row[k] -= lij * col[k];
+      for(int k = j + 1 + lane; k <= i; k += 32)
+      {
+        const double v = row[k] - lij * col[k];
+        row[k] = v;
+        if(i == j + 1 && k == j + 1) col[N] = v; // the next pivot
+      }
     }
+    __syncthreads();
   }
-  __syncthreads();
 }
 
 // x <- L^-T L^-1 x for the leading n x n block, executed by warp 0 (other threads idle); result in x
@@ -955,7 +963,7 @@ __device__ void warp_chol_solve(const double * L, int n, double * x, int tid)
 
 __global__ void __launch_bounds__(c2::THREADS, 4) ik_solve_kernel(const IkSolveParams p)
 {
-  using namespace c2;
+  const int THREADS = blockDim.x; // chosen by the host from the number of 4x4 tiles of A (<= c2::THREADS)
   extern __shared__ __align__(16) double smd[];
   const int tid = threadIdx.x;
   const int f = blockIdx.x;
@@ -966,11 +974,11 @@ __global__ void __launch_bounds__(c2::THREADS, 4) ik_solve_kernel(const IkSolveP
   double * x = bvec + D;       // D
   double * g = x + D;          // D
   double * dstep = g + D;      // D
-  double * colbuf = dstep + D; // D + 2: pivot column of block_cholesky
+  double * colbuf = dstep + D; // D + 2: pivot column of block_cholesky (+ the next pivot at [N], N <= D + 1)
   int * state = reinterpret_cast<int *>(colbuf + D + 2); // D: 0 free, -1 at lower, +1 at upper, 2 pinned
   __shared__ double s_esq;
   __shared__ int s_ok, s_flag, s_iter;
-  __shared__ double s_red[THREADS / 32];
+  __shared__ double s_red[c2::THREADS / 32];
 
   const int rows = 4 * p.n;
   const float * J = p.J + static_cast<size_t>(f) * rows * p.ld;
@@ -1742,7 +1750,7 @@ struct IkLayout
 {
   int n, theta_dim, phi_cols, beta_cols, D, ld, ldfull, dim_ref, rows_per_task, use_ring, nUse;
   bool vposer, qp_ws;
-  size_t off_theta, off_coef, off_xf, off_verts, off_rest, off_e, off_j, off_jfull, off_vaa, off_vjac, off_info,
+  size_t off_theta, off_coef, off_xf, off_verts, off_rest, off_e, off_j, off_jfull, off_vaa, off_vjac, off_vaux, off_info,
       off_aws, off_schur, off_factor, off_misc, total;
   int chunk;
 };
@@ -1781,6 +1789,7 @@ IkLayout make_layout(const smplpp_tasks_t * tasks, const smplpp_ik_options * o, 
   L.off_j = take(C * 4 * L.n * L.ld * sizeof(float));
   L.off_jfull = L.vposer ? take(C * 4 * L.n * L.ldfull * sizeof(float)) : L.off_j;
   L.off_vjac = L.vposer ? take(C * 63 * 32 * sizeof(float)) : 0;
+  L.off_vaux = L.vposer ? take(C * vposer_tc_aux_floats() * sizeof(float)) : 0; // d1 | d2 | daa of the tensor-core Jacobian
   L.off_info = take(C * 2 * sizeof(int));
   L.off_aws = L.qp_ws ? take(C * (static_cast<size_t>(L.D) * (L.D + 1) / 2) * sizeof(double)) : 0;
   L.off_schur = schur ? take(static_cast<size_t>(batch) * 111 * sizeof(double)) : 0;
@@ -1805,6 +1814,15 @@ size_t jac_smem_bytes(const TasksDev & t, const IkLayout & L)
   fl += 12 * static_cast<size_t>(t.nPairs);
   fl += 4 * static_cast<size_t>(L.nUse) * t.kmax; // normalised weights + wn * x
   return fl * sizeof(float) + static_cast<size_t>(L.nUse) * t.kmax + 64;
+}
+
+// one thread per 4x4 tile of the lower triangle of A, rounded up to whole warps: 192 for D = 75 (190 tiles)
+int solve_block_threads(int D)
+{
+  const int nb = (D + 3) / 4;
+  const int tiles = nb * (nb + 1) / 2;
+  const int th = (tiles + 31) / 32 * 32;
+  return (th < 160 || th > c2::THREADS) ? c2::THREADS : th; // small problems keep 8 warps for the Cholesky / QP phases
 }
 
 size_t solve_smem_bytes(const IkLayout & L, bool schur)
@@ -1832,7 +1850,8 @@ int run_chunk(const smplpp_model_t * model, const smplpp_vposer_t * vposer, cons
   {
     theta_assemble_kernel<<<(B * 12 + 127) / 128, 128, 0, st>>>(B, theta_state, theta);
     SB_LAUNCHED();
-    int rc = launch_vposer_decode(vposer, st, B, theta_state + 6, 44, theta + 6, 75, vjac);
+    int rc = launch_vposer_decode(vposer, st, B, theta_state + 6, 44, theta + 6, 75, vjac,
+                                  reinterpret_cast<float *>(ws + L.off_vaux));
     if(rc != SMPLPP_OK) return rc;
     theta_in = theta;
   }
@@ -1975,7 +1994,7 @@ extern "C" int smplpp_ik_step(const smplpp_model_t * model, const smplpp_vposer_
     const size_t smem = solve_smem_bytes(L, false);
     if(smem > 227 * 1024) return fail(SMPLPP_ERR_INVALID, "IkTask", "IK problem too large for one CTA per frame");
     SB_CUDA(cudaFuncSetAttribute(ik_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    ik_solve_kernel<<<B, c2::THREADS, smem, st>>>(sp);
+    ik_solve_kernel<<<B, solve_block_threads(L.D), smem, st>>>(sp);
     SB_LAUNCHED();
   }
   return SMPLPP_OK;
@@ -2021,7 +2040,7 @@ extern "C" int smplpp_ik_shared_beta_reduce(const smplpp_model_t * model, const 
     sp.factor_ws = reinterpret_cast<double *>(ws + L.off_factor) + s * P;
     const size_t smem = solve_smem_bytes(L, true);
     SB_CUDA(cudaFuncSetAttribute(ik_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    ik_solve_kernel<<<B, c2::THREADS, smem, st>>>(sp);
+    ik_solve_kernel<<<B, solve_block_threads(L.D), smem, st>>>(sp);
     SB_LAUNCHED();
   }
   schur_reduce_kernel<<<111, 256, 0, st>>>(static_cast<int>(batch), reinterpret_cast<const double *>(ws + L.off_schur), reduced);

@@ -467,7 +467,7 @@ namespace sb
 int g_vposer_jac_variant = 0;
 
 int launch_vposer_decode(const smplpp_vposer * vposer, cudaStream_t st, int B, const float * latent,
-                         long long latent_stride, float * aa, long long aa_stride, float * jac)
+                         long long latent_stride, float * aa, long long aa_stride, float * jac, float * aux_ws)
 {
   static bool configured = false;
   if(!configured)
@@ -486,18 +486,29 @@ int launch_vposer_decode(const smplpp_vposer * vposer, cudaStream_t st, int B, c
   if(jac && vposer->tc_ready && g_vposer_jac_variant == 0)
   {
     // forward pass (FFMA, 0.7 MFLOP per frame) leaves LeakyReLU'(h1), LeakyReLU'(h2) and d aa / d y6 of every frame in a
-    // stream-ordered scratch buffer; the 21 MFLOP per frame of the Jacobian chain run on the tensor cores (vposer_tc.cu)
+    // scratch buffer; the 21 MFLOP per frame of the Jacobian chain run on the tensor cores (vposer_tc.cu)
     const int aux_ld = static_cast<int>(vposer_tc_aux_floats());
-    float * aux = nullptr;
-    SB_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&aux), static_cast<size_t>(B) * aux_ld * sizeof(float), st));
+    float * aux = aux_ws;
+    if(!aux)
+    {
+      const size_t need = static_cast<size_t>(B) * aux_ld;
+      if(vposer->tc_aux_floats < need)
+      {
+        SB_CUDA(cudaStreamSynchronize(st)); // earlier launches may still read the old buffer
+        if(vposer->tc_aux) cudaFree(vposer->tc_aux);
+        vposer->tc_aux = nullptr;
+        vposer->tc_aux_floats = 0;
+        SB_CUDA(cudaMalloc(reinterpret_cast<void **>(&vposer->tc_aux), need * sizeof(float)));
+        vposer->tc_aux_floats = need;
+      }
+      aux = vposer->tc_aux;
+    }
     int grid = passes < 2 * sms ? passes : 2 * sms;
     vposer_decode_kernel<false><<<grid, vp::THREADS, sizeof(vp::SmemFwd), st>>>(
         vposer->w0, vposer->b0, vposer->w3t, vposer->b3, vposer->w5t, vposer->b5, B, latent, latent_stride, aa,
         aa_stride, nullptr, aux, aux_ld);
     SB_LAUNCHED();
-    const int rc = launch_vposer_jac_tc(*vposer, st, B, aux, jac);
-    SB_CUDA(cudaFreeAsync(aux, st));
-    return rc;
+    return launch_vposer_jac_tc(*vposer, st, B, aux, jac);
   }
   if(jac)
   {
@@ -561,6 +572,7 @@ extern "C" void smplpp_vposer_destroy(smplpp_vposer_t * v)
   cudaFree(v->w5t);
   cudaFree(v->b5);
   vposer_tc_release(*v);
+  if(v->tc_aux) cudaFree(v->tc_aux);
   delete v;
 }
 

@@ -17,13 +17,17 @@ struct smplpp_vposer
   float tc_conv_scale = 1.f, tc_out_scale = 1.f;
   int tc_sms = 0;
   bool tc_ready = false;
+  mutable float * tc_aux = nullptr; // grow-only scratch of smplpp_vposer_decode (the IK step passes its own workspace)
+  mutable size_t tc_aux_floats = 0;
 };
 
 namespace sb
 {
 // latent (B, 32) with row stride latent_stride -> aa (B, 63) with row stride aa_stride; jac (B, 63, 32) nullable
+// aux: B * vposer_tc_aux_floats() floats of caller-owned scratch for the tensor-core Jacobian (nullable: the handle's own
+// grow-only buffer is used, which restricts Jacobian calls on one handle to one stream at a time)
 int launch_vposer_decode(const smplpp_vposer * vposer, cudaStream_t st, int B, const float * latent,
-                         long long latent_stride, float * aa, long long aa_stride, float * jac);
+                         long long latent_stride, float * aa, long long aa_stride, float * jac, float * aux = nullptr);
 // tensor-core Jacobian path (vposer_tc.cu)
 int vposer_tc_prepare(smplpp_vposer & v, const float * w0, const float * w3, const float * w5);
 void vposer_tc_release(smplpp_vposer & v);
