@@ -244,7 +244,11 @@ __global__ void rotmat_to_axis_angle_kernel(long long n, const float * __restric
 namespace vp
 {
 constexpr int H = SMPLPP_VPOSER_HIDDEN, L = SMPLPP_LATENT_DIM, NJ = SMPLPP_VPOSER_JOINTS, OUT = 6 * NJ;
-constexpr int FB = 2, THREADS = 512;
+constexpr int THREADS = 512;
+constexpr int FB_JAC = 2; // frames per pass of the FFMA Jacobian variant (bounded by the T2 tile in shared memory)
+constexpr int FB_FWD = 8; // forward-only variant: W3 (1 MB from L2) is re-read once per pass, so more frames per pass
+                          // (ncu r01h: 1.8 ms per 16384 frames at 2 frames per pass, FMA pipe 10 % active)
+template<int FB>
 struct Smem
 {
   float w0[H][L];          // decoder_net.0.weight (out, in) = [k][t] of the tangent recursion
@@ -254,6 +258,7 @@ struct Smem
   float y[FB][OUT + 2];
   float daa[FB][NJ][18];
 };
+template<int FB>
 struct SmemFwd
 {
   float w0[H][L];
@@ -264,7 +269,7 @@ struct SmemFwd
 };
 } // namespace vp
 
-template<bool kJac>
+template<bool kJac, int FB>
 __global__ void __launch_bounds__(vp::THREADS, 1)
     vposer_decode_kernel(const float * __restrict__ w0, const float * __restrict__ b0, const float * __restrict__ w3t,
                          const float * __restrict__ b3, const float * __restrict__ w5t, const float * __restrict__ b5,
@@ -272,7 +277,7 @@ __global__ void __launch_bounds__(vp::THREADS, 1)
                          long long aa_stride, float * __restrict__ jac_out, float * __restrict__ aux_out, int aux_ld)
 {
   using namespace vp;
-  using S = typename std::conditional<kJac, Smem, SmemFwd>::type;
+  using S = typename std::conditional<kJac, Smem<FB>, SmemFwd<FB>>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   S & s = *reinterpret_cast<S *>(smem_raw);
   const int tid = threadIdx.x;
@@ -334,16 +339,24 @@ __global__ void __launch_bounds__(vp::THREADS, 1)
       }
     }
     __syncthreads();
-    // layer 5: threads (f, o)
-    if(tid < FB * 128)
+    // layer 5: threads (frame group, o): every thread covers FB * 128 / THREADS frames so that a weight is loaded once
     {
-      int f = tid >> 7, o = tid & 127;
-      if(o < OUT)
+      constexpr int FPT = FB * 128 > THREADS ? FB * 128 / THREADS : 1; // frames per thread
+      const int o = tid & 127, fg = tid >> 7;
+      if(o < OUT && fg * FPT < FB)
       {
-        float acc = b5[o];
+        float acc[FPT];
+#pragma unroll
+        for(int i = 0; i < FPT; i++) acc[i] = b5[o];
 #pragma unroll 8
-        for(int k = 0; k < H; k++) acc = fmaf(__ldg(w5t + static_cast<size_t>(k) * 128 + o), s.h2[f][k], acc);
-        s.y[f][o] = acc;
+        for(int k = 0; k < H; k++)
+        {
+          const float w = __ldg(w5t + static_cast<size_t>(k) * 128 + o);
+#pragma unroll
+          for(int i = 0; i < FPT; i++) acc[i] = fmaf(w, s.h2[fg * FPT + i][k], acc[i]);
+        }
+#pragma unroll
+        for(int i = 0; i < FPT; i++) s.y[fg * FPT + i][o] = acc[i];
       }
     }
     __syncthreads();
@@ -367,7 +380,7 @@ __global__ void __launch_bounds__(vp::THREADS, 1)
     }
     if(kJac)
     {
-      Smem & sj = *reinterpret_cast<Smem *>(smem_raw);
+      Smem<FB> & sj = *reinterpret_cast<Smem<FB> *>(smem_raw);
       // T2[f][i][t] = d2[f][i] * sum_k W3[i][k] d1[f][k] W0[k][t]   (thread i = tid)
       float acc[FB][L];
 #pragma unroll
@@ -472,17 +485,19 @@ int launch_vposer_decode(const smplpp_vposer * vposer, cudaStream_t st, int B, c
   static bool configured = false;
   if(!configured)
   {
-    SB_CUDA(cudaFuncSetAttribute(vposer_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(sizeof(vp::Smem))));
-    SB_CUDA(cudaFuncSetAttribute(vposer_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(sizeof(vp::SmemFwd))));
+    SB_CUDA(cudaFuncSetAttribute(vposer_decode_kernel<true, vp::FB_JAC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(sizeof(vp::Smem<vp::FB_JAC>))));
+    SB_CUDA(cudaFuncSetAttribute(vposer_decode_kernel<false, vp::FB_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(sizeof(vp::SmemFwd<vp::FB_FWD>))));
     configured = true;
   }
   int sms = 148;
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int passes = (B + vp::FB - 1) / vp::FB;
+  const bool jac_ffma = jac && !(vposer->tc_ready && g_vposer_jac_variant == 0);
+  const int fb = jac_ffma ? vp::FB_JAC : vp::FB_FWD;
+  int passes = (B + fb - 1) / fb;
   if(jac && vposer->tc_ready && g_vposer_jac_variant == 0)
   {
     // forward pass (FFMA, 0.7 MFLOP per frame) leaves LeakyReLU'(h1), LeakyReLU'(h2) and d aa / d y6 of every frame in a
@@ -504,7 +519,7 @@ int launch_vposer_decode(const smplpp_vposer * vposer, cudaStream_t st, int B, c
       aux = vposer->tc_aux;
     }
     int grid = passes < 2 * sms ? passes : 2 * sms;
-    vposer_decode_kernel<false><<<grid, vp::THREADS, sizeof(vp::SmemFwd), st>>>(
+    vposer_decode_kernel<false, vp::FB_FWD><<<grid, vp::THREADS, sizeof(vp::SmemFwd<vp::FB_FWD>), st>>>(
         vposer->w0, vposer->b0, vposer->w3t, vposer->b3, vposer->w5t, vposer->b5, B, latent, latent_stride, aa,
         aa_stride, nullptr, aux, aux_ld);
     SB_LAUNCHED();
@@ -513,14 +528,14 @@ int launch_vposer_decode(const smplpp_vposer * vposer, cudaStream_t st, int B, c
   if(jac)
   {
     int grid = passes < sms ? passes : sms;
-    vposer_decode_kernel<true><<<grid, vp::THREADS, sizeof(vp::Smem), st>>>(
+    vposer_decode_kernel<true, vp::FB_JAC><<<grid, vp::THREADS, sizeof(vp::Smem<vp::FB_JAC>), st>>>(
         vposer->w0, vposer->b0, vposer->w3t, vposer->b3, vposer->w5t, vposer->b5, B, latent, latent_stride, aa,
         aa_stride, jac, nullptr, 0);
   }
   else
   {
     int grid = passes < 2 * sms ? passes : 2 * sms;
-    vposer_decode_kernel<false><<<grid, vp::THREADS, sizeof(vp::SmemFwd), st>>>(
+    vposer_decode_kernel<false, vp::FB_FWD><<<grid, vp::THREADS, sizeof(vp::SmemFwd<vp::FB_FWD>), st>>>(
         vposer->w0, vposer->b0, vposer->w3t, vposer->b3, vposer->w5t, vposer->b5, B, latent, latent_stride, aa,
         aa_stride, nullptr, nullptr, 0);
   }
