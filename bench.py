@@ -187,6 +187,9 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH, help="frames per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ik", action="store_true")
+    ap.add_argument("--ik-frames-total", type=int, default=0,
+                    help="BASELINE configs[4]: total mocap frames of the IK leg, sharded over the ranks as contiguous "
+                         "blocks (default 0 = 16384 frames per GPU)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     # rank 0 prints ONE JSON line on stdout: libraries that write to fd 1 (NCCL's version banner) go to stderr instead
@@ -373,7 +376,13 @@ def main():
     if not args.no_ik:
         try:
             from smplpp_b200 import ik_bench
-            ik = ik_bench.run(dev, rank, world, max_over_ranks, barrier)
+            if args.ik_frames_total > 0:
+                from smplpp_b200 import parallel
+                _, nloc = parallel.frame_block(args.ik_frames_total, rank, world)
+                ik = ik_bench.run(dev, rank, world, max_over_ranks, barrier, frames=nloc, iters=3, warmup=1,
+                                  frames_total=args.ik_frames_total)
+            else:
+                ik = ik_bench.run(dev, rank, world, max_over_ranks, barrier)
         except ImportError:
             ik = None
 

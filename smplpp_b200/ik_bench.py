@@ -52,7 +52,10 @@ def time_steps(fn, iters, warmup, barrier, max_over_ranks, dev):
     return max_over_ranks(a.elapsed_time(b)) / iters
 
 
-def run(dev, rank, world, max_over_ranks, barrier, frames: int = 16384, iters: int = 10, warmup: int = 3):
+def run(dev, rank, world, max_over_ranks, barrier, frames: int = 16384, iters: int = 10, warmup: int = 3,
+        frames_total: int = 0):
+    """frames = frames of THIS rank.  frames_total > 0: a strong-scaling run (configs[4]) whose ranks hold unequal
+    contiguous blocks; values are then total frames / max-over-ranks time."""
     params = synth.make_smpl_params(0)
     smpl = api.SMPL(params, device=dev)
     vposer = api.VPoserDecoder(synth.make_vposer_params(1), device=dev)
@@ -61,6 +64,10 @@ def run(dev, rank, world, max_over_ranks, barrier, frames: int = 16384, iters: i
     prob = make_problem(smpl, tasks, frames, 20 + rank, dev)
     out = {"unit": "frame-iters/s", "frames_per_gpu": frames, "markers": tasks.n, "task_vertices": tasks.vertex_count,
            "iterations_timed": iters}
+    all_frames = frames_total if frames_total > 0 else world * frames
+    if frames_total > 0:
+        out["frames_total"] = frames_total
+        out["scaling"] = "strong"
 
     # (1) MoSh direct (configs[2]): theta + translation per frame (D = 75), fixed beta, normal offset 15 mm
     opt = api.ik_options()
@@ -70,7 +77,7 @@ def run(dev, rank, world, max_over_ranks, barrier, frames: int = 16384, iters: i
         tasks.step(opt, theta, prob["beta"], vw, prob["target"], pos_task_weight=prob["valid"])
 
     ms = time_steps(step_direct, iters, warmup, barrier, max_over_ranks, dev)
-    out["mosh_direct"] = {"value": world * frames / (ms * 1e-3), "ms_per_iter": ms, "unknowns_per_frame": 75}
+    out["mosh_direct"] = {"value": all_frames / (ms * 1e-3), "ms_per_iter": ms, "unknowns_per_frame": 75}
     # residual after the timed iterations (sanity: the solver is converging on real work)
     status, o = tasks.step(opt, theta, prob["beta"], vw, prob["target"], pos_task_weight=prob["valid"], outputs=False), None
     del o
@@ -86,7 +93,7 @@ def run(dev, rank, world, max_over_ranks, barrier, frames: int = 16384, iters: i
         tasks.step(optv, xv, prob["beta"], vw2, prob["target"], pos_task_weight=prob["valid"])
 
     ms = time_steps(step_vposer, max(3, iters // 2), 2, barrier, max_over_ranks, dev)
-    out["moshpp_vposer"] = {"value": world * frames / (ms * 1e-3), "ms_per_iter": ms, "unknowns_per_frame": 44}
+    out["moshpp_vposer"] = {"value": all_frames / (ms * 1e-3), "ms_per_iter": ms, "unknowns_per_frame": 44}
 
     # (3) shared-beta stage (configs[3]/[4]): Schur complement per frame + ONE all-reduce of 111 doubles
     sbeta = torch.zeros(10, dtype=torch.float32, device=dev)
@@ -96,7 +103,7 @@ def run(dev, rank, world, max_over_ranks, barrier, frames: int = 16384, iters: i
         tasks.shared_beta_step(opt, th3, sbeta, vw3, prob["target"], pos_task_weight=prob["valid"])
 
     ms = time_steps(step_shared, max(3, iters // 2), 2, barrier, max_over_ranks, dev)
-    out["shared_beta"] = {"value": world * frames / (ms * 1e-3), "ms_per_iter": ms,
+    out["shared_beta"] = {"value": all_frames / (ms * 1e-3), "ms_per_iter": ms,
                           "collective": "all_reduce(sum) of 111 float64 per iteration" if world > 1 else "none (1 GPU)"}
     # (4) projection of the task points onto the posed mesh + re-seated face / weights (node.cpp:970-1001):
     # full forward pass of a block of frames, then smplpp_closest_points (41 points x 13776 faces per frame)
