@@ -714,9 +714,12 @@ class IkTaskSet:
         self._ws = None
 
     def __del__(self):
-        if getattr(self, "_h", None) is not None and capi._lib is not None:
-            capi._lib.smplpp_tasks_destroy(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None) is not None and capi is not None and capi._lib is not None:
+                capi._lib.smplpp_tasks_destroy(self._h)
+                self._h = None
+        except Exception:  # interpreter shutdown
+            pass
 
     @property
     def vertex_count(self) -> int:
