@@ -47,6 +47,7 @@ typedef struct smplpp_vposer smplpp_vposer_t;
 typedef struct smplpp_tasks smplpp_tasks_t;
 typedef struct smplpp_json smplpp_json_t;
 typedef struct smplpp_c3d smplpp_c3d_t;
+typedef struct smplpp_mocap_body smplpp_mocap_body_t;
 
 const char * smplpp_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches evidence) */
@@ -321,6 +322,20 @@ int64_t smplpp_c3d_find_label(const smplpp_c3d_t * c3d, const char * name);
 /* frames [first, first + count) -> xyz_host (count, points, 3), valid_host (count, points): 0 = point.isEmpty(),
  * whose coordinates are returned as 0 (node.cpp:682-683 zeroes the target of a missing marker) */
 int smplpp_c3d_read(const smplpp_c3d_t * c3d, int64_t first, int64_t count, float * xyz_host, uint8_t * valid_host);
+
+/* Result files of the mocap modes.
+ * MocapBody.yaml: written by the body stage (node/node.cpp:1425-1441: beta, then name / faceIdx / vertexWeights of every
+ * IkTask) and loaded by the motion stage (node/node.cpp:509-535). */
+int smplpp_write_mocap_body_yaml(const char * path, const float * beta10, int32_t n_tasks, const char * const * names,
+                                 const int64_t * face_idx, const float * vertex_weights);
+int smplpp_mocap_body_open(const char * path, smplpp_mocap_body_t ** out);
+void smplpp_mocap_body_close(smplpp_mocap_body_t * body);
+int32_t smplpp_mocap_body_task_count(const smplpp_mocap_body_t * body);
+const char * smplpp_mocap_body_task_name(const smplpp_mocap_body_t * body, int32_t task);
+int smplpp_mocap_body_get(const smplpp_mocap_body_t * body, float * beta10, int64_t * face_idx, float * vertex_weights);
+/* Motion as text, one frame per line, 75 values of theta (scripts/convertRosbagToText.py:13-19) */
+int smplpp_write_motion_text(const char * path, int64_t frames, const float * theta75_host);
+int smplpp_read_motion_text(const char * path, int64_t max_frames, float * theta75_host, int64_t * frames_out);
 
 #ifdef __cplusplus
 }

@@ -418,6 +418,45 @@ class C3D:
             pass
 
 
+def write_mocap_body(path: str, beta, names, face_idx, vertex_weights) -> None:
+    """MocapBody.yaml of the body stage (node/node.cpp:1425-1441)."""
+    beta = _np_f32(beta).reshape(-1)
+    w = _np_f32(vertex_weights).reshape(-1, 3)
+    fi = np.ascontiguousarray(face_idx, dtype=np.int64)
+    arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+    check(lib().smplpp_write_mocap_body_yaml(path.encode(), beta.ctypes.data_as(capi.c_f32p), C.c_int32(len(names)), arr,
+                                             fi.ctypes.data_as(capi.c_i64p), w.ctypes.data_as(capi.c_f32p)))
+
+
+def read_mocap_body(path: str):
+    """(beta (10,), names, face_idx (n,), vertex_weights (n, 3)) as the motion stage loads them (node/node.cpp:509-535)."""
+    h = C.c_void_p()
+    check(lib().smplpp_mocap_body_open(path.encode(), C.byref(h)))
+    try:
+        n = int(lib().smplpp_mocap_body_task_count(h))
+        beta, fi, w = np.empty(10, np.float32), np.empty(n, np.int64), np.empty((n, 3), np.float32)
+        check(lib().smplpp_mocap_body_get(h, beta.ctypes.data_as(capi.c_f32p), fi.ctypes.data_as(capi.c_i64p),
+                                          w.ctypes.data_as(capi.c_f32p)))
+        names = [lib().smplpp_mocap_body_task_name(h, C.c_int32(i)).decode() for i in range(n)]
+        return beta, names, fi, w
+    finally:
+        lib().smplpp_mocap_body_close(h)
+
+
+def write_motion_text(path: str, theta) -> None:
+    """One frame per line, 75 values (scripts/convertRosbagToText.py:13-19)."""
+    th = _np_f32(theta).reshape(-1, 75)
+    check(lib().smplpp_write_motion_text(path.encode(), C.c_int64(th.shape[0]), th.ctypes.data_as(capi.c_f32p)))
+
+
+def read_motion_text(path: str) -> np.ndarray:
+    n = C.c_int64()
+    check(lib().smplpp_read_motion_text(path.encode(), C.c_int64(0), None, C.byref(n)))
+    th = np.empty((n.value, 25, 3), np.float32)
+    check(lib().smplpp_read_motion_text(path.encode(), n, th.ctypes.data_as(capi.c_f32p), C.byref(n)))
+    return th
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # the four pipeline modules (setter -> compute -> getter, like the reference)
 # ----------------------------------------------------------------------------------------------------------------

@@ -53,6 +53,8 @@ EXPORTS = [
     "smplpp_json_open", "smplpp_json_close", "smplpp_json_array", "smplpp_model_load_json", "smplpp_vposer_load_json",
     "smplpp_c3d_open", "smplpp_c3d_close", "smplpp_c3d_frame_count", "smplpp_c3d_point_count", "smplpp_c3d_frame_rate",
     "smplpp_c3d_label", "smplpp_c3d_units", "smplpp_c3d_find_label", "smplpp_c3d_read",
+    "smplpp_write_mocap_body_yaml", "smplpp_mocap_body_open", "smplpp_mocap_body_close", "smplpp_mocap_body_task_count",
+    "smplpp_mocap_body_task_name", "smplpp_mocap_body_get", "smplpp_write_motion_text", "smplpp_read_motion_text",
 ]
 
 _lib = None
@@ -78,6 +80,7 @@ def lib() -> C.CDLL:
         _lib.smplpp_c3d_frame_rate.restype = C.c_double
         _lib.smplpp_c3d_label.restype = C.c_char_p
         _lib.smplpp_c3d_units.restype = C.c_char_p
+        _lib.smplpp_mocap_body_task_name.restype = C.c_char_p
         for name in ("smplpp_forward_workspace_bytes", "smplpp_ik_workspace_bytes",
                      "smplpp_ik_shared_beta_workspace_bytes"):
             if hasattr(_lib, name):

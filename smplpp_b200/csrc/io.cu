@@ -586,3 +586,162 @@ extern "C" int smplpp_c3d_read(const smplpp_c3d_t * c, int64_t first, int64_t co
   }
   return SMPLPP_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// result files of the mocap modes
+// ------------------------------------------------------------------------------------------------------------
+// MocapBody.yaml (node/node.cpp:1425-1441): the body stage's result, loaded back as ROS parameters for the motion
+// stage (node/node.cpp:509-535).  Layout:
+//   beta: [b0, ..., b9]
+//   ikTaskList:
+//     - name: <marker>
+//       faceIdx: <int>
+//       vertexWeights: [w0, w1, w2]
+// The reference formats the numbers with Eigen::FullPrecision (Eigen is not under /root/reference, its digit count for
+// float is version dependent); here every float is written with 9 significant digits, which round-trips exactly.
+extern "C" int smplpp_write_mocap_body_yaml(const char * path, const float * beta10, int32_t n, const char * const * names,
+                                            const int64_t * face_idx, const float * vertex_weights)
+{
+  if(!path || !beta10 || n < 0 || (n > 0 && (!names || !face_idx || !vertex_weights)))
+    return fail(SMPLPP_ERR_INVALID, "node", "invalid mocap body description");
+  FILE * f = fopen(path, "w");
+  if(!f) return fail(SMPLPP_ERR_IO, "node", std::string("Cannot write ") + path);
+  fprintf(f, "beta: [");
+  for(int i = 0; i < kShapeDim; i++) fprintf(f, "%s%.9g", i ? ", " : "", static_cast<double>(beta10[i]));
+  fprintf(f, "]\nikTaskList:\n");
+  for(int i = 0; i < n; i++)
+  {
+    fprintf(f, "  - name: %s\n    faceIdx: %lld\n    vertexWeights: [%.9g, %.9g, %.9g]\n", names[i],
+            static_cast<long long>(face_idx[i]), static_cast<double>(vertex_weights[3 * i]),
+            static_cast<double>(vertex_weights[3 * i + 1]), static_cast<double>(vertex_weights[3 * i + 2]));
+  }
+  fclose(f);
+  return SMPLPP_OK;
+}
+
+struct smplpp_mocap_body
+{
+  std::vector<float> beta;
+  std::vector<std::string> names;
+  std::vector<int64_t> face_idx;
+  std::vector<float> weights;
+};
+
+namespace
+{
+bool parse_bracket_list(const std::string & line, size_t from, std::vector<float> & out)
+{
+  const size_t a = line.find('[', from), b = line.find(']', from);
+  if(a == std::string::npos || b == std::string::npos || b < a) return false;
+  const char * p = line.c_str() + a + 1;
+  const char * end = line.c_str() + b;
+  while(p < end)
+  {
+    char * stop = nullptr;
+    const double v = strtod(p, &stop);
+    if(stop == p) break;
+    out.push_back(static_cast<float>(v));
+    p = stop;
+    while(p < end && (*p == ',' || *p == ' ')) p++;
+  }
+  return true;
+}
+} // namespace
+
+extern "C" int smplpp_mocap_body_open(const char * path, smplpp_mocap_body_t ** out)
+{
+  if(!out) return fail(SMPLPP_ERR_INVALID, "node", "null output");
+  std::ifstream f(path ? path : "");
+  if(!f) return fail(SMPLPP_ERR_IO, "node", std::string("Cannot open ") + (path ? path : ""));
+  std::unique_ptr<smplpp_mocap_body> b(new smplpp_mocap_body());
+  std::string line;
+  while(std::getline(f, line))
+  {
+    size_t p;
+    if(line.compare(0, 5, "beta:") == 0)
+      parse_bracket_list(line, 5, b->beta);
+    else if((p = line.find("- name:")) != std::string::npos)
+    {
+      std::string name = line.substr(p + 7);
+      while(!name.empty() && name.front() == ' ') name.erase(name.begin());
+      while(!name.empty() && (name.back() == ' ' || name.back() == '\r')) name.pop_back();
+      b->names.push_back(name);
+    }
+    else if((p = line.find("faceIdx:")) != std::string::npos)
+      b->face_idx.push_back(strtoll(line.c_str() + p + 8, nullptr, 10));
+    else if((p = line.find("vertexWeights:")) != std::string::npos)
+      parse_bracket_list(line, p, b->weights);
+  }
+  if(b->beta.size() != static_cast<size_t>(kShapeDim))
+    return fail(SMPLPP_ERR_IO, "node", "Size of beta must be " + std::to_string(kShapeDim) + " but " + std::to_string(b->beta.size())); // node.cpp:511-515
+  if(b->face_idx.size() != b->names.size() || b->weights.size() != 3 * b->names.size())
+    return fail(SMPLPP_ERR_IO, "node", "malformed ikTaskList in the mocap body file");
+  *out = b.release();
+  return SMPLPP_OK;
+}
+extern "C" void smplpp_mocap_body_close(smplpp_mocap_body_t * b)
+{
+  delete b;
+}
+extern "C" int32_t smplpp_mocap_body_task_count(const smplpp_mocap_body_t * b)
+{
+  return b ? static_cast<int32_t>(b->names.size()) : 0;
+}
+extern "C" const char * smplpp_mocap_body_task_name(const smplpp_mocap_body_t * b, int32_t i)
+{
+  return (b && i >= 0 && i < static_cast<int32_t>(b->names.size())) ? b->names[static_cast<size_t>(i)].c_str() : "";
+}
+// beta10 (10), face_idx (n), vertex_weights (n, 3)
+extern "C" int smplpp_mocap_body_get(const smplpp_mocap_body_t * b, float * beta10, int64_t * face_idx, float * vertex_weights)
+{
+  if(!b || !beta10 || !face_idx || !vertex_weights) return fail(SMPLPP_ERR_INVALID, "node", "null argument");
+  std::copy(b->beta.begin(), b->beta.end(), beta10);
+  std::copy(b->face_idx.begin(), b->face_idx.end(), face_idx);
+  std::copy(b->weights.begin(), b->weights.end(), vertex_weights);
+  return SMPLPP_OK;
+}
+
+// Motion as text: one line per frame, the 75 values of theta (25 x 3 row-major: translation, then 24 axis-angles)
+// separated by blanks (scripts/convertRosbagToText.py:13-19 writes exactly this from the smplpp/motion message)
+extern "C" int smplpp_write_motion_text(const char * path, int64_t frames, const float * theta75)
+{
+  if(!path || frames < 0 || (frames > 0 && !theta75)) return fail(SMPLPP_ERR_INVALID, "node", "invalid motion");
+  FILE * f = fopen(path, "w");
+  if(!f) return fail(SMPLPP_ERR_IO, "node", std::string("Cannot write ") + path);
+  for(int64_t i = 0; i < frames; i++)
+  {
+    for(int k = 0; k < 75; k++) fprintf(f, "%s%.9g", k ? " " : "", static_cast<double>(theta75[i * 75 + k]));
+    fputc('\n', f);
+  }
+  fclose(f);
+  return SMPLPP_OK;
+}
+
+// frames_out = number of lines; theta75 may be null to query the count first; at most max_frames lines are stored
+extern "C" int smplpp_read_motion_text(const char * path, int64_t max_frames, float * theta75, int64_t * frames_out)
+{
+  if(!frames_out) return fail(SMPLPP_ERR_INVALID, "node", "null argument");
+  std::ifstream f(path ? path : "");
+  if(!f) return fail(SMPLPP_ERR_IO, "node", std::string("Cannot open ") + (path ? path : ""));
+  std::string line;
+  int64_t n = 0;
+  while(std::getline(f, line))
+  {
+    if(line.find_first_not_of(" \t\r") == std::string::npos) continue;
+    const char * p = line.c_str();
+    float v[75];
+    int k = 0;
+    for(; k < 75; k++)
+    {
+      char * stop = nullptr;
+      v[k] = strtof(p, &stop);
+      if(stop == p) break;
+      p = stop;
+    }
+    if(k != 75) return fail(SMPLPP_ERR_IO, "node", "a motion line does not hold 75 values (line " + std::to_string(n + 1) + ")");
+    if(theta75 && n < max_frames) std::copy(v, v + 75, theta75 + n * 75);
+    n++;
+  }
+  *frames_out = n;
+  return SMPLPP_OK;
+}

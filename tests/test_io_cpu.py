@@ -142,3 +142,39 @@ def test_c3d_reference_sample_walk(api):
     assert int(ok[:, idx].all(axis=1).sum()) == 2544
     v = xyz[:, idx][ok[:, idx]]
     assert -1.81 < v[:, 0].min() and v[:, 0].max() < 0.35 and 0.02 < v[:, 2].min() and v[:, 2].max() < 2.09
+
+
+def test_mocap_body_yaml_and_motion_text_round_trip(tmp_path, api):
+    """Result files of the mocap modes: MocapBody.yaml (node.cpp:1425-1441 writes it, :509-535 loads it back) and the
+    75-values-per-line motion dump (scripts/convertRosbagToText.py).  Exact float32 round trip; the YAML is also valid
+    for a generic YAML parser."""
+    import yaml
+    from smplpp_b200 import capi
+    rng = np.random.default_rng(2)
+    beta = rng.normal(size=10).astype(np.float32)
+    names = ["HeadTop", "WaistLFront", "RToeOut"]
+    face_idx = np.array([7324, 2162, 13775], dtype=np.int64)
+    w = rng.dirichlet(np.ones(3), size=3).astype(np.float32)
+    path = str(tmp_path / "MocapBody.yaml")
+    api.write_mocap_body(path, beta, names, face_idx, w)
+    b2, n2, f2, w2 = api.read_mocap_body(path)
+    assert np.array_equal(b2, beta) and n2 == names and np.array_equal(f2, face_idx) and np.array_equal(w2, w)
+    with open(path) as f:
+        doc = yaml.safe_load(f)
+    assert np.array_equal(np.float32(doc["beta"]), beta) and doc["ikTaskList"][1]["faceIdx"] == 2162
+    assert doc["ikTaskList"][2]["name"] == "RToeOut" and np.array_equal(np.float32(doc["ikTaskList"][0]["vertexWeights"]), w[0])
+    with open(str(tmp_path / "short.yaml"), "w") as f:
+        f.write("beta: [1, 2, 3]\nikTaskList:\n")
+    with pytest.raises(capi.SmplppError, match="Size of beta must be 10 but 3"):   # node.cpp:511-515
+        api.read_mocap_body(str(tmp_path / "short.yaml"))
+    theta = rng.normal(size=(17, 25, 3)).astype(np.float32)
+    tpath = str(tmp_path / "motion.txt")
+    api.write_motion_text(tpath, theta)
+    assert np.array_equal(api.read_motion_text(tpath), theta)
+    with open(tpath) as f:
+        first = f.readline().split()
+    assert len(first) == 75 and np.float32(first[0]) == theta[0, 0, 0]
+    with open(str(tmp_path / "bad.txt"), "w") as f:
+        f.write("1 2 3\n")
+    with pytest.raises(capi.SmplppError, match="does not hold 75 values"):
+        api.read_motion_text(str(tmp_path / "bad.txt"))
