@@ -448,13 +448,8 @@ int tc_prepare_model(ModelDev & d)
       return fail(SMPLPP_ERR_CUDA, "CUDA", "cuTensorMapEncodeTiled failed for the blend basis");
   }
   SB_CUDA(cudaDeviceSynchronize());
-  static bool configured = false;
-  if(!configured)
-  {
-    SB_CUDA(cudaFuncSetAttribute(blend_skin_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-    SB_CUDA(cudaFuncSetAttribute(blend_skin_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-    configured = true;
-  }
+  SB_CUDA(cudaFuncSetAttribute(blend_skin_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+  SB_CUDA(cudaFuncSetAttribute(blend_skin_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
   d.tc_ready = true;
   return SMPLPP_OK;
 }

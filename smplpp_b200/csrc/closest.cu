@@ -241,12 +241,8 @@ extern "C" int smplpp_closest_points(const smplpp_model_t * model, void * stream
   p.sqdist_out = sq_dist;
   p.weights_out = vertex_weights;
   const size_t smem = (static_cast<size_t>(3) * d.V + 2 * CP_THREADS) * sizeof(float) + (static_cast<size_t>(d.F) + 8) * sizeof(__half);
-  static bool attr_set = false;
-  if(!attr_set)
-  {
-    SB_CUDA(cudaFuncSetAttribute(closest_point_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 115000));
-    attr_set = true;
-  }
+  // per launch: the attribute is per device, and one process may drive several
+  SB_CUDA(cudaFuncSetAttribute(closest_point_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 115000));
   if(smem > 115000) return fail(SMPLPP_ERR_INVALID, "IkTask", "Failed to project points onto the mesh! (mesh too large)");
   closest_point_kernel<<<static_cast<unsigned>(batch), CP_THREADS, smem, as_stream(stream)>>>(p);
   SB_LAUNCHED();

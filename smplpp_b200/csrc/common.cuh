@@ -60,6 +60,17 @@ inline size_t align_up(size_t n, size_t a = 256)
   return (n + a - 1) / a * a;
 }
 
+// true the first time it is called on the current device with this flag array (function attributes and memory-pool
+// settings are per device; one process may drive several devices)
+inline bool first_call_on_device(bool (&done)[64])
+{
+  int dev = 0;
+  if(cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  if(done[dev]) return false;
+  done[dev] = true;
+  return true;
+}
+
 // Device-resident constants of one model.  Immutable after create => shareable across streams/threads.
 struct ModelDev
 {

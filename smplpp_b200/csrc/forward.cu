@@ -799,14 +799,13 @@ int launch_pose_chain(const ModelDev & d, cudaStream_t st, int B, const float * 
 int launch_blend_skin_ffma(const ModelDev & d, cudaStream_t st, int B, const float * coef, const float * xforms,
                            const float * theta, float * out, bool skin)
 {
-  static bool configured = false;
-  if(!configured)
+  static bool configured[64] = {};
+  if(first_call_on_device(configured))
   {
     SB_CUDA(cudaFuncSetAttribute(blend_skin_ffma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(k2::SMEM_TOTAL)));
     SB_CUDA(cudaFuncSetAttribute(blend_skin_ffma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(k2::SMEM_AB)));
-    configured = true;
   }
   dim3 grid(d.Vpad / k2::BNV, (B + k2::BM - 1) / k2::BM);
   if(skin)

@@ -375,8 +375,8 @@ bool lbs_tc_usable(const ModelDev & d, const float * rest, const float * out, co
 int launch_lbs_tc(const ModelDev & d, cudaStream_t st, int B, const float * rest, const float * xforms, int xf_floats,
                   const float * root, int root_stride, float * out)
 {
-  static bool configured = false;
-  if(!configured)
+  static bool configured[64] = {};
+  if(first_call_on_device(configured))
   {
     SB_CUDA(cudaFuncSetAttribute(lbs_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k3c::SMEM_BYTES));
     // the per-call transform scratch comes from the stream-ordered pool: keep freed blocks cached across synchronisations
@@ -388,7 +388,6 @@ int launch_lbs_tc(const ModelDev & d, cudaStream_t st, int B, const float * rest
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
     cudaGetLastError();
-    configured = true;
   }
   const int Bpad = static_cast<int>(align_up(static_cast<size_t>(B), k3c::SUBF));
   const size_t xf_bytes = static_cast<size_t>(2) * Bpad * kXformFloats * skin::KJ * sizeof(__half);

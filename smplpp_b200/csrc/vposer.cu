@@ -482,15 +482,11 @@ int g_vposer_jac_variant = 0;
 int launch_vposer_decode(const smplpp_vposer * vposer, cudaStream_t st, int B, const float * latent,
                          long long latent_stride, float * aa, long long aa_stride, float * jac, float * aux_ws)
 {
-  static bool configured = false;
-  if(!configured)
-  {
-    SB_CUDA(cudaFuncSetAttribute(vposer_decode_kernel<true, vp::FB_JAC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(sizeof(vp::Smem<vp::FB_JAC>))));
-    SB_CUDA(cudaFuncSetAttribute(vposer_decode_kernel<false, vp::FB_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(sizeof(vp::SmemFwd<vp::FB_FWD>))));
-    configured = true;
-  }
+  // per launch: the attribute is per device, and one process may drive several
+  SB_CUDA(cudaFuncSetAttribute(vposer_decode_kernel<true, vp::FB_JAC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(sizeof(vp::Smem<vp::FB_JAC>))));
+  SB_CUDA(cudaFuncSetAttribute(vposer_decode_kernel<false, vp::FB_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(sizeof(vp::SmemFwd<vp::FB_FWD>))));
   int sms = 148;
   int dev = 0;
   cudaGetDevice(&dev);

@@ -407,3 +407,23 @@ def test_native_json_loaders_match_python_loaders(tmp_path, params, vposer_param
     vb.loadParamsFromJsonNative(vpath)
     z = np.random.default_rng(0).normal(size=(5, 32)).astype(np.float32)
     assert torch.equal(va.forward(z), vb.forward(z))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_in_one_process(params, vposer_params):
+    """One process driving two devices (function attributes, memory pools and model constants are per device): the same
+    forward pass, projection and VPoser Jacobian on cuda:0 and cuda:1 give identical results."""
+    from smplpp_b200 import api, synth
+    beta, theta = synth.make_forward_inputs(200, 5)
+    z = np.random.default_rng(1).normal(size=(9, 32)).astype(np.float32)
+    res = []
+    for dev in ("cuda:0", "cuda:1"):
+        smpl = api.SMPL(params, device=dev)
+        smpl.launch(beta, theta)
+        v = smpl.getVertex()
+        face, closest, sq, w = smpl.projectPoints(v[:, ::200][:, :30].contiguous() + 0.01)
+        vp = api.VPoserDecoder(vposer_params, device=dev)
+        aa, jac = vp.forward(z, jacobian=True)
+        res.append([t.cpu() for t in (v, face, closest, aa, jac)])
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
