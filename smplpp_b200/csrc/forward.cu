@@ -10,6 +10,7 @@
 //   skinning            src/LinearBlendSkinning.cpp:445-553 (homogeneous divide kept, root translation added)
 #include "common.cuh"
 #include "forward.cuh"
+#include "tc3_layout.cuh"
 #include "vposer.cuh"
 
 using namespace sb;
@@ -55,14 +56,39 @@ __global__ void __launch_bounds__(kChainWarps * 32)
     pose_chain_kernel(ChainTopo topo, const float * __restrict__ joint_template,
                       const float * __restrict__ joint_shape, int B, const float * __restrict__ beta,
                       long long beta_stride, const float * __restrict__ theta, float * __restrict__ coef,
-                      float * __restrict__ xforms, float * __restrict__ joints_out, float * __restrict__ xforms44_out)
+                      float * __restrict__ xforms, float * __restrict__ joints_out, float * __restrict__ xforms44_out,
+                      uint8_t * __restrict__ img_b, uint8_t * __restrict__ img_g, int Bpad)
 {
   __shared__ float sG[kChainWarps][kJoints][12];
   __shared__ float sJ[kChainWarps][kJoints][3];
   __shared__ float sC[kChainWarps][kBlendK];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long b = static_cast<long long>(blockIdx.x) * kChainWarps + warp;
-  if(b >= B) return; // whole warp leaves together; only __syncwarp below
+  if(b >= B)
+  {
+    // padding frames of the last 96-frame block: their rows of the K2''' stage images are zero
+    if(img_b && b < Bpad)
+    {
+      const long long fb = b / tc3::NF;
+      const int nf = static_cast<int>(b - fb * tc3::NF);
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      if(lane < tc3::KP / 8)
+      {
+        uint8_t * blk = img_b + (static_cast<size_t>(fb) * tc3::NKB + lane / 4) * (2 * tc3::B_PART);
+        const uint32_t o = static_cast<uint32_t>(tc3::coef_row(nf) * tc3::ROWB + (lane % 4) * 16);
+        *reinterpret_cast<uint4 *>(blk + tc3::swz64(o)) = z;
+        *reinterpret_cast<uint4 *>(blk + tc3::swz64(tc3::B_PART + o)) = z;
+      }
+      uint8_t * blk = img_g + (static_cast<size_t>(fb) * tc3::NSUB + nf / tc3::SUBF) * tc3::G_STAGE;
+      for(int c = lane; c < kXformFloats * 4; c += 32)
+      {
+        const uint32_t o = static_cast<uint32_t>(((nf % tc3::SUBF) * kXformFloats + c / 4) * tc3::ROWB + (c % 4) * 16);
+        *reinterpret_cast<uint4 *>(blk + tc3::swz64(o)) = z;
+        *reinterpret_cast<uint4 *>(blk + tc3::swz64(tc3::G_PART + o)) = z;
+      }
+    }
+    return; // whole warp leaves together; only __syncwarp below
+  }
 
   const float * bp = beta + b * beta_stride;
   float R[9], Jt[3] = {0.f, 0.f, 0.f}, t[3];
@@ -148,6 +174,35 @@ __global__ void __launch_bounds__(kChainWarps * 32)
       for(int k = 0; k < 3; k++) joints_out[(b * kJoints + lane) * 3 + k] = Jt[k];
     }
   }
+  if(img_g)
+  {
+    // transform stage image of K2''' (row = frame in its 8-frame sub-batch * 12 + element, column = joint, fp16 hi | lo
+    // x 2^4, SWIZZLE_64B): the relative transforms go back to shared memory and every lane writes 16-byte chunks
+    // (8 joints of one element); this replaces a separate pass over the fp32 transforms
+    __syncwarp();
+    if(lane < kJoints)
+    {
+#pragma unroll
+      for(int e = 0; e < 12; e++) sG[warp][lane][e] = G[e];
+    }
+    __syncwarp();
+    const long long fb = b / tc3::NF;
+    const int nf = static_cast<int>(b - fb * tc3::NF);
+    uint8_t * blk = img_g + (static_cast<size_t>(fb) * tc3::NSUB + nf / tc3::SUBF) * tc3::G_STAGE;
+    for(int c = lane; c < kXformFloats * 4; c += 32)
+    {
+      const int e = c / 4, cj = c % 4;
+      float x[8];
+#pragma unroll
+      for(int jj = 0; jj < 8; jj++)
+      {
+        const int j = cj * 8 + jj;
+        x[jj] = j < kJoints ? sG[warp][j][e] * static_cast<float>(1 << tc3::G_EXP) : 0.f;
+      }
+      const uint32_t o = static_cast<uint32_t>(((nf % tc3::SUBF) * kXformFloats + e) * tc3::ROWB + cj * 16);
+      tc3::split8_store(x, blk + tc3::swz64(o), blk + tc3::swz64(tc3::G_PART + o));
+    }
+  }
   if(coef)
   {
     if(lane >= 1 && lane < kJoints)
@@ -160,6 +215,19 @@ __global__ void __launch_bounds__(kChainWarps * 32)
       sC[warp][kPoseDim + lane] = lane == kShapeDim ? 1.f : 0.f;
     __syncwarp();
     for(int i = lane; i < kBlendK; i += 32) coef[b * kBlendK + i] = sC[warp][i];
+    if(img_b && lane < tc3::KP / 8)
+    {
+      // coefficient stage image (rows of a 96-frame block permuted by coef_row, fp16 hi | lo x 2^6); the template
+      // column and the padding stay out of the tensor-core product
+      float x[8];
+#pragma unroll
+      for(int e = 0; e < 8; e++) x[e] = lane * 8 + e < tc3::KUSED ? sC[warp][lane * 8 + e] * static_cast<float>(1 << tc3::COEF_EXP) : 0.f;
+      const long long fb = b / tc3::NF;
+      const int r = tc3::coef_row(static_cast<int>(b - fb * tc3::NF));
+      uint8_t * blk = img_b + (static_cast<size_t>(fb) * tc3::NKB + lane / 4) * (2 * tc3::B_PART);
+      const uint32_t o = static_cast<uint32_t>(r * tc3::ROWB + (lane % 4) * 16);
+      tc3::split8_store(x, blk + tc3::swz64(o), blk + tc3::swz64(tc3::B_PART + o));
+    }
   }
 }
 
@@ -787,11 +855,17 @@ ChainTopo make_topo(const ModelDev & d)
 }
 
 int launch_pose_chain(const ModelDev & d, cudaStream_t st, int B, const float * beta, long long beta_stride,
-                      const float * theta, float * coef, float * xforms, float * joints, float * xforms44)
+                      const float * theta, float * coef, float * xforms, float * joints, float * xforms44,
+                      void * tc3_scratch)
 {
-  int grid = (B + kChainWarps - 1) / kChainWarps;
+  // with tc3_scratch the kernel also writes the coefficient / transform stage images of K2''' (and zero rows for the
+  // frames that pad the last 96-frame block)
+  const int Bpad = tc3_scratch ? static_cast<int>(align_up(static_cast<size_t>(B), tc3::NF)) : B;
+  uint8_t * img_b = static_cast<uint8_t *>(tc3_scratch);
+  uint8_t * img_g = tc3_scratch ? img_b + tc3::img_g_offset(Bpad) : nullptr;
+  int grid = (Bpad + kChainWarps - 1) / kChainWarps;
   pose_chain_kernel<<<grid, kChainWarps * 32, 0, st>>>(make_topo(d), d.joint_template, d.joint_shape, B, beta,
-                                                       beta_stride, theta, coef, xforms, joints, xforms44);
+                                                       beta_stride, theta, coef, xforms, joints, xforms44, img_b, img_g, Bpad);
   SB_LAUNCHED();
   return SMPLPP_OK;
 }
@@ -908,14 +982,16 @@ extern "C" int smplpp_forward(const smplpp_model_t * model, void * stream, int64
 
   const bool need_verts = vertices != nullptr;
   const bool need_rest = rest_shape != nullptr;
-  int rc = launch_pose_chain(d, st, B, beta, beta_stride, theta, (need_verts || need_rest) ? coef : nullptr, xforms,
-                             joints, transforms);
-  if(rc != SMPLPP_OK) return rc;
   int variant = g_forward_variant;
   if(variant == 0) variant = model->d.tc3_ready ? 6 : (model->d.tc2_ready ? 5 : (model->d.tc_ready ? 2 : 1));
   if(((variant == 2 || variant == 4) && !model->d.tc_ready) || (variant == 5 && !model->d.tc2_ready)
      || (variant == 6 && !model->d.tc3_ready))
     return fail(SMPLPP_ERR_INVALID, "SMPL", "tcgen05 blend variant is not available for this model");
+  // K1 writes the stage images of K2''' itself when that kernel follows
+  const bool fused_images = variant == 6 && need_verts && !need_rest;
+  int rc = launch_pose_chain(d, st, B, beta, beta_stride, theta, (need_verts || need_rest) ? coef : nullptr, xforms,
+                             joints, transforms, fused_images ? tc2_scratch : nullptr);
+  if(rc != SMPLPP_OK) return rc;
   if(need_rest || (need_verts && variant == 3))
   {
     float * rest = need_rest ? rest_shape : rest_ws;
@@ -927,7 +1003,7 @@ extern "C" int smplpp_forward(const smplpp_model_t * model, void * stream, int64
   if(need_verts)
   {
     if(variant == 6)
-      rc = launch_blend_skin_tc3(d, st, B, coef, xforms, tc2_scratch, theta, vertices);
+      rc = launch_blend_skin_tc3(d, st, B, coef, xforms, tc2_scratch, theta, vertices, /*images_ready=*/true);
     else if(variant == 5)
       rc = launch_blend_skin_tc2(d, st, B, coef, xforms, tc2_scratch, theta, vertices);
     else if(variant == 2 || variant == 4)

@@ -14,8 +14,10 @@ struct ChainTopo
 ChainTopo make_topo(const ModelDev & d);
 
 // K1: rodrigues + pose features + joints + kinematic chain (one warp per frame)
+// tc3_scratch (nullable, tc3_frame_operand_bytes(B) bytes): also write the stage images of K2'''
 int launch_pose_chain(const ModelDev & d, cudaStream_t st, int B, const float * beta, long long beta_stride,
-                      const float * theta, float * coef, float * xforms, float * joints, float * xforms44);
+                      const float * theta, float * coef, float * xforms, float * joints, float * xforms44,
+                      void * tc3_scratch = nullptr);
 // K2 (FFMA): fused blend contraction (+ skinning when skin == true, else writes the rest shape)
 int launch_blend_skin_ffma(const ModelDev & d, cudaStream_t st, int B, const float * coef, const float * xforms,
                            const float * theta, float * out, bool skin);
@@ -36,8 +38,9 @@ int launch_blend_skin_tc2(const ModelDev & d, cudaStream_t st, int B, const floa
 int tc3_prepare_model(ModelDev & d);
 void tc3_release_model(ModelDev & d);
 size_t tc3_frame_operand_bytes(int64_t batch);
+// images_ready: the scratch area already holds the stage images (written by K1); else they are built from coef / xforms
 int launch_blend_skin_tc3(const ModelDev & d, cudaStream_t st, int B, const float * coef, const float * xforms, void * scratch,
-                          const float * theta, float * out);
+                          const float * theta, float * out, bool images_ready = false);
 bool tc_encode_f16(void * out_map, void * base, uint64_t rows, uint64_t cols, uint32_t box_rows);
 // K3: standalone skinning; affine: xforms are (B,24,3,4) else (B,24,4,4)
 int launch_lbs(const ModelDev & d, cudaStream_t st, int B, const float * rest, const float * xforms, bool affine,

@@ -37,53 +37,13 @@
 
 #include "forward.cuh"
 #include "skin_common.cuh"
+#include "tc3_layout.cuh"
 #include "tc_ptx.cuh"
 
 using namespace sb;
 
 namespace tc3
 {
-constexpr int MV = 128;                          // vertices per tile (UMMA M)
-constexpr int NF = 96;                           // frames per block (UMMA N of GEMM 1)
-constexpr int ROWB = 64;                         // bytes of K per shared-memory row (one SWIZZLE_64B span = 32 fp16)
-constexpr int KP = kBlendK;                      // 224
-constexpr int KUSED = kPoseDim + kShapeDim;      // 217: the template column is excluded
-constexpr int NKB = KP * 2 / ROWB;               // 7 K-blocks of 32
-constexpr int A_PART = 3 * MV * ROWB;            // 24576: one part (hi or lo) of the basis tile, 3 planes
-constexpr int B_PART = NF * ROWB;                // 6144
-constexpr int STAGE = 2 * A_PART + 2 * B_PART;   // 61440
-constexpr int SUBF = 8;                          // frames per skinning sub-batch
-constexpr int SUBN = SUBF * kXformFloats;        // 96 = UMMA N of GEMM 2
-constexpr int KJ = skin::KJ;                     // joints padded to two K = 16 steps
-constexpr int G_PART = SUBN * ROWB;              // 6144
-constexpr int G_STAGE = 2 * G_PART;              // 12288
-constexpr int NSUB = NF / SUBF;                  // 12 sub-batches per item
-constexpr int EPI_WARPS = 16;
-constexpr int EPI_FR = 2;                        // frames of a sub-batch handled by one epilogue warp
-constexpr int FR_WARP = NSUB * EPI_FR;           // 24 frames of an item per epilogue warp
-constexpr int CTRL_WARPS = 4;                     // one warpgroup: producer, MMA issuer, two idle
-constexpr int THREADS = 32 * (CTRL_WARPS + EPI_WARPS);
-constexpr int STG_FLOATS = EPI_FR * 32 * 3;      // per warp: 2 frames x 32 vertices x 3
-constexpr int STG_BYTES = EPI_WARPS * STG_FLOATS * 4;
-// shared memory: [ST GEMM 1 stages][GS transform sub-batch slots][output staging][barriers]
-template<int ST, int GS, int EPI>
-struct Layout
-{
-  static constexpr int OFF_G = ST * STAGE;
-  static constexpr int OFF_STG = OFF_G + GS * G_STAGE;
-  static constexpr int OFF_BAR = OFF_STG + (EPI == 0 ? STG_BYTES : 0); // only the staged epilogue needs the staging area
-  static constexpr int SMEM_BYTES = 1024 + OFF_BAR + 512;
-  static_assert(OFF_STG % 1024 == 0, "swizzle atoms stay aligned");
-  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-};
-constexpr int TMEM_COLS = 512;
-constexpr int COL_M = 3 * NF;                    // 288
-constexpr int COL_W = COL_M + 2 * SUBN;          // 480
-constexpr int TRIPLES = NKB * 6;                 // GEMM 1 = 42 (K-block, product, K-step) triples of 3 MMAs (planes)
-constexpr int COEF_EXP = 6, W_EXP = skin::W_EXP, G_EXP = skin::G_EXP;
-static_assert(COL_W + 2 * (KJ / 2) == TMEM_COLS, "TMEM column map");
-static_assert(STAGE % 1024 == 0 && G_STAGE % 1024 == 0, "swizzle atoms stay aligned");
-
 struct Params
 {
   int V, B, Bpad, ntiles, nfb, nitems;
@@ -99,20 +59,6 @@ struct Params
   long long * dbg;              // optional per-CTA timestamps (SMPLPP_TC3_DBG)
 };
 
-// frame n of a 96-frame block -> row of the block in the fp16 coefficient operand (= accumulator column of GEMM 1):
-// the 24 frames epilogue warp group fp owns (frame pair fp of every 8-frame sub-batch) become adjacent columns
-__host__ __device__ constexpr int coef_row(int n)
-{
-  return ((n % SUBF) / EPI_FR) * FR_WARP + (n / SUBF) * EPI_FR + (n % EPI_FR);
-}
-
-
-// byte offset inside a 1024-byte aligned stage region -> SWIZZLE_64B position (16-byte chunk index XOR bits [7,9) of the
-// offset: what a tiled TMA load with CU_TENSOR_MAP_SWIZZLE_64B writes and what the UMMA descriptor expects)
-__host__ __device__ constexpr uint32_t swz64(uint32_t o)
-{
-  return o ^ (((o >> 7) & 3u) << 4);
-}
 } // namespace tc3
 
 // basis (3 Vpad, 224) fp32 -> stage images [tile][K-block][part hi | lo][plane][128 rows][32 fp16], scaled by 2^e
@@ -140,21 +86,6 @@ __global__ void basis_image_f16_kernel(const float * __restrict__ basis, int V, 
 // xforms (B,24,12) fp32 -> img_g (row = frame in sub-batch * 12 + element of the 3x4, column = joint, x 2^4).
 // Padding (frames >= B, K >= 217, joints >= 24) is zero-filled.  One thread per 16-byte chunk (8 fp16 of one row:
 // the swizzle moves whole chunks), hi and lo written as one 16-byte store each.
-__device__ __forceinline__ void split8_store(const float (&x)[8], uint8_t * hi_dst, uint8_t * lo_dst)
-{
-  uint32_t h[4], l[4];
-#pragma unroll
-  for(int i = 0; i < 4; i++)
-  {
-    const float a = x[2 * i], b = x[2 * i + 1];
-    const float ah = __half2float(__float2half_rn(a)), bh = __half2float(__float2half_rn(b));
-    h[i] = skin::pack_half2(ah, bh);
-    l[i] = skin::pack_half2(a - ah, b - bh);
-  }
-  *reinterpret_cast<uint4 *>(hi_dst) = make_uint4(h[0], h[1], h[2], h[3]);
-  *reinterpret_cast<uint4 *>(lo_dst) = make_uint4(l[0], l[1], l[2], l[3]);
-}
-
 __global__ void frame_images3_kernel(const float * __restrict__ coef, const float * __restrict__ xforms, int B, int Bpad,
                                      uint8_t * __restrict__ img_b, uint8_t * __restrict__ img_g)
 {
@@ -180,7 +111,7 @@ __global__ void frame_images3_kernel(const float * __restrict__ coef, const floa
     const int r = tc3::coef_row(static_cast<int>(f - fb * tc3::NF));
     uint8_t * blk = img_b + (static_cast<size_t>(fb) * tc3::NKB + ck / 4) * (2 * tc3::B_PART);
     const uint32_t o = static_cast<uint32_t>(r * tc3::ROWB + (ck % 4) * 16);
-    split8_store(x, blk + tc3::swz64(o), blk + tc3::swz64(tc3::B_PART + o));
+    tc3::split8_store(x, blk + tc3::swz64(o), blk + tc3::swz64(tc3::B_PART + o));
   }
   else if(i < n_coef + n_xf)
   {
@@ -199,7 +130,7 @@ __global__ void frame_images3_kernel(const float * __restrict__ coef, const floa
     const int nf = static_cast<int>(f - fb * tc3::NF);
     uint8_t * blk = img_g + (static_cast<size_t>(fb) * tc3::NSUB + nf / tc3::SUBF) * tc3::G_STAGE;
     const uint32_t o = static_cast<uint32_t>(((nf % tc3::SUBF) * kXformFloats + e) * tc3::ROWB + cj * 16);
-    split8_store(x, blk + tc3::swz64(o), blk + tc3::swz64(tc3::G_PART + o));
+    tc3::split8_store(x, blk + tc3::swz64(o), blk + tc3::swz64(tc3::G_PART + o));
   }
 }
 
@@ -604,17 +535,20 @@ void tc3_release_model(ModelDev & d)
 
 // coef (B,224) and xforms (B,24,12) fp32 from K1; scratch: tc3_frame_operand_bytes(B)
 int launch_blend_skin_tc3(const ModelDev & d, cudaStream_t st, int B, const float * coef, const float * xforms, void * scratch,
-                          const float * theta, float * out)
+                          const float * theta, float * out, bool images_ready)
 {
   if(!d.tc3_ready) return fail(SMPLPP_ERR_INVALID, "SMPL", "pipelined tcgen05 skinning variant is not available for this model");
   if(reinterpret_cast<uintptr_t>(out) & 7) return fail(SMPLPP_ERR_INVALID, "SMPL", "tcgen05 variants need 8-byte aligned vertices");
   if(reinterpret_cast<uintptr_t>(scratch) & 127) return fail(SMPLPP_ERR_INVALID, "SMPL", "tcgen05 variants need a 128-byte aligned workspace");
   const int Bpad = static_cast<int>(align_up(static_cast<size_t>(B), tc3::NF));
   uint8_t * img_b = static_cast<uint8_t *>(scratch);
-  uint8_t * img_g = img_b + align_up(static_cast<size_t>(2) * Bpad * tc3::KP * sizeof(__half));
-  const long long n = static_cast<long long>(Bpad) * (tc3::KP + kXformFloats * tc3::KJ) / 8; // 16-byte chunks
-  frame_images3_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(coef, xforms, B, Bpad, img_b, img_g);
-  SB_LAUNCHED();
+  uint8_t * img_g = img_b + tc3::img_g_offset(Bpad);
+  if(!images_ready)
+  {
+    const long long n = static_cast<long long>(Bpad) * (tc3::KP + kXformFloats * tc3::KJ) / 8; // 16-byte chunks
+    frame_images3_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(coef, xforms, B, Bpad, img_b, img_g);
+    SB_LAUNCHED();
+  }
   tc3::Params p;
   p.V = d.V;
   p.B = B;
