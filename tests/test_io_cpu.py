@@ -178,3 +178,28 @@ def test_mocap_body_yaml_and_motion_text_round_trip(tmp_path, api):
         f.write("1 2 3\n")
     with pytest.raises(capi.SmplppError, match="does not hold 75 values"):
         api.read_motion_text(str(tmp_path / "bad.txt"))
+
+
+def test_json_reader_random_documents(tmp_path, api):
+    """Property test (hypothesis): rectangular float / int arrays of random rank, shape and formatting come back with
+    the same shape and bit-identical values as Python's json module reads them."""
+    from hypothesis import given, settings, strategies as st
+
+    shapes = st.lists(st.integers(1, 4), min_size=1, max_size=4)
+    counter = [0]
+
+    @settings(max_examples=40, deadline=None)
+    @given(shape=shapes, seed=st.integers(0, 2 ** 31 - 1), indent=st.sampled_from([None, 0, 2]), ints=st.booleans())
+    def check(shape, seed, indent, ints):
+        rng = np.random.default_rng(seed)
+        arr = rng.integers(-2 ** 40, 2 ** 40, size=shape) if ints else rng.normal(size=shape) * 10.0 ** rng.integers(-30, 30)
+        counter[0] += 1
+        path = str(tmp_path / ("h%d.json" % counter[0]))
+        with open(path, "w") as f:
+            json.dump({"skip": {"x": [1, [2]]}, "a": arr.tolist(), "tail": "s"}, f, indent=indent)
+        got = api.read_json_arrays(path, ["a"])["a"]
+        with open(path) as f:
+            want = np.asarray(json.load(f)["a"], dtype=np.float64)
+        assert got.shape == want.shape and np.array_equal(got, want)
+
+    check()
