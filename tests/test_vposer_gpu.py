@@ -123,3 +123,27 @@ def test_tensor_core_jacobian_matches_ffma_kernel(vposer_gpu, batch):
     rel = ((out[300][1] - out[301][1]).abs() / scale).max()
     assert float(rel) < 1e-4
     assert float(rel) < 2e-5
+
+
+@pytest.mark.parametrize("scales", [(8.0, 0.05, 3.0), (0.02, 6.0, 0.3), (1.0, 1.0, 40.0)])
+def test_tensor_core_jacobian_weight_scales(vposer_params, scales):
+    """The power-of-two operand scales of the tcgen05 Jacobian are derived from the weights at create time: decoders whose
+    layers are much larger / smaller than the synthetic ones (x8, x0.02, x40 ...) must neither overflow fp16 nor lose the
+    low parts to subnormals."""
+    from smplpp_b200 import api, capi
+    p = {k: np.array(v, dtype=np.float32, copy=True) for k, v in vposer_params.items()}
+    p["decoder_net.0.weight"] *= scales[0]
+    p["decoder_net.3.weight"] *= scales[1]
+    p["decoder_net.5.weight"] *= scales[2]
+    vp = api.VPoserDecoder(p, device="cuda:0")
+    z = np.random.default_rng(7).normal(size=(64, 32)).astype(np.float32)
+    out = {}
+    for var in (301, 300):
+        capi.check(capi.lib().smplpp_set_forward_variant(var))
+        try:
+            out[var] = vp.forward(z, jacobian=True)[1].clone()
+        finally:
+            capi.check(capi.lib().smplpp_set_forward_variant(300))
+    assert bool(torch.isfinite(out[300]).all())
+    scale = out[301].abs().amax(dim=(1, 2), keepdim=True).clamp_min(1e-30)
+    assert float(((out[300] - out[301]).abs() / scale).max()) < 1e-4
