@@ -67,10 +67,10 @@ def ncu_traffic(kernel: str):
             with open(path) as f:
                 t = json.load(f)
             if kernel in t.get("bytes_per_launch", {}):
-                return {"bytes_per_launch": t["bytes_per_launch"][kernel], "source": os.path.basename(path)}
+                return float(t["bytes_per_launch"][kernel]), os.path.basename(path)
         except Exception:
             continue
-    return None
+    return None, None
 
 
 class ClockSampler:
@@ -290,9 +290,12 @@ def main():
     ms_full = time_kernel(step, 20)
     ms_k2 = max(ms_full - ms_k1, 1e-6)
     peak, peak_src = measured_peaks()
+    traffic_k2, traffic_k2_src = ncu_traffic("blend_skin_tc3_kernel")
+    traffic_lbs, traffic_lbs_src = ncu_traffic("lbs_tc_kernel")
     ach = BYTES_FUSED * B / (ms_k2 * 1e-3) / 1e9
     roofline = {"kernel": "blend_skin (fused pose/shape blend contraction + linear blend skinning)", "bound": "hbm",
-                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": ncu_traffic("blend_skin_tc3_kernel") or ncu_traffic("blend_skin_tc2_kernel"),
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic_k2, "traffic_unit": "bytes per launch (dram read + write, ncu --set full)",
+                "traffic_source": traffic_k2_src,
                 "algorithmic_bytes_per_launch": BYTES_FUSED * B,
                 "peak_source": peak_src, "ms_per_launch": ms_k2,
                 "fp32_tflops_algorithmic": FLOPS_BLEND * B / (ms_k2 * 1e-3) / 1e12}
@@ -338,7 +341,7 @@ def main():
     capi.check(lib.smplpp_set_forward_variant(202))
     ach_lbs = BYTES_LBS * B / (ms_lbs * 1e-3) / 1e9
     roofline["lbs"] = {"kernel": "lbs_tc_kernel (standalone skinning, skinning matrices on tcgen05)", "bound": "hbm", "achieved": ach_lbs, "peak": peak,
-                       "unit": "GB/s", "frac": ach_lbs / peak, "ms_per_launch": ms_lbs, "traffic": ncu_traffic("lbs_tc_kernel"),
+                       "unit": "GB/s", "frac": ach_lbs / peak, "ms_per_launch": ms_lbs, "traffic": traffic_lbs, "traffic_source": traffic_lbs_src,
                        "algorithmic_bytes_per_launch": BYTES_LBS * B,
                        "meshes_per_s": B / (ms_lbs * 1e-3), "ms_per_launch_other_variants": ms_lbs_var,
                        "ms_per_launch_4x4_transforms": time_kernel(lbs_only44, 20)}
