@@ -718,81 +718,99 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
   }
   __syncthreads();
   // ---- P5d: pose-blend (and shape-blend) columns: Q_m = sum_u CA4_u P_u (ROWS x 218), J += Q_m dvec(R_k)/dtheta.
-  //      Warp w owns joints 3w+1..3w+3 (27 lanes, 9 basis columns each); warp 7 also owns the 10 shape columns.
-  //      The 9-term contraction per (joint, axis) is a segmented shuffle reduction: no block barrier per task. ----
+  //      Warp w works for joint group g = w & 3 on the tasks of parity w >> 2.  Every lane owns TWO basis columns: set A
+  //      = joints 6g+1..6g+3, set B = joints 6g+4..6g+6 (27 lanes x 9 columns each; group 3's set B also holds the 10
+  //      shape columns in lanes 18..27), so that the pair's vertex id, its 12 C4 floats and the loop overhead are
+  //      paid once per 18 FMAs instead of once per 9.  The 9-term contraction per (joint, axis) is a segmented shuffle
+  //      reduction: no block barrier per task. ----
   {
     const int warp = tid >> 5, lane = tid & 31;
     const int bcol = 75 + p.phi_cols;
-    int k = 3 * warp + 1 + lane / 9, e = lane % 9, d = -1, ib = -1;
-    if(lane < 27 && k < kJoints) d = 9 * (k - 1) + e;
-    if(warp == 7 && lane >= 18 && lane < 18 + kShapeDim && p.beta_cols) ib = lane - 18, d = kPoseDim + ib;
-    const bool joint_lane = d >= 0 && ib < 0;
-    float dv[3] = {0.f, 0.f, 0.f};
-    if(joint_lane) dv[0] = s_dR[27 * k + e], dv[1] = s_dR[27 * k + 9 + e], dv[2] = s_dR[27 * k + 18 + e];
-    const bool warp_active = __any_sync(0xffffffffu, d >= 0);
-    if(warp_active)
-    {
-      for(int m = 0; m < n; m++)
-      {
-        float q4[ROWS];
+    const int g = warp & 3, parity = warp >> 2;
+    const int e = lane % 9;
+    int kk[2] = {6 * g + 1 + lane / 9, 6 * g + 4 + lane / 9}, dd[2] = {-1, -1}, ib = -1;
 #pragma unroll
-        for(int r = 0; r < ROWS; r++) q4[r] = 0.f;
-        const int p0 = t.pair_off[m];
-        const int np = p.use_ring ? t.pair_off[m + 1] - p0 : 3;
-        // the rigid part of these entries was written by an earlier phase: fetch it now so that the global round trip
-        // overlaps the contraction (ncu: the dependent read-modify-write at the end of every task was 30 % of the samples)
-        float jprev[ROWS][3];
-        if(joint_lane && e == 0)
+    for(int sset = 0; sset < 2; sset++)
+      if(lane < 27 && kk[sset] < kJoints) dd[sset] = 9 * (kk[sset] - 1) + e;
+    if(g == 3 && lane >= 18 && lane < 18 + kShapeDim && p.beta_cols) ib = lane - 18, dd[1] = kPoseDim + ib;
+    const bool joint_lane[2] = {dd[0] >= 0, dd[1] >= 0 && ib < 0};
+    float dv[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+#pragma unroll
+    for(int sset = 0; sset < 2; sset++)
+      if(joint_lane[sset])
+        dv[sset][0] = s_dR[27 * kk[sset] + e], dv[sset][1] = s_dR[27 * kk[sset] + 9 + e], dv[sset][2] = s_dR[27 * kk[sset] + 18 + e];
+    // lanes without a column in a set read column 0 (always valid) and their products are dropped
+    const int da = dd[0] >= 0 ? dd[0] : 0, db = dd[1] >= 0 ? dd[1] : 0;
+    for(int m = parity; m < n; m += 2)
+    {
+      float qa[ROWS], qb[ROWS];
+#pragma unroll
+      for(int r = 0; r < ROWS; r++) qa[r] = qb[r] = 0.f;
+      const int p0 = t.pair_off[m];
+      const int np = p.use_ring ? t.pair_off[m + 1] - p0 : 3;
+      // the rigid part of these entries was written by an earlier phase: fetch it now so that the global round trip
+      // overlaps the contraction (ncu: the dependent read-modify-write at the end of every task was 30 % of the samples)
+      float jprev[2][ROWS][3];
+#pragma unroll
+      for(int sset = 0; sset < 2; sset++)
+        if(joint_lane[sset] && e == 0)
         {
 #pragma unroll
           for(int r = 0; r < ROWS; r++)
 #pragma unroll
-            for(int c = 0; c < 3; c++) jprev[r][c] = Jf[(4 * m + r) * p.ldfull + 3 + 3 * k + c];
+            for(int c = 0; c < 3; c++) jprev[sset][r][c] = Jf[(4 * m + r) * p.ldfull + 3 + 3 * kk[sset] + c];
         }
-        if(d >= 0)
+      {
+        // basis rows come from L2 (~300 cycles): two pairs x two columns per trip keep four 16-byte loads in flight
+        constexpr int UQ = 2;
+        int q = 0;
+        for(; q + UQ <= np; q += UQ)
         {
-          // basis rows come from L2 (~300 cycles): four pairs per trip keep 12 loads in flight instead of 3
-          // (ncu: this loop was 28 % of the samples, latency-bound with 4 warps per scheduler)
-          constexpr int UQ = 4;
-          int q = 0;
-          for(; q + UQ <= np; q += UQ)
+          float4 ba[UQ], bb[UQ];
+#pragma unroll
+          for(int i = 0; i < UQ; i++)
           {
-            float b0[UQ], b1[UQ], b2[UQ];
-#pragma unroll
-            for(int i = 0; i < UQ; i++)
-            {
-              const int u = t.pair_vert[p0 + q + i];
-              const float4 bb = __ldg(t.basis4 + static_cast<size_t>(u) * kBlendK + d); // x, y, z rows in one load
-              b0[i] = bb.x, b1[i] = bb.y, b2[i] = bb.z;
-            }
-#pragma unroll
-            for(int i = 0; i < UQ; i++)
-            {
-              // the 12 floats of a pair are warp-uniform: three 16-byte broadcast loads instead of nine / twelve scalar ones
-              const float4 * C4 = reinterpret_cast<const float4 *>(s_C4 + 12 * (p0 + q + i));
-              const float4 c0 = C4[0], c1 = C4[1], c2 = C4[2];
-              const float C[12] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w};
-#pragma unroll
-              for(int r = 0; r < ROWS; r++) q4[r] = fmaf(C[3 * r], b0[i], fmaf(C[3 * r + 1], b1[i], fmaf(C[3 * r + 2], b2[i], q4[r])));
-            }
+            const float4 * row = t.basis4 + static_cast<size_t>(t.pair_vert[p0 + q + i]) * kBlendK;
+            ba[i] = __ldg(row + da), bb[i] = __ldg(row + db); // x, y, z rows of a column in one load
           }
-          for(; q < np; q++)
-          {
-            const int u = t.pair_vert[p0 + q];
-            const float4 bb = __ldg(t.basis4 + static_cast<size_t>(u) * kBlendK + d);
-            const float b0 = bb.x, b1 = bb.y, b2 = bb.z;
-            const float * C = s_C4 + 12 * (p0 + q);
 #pragma unroll
-            for(int r = 0; r < ROWS; r++) q4[r] = fmaf(C[3 * r], b0, fmaf(C[3 * r + 1], b1, fmaf(C[3 * r + 2], b2, q4[r])));
+          for(int i = 0; i < UQ; i++)
+          {
+            // the 12 floats of a pair are warp-uniform: three 16-byte broadcast loads
+            const float4 * C4 = reinterpret_cast<const float4 *>(s_C4 + 12 * (p0 + q + i));
+            const float4 c0 = C4[0], c1 = C4[1], c2 = C4[2];
+            const float C[12] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w};
+#pragma unroll
+            for(int r = 0; r < ROWS; r++)
+            {
+              qa[r] = fmaf(C[3 * r], ba[i].x, fmaf(C[3 * r + 1], ba[i].y, fmaf(C[3 * r + 2], ba[i].z, qa[r])));
+              qb[r] = fmaf(C[3 * r], bb[i].x, fmaf(C[3 * r + 1], bb[i].y, fmaf(C[3 * r + 2], bb[i].z, qb[r])));
+            }
           }
         }
+        for(; q < np; q++)
+        {
+          const float4 * row = t.basis4 + static_cast<size_t>(t.pair_vert[p0 + q]) * kBlendK;
+          const float4 ba = __ldg(row + da), bb = __ldg(row + db);
+          const float * C = s_C4 + 12 * (p0 + q);
+#pragma unroll
+          for(int r = 0; r < ROWS; r++)
+          {
+            qa[r] = fmaf(C[3 * r], ba.x, fmaf(C[3 * r + 1], ba.y, fmaf(C[3 * r + 2], ba.z, qa[r])));
+            qb[r] = fmaf(C[3 * r], bb.x, fmaf(C[3 * r + 1], bb.y, fmaf(C[3 * r + 2], bb.z, qb[r])));
+          }
+        }
+      }
+#pragma unroll
+      for(int sset = 0; sset < 2; sset++)
+      {
         float val[ROWS][3];
 #pragma unroll
         for(int r = 0; r < ROWS; r++)
 #pragma unroll
           for(int c = 0; c < 3; c++)
           {
-            float v = q4[r] * dv[c];
+            float v = (sset == 0 ? qa[r] : qb[r]) * dv[sset][c]; // dv = 0 on lanes without a joint column in this set
 #pragma unroll
             for(int o = 1; o < 16; o <<= 1)
             {
@@ -801,18 +819,18 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
             }
             val[r][c] = v;
           }
-        if(joint_lane && e == 0)
+        if(joint_lane[sset] && e == 0)
         {
 #pragma unroll
           for(int r = 0; r < ROWS; r++)
 #pragma unroll
-            for(int c = 0; c < 3; c++) Jf[(4 * m + r) * p.ldfull + 3 + 3 * k + c] = jprev[r][c] + val[r][c];
+            for(int c = 0; c < 3; c++) Jf[(4 * m + r) * p.ldfull + 3 + 3 * kk[sset] + c] = jprev[sset][r][c] + val[r][c];
         }
-        if(ib >= 0)
-        {
+      }
+      if(ib >= 0)
+      {
 #pragma unroll
-          for(int r = 0; r < ROWS; r++) Jf[(4 * m + r) * p.ldfull + bcol + ib] += q4[r];
-        }
+        for(int r = 0; r < ROWS; r++) Jf[(4 * m + r) * p.ldfull + bcol + ib] += qb[r];
       }
     }
   }
