@@ -210,6 +210,22 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # one process per GPU: run on the CPUs next to it, so that the page-locked buffers of the host-buffer call and its
+    # staging threads live on the GPU's NUMA node (matters once several ranks share the host)
+    affinity = None
+    if world > 1 and os.environ.get("SMPLPP_BENCH_NO_AFFINITY") is None:
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                affinity = len(cpus)
+        except Exception:
+            affinity = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -365,7 +381,8 @@ def main():
     e2e = {"value": world * B / e2e_s, "unit": "meshes/s", "h2d_bytes_per_step": int(beta_h.nbytes + theta_h.nbytes),
            "d2h_bytes_per_step": int(B * VERTS * 3 * 4 + B * 24 * 3 * 4), "ms_per_step": 1e3 * e2e_s,
            "d2h_gbs": (B * VERTS * 12 + B * 288) / e2e_s / 1e9, "max_abs_diff_vs_device_path": e2e_check,
-           "api": "smplpp_forward_host (smplpp::SMPL::launch + getVertex + getRestJoint), page-locked host buffers"}
+           "api": "smplpp_forward_host (smplpp::SMPL::launch + getVertex + getRestJoint), page-locked host buffers",
+           "cpu_affinity_cores": affinity}
     # the same call with ordinary pageable numpy arrays (staged through pinned chunks by host threads)
     pg_v, pg_j = np.empty((B, VERTS, 3), np.float32), np.empty((B, 24, 3), np.float32)
     smpl.launch_host(beta_h, theta_h, out_vertices=pg_v, out_joints=pg_j)

@@ -841,17 +841,21 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
     float * Jo = p.jout + static_cast<size_t>(f) * 4 * n * p.ld;
     const float * Jv = p.vposer_jac + static_cast<size_t>(f) * 63 * 32;
     const int extra = p.phi_cols + p.beta_cols;
-    for(int i = tid; i < 4 * n * 32; i += THREADS)
+    // thread = (task m, latent column tt): the decoder Jacobian entry is loaded once for the task's ROWS rows
+    for(int i = tid; i < n * 32; i += THREADS)
     {
-      const int row = i >> 5, tt = i & 31;
-      const float * jr = Jf + row * p.ldfull + 6;
-      float acc = 0.f;
-      if((row & 3) < ROWS)
-      {
+      const int m = i >> 5, tt = i & 31;
+      const float * jr = Jf + (4 * m) * p.ldfull + 6;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 7
-        for(int q = 0; q < 63; q++) acc = fmaf(jr[q], __ldg(Jv + q * 32 + tt), acc);
+      for(int q = 0; q < 63; q++)
+      {
+        const float v = __ldg(Jv + q * 32 + tt);
+#pragma unroll
+        for(int r = 0; r < ROWS; r++) acc[r] = fmaf(jr[r * p.ldfull + q], v, acc[r]);
       }
-      Jo[row * p.ld + 6 + tt] = acc;
+#pragma unroll
+      for(int r = 0; r < 4; r++) Jo[(4 * m + r) * p.ld + 6 + tt] = acc[r];
     }
     for(int i = tid; i < 4 * n * (12 + extra); i += THREADS)
     {
