@@ -270,9 +270,11 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
   float * s_sw = s_task + TS * n;                              // nUse*kmax   normalised skinning weights w_j / sum w
   float * s_xw = s_sw + p.nUse * t.kmax;                       // nUse*kmax*3 wn_j * x_uj (vertex carried by bone j)
   uint8_t * s_sj = reinterpret_cast<uint8_t *>(s_xw + 3 * p.nUse * t.kmax); // nUse*kmax joint ids
-  __shared__ int s_valid, s_bad;
+  // compact list of the (task, joint) pairs whose joint moves the task (P5b), 2-byte aligned after s_sj
+  uint16_t * s_act = reinterpret_cast<uint16_t *>(s_sj + ((p.nUse * t.kmax + 1) & ~1));
+  __shared__ int s_valid, s_bad, s_nact;
 
-  if(tid == 0) s_valid = 0, s_bad = 0;
+  if(tid == 0) s_valid = 0, s_bad = 0, s_nact = 0;
   for(int i = tid; i < 75; i += THREADS) s_theta[i] = p.theta[static_cast<size_t>(f) * 75 + i];
   if(tid < kShapeDim) s_beta[tid] = p.beta[static_cast<size_t>(f) * p.beta_stride + tid];
   {
@@ -603,14 +605,30 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
     Jf[(4 * m + r) * p.ldfull + c] = acc;
   }
   // ---- P5b: kinematic-chain columns: sum_u C4_u M_kc y_uk,  y_uk = sum_{j in desc*(k)} wn_j (x_uj - tg_k) ----
+  // Only ~1/3 of the (task, joint) pairs are live (the joint must be an ancestor of a vertex of the task): they are
+  // compacted first, so that the heavy loop below runs with full warps; the dead entries are zero-filled here.
   for(int i = tid; i < n * kJoints; i += THREADS)
   {
     const int m = i / kJoints, k = i % kJoints;
     const uint32_t mask = p.use_ring ? t.task_joint_mask[m] : t.task_joint_mask_corner[m];
+    if((mask >> k) & 1u)
+      s_act[atomicAdd(&s_nact, 1)] = static_cast<uint16_t>(i);
+    else
+    {
+#pragma unroll
+      for(int r = 0; r < 4; r++)
+#pragma unroll
+        for(int c = 0; c < 3; c++) Jf[(4 * m + r) * p.ldfull + 3 + 3 * k + c] = 0.f;
+    }
+  }
+  __syncthreads();
+  for(int ia = tid; ia < s_nact; ia += THREADS)
+  {
+    const int i = s_act[ia];
+    const int m = i / kJoints, k = i % kJoints;
     float out[4][3];
 #pragma unroll
     for(int r = 0; r < 4; r++) out[r][0] = out[r][1] = out[r][2] = 0.f;
-    if((mask >> k) & 1u)
     {
       float W[ROWS][9];
 #pragma unroll
@@ -1835,7 +1853,8 @@ size_t jac_smem_bytes(const TasksDev & t, const IkLayout & L)
   fl += c1::TS * static_cast<size_t>(t.n);
   fl += 12 * static_cast<size_t>(t.nPairs);
   fl += 4 * static_cast<size_t>(L.nUse) * t.kmax; // normalised weights + wn * x
-  return fl * sizeof(float) + static_cast<size_t>(L.nUse) * t.kmax + 64;
+  return fl * sizeof(float) + static_cast<size_t>(L.nUse) * t.kmax + 2 + static_cast<size_t>(t.n) * kJoints * sizeof(uint16_t)
+         + 64;
 }
 
 // one thread per 4x4 tile of the lower triangle of A, rounded up to whole warps: 192 for D = 75 (190 tiles)
