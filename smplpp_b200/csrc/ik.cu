@@ -768,15 +768,18 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
       const int np = p.use_ring ? t.pair_off[m + 1] - p0 : 3;
       // the rigid part of these entries was written by an earlier phase: fetch it now so that the global round trip
       // overlaps the contraction (ncu: the dependent read-modify-write at the end of every task was 30 % of the samples)
+      // (only ~1/3 of the (task, joint) entries have a rigid part: the others are known to be zero from the joint mask)
+      const uint32_t jmask = p.use_ring ? t.task_joint_mask[m] : t.task_joint_mask_corner[m];
       float jprev[2][ROWS][3];
 #pragma unroll
       for(int sset = 0; sset < 2; sset++)
         if(joint_lane[sset] && e == 0)
         {
+          const bool live = (jmask >> kk[sset]) & 1u;
 #pragma unroll
           for(int r = 0; r < ROWS; r++)
 #pragma unroll
-            for(int c = 0; c < 3; c++) jprev[sset][r][c] = Jf[(4 * m + r) * p.ldfull + 3 + 3 * kk[sset] + c];
+            for(int c = 0; c < 3; c++) jprev[sset][r][c] = live ? Jf[(4 * m + r) * p.ldfull + 3 + 3 * kk[sset] + c] : 0.f;
         }
       {
         // basis rows come from L2 (~300 cycles): two pairs x two columns per trip keep four 16-byte loads in flight
