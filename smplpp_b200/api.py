@@ -782,6 +782,57 @@ class IkTaskSet:
                                               C.c_float(normal_offset), _ptr(pos), _ptr(nrm)))
         return (pos, nrm) if want_normals else pos
 
+    def assemble_theta(self, theta_state: torch.Tensor) -> torch.Tensor:
+        """(B,75) -> (B,25,3) as is; (B,44) VPoser state [trans 3 | root 3 | latent 32 | hands 6] through the decoder
+        (node/node.cpp:761-772)."""
+        b = theta_state.shape[0]
+        if theta_state.shape[1] == 75:
+            return theta_state.reshape(b, 25, 3)
+        if self.vposer is None:
+            raise SmplppError("VPoser Error: Cannot find a JSON file!")
+        body = self.vposer.forward(theta_state[:, 6:38].contiguous())
+        return torch.cat([theta_state[:, 0:3].reshape(b, 1, 3), theta_state[:, 3:6].reshape(b, 1, 3), body,
+                          theta_state[:, 38:41].reshape(b, 1, 3), theta_state[:, 41:44].reshape(b, 1, 3)], dim=1).contiguous()
+
+    def reproject(self, theta_state: torch.Tensor, beta: torch.Tensor, vertex_weights: torch.Tensor,
+                  normal_offset: float = 0.015, phi: Optional[torch.Tensor] = None, apply: bool = True, chunk: int = 4096):
+        """The tail of an IK iteration in the reference (node/node.cpp:949-1001) for every frame: the point
+        p = calcActualPos() + tangents * phi of every task is projected onto the posed mesh
+        (igl::point_mesh_squared_distance there, smplpp_closest_points here) and the attachment is re-seated:
+        faceIdx_ = closest face, vertexWeights_ = calcTriangleVertexWeights(closest point, face).
+
+        Returns (face (B,n) int32 0-based, weights (B,n,3), same_face (B,n) bool).  With apply=True `vertex_weights` is
+        updated in place where the face did not change; a changed face is only REPORTED, because the task set shares
+        one attachment topology between all frames (per-frame topologies are the next step)."""
+        dev = self.smpl.m__device
+        b = theta_state.shape[0]
+        faces0 = torch.as_tensor(self.smpl._faces_host.astype(np.int64) - 1, device=dev)      # (F,3)
+        task_faces = torch.as_tensor(self.face_idx, device=dev)                                # (n,)
+        face_out = torch.empty((b, self.n), dtype=torch.int32, device=dev)
+        w_out = torch.empty((b, self.n, 3), dtype=torch.float32, device=dev)
+        beta_t = _dev_f32(beta, dev)
+        for s0 in range(0, b, chunk):
+            s1 = min(b, s0 + chunk)
+            theta = self.assemble_theta(theta_state[s0:s1])
+            self.smpl.launch(beta_t if beta_t.dim() == 1 or beta_t.shape[0] == 1 else beta_t[s0:s1], theta)
+            verts = self.smpl._vertices
+            pts = self.positions(verts, vertex_weights[s0:s1].contiguous(), normal_offset)
+            if phi is not None:
+                # IkTask::calcTangents (src/IkTask.cpp:33-47): t1 = normalize(v1 - v0), t2 = normalize((t1 x (v2 - v0)) x t1)
+                tri = verts[:, faces0[task_faces]]                                             # (c,n,3,3)
+                e1, e2 = tri[:, :, 1] - tri[:, :, 0], tri[:, :, 2] - tri[:, :, 0]
+                nrm = torch.cross(e1, e2, dim=-1)
+                t1 = torch.nn.functional.normalize(e1, dim=-1)
+                t2 = torch.nn.functional.normalize(torch.cross(nrm, e1, dim=-1), dim=-1)
+                ph = _dev_f32(phi, dev)[s0:s1]
+                pts = pts + t1 * ph[..., 0:1] + t2 * ph[..., 1:2]
+            face, _, _, w = self.smpl.projectPoints(pts.contiguous(), verts)
+            face_out[s0:s1], w_out[s0:s1] = face, w
+        same = face_out.long() == task_faces[None, :]
+        if apply:
+            vertex_weights.copy_(torch.where(same[..., None], w_out, vertex_weights))
+        return face_out, w_out, same
+
     def _workspace(self, nbytes: int) -> torch.Tensor:
         if self._ws is None or self._ws.numel() < nbytes:
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.smpl.m__device)

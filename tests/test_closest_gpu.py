@@ -104,3 +104,52 @@ def test_closest_points_round_trip_full_batch(smpl_gpu, marker_tasks, params):
     tri2 = verts[torch.arange(B, device="cuda:0")[:, None, None], faces0[face.long()]]   # (B, n, 3, 3)
     rec = (w[..., None] * tri2).sum(2)
     assert float((rec - pts).abs().max()) < 5e-6
+
+
+@pytest.mark.parametrize("with_phi", [False, True])
+def test_reproject_vs_oracle(smpl_gpu, oracle_model, marker_tasks, params, vposer_params, with_phi):
+    """IkTaskSet.reproject = the tail of the reference's IK iteration (node/node.cpp:949-1001) batched over frames:
+    p = calcActualPos() + tangents * phi -> closest point on the posed mesh -> faceIdx_ / vertexWeights_, against the
+    oracle's IkTask (calc_actual_pos, calc_tangents) + float64 mesh projection on the oracle's own vertices."""
+    from oracle import smpl_oracle as so
+    from smplpp_b200 import api, synth
+    faces0 = (np.asarray(params.face_indices, dtype=np.int64) - 1)
+    _, face_idx, vw = marker_tasks
+    tasks = api.IkTaskSet(smpl_gpu, face_idx, vposer=api.VPoserDecoder(vposer_params))
+    B, n = 3, len(face_idx)
+    beta, theta = synth.make_forward_inputs(B, 61)
+    beta_shared = beta[0]
+    rng = np.random.default_rng(8)
+    phi = (rng.uniform(-0.01, 0.01, (B, n, 2)).astype(np.float32)) if with_phi else None
+    w = torch.as_tensor(np.repeat(vw[None], B, axis=0), device="cuda:0").contiguous()
+    state = torch.as_tensor(theta.reshape(B, 75), device="cuda:0").contiguous()
+    w_before = w.clone()
+    face, wn, same = tasks.reproject(state, torch.as_tensor(beta_shared, device="cuda:0"), w, 0.015,
+                                     phi=None if phi is None else torch.as_tensor(phi, device="cuda:0"))
+    face, wn, same = face.cpu().numpy(), wn.cpu().numpy(), same.cpu().numpy()
+    agree = 0
+    with torch.no_grad():
+        r = so.smpl_launch(oracle_model, torch.as_tensor(np.repeat(beta_shared[None], B, 0)), torch.as_tensor(theta))
+        for b in range(B):
+            verts_o = r.vertices[b]
+            pts = []
+            for m in range(n):
+                t = so.IkTask(int(face_idx[m]), normal_offset=0.015, vertex_weights=torch.as_tensor(vw[m]))
+                p = t.calc_actual_pos(oracle_model, verts_o)
+                if with_phi:
+                    t.calc_tangents(oracle_model, verts_o)
+                    p = p + torch.matmul(t.tangents, torch.as_tensor(phi[b, m]))
+                pts.append(p.numpy())
+            o_face, o_closest, o_sq, o_w = so.project_points_on_mesh(verts_o.numpy(), faces0, np.stack(pts))
+            v64 = verts_o.numpy().astype(np.float64)
+            for m in range(n):
+                if face[b, m] == o_face[m]:
+                    agree += 1
+                    # weights are 1 / edge-length conditioned: compare the point they reproduce
+                    got = (wn[b, m][:, None] * v64[faces0[face[b, m]]]).sum(0)
+                    assert np.abs(got - o_closest[m]).max() < 1e-5
+                assert same[b, m] == (face[b, m] == face_idx[m])
+    assert agree >= 0.95 * B * n
+    # applied in place exactly where the face did not change
+    w_after = w.cpu().numpy()
+    assert np.array_equal(w_after[same], wn[same]) and np.array_equal(w_after[~same], w_before.cpu().numpy()[~same])
