@@ -105,6 +105,18 @@ def run(dev, rank, world, max_over_ranks, barrier, frames: int = 16384, iters: i
     ms = time_steps(step_shared, max(3, iters // 2), 2, barrier, max_over_ranks, dev)
     out["shared_beta"] = {"value": all_frames / (ms * 1e-3), "ms_per_iter": ms,
                           "collective": "all_reduce(sum) of 111 float64 per iteration" if world > 1 else "none (1 GPU)"}
+    # (3b) configs[3] proper: VPoser latent prior (D = 44) AND the shared-beta stage
+    sbeta_v = torch.zeros(10, dtype=torch.float32, device=dev)
+    xv3 = torch.zeros((frames, 44), dtype=torch.float32, device=dev)
+    xv3[:, :6] = prob["x0"][:, :6]
+    vw4 = prob["w0"].clone()
+
+    def step_shared_vposer():
+        tasks.shared_beta_step(optv, xv3, sbeta_v, vw4, prob["target"], pos_task_weight=prob["valid"])
+
+    ms = time_steps(step_shared_vposer, max(3, iters // 2), 2, barrier, max_over_ranks, dev)
+    out["shared_beta_vposer"] = {"value": all_frames / (ms * 1e-3), "ms_per_iter": ms, "unknowns_per_frame": 44,
+                                 "finite": bool(torch.isfinite(xv3).all().item() and torch.isfinite(sbeta_v).all().item())}
     # (4) projection of the task points onto the posed mesh + re-seated face / weights (node.cpp:970-1001):
     # full forward pass of a block of frames, then smplpp_closest_points (41 points x 13776 faces per frame)
     rb = min(frames, 4096)
