@@ -333,6 +333,9 @@ void smplpp_mocap_body_close(smplpp_mocap_body_t * body);
 int32_t smplpp_mocap_body_task_count(const smplpp_mocap_body_t * body);
 const char * smplpp_mocap_body_task_name(const smplpp_mocap_body_t * body, int32_t task);
 int smplpp_mocap_body_get(const smplpp_mocap_body_t * body, float * beta10, int64_t * face_idx, float * vertex_weights);
+/* SMPL::out (src/SMPL.cpp:757-790): Wavefront OBJ of one mesh (host arrays; faces 1-based as stored) */
+int smplpp_write_obj(const char * path, int64_t n_vertices, const float * vertices_host, int64_t n_faces,
+                     const int32_t * face_indices_1based);
 /* Motion as text, one frame per line, 75 values of theta (scripts/convertRosbagToText.py:13-19) */
 int smplpp_write_motion_text(const char * path, int64_t frames, const float * theta75_host);
 int smplpp_read_motion_text(const char * path, int64_t max_frames, float * theta75_host, int64_t * frames_out);

@@ -169,6 +169,15 @@ public:
     if(!m__launched) throw Exception("JointRegression Error: Failed to get joints!");
     return m__joints;
   }
+  /// SMPL::setVertPath + SMPL::out (SMPL.cpp:341-355, 757-790): mesh `index` of the batch as Wavefront OBJ
+  void setVertPath(const std::string & vertexPath) { m__vertPath = vertexPath; }
+  void out(int64_t index) const
+  {
+    if(!m__launched || index < 0 || index >= m__vertices.size(0) || m__vertPath.empty())
+      throw Exception("SMPL Error: Cannot export the deformed mesh!"); // SMPL.cpp:785
+    check(smplpp_write_obj(m__vertPath.c_str(), m__vertexNum, m__vertices.ptr() + index * m__vertexNum * 3,
+                           static_cast<int64_t>(m__faceIndices.size() / 3), m__faceIndices.data()));
+  }
   /// SMPL::getFaceIndex (SMPL.cpp:386-405): (F,3), 1-based like the stored tensor
   const std::vector<int32_t> & getFaceIndex() const { return m__faceIndices; }
   int64_t getVertexNum() const { return m__vertexNum; }
@@ -177,7 +186,7 @@ public:
 
 private:
   smplpp_model_t * m__model = nullptr;
-  std::string m__modelPath;
+  std::string m__modelPath, m__vertPath;
   std::vector<int32_t> m__faceIndices;
   int64_t m__vertexNum = 0;
   Array m__vertices, m__joints;

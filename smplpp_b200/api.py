@@ -261,6 +261,19 @@ class SMPL:
                                               C.c_void_p(face.data_ptr()), _ptr(closest), _ptr(sq), _ptr(w)))
         return face, closest, sq, w
 
+    def setVertPath(self, path: str):
+        self.m__vertPath = path
+
+    def out(self, index: int):
+        """SMPL::out (src/SMPL.cpp:757-790): the mesh of batch element `index` as Wavefront OBJ at the vertex path."""
+        self._launched("SMPL Error: Cannot export the deformed mesh!")
+        if getattr(self, "m__vertPath", None) is None:
+            raise SmplppError("SMPL Error: Cannot export the deformed mesh!")
+        v = np.ascontiguousarray(self._vertices[index].cpu().numpy(), dtype=np.float32)
+        fi = np.ascontiguousarray(self._faces_host, dtype=np.int32)
+        check(lib().smplpp_write_obj(self.m__vertPath.encode(), C.c_int64(v.shape[0]), v.ctypes.data_as(capi.c_f32p),
+                                     C.c_int64(fi.shape[0]), fi.ctypes.data_as(capi.c_i32p)))
+
     def getVertexRaw(self, idx):
         """Batch element 0 only, like the reference (LinearBlendSkinning.cpp:419-427)."""
         self._launched("LinearBlendSknning Error: Failed to get vertices of new pose!")

@@ -54,7 +54,7 @@ EXPORTS = [
     "smplpp_c3d_open", "smplpp_c3d_close", "smplpp_c3d_frame_count", "smplpp_c3d_point_count", "smplpp_c3d_frame_rate",
     "smplpp_c3d_label", "smplpp_c3d_units", "smplpp_c3d_find_label", "smplpp_c3d_read",
     "smplpp_write_mocap_body_yaml", "smplpp_mocap_body_open", "smplpp_mocap_body_close", "smplpp_mocap_body_task_count",
-    "smplpp_mocap_body_task_name", "smplpp_mocap_body_get", "smplpp_write_motion_text", "smplpp_read_motion_text",
+    "smplpp_mocap_body_task_name", "smplpp_mocap_body_get", "smplpp_write_motion_text", "smplpp_read_motion_text", "smplpp_write_obj",
 ]
 
 _lib = None

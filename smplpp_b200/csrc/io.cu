@@ -745,3 +745,21 @@ extern "C" int smplpp_read_motion_text(const char * path, int64_t max_frames, fl
   *frames_out = n;
   return SMPLPP_OK;
 }
+
+// SMPL::out (src/SMPL.cpp:757-790): Wavefront OBJ of one mesh, "v x y z" per vertex in the default ostream float format
+// (6 significant digits = printf %g) and "f a b c" per face with the stored 1-based indices
+extern "C" int smplpp_write_obj(const char * path, int64_t n_vertices, const float * vertices, int64_t n_faces,
+                                const int32_t * face_indices_1based)
+{
+  if(!path || n_vertices < 1 || !vertices || n_faces < 0 || (n_faces > 0 && !face_indices_1based))
+    return fail(SMPLPP_ERR_INVALID, "SMPL", "Cannot export the deformed mesh!"); // SMPL.cpp:785
+  FILE * f = fopen(path, "w");
+  if(!f) return fail(SMPLPP_ERR_IO, "SMPL", "Cannot export the deformed mesh!");
+  for(int64_t i = 0; i < n_vertices; i++)
+    fprintf(f, "v %g %g %g\n", static_cast<double>(vertices[3 * i]), static_cast<double>(vertices[3 * i + 1]),
+            static_cast<double>(vertices[3 * i + 2]));
+  for(int64_t i = 0; i < n_faces; i++)
+    fprintf(f, "f %d %d %d\n", face_indices_1based[3 * i], face_indices_1based[3 * i + 1], face_indices_1based[3 * i + 2]);
+  fclose(f);
+  return SMPLPP_OK;
+}

@@ -203,3 +203,22 @@ def test_json_reader_random_documents(tmp_path, api):
         assert got.shape == want.shape and np.array_equal(got, want)
 
     check()
+
+
+def test_obj_export_text(tmp_path):
+    """SMPL::out (src/SMPL.cpp:757-790): "v x y z" with ostream's default float format (= %g) and 1-based "f a b c"."""
+    import ctypes as C
+    from smplpp_b200 import capi
+    rng = np.random.default_rng(6)
+    v = (rng.normal(size=(7, 3)) * np.array([1.0, 1e-5, 1e5])).astype(np.float32)
+    f = np.array([[1, 2, 3], [5, 6, 7]], dtype=np.int32)
+    path = str(tmp_path / "mesh.obj")
+    capi.check(capi.lib().smplpp_write_obj(path.encode(), C.c_int64(7), v.ctypes.data_as(capi.c_f32p), C.c_int64(2),
+                                           f.ctypes.data_as(capi.c_i32p)))
+    lines = open(path).read().splitlines()
+    assert len(lines) == 9
+    for i in range(7):
+        assert lines[i] == "v %g %g %g" % tuple(float(x) for x in v[i])
+    assert lines[7] == "f 1 2 3" and lines[8] == "f 5 6 7"
+    assert capi.lib().smplpp_write_obj(path.encode(), C.c_int64(0), None, C.c_int64(0), None) != 0
+    assert "Cannot export the deformed mesh!" in capi.lib().smplpp_last_error().decode()
