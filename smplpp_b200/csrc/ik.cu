@@ -906,6 +906,7 @@ struct IkSolveParams
   int B, n, rows_per_task; // rows actually populated per task (3 or 4)
   int theta_dim, phi_cols, beta_cols, D; // D = theta_dim + phi_cols + beta_cols (compact)
   int ld;                  // row stride of J
+  int rows_off;            // byte offset of the row staging area [2][4][ld] floats in the dynamic shared memory
   int vposer, enable_qp, skip_if_too_few, update_state;
   int schur;               // shared-beta stage: eliminate only the first D - beta_cols pivots
   float reg_theta, reg_phi, reg_beta, phi_limit, beta_limit, latent_reg, hand_reg;
@@ -1044,59 +1045,105 @@ __global__ void __launch_bounds__(c2::THREADS, 4) ik_solve_kernel(const IkSolveP
       s_esq = s;
     }
   }
-  // ---- A = J'J in 4x4 tiles of the lower triangle; fp32 entries widened exactly, fp64 accumulation ----
-  const int nb = (D + 3) / 4;
-  const int ntiles = nb * (nb + 1) / 2;
-  for(int tl = tid; tl < ntiles; tl += THREADS)
+  // ---- A = J'J in 4x4 tiles of the lower triangle and b = J'e; fp32 entries widened exactly, fp64 accumulation.
+  //      The rows of one task (rows_per_task x ld floats) are staged in shared memory, double buffered: the global loads
+  //      of task m+1 are coalesced, issued by the first threads and in flight while task m is consumed (every thread
+  //      fetching its own two float4 per row from L1 / L2 was 25 % long-scoreboard stalls, and b = J'e another serial
+  //      pass over the rows). ----
   {
-    int bi = static_cast<int>((sqrt(8.0 * tl + 1.0) - 1.0) * 0.5);
-    while((bi + 1) * (bi + 2) / 2 <= tl) bi++;
-    while(bi * (bi + 1) / 2 > tl) bi--;
-    const int bj = tl - bi * (bi + 1) / 2;
-    double acc[4][4];
-#pragma unroll
-    for(int a = 0; a < 4; a++)
-#pragma unroll
-      for(int b = 0; b < 4; b++) acc[a][b] = 0.0;
-    // one task (4 rows, rows_per_task of them live) per trip: its 6-8 row loads are issued together (the row-by-row
-    // loop with a `continue` kept two L2 loads in flight and was 17 % of the samples)
-    for(int m = 0; m < p.n; m++)
+    const int nb = (D + 3) / 4;
+    const int ntiles = nb * (nb + 1) / 2;
+    const int rpt = p.rows_per_task;
+    const int ld4 = p.ld >> 2;                                   // float4 per row (ld is a multiple of 4)
+    float4 * s_rows = reinterpret_cast<float4 *>(reinterpret_cast<char *>(smd) + p.rows_off); // [2][4][ld4]
+    const int per_task = rpt * ld4;
+    auto fetch = [&](int m, int i) -> float4 { // float4 i of the staged rows of task m
+      const int q = i / ld4, c4 = i - q * ld4;
+      return __ldg(reinterpret_cast<const float4 *>(J + static_cast<size_t>(4 * m + q) * p.ld) + c4);
+    };
+    double accb = 0.0;
+    for(int tl0 = 0; tl0 < ntiles; tl0 += THREADS)
     {
-      float4 ja[4], jb[4];
-#pragma unroll
-      for(int q = 0; q < 4; q++)
-        if(q < p.rows_per_task)
-        {
-          ja[q] = *reinterpret_cast<const float4 *>(J + static_cast<size_t>(4 * m + q) * p.ld + 4 * bi);
-          jb[q] = *reinterpret_cast<const float4 *>(J + static_cast<size_t>(4 * m + q) * p.ld + 4 * bj);
-        }
-#pragma unroll
-      for(int q = 0; q < 4; q++)
-        if(q < p.rows_per_task)
-        {
-          const double a4[4] = {ja[q].x, ja[q].y, ja[q].z, ja[q].w};
-          const double b4[4] = {jb[q].x, jb[q].y, jb[q].z, jb[q].w};
-#pragma unroll
-          for(int a = 0; a < 4; a++)
-#pragma unroll
-            for(int b = 0; b < 4; b++) acc[a][b] = fma(a4[a], b4[b], acc[a][b]);
-        }
-    }
-#pragma unroll
-    for(int a = 0; a < 4; a++)
-#pragma unroll
-      for(int b = 0; b < 4; b++)
+      const int tl = tl0 + tid;
+      const bool valid = tl < ntiles;
+      int bi = 0, bj = 0;
+      if(valid)
       {
-        const int i = 4 * bi + a, j = 4 * bj + b;
-        if(i < D && j <= i) L[tri_idx(i, j)] = acc[a][b];
+        bi = static_cast<int>((sqrt(8.0 * tl + 1.0) - 1.0) * 0.5);
+        while((bi + 1) * (bi + 2) / 2 <= tl) bi++;
+        while(bi * (bi + 1) / 2 > tl) bi--;
+        bj = tl - bi * (bi + 1) / 2;
       }
-  }
-  for(int i = tid; i < D; i += THREADS)
-  {
-    double acc = 0.0;
-    for(int r = 0; r < rows; r++)
-      if((r & 3) < p.rows_per_task) acc = fma(static_cast<double>(J[static_cast<size_t>(r) * p.ld + i]), static_cast<double>(e[r]), acc);
-    bvec[i] = acc;
+      double acc[4][4];
+#pragma unroll
+      for(int a = 0; a < 4; a++)
+#pragma unroll
+        for(int b = 0; b < 4; b++) acc[a][b] = 0.0;
+      __syncthreads(); // the previous pass is done with both buffers
+      for(int i = tid; i < per_task; i += THREADS) s_rows[(i / ld4) * ld4 + (i % ld4)] = fetch(0, i);
+      __syncthreads();
+      for(int m = 0; m < p.n; m++)
+      {
+        const int buf = m & 1;
+        // next task: global -> registers now, registers -> shared memory after this task's arithmetic
+        float4 nxt[2];
+        const bool more = m + 1 < p.n;
+#pragma unroll
+        for(int u = 0; u < 2; u++)
+          if(more && tid + u * THREADS < per_task) nxt[u] = fetch(m + 1, tid + u * THREADS);
+        const float4 * rows = s_rows + buf * 4 * ld4;
+        if(valid)
+        {
+#pragma unroll
+          for(int q = 0; q < 4; q++)
+            if(q < rpt)
+            {
+              const float4 ja = rows[q * ld4 + bi], jb = rows[q * ld4 + bj];
+              const double a4[4] = {ja.x, ja.y, ja.z, ja.w};
+              const double b4[4] = {jb.x, jb.y, jb.z, jb.w};
+#pragma unroll
+              for(int a = 0; a < 4; a++)
+#pragma unroll
+                for(int b = 0; b < 4; b++) acc[a][b] = fma(a4[a], b4[b], acc[a][b]);
+            }
+        }
+        if(tl0 == 0 && tid < D)
+        {
+          const float * rf = reinterpret_cast<const float *>(rows);
+#pragma unroll
+          for(int q = 0; q < 4; q++)
+            if(q < rpt) accb = fma(static_cast<double>(rf[q * p.ld + tid]), static_cast<double>(e[4 * m + q]), accb);
+        }
+#pragma unroll
+        for(int u = 0; u < 2; u++)
+          if(more && tid + u * THREADS < per_task)
+          {
+            const int i = tid + u * THREADS;
+            s_rows[(buf ^ 1) * 4 * ld4 + (i / ld4) * ld4 + (i % ld4)] = nxt[u];
+          }
+        __syncthreads();
+      }
+      if(valid)
+      {
+#pragma unroll
+        for(int a = 0; a < 4; a++)
+#pragma unroll
+          for(int b = 0; b < 4; b++)
+          {
+            const int i = 4 * bi + a, j = 4 * bj + b;
+            if(i < D && j <= i) L[tri_idx(i, j)] = acc[a][b];
+          }
+      }
+    }
+    // D may exceed the block size only for the largest problems: the remaining entries of b the plain way
+    if(tid < D) bvec[tid] = accb;
+    for(int i = tid + THREADS; i < D; i += THREADS)
+    {
+      double acc = 0.0;
+      for(int r = 0; r < rows; r++)
+        if((r & 3) < rpt) acc = fma(static_cast<double>(J[static_cast<size_t>(r) * p.ld + i]), static_cast<double>(e[r]), acc);
+      bvec[i] = acc;
+    }
   }
   __syncthreads();
   // ---- damping (node.cpp:887-893) and the VPoser prior (:895-904) ----
@@ -1869,11 +1916,18 @@ int solve_block_threads(int D)
   return (th < 160 || th > c2::THREADS) ? c2::THREADS : th; // small problems keep 8 warps for the Cholesky / QP phases
 }
 
-size_t solve_smem_bytes(const IkLayout & L, bool schur)
+// byte offset of the J row staging area of ik_solve_kernel (16-byte aligned, behind everything else)
+size_t solve_rows_off(const IkLayout & L, bool schur)
 {
   const size_t D = L.D;
   size_t dbl = D * (D + 1) / 2 + 5 * D + 4 + (schur ? D + 2 : 0);
-  return dbl * sizeof(double) + D * sizeof(int) + 64;
+  return (dbl * sizeof(double) + D * sizeof(int) + 64 + 15) / 16 * 16;
+}
+
+size_t solve_smem_bytes(const IkLayout & L, bool schur)
+{
+  const size_t D = L.D;
+  return solve_rows_off(L, schur) + 2 * 4 * static_cast<size_t>(L.ld) * sizeof(float) + 16;
 }
 
 // shared front end of smplpp_ik_step and smplpp_ik_shared_beta_reduce for one chunk of frames
@@ -2036,6 +2090,7 @@ extern "C" int smplpp_ik_step(const smplpp_model_t * model, const smplpp_vposer_
     sp.b_out = b_out ? b_out + s * L.dim_ref : nullptr;
     sp.delta_out = delta_out ? delta_out + s * L.dim_ref : nullptr;
     const size_t smem = solve_smem_bytes(L, false);
+    sp.rows_off = static_cast<int>(solve_rows_off(L, false));
     if(smem > 227 * 1024) return fail(SMPLPP_ERR_INVALID, "IkTask", "IK problem too large for one CTA per frame");
     SB_CUDA(cudaFuncSetAttribute(ik_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     ik_solve_kernel<<<B, solve_block_threads(L.D), smem, st>>>(sp);
@@ -2083,6 +2138,7 @@ extern "C" int smplpp_ik_shared_beta_reduce(const smplpp_model_t * model, const 
     sp.schur_out = reinterpret_cast<double *>(ws + L.off_schur) + s * 111;
     sp.factor_ws = reinterpret_cast<double *>(ws + L.off_factor) + s * P;
     const size_t smem = solve_smem_bytes(L, true);
+    sp.rows_off = static_cast<int>(solve_rows_off(L, true));
     SB_CUDA(cudaFuncSetAttribute(ik_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     ik_solve_kernel<<<B, solve_block_threads(L.D), smem, st>>>(sp);
     SB_LAUNCHED();
