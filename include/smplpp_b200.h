@@ -302,6 +302,11 @@ int smplpp_json_open(const char * path, smplpp_json_t ** out);
 void smplpp_json_close(smplpp_json_t * json);
 int smplpp_json_array(const smplpp_json_t * json, const char * key, int32_t * ndim, int64_t * shape8,
                       const double ** data);
+/* The .npz twin of a parameter file (np.savez of scripts/preprocess.py:98-117: a ZIP of stored .npy members, zip64 extra
+ * fields, little-endian f4 / f8 / i4 / i8 / u4 / u8, C order); arrays are read with smplpp_json_array, closed with
+ * smplpp_json_close. */
+int smplpp_npz_open(const char * path, smplpp_json_t ** out);
+int smplpp_model_load_npz(const char * path, smplpp_model_t ** out);
 /* SMPL::setModelPath + SMPL::init (src/SMPL.cpp:560-643): keys face_indices, shape_blend_shapes, pose_blend_shapes,
  * vertices_template, joint_regressor, kinematic_tree, weights; the reference's messages ("Cannot initialize a SMPL
  * model!", "Shape parameter dimensions are invalid: 9 != 10", ...) come back through smplpp_last_error(). */

@@ -151,7 +151,8 @@ class SMPL:
         self.m__modelPath = path
         h = C.c_void_p()
         with torch.cuda.device(self.m__device):
-            check(lib().smplpp_model_load_json(path.encode(), C.byref(h)))
+            loader = lib().smplpp_model_load_npz if path.endswith(".npz") else lib().smplpp_model_load_json
+            check(loader(path.encode(), C.byref(h)))
         self._h = h
         self.vertex_num = int(lib().smplpp_model_vertex_num(h))
         self._faces_host = np.ascontiguousarray(read_json_arrays(path, ["face_indices"])["face_indices"], dtype=np.int32)
@@ -366,9 +367,11 @@ def load_model_file(path: str):
 
 
 def read_json_arrays(path: str, keys):
-    """Numeric arrays of a parameter file through the C-ABI reader (smplpp_json_*): {key: float64 ndarray}."""
+    """Numeric arrays of a parameter file (.json, or its .npz twin) through the C-ABI reader (smplpp_json_* /
+    smplpp_npz_open): {key: float64 ndarray}."""
     h = C.c_void_p()
-    check(lib().smplpp_json_open(path.encode(), C.byref(h)))
+    opener = lib().smplpp_npz_open if path.endswith(".npz") else lib().smplpp_json_open
+    check(opener(path.encode(), C.byref(h)))
     try:
         out = {}
         for k in keys:

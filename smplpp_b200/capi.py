@@ -51,6 +51,7 @@ EXPORTS = [
     "smplpp_task_positions", "smplpp_closest_points", "smplpp_ik_workspace_bytes", "smplpp_ik_step",
     "smplpp_ik_shared_beta_workspace_bytes", "smplpp_ik_shared_beta_reduce", "smplpp_ik_shared_beta_apply",
     "smplpp_json_open", "smplpp_json_close", "smplpp_json_array", "smplpp_model_load_json", "smplpp_vposer_load_json",
+    "smplpp_npz_open", "smplpp_model_load_npz",
     "smplpp_c3d_open", "smplpp_c3d_close", "smplpp_c3d_frame_count", "smplpp_c3d_point_count", "smplpp_c3d_frame_rate",
     "smplpp_c3d_label", "smplpp_c3d_units", "smplpp_c3d_find_label", "smplpp_c3d_read",
     "smplpp_write_mocap_body_yaml", "smplpp_mocap_body_open", "smplpp_mocap_body_close", "smplpp_mocap_body_task_count",

@@ -277,12 +277,30 @@ extern "C" int smplpp_json_array(const smplpp_json_t * j, const char * key, int3
 }
 
 // SMPL::init (src/SMPL.cpp:560-617): same keys, same shape checks, same messages
+static int model_from_arrays(const smplpp_json * j, smplpp_model_t ** out);
+
 extern "C" int smplpp_model_load_json(const char * path, smplpp_model_t ** out)
 {
   if(!out) return fail(SMPLPP_ERR_INVALID, "SMPL", "Cannot initialize a SMPL model!");
   std::unique_ptr<smplpp_json> j;
   int rc = load_json(path, "SMPL", "Cannot initialize a SMPL model!", j); // SMPL.cpp:614-617: the file does not exist
   if(rc != SMPLPP_OK) return rc;
+  return model_from_arrays(j.get(), out);
+}
+
+// the .npz twin of the model JSON (scripts/preprocess.py:98-117)
+extern "C" int smplpp_model_load_npz(const char * path, smplpp_model_t ** out)
+{
+  if(!out) return fail(SMPLPP_ERR_INVALID, "SMPL", "Cannot initialize a SMPL model!");
+  smplpp_json_t * j = nullptr;
+  int rc = smplpp_npz_open(path, &j);
+  if(rc != SMPLPP_OK) return rc;
+  std::unique_ptr<smplpp_json> hold(j);
+  return model_from_arrays(j, out);
+}
+
+static int model_from_arrays(const smplpp_json * j, smplpp_model_t ** out)
+{
   const char * keys[] = {"face_indices", "shape_blend_shapes", "pose_blend_shapes", "vertices_template", "joint_regressor",
                          "kinematic_tree", "weights"};
   const smplpp_json::Array * a[7];
@@ -761,5 +779,136 @@ extern "C" int smplpp_write_obj(const char * path, int64_t n_vertices, const flo
   for(int64_t i = 0; i < n_faces; i++)
     fprintf(f, "f %d %d %d\n", face_indices_1based[3 * i], face_indices_1based[3 * i + 1], face_indices_1based[3 * i + 2]);
   fclose(f);
+  return SMPLPP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// .npz twin of the model file (scripts/preprocess.py:98-117 writes it with np.savez next to the JSON): a ZIP archive of
+// STORED .npy members.  Read through the central directory (numpy writes zip64 extra fields), C-ordered little-endian
+// f4 / f8 / i4 / i8 / u4 / u8 arrays.  Values are widened to double like the JSON reader's, so both loaders share the
+// model assembly below.
+// ------------------------------------------------------------------------------------------------------------
+namespace
+{
+bool npz_read(const std::string & b, smplpp_json & out, std::string & err)
+{
+  // end of central directory: scan back for its signature
+  if(b.size() < 22) return err = "not a zip archive", false;
+  size_t eocd = std::string::npos;
+  for(size_t i = b.size() - 22 + 1; i-- > 0;)
+  {
+    if(rd<uint32_t>(b, i) == 0x06054b50u)
+    {
+      eocd = i;
+      break;
+    }
+    if(b.size() - i > 22 + 65535) break;
+  }
+  if(eocd == std::string::npos) return err = "not a zip archive (no end-of-central-directory record)", false;
+  uint64_t n_entries = rd<uint16_t>(b, eocd + 10), cd_off = rd<uint32_t>(b, eocd + 16);
+  if(cd_off == 0xFFFFFFFFu || n_entries == 0xFFFFu)
+  {
+    // zip64: locator 20 bytes before the EOCD points at the zip64 EOCD record
+    if(eocd < 20 || rd<uint32_t>(b, eocd - 20) != 0x07064b50u) return err = "zip64 locator missing", false;
+    const uint64_t z = rd<uint64_t>(b, eocd - 20 + 8);
+    if(z + 56 > b.size() || rd<uint32_t>(b, z) != 0x06064b50u) return err = "zip64 end-of-central-directory record missing", false;
+    n_entries = rd<uint64_t>(b, z + 32);
+    cd_off = rd<uint64_t>(b, z + 48);
+  }
+  size_t pos = cd_off;
+  for(uint64_t e = 0; e < n_entries; e++)
+  {
+    if(pos + 46 > b.size() || rd<uint32_t>(b, pos) != 0x02014b50u) return err = "corrupt central directory", false;
+    const int method = rd<uint16_t>(b, pos + 10);
+    uint64_t csize = rd<uint32_t>(b, pos + 20), usize = rd<uint32_t>(b, pos + 24), lho = rd<uint32_t>(b, pos + 42);
+    const int nlen = rd<uint16_t>(b, pos + 28), xlen = rd<uint16_t>(b, pos + 30), clen = rd<uint16_t>(b, pos + 32);
+    std::string name(b.data() + pos + 46, nlen);
+    // zip64 extended information (header id 1): the fields that are 0xFFFFFFFF above, in order
+    size_t x = pos + 46 + nlen;
+    const size_t xend = x + xlen;
+    while(x + 4 <= xend)
+    {
+      const int id = rd<uint16_t>(b, x), sz = rd<uint16_t>(b, x + 2);
+      if(id == 1)
+      {
+        size_t q = x + 4;
+        if(usize == 0xFFFFFFFFu) usize = rd<uint64_t>(b, q), q += 8;
+        if(csize == 0xFFFFFFFFu) csize = rd<uint64_t>(b, q), q += 8;
+        if(lho == 0xFFFFFFFFu) lho = rd<uint64_t>(b, q), q += 8;
+      }
+      x += 4 + sz;
+    }
+    pos = xend + clen;
+    if(name.size() < 4 || name.compare(name.size() - 4, 4, ".npy") != 0) continue;
+    if(method != 0) return err = "compressed .npz members are not supported (np.savez writes them stored): " + name, false;
+    if(lho + 30 > b.size() || rd<uint32_t>(b, lho) != 0x04034b50u) return err = "corrupt local header of " + name, false;
+    const size_t data = lho + 30 + rd<uint16_t>(b, lho + 26) + rd<uint16_t>(b, lho + 28);
+    if(data + usize > b.size() || usize < 12) return err = "truncated member " + name, false;
+    // .npy: magic, version, header length, python dict literal
+    if(memcmp(b.data() + data, "\x93NUMPY", 6) != 0) return err = "not a .npy member: " + name, false;
+    const int major = static_cast<uint8_t>(b[data + 6]);
+    const size_t hlen = major >= 2 ? rd<uint32_t>(b, data + 8) : rd<uint16_t>(b, data + 8);
+    const size_t hoff = data + (major >= 2 ? 12 : 10);
+    if(hoff + hlen > data + usize) return err = "truncated .npy header of " + name, false;
+    const std::string hdr(b.data() + hoff, hlen);
+    auto after = [&](const char * key) -> size_t {
+      const size_t k = hdr.find(key);
+      return k == std::string::npos ? k : hdr.find(':', k) + 1;
+    };
+    size_t p = after("'descr'");
+    if(p == std::string::npos) return err = "no descr in " + name, false;
+    const size_t q1 = hdr.find('\'', p), q2 = hdr.find('\'', q1 + 1);
+    const std::string descr = hdr.substr(q1 + 1, q2 - q1 - 1);
+    p = after("'fortran_order'");
+    if(p != std::string::npos && hdr.compare(hdr.find_first_not_of(' ', p), 4, "True") == 0)
+      return err = "Fortran-ordered array " + name + " is not supported", false;
+    p = after("'shape'");
+    const size_t s1 = hdr.find('(', p), s2 = hdr.find(')', s1);
+    smplpp_json::Array a;
+    {
+      const char * c = hdr.c_str() + s1 + 1;
+      const char * cend = hdr.c_str() + s2;
+      while(c < cend)
+      {
+        char * stop = nullptr;
+        const long long v = strtoll(c, &stop, 10);
+        if(stop == c) break;
+        a.shape.push_back(v);
+        c = stop;
+        while(c < cend && (*c == ',' || *c == ' ')) c++;
+      }
+    }
+    size_t count = 1;
+    for(int64_t d : a.shape) count *= static_cast<size_t>(d);
+    const size_t payload = hoff + hlen;
+    const size_t esz = descr.size() >= 3 ? static_cast<size_t>(descr[2] - '0') : 0;
+    if((descr[0] != '<' && descr[0] != '|') || (esz != 4 && esz != 8) || payload + count * esz > data + usize)
+      return err = "unsupported dtype " + descr + " of " + name, false;
+    a.data.resize(count);
+    for(size_t i = 0; i < count; i++)
+    {
+      const size_t o = payload + i * esz;
+      double v = 0.0;
+      if(descr[1] == 'f') v = esz == 4 ? static_cast<double>(rd<float>(b, o)) : rd<double>(b, o);
+      else if(descr[1] == 'i') v = esz == 4 ? static_cast<double>(rd<int32_t>(b, o)) : static_cast<double>(rd<int64_t>(b, o));
+      else if(descr[1] == 'u') v = esz == 4 ? static_cast<double>(rd<uint32_t>(b, o)) : static_cast<double>(rd<uint64_t>(b, o));
+      else return err = "unsupported dtype " + descr + " of " + name, false;
+      a.data[i] = v;
+    }
+    out.arrays[name.substr(0, name.size() - 4)] = std::move(a);
+  }
+  return true;
+}
+} // namespace
+
+// the same handle type and accessor (smplpp_json_array) as the JSON reader
+extern "C" int smplpp_npz_open(const char * path, smplpp_json_t ** out)
+{
+  if(!out) return fail(SMPLPP_ERR_INVALID, "NPZ", "null output");
+  std::string bytes, err;
+  if(!path || !read_file(path, bytes)) return fail(SMPLPP_ERR_IO, "NPZ", "Cannot find the .npz file!");
+  std::unique_ptr<smplpp_json> j(new smplpp_json());
+  if(!npz_read(bytes, *j, err)) return fail(SMPLPP_ERR_IO, "NPZ", "Cannot read the .npz file: " + err);
+  *out = j.release();
   return SMPLPP_OK;
 }

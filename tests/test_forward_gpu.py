@@ -402,6 +402,14 @@ def test_native_json_loaders_match_python_loaders(tmp_path, params, vposer_param
     b.launch(beta, theta)
     assert torch.equal(a.getVertex(), b.getVertex()) and torch.equal(a.getRestJoint(), b.getRestJoint())
     assert torch.equal(a.getFaceIndex(), b.getFaceIndex())
+    # the .npz twin (np.savez, scripts/preprocess.py:98-117) through smplpp_model_load_npz
+    npath = str(tmp_path / "model.npz")
+    np.savez(npath, vertices_template=params.vertices_template, face_indices=params.face_indices, weights=params.weights,
+             shape_blend_shapes=params.shape_blend_shapes, pose_blend_shapes=params.pose_blend_shapes,
+             joint_regressor=params.joint_regressor, kinematic_tree=params.kinematic_tree)
+    c = api.SMPL.from_json_native(npath, device="cuda:0")
+    c.launch(beta, theta)
+    assert torch.equal(a.getVertex(), c.getVertex()) and torch.equal(a.getFaceIndex(), c.getFaceIndex())
     va = api.VPoserDecoder(vposer_params, device="cuda:0")
     vb = api.VPoserDecoder(device="cuda:0")
     vb.loadParamsFromJsonNative(vpath)

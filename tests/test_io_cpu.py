@@ -222,3 +222,38 @@ def test_obj_export_text(tmp_path):
     assert lines[7] == "f 1 2 3" and lines[8] == "f 5 6 7"
     assert capi.lib().smplpp_write_obj(path.encode(), C.c_int64(0), None, C.c_int64(0), None) != 0
     assert "Cannot export the deformed mesh!" in capi.lib().smplpp_last_error().decode()
+
+
+def test_npz_reader_matches_numpy(tmp_path, api):
+    """The .npz twin (np.savez, scripts/preprocess.py:98-117): every array and dtype numpy stores for a model comes back
+    with the same shape and values; compressed archives and Fortran order are refused with a clear message."""
+    from smplpp_b200 import capi
+    rng = np.random.default_rng(12)
+    arrays = {
+        "vertices_template": rng.normal(size=(11, 3)).astype(np.float32),
+        "face_indices": rng.integers(1, 12, size=(7, 3)).astype(np.int32),
+        "kinematic_tree": np.array([[4294967295, 0, 1], [0, 1, 2]], dtype=np.int64),
+        "weights": rng.random((11, 24)),                                   # float64
+        "pose_blend_shapes": rng.normal(size=(11, 3, 207)).astype(np.float32),
+        "u4": np.arange(5, dtype=np.uint32), "scalar": np.float32(2.5),
+    }
+    path = str(tmp_path / "model.npz")
+    np.savez(path, **arrays)
+    got = api.read_json_arrays(path, list(arrays))
+    for k, v in arrays.items():
+        assert got[k].shape == np.shape(v), k
+        assert np.array_equal(got[k], np.asarray(v, dtype=np.float64)), k
+    cpath = str(tmp_path / "compressed.npz")
+    np.savez_compressed(cpath, a=np.zeros((4, 4), np.float32))
+    with pytest.raises(capi.SmplppError, match="compressed .npz members are not supported"):
+        api.read_json_arrays(cpath, ["a"])
+    fpath = str(tmp_path / "fortran.npz")
+    np.savez(fpath, a=np.asfortranarray(rng.normal(size=(3, 4))))
+    with pytest.raises(capi.SmplppError, match="Fortran-ordered"):
+        api.read_json_arrays(fpath, ["a"])
+    with pytest.raises(capi.SmplppError, match="Cannot find the .npz file"):
+        api.read_json_arrays(str(tmp_path / "absent.npz"), ["a"])
+    with open(str(tmp_path / "junk.npz"), "wb") as f:
+        f.write(bytes(100))
+    with pytest.raises(capi.SmplppError, match="not a zip archive"):
+        api.read_json_arrays(str(tmp_path / "junk.npz"), ["a"])
