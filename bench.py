@@ -143,36 +143,63 @@ def cpu_reference_forward(batch_total: int, threads: int | None = None, chunk: i
     return chunk / best, cores, sample
 
 
+def bench_config(B: int) -> dict:
+    """The workload both arms (this library and `--impl reference`) are measured on: identical dict in both lines."""
+    return {"workload": "configs[1]: batched SMPL forward B=%d poses/GPU fp32 (pose-blend GEMM + joint chain + LBS), "
+                        "synthetic smpl_male-shaped model (6890 verts, 207 pose dims, 10 betas)" % B,
+            "frames_per_gpu": B,
+            "l2": "no flush: every forward pass writes %d MB of vertices (> 126 MB L2); the 18 MB blend basis is model "
+                  "state that stays resident" % (B * VERTS * 12 >> 20),
+            "variant": "auto"}
+
+
 def run_reference(args, json_out):
+    """The reference's own CPU implementation (unmodified sources, oracle/_ref) on the same config: every step is one
+    pass over the B = 4096 poses (16 chunks of the batched N = 256 build), all host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    per_step = 1024  # bounded sample of the B=4096 workload per step
+    B, chunk = args.batch, 256
     from oracle import ref_lib
     from smplpp_b200 import synth
     cores = os.cpu_count() or 1
     ref_lib.set_num_threads(cores)
     ref = ref_lib.RefSMPL(ref_lib.model_json_path(0))
-    beta, theta = synth.make_forward_inputs(256, 11)
-    for _ in range(max(1, args.warmup)):
-        ref.forward(beta, theta, batched=True, want=("vertices",))
+    beta, theta = synth.make_forward_inputs(B, 11)
+    nchunks = (B + chunk - 1) // chunk
+
+    def one_pass():
+        for c in range(nchunks):
+            ref.forward(beta[c * chunk:(c + 1) * chunk], theta[c * chunk:(c + 1) * chunk], batched=True, want=("vertices",))
+
+    ref.forward(beta[:chunk], theta[:chunk], batched=True, want=("vertices",))  # untimed: allocator / thread-pool warm-up
+    for _ in range(max(0, min(args.warmup, 2) - 1)):
+        one_pass()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        for _ in range(per_step // 256):
-            ref.forward(beta, theta, batched=True, want=("vertices",))
+        one_pass()
     dt = time.perf_counter() - t0
-    value = args.steps * per_step / dt
+    value = args.steps * B / dt
     line = {
         "impl": "reference", "metric": "SMPL FK+LBS meshes/s", "value": value, "unit": "meshes/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1] batched SMPL forward (pose-blend GEMM + joint chain + LBS), reference CPU "
-                               "path; each step = bounded sample of %d of the 4096 poses" % per_step},
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": bench_config(B),
         "cpu_baseline": {"value": value, "unit": "meshes/s", "cores": ref_lib.get_num_threads(), "kind": "reference",
-                         "sample": "unmodified reference sources (oracle/_ref, libtorch CPU, batched build N=256), "
-                                   "%d meshes per step" % per_step},
+                         "sample": "unmodified reference sources (oracle/_ref, libtorch CPU, batched build N=%d): one "
+                                   "pass over the %d poses per step, %d steps" % (chunk, B, args.steps)},
         "e2e": {"value": value, "unit": "meshes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if not args.no_ik:
+        try:
+            from bench_ik import cpu_reference_ik
+            v, c, sample = cpu_reference_ik(2, 2)
+            line["ik"] = {"value": v, "unit": "frame-iters/s",
+                          "cpu_baseline": {"value": v, "unit": "frame-iters/s", "cores": c, "kind": "reference", "sample": sample}}
+            line["cpu_baseline"]["ik_value"] = v
+            line["cpu_baseline"]["ik_unit"] = "frame-iters/s"
+            line["cpu_baseline"]["ik_sample"] = sample
+        except Exception as ex:
+            line["ik"] = {"value": None, "unavailable": str(ex)}
     json_out.write(json.dumps(line) + "\n")
     json_out.flush()
     return 0
@@ -184,7 +211,10 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH, help="frames per GPU per step")
+    ap.add_argument("--batch", type=int, default=BATCH, help="frames per GPU per forward pass")
+    ap.add_argument("--passes", type=int, default=160,
+                    help="forward passes over the batch inside ONE timed step (a pass is 0.19 ms: 160 of them make a "
+                         "step long enough for the clock sampler and the driver's consistency check)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ik", action="store_true")
     ap.add_argument("--ik-frames-total", type=int, default=0,
@@ -255,11 +285,17 @@ def main():
     joints = torch.empty((B, 24, 3), dtype=torch.float32, device=dev)
     stream = torch.cuda.current_stream(dev)
 
-    def step():
+    P = max(1, args.passes)
+
+    def one_pass():
         capi.check(lib.smplpp_forward(smpl.handle, C.c_void_p(stream.cuda_stream), C.c_int64(B),
                                       C.c_void_p(beta.data_ptr()), C.c_int64(10), C.c_void_p(theta.data_ptr()),
                                       C.c_void_p(verts.data_ptr()), C.c_void_p(joints.data_ptr()), None, None,
                                       C.c_void_p(ws.data_ptr()), C.c_size_t(ws_bytes)))
+
+    def step():  # one timed step = P passes of the hot path over the batch
+        for _ in range(P):
+            one_pass()
 
     for _ in range(args.warmup):
         step()
@@ -280,7 +316,7 @@ def main():
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     launches = int(lib.smplpp_launch_count() - launches0)
     ms_step = ms_total / args.steps
-    value = world * B / (ms_step * 1e-3)
+    value = world * B * P / (ms_step * 1e-3)
 
     # ---- per-kernel device times (CUDA events on the launching stream), same workload ----
     def time_kernel(fn, reps):
@@ -302,24 +338,31 @@ def main():
                                       None, C.c_void_p(joints.data_ptr()), None, None, C.c_void_p(ws.data_ptr()),
                                       C.c_size_t(ws_bytes)))
 
-    ms_k1 = time_kernel(k1_only, 20)
-    ms_full = time_kernel(step, 20)
+    ms_k1 = time_kernel(k1_only, 200)
+    ms_full = time_kernel(one_pass, 200)
     ms_k2 = max(ms_full - ms_k1, 1e-6)
     peak, peak_src = measured_peaks()
     traffic_k2, traffic_k2_src = ncu_traffic("blend_skin_tc3_kernel")
     traffic_lbs, traffic_lbs_src = ncu_traffic("lbs_tc_kernel")
     ach = BYTES_FUSED * B / (ms_k2 * 1e-3) / 1e9
-    roofline = {"kernel": "blend_skin (fused pose/shape blend contraction + linear blend skinning)", "bound": "hbm",
-                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic_k2, "traffic_unit": "bytes per launch (dram read + write, ncu --set full)",
-                "traffic_source": traffic_k2_src,
+    tpeak, tpeak_src = measured_tensor_peak()
+    # The reference computes both products in fp32; on the tensor cores an fp32 product that holds the 1e-5 m tolerance
+    # is THREE fp16 passes (hi.hi + lo.hi + hi.lo, fp32 accumulation): the algorithmic tensor work of the kernel is 3 x
+    # (blend contraction 2.217.3V + skinning matrices 2.24.12.V) flops per mesh.
+    flops_split = 3 * (2 * 217 * VERTS * 3 + 2 * 24 * 12 * VERTS) * B
+    ach_t = flops_split / (ms_k2 * 1e-3) / 1e12
+    roofline = {"kernel": "blend_skin_tc3_kernel (fused pose/shape blend contraction + linear blend skinning, tcgen05)",
+                "bound": "tensor", "achieved": ach_t, "peak": tpeak, "unit": "TFLOP/s", "frac": ach_t / tpeak,
+                "traffic": traffic_k2, "traffic_unit": "bytes per launch (dram read + write, ncu --set full)",
+                "traffic_source": traffic_k2_src, "peak_source": tpeak_src, "ms_per_launch": ms_k2,
+                "algorithmic_flops_per_launch": flops_split,
+                "algorithmic_flops_note": "3 fp16 tensor passes per fp32 product (split precision), unpadded shapes",
+                "fp32_tflops_algorithmic": FLOPS_BLEND * B / (ms_k2 * 1e-3) / 1e12,
                 "algorithmic_bytes_per_launch": BYTES_FUSED * B,
-                "peak_source": peak_src, "ms_per_launch": ms_k2,
-                "fp32_tflops_algorithmic": FLOPS_BLEND * B / (ms_k2 * 1e-3) / 1e12}
+                "hbm_achieved_gbs": ach, "hbm_peak_gbs": peak, "hbm_frac": ach / peak, "hbm_peak_source": peak_src}
     # the same kernel against the tensor pipe: its two products are computed as 3 fp16 passes each (hi.hi + lo.hi +
     # hi.lo, fp32 accumulation).  "split_algorithmic" counts 3 x the unpadded fp32 products (217 blend columns, 24
     # joints x 12 matrix entries), "executed" the padded tiles the MMAs really run (128 x 96 x 16 per instruction).
-    tpeak, tpeak_src = measured_tensor_peak()
-    flops_split = 3 * (2 * 217 * VERTS * 3 + 2 * 24 * 12 * VERTS) * B
     tiles, fblocks = (VERTS + 127) // 128, (B + 95) // 96
     flops_exec = tiles * fblocks * (126 + 72) * (2 * 128 * 96 * 16)
     roofline["tensor"] = {"unit": "TFLOP/s", "peak": tpeak, "peak_source": tpeak_src,
@@ -356,6 +399,8 @@ def main():
         ms_lbs_var[name] = time_kernel(lbs_only, 20)
     capi.check(lib.smplpp_set_forward_variant(202))
     ach_lbs = BYTES_LBS * B / (ms_lbs * 1e-3) / 1e9
+    # flat copies (the driver keeps scalar keys of `roofline`): the HBM-bound row of SURVEY 8d
+    roofline["lbs_achieved_gbs"], roofline["lbs_frac"], roofline["lbs_ms_per_launch"] = ach_lbs, ach_lbs / peak, ms_lbs
     roofline["lbs"] = {"kernel": "lbs_tc_kernel (standalone skinning, skinning matrices on tcgen05)", "bound": "hbm", "achieved": ach_lbs, "peak": peak,
                        "unit": "GB/s", "frac": ach_lbs / peak, "ms_per_launch": ms_lbs, "traffic": traffic_lbs, "traffic_source": traffic_lbs_src,
                        "algorithmic_bytes_per_launch": BYTES_LBS * B,
@@ -390,36 +435,42 @@ def main():
     for _ in range(3):
         smpl.launch_host(beta_h, theta_h, out_vertices=pg_v, out_joints=pg_j)
     e2e["pageable_value"] = world * B / max_over_ranks((time.perf_counter() - t0) / 3)
-    del pin_v, pg_v
+    del pg_v
+    # the box's own device->host ceiling on this rank, all ranks copying at once: plain cudaMemcpyAsync of the same
+    # 340 MB from device memory into the same page-locked buffer (what the link + host memory system can take)
+    pin_t = torch.from_numpy(pin_v)
+    for _ in range(2):
+        pin_t.copy_(verts, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        pin_t.copy_(verts, non_blocking=True)
+    torch.cuda.synchronize()
+    d2h_s = max_over_ranks((time.perf_counter() - t0) / 5)
+    e2e["d2h_ceiling_gbs"] = B * VERTS * 12 / d2h_s / 1e9
+    e2e["d2h_ceiling_note"] = "per rank, all %d ranks copying concurrently; e2e d2h_gbs / ceiling = %.2f" % (
+        world, e2e["d2h_gbs"] / e2e["d2h_ceiling_gbs"])
+    del pin_v, pin_t
 
     ik = None
     if not args.no_ik:
-        try:
-            from smplpp_b200 import ik_bench
-            if args.ik_frames_total > 0:
-                from smplpp_b200 import parallel
-                _, nloc = parallel.frame_block(args.ik_frames_total, rank, world)
-                ik = ik_bench.run(dev, rank, world, max_over_ranks, barrier, frames=nloc, iters=3, warmup=1,
-                                  frames_total=args.ik_frames_total)
-            else:
-                ik = ik_bench.run(dev, rank, world, max_over_ranks, barrier)
-        except ImportError:
-            ik = None
+        import bench_ik
+        if args.ik_frames_total > 0:
+            from smplpp_b200 import parallel
+            _, nloc = parallel.frame_block(args.ik_frames_total, rank, world)
+            ik = bench_ik.run(dev, rank, world, max_over_ranks, barrier, frames=nloc, iters=3, warmup=1,
+                              frames_total=args.ik_frames_total)
+        else:
+            ik = bench_ik.run(dev, rank, world, max_over_ranks, barrier)
 
     clocks.__exit__(None, None, None)
     line = {
         "metric": "SMPL FK+LBS meshes/s", "value": value, "unit": "meshes/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: batched SMPL forward B=%d poses/GPU fp32 (pose-blend GEMM + joint chain + "
-                               "LBS), synthetic smpl_male-shaped model (6890 verts, 207 pose dims, 10 betas)" % B,
-                   "frames_per_gpu": B, "l2": "no flush: every step writes %d MB of vertices (> 126 MB L2); the 18 MB "
-                                              "blend basis is model state that stays resident" % (B * VERTS * 12 >> 20),
-                   "variant": "auto"},
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": bench_config(B),
+        "passes_per_step": P, "timed_region_s": ms_total * 1e-3,
         "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roofline, "e2e": e2e,
     }
-    if ik is not None:
-        line["ik"] = ik
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         try:
             v, cores, sample = cpu_reference_forward(1024)
@@ -427,6 +478,29 @@ def main():
         except Exception as ex:  # the oracle library is test infrastructure; say so instead of failing the bench
             line["cpu_baseline"] = {"value": None, "unit": "meshes/s", "cores": 0, "kind": "reference",
                                     "sample": "unavailable: %s" % ex}
+    if ik is not None:
+        # IK is the other half of BASELINE's metric: its own roofline / e2e / cpu_baseline objects under `ik`, and flat
+        # scalar copies inside the keys the driver records (nested objects are dropped from its `parsed` view)
+        if rank == 0 and not args.no_cpu_baseline and world == 1:
+            try:
+                v, cores, sample = bench_ik.cpu_reference_ik(2, 2)
+                ik["cpu_baseline"] = {"value": v, "unit": "frame-iters/s", "cores": cores, "kind": "reference", "sample": sample}
+                line["cpu_baseline"].update(ik_value=v, ik_unit="frame-iters/s", ik_sample=sample)
+            except Exception as ex:
+                ik["cpu_baseline"] = {"value": None, "unit": "frame-iters/s", "cores": 0, "kind": "reference",
+                                      "sample": "unavailable: %s" % ex}
+        line["ik"] = ik
+        line["ik_value"], line["ik_unit"] = ik["value"], "frame-iters/s"
+        for k in ("mosh_direct", "moshpp_vposer", "shared_beta", "shared_beta_vposer"):
+            if k in ik:
+                line["ik_" + k] = ik[k]["value"]
+        if "roofline" in ik:
+            r = ik["roofline"]
+            roofline.update(ik_bound=r["bound"], ik_achieved=r["achieved"], ik_peak=r["peak"], ik_unit=r["unit"],
+                            ik_frac=r["frac"], ik_traffic=r.get("traffic"), ik_ms_per_iter=r.get("ms_per_launch"))
+        if "e2e" in ik:
+            e2e.update(ik_value=ik["e2e"]["value"], ik_unit="frame-iters/s", ik_h2d_bytes_per_step=ik["e2e"]["h2d_bytes_per_step"],
+                       ik_d2h_bytes_per_step=ik["e2e"]["d2h_bytes_per_step"])
     if rank == 0:
         json_out.write(json.dumps(line) + "\n")
         json_out.flush()

@@ -1,16 +1,42 @@
-"""IK leg of bench.py: frame-iterations/s of the batched MoSh step (BASELINE configs[2]-[4] shaped workloads).
+"""IK leg of bench.py (lives beside it, outside the product package: `cpu_reference_ik` runs oracle/ as the checker /
+CPU baseline): frame-iterations/s of the batched MoSh step (BASELINE configs[2]-[4] shaped workloads).
 
 Synthetic 'sample_walk-shaped' mocap is generated ON THE DEVICE from the seed: ground-truth theta(t) (smooth
 random walk) -> product forward pass -> 41 marker positions (15 mm normal offset) + 1 mm noise + 3.4 % dropout.
 Every frame starts from the common initial pose (batched frames cannot warm-start from their predecessor)."""
 from __future__ import annotations
 
+import glob
+import json
+import os
 import time
 
 import numpy as np
 import torch
 
-from . import api, synth
+from smplpp_b200 import api, synth
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+# algorithmic FLOPs per frame-iteration of the fused IK step with the 15 mm normal offset (sparse
+# forward + Jacobian over the ~600 ring vertices ~3 M, J'J 3M.D(D+1) ~0.7 M, Cholesky D^3/3 ~0.14 M), and the 63x32
+# forward-mode Jacobian of the VPoser decoder (2.512.512.32 dominates)
+FLOPS_DIRECT = 4.0e6
+FLOPS_VPOSER_JAC = 22.0e6
+# no measured fp32 figure in MEASURED_PEAKS.json: nominal CUDA-core peak 148 SM x 128 lanes x 2 x 1.965 GHz
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
+
+
+def ncu_counter(kernel: str, key: str):
+    """per-launch counter of `kernel` from the newest committed ncu capture (profiles/*_traffic.json)"""
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")), reverse=True):
+        try:
+            with open(path) as f:
+                t = json.load(f)
+            if kernel in t.get(key, {}):
+                return float(t[key][kernel]), os.path.basename(path)
+        except Exception:
+            continue
+    return None, None
 
 
 def make_problem(smpl, tasks, frames: int, seed: int, dev):
@@ -82,6 +108,45 @@ def run(dev, rank, world, max_over_ranks, barrier, frames: int = 16384, iters: i
     status, o = tasks.step(opt, theta, prob["beta"], vw, prob["target"], pos_task_weight=prob["valid"], outputs=False), None
     del o
     out["mosh_direct"]["frames_ok"] = int((status == 0).sum().item())
+    # roofline of the IK step: CUDA-core fp32 work (not HBM, not tensor) per SURVEY 8(d)
+    ach = FLOPS_DIRECT * frames / (ms * 1e-3) / 1e12
+    l2b, l2src = ncu_counter(kernel_names()[0], "l2_to_sm_bytes_per_launch")
+    drb, _ = ncu_counter(kernel_names()[0], "bytes_per_launch")
+    out["roofline"] = {"kernel": " + ".join(kernel_names()), "bound": "fp32 (CUDA-core FFMA / issue; neither hbm nor tensor)",
+                       "achieved": ach, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach / FP32_PEAK_TFLOPS,
+                       "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz (MEASURED_PEAKS.json has no fp32 figure)",
+                       "algorithmic_flops_per_frame_iter": FLOPS_DIRECT, "ms_per_launch": ms, "frames_per_launch": frames,
+                       "traffic": drb, "l2_to_sm_bytes_per_launch": l2b, "traffic_source": l2src,
+                       "hbm_state_bytes_per_frame_iter": 2 * 4 * 75 + 16 * tasks.n}
+
+    # e2e through the host-buffer C-ABI call smplpp_ik_solve_host: theta / attachments / targets / marker weights in
+    # page-locked host arrays, H2D + ONE iteration + D2H of theta, weights, status, residual inside the timed region
+    th_h, vw_h = api.pinned_empty((frames, 75)), api.pinned_empty((frames, tasks.n, 3))
+    tg_h, pw_h = api.pinned_empty((frames, tasks.n, 3)), api.pinned_empty((frames, tasks.n))
+    th0 = prob["x0"].cpu().numpy()
+    vw_h[...], tg_h[...], pw_h[...] = prob["w0"].cpu().numpy(), prob["target"].cpu().numpy(), prob["valid"].cpu().numpy()
+    beta_h = prob["beta"].cpu().numpy()
+    e2e_iters = 1
+
+    def host_call():
+        th_h[...] = th0
+        return tasks.solve_host(opt, e2e_iters, th_h, beta_h, vw_h, tg_h, pos_task_weight=pw_h)
+
+    for _ in range(2):
+        host_call()
+    barrier()
+    reps = max(3, iters // 2)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        st_h, res_h = host_call()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / reps)
+    h2d = th_h.nbytes + beta_h.nbytes + vw_h.nbytes + tg_h.nbytes + pw_h.nbytes
+    d2h = th_h.nbytes + vw_h.nbytes + 4 * frames + 4 * frames
+    out["e2e"] = {"value": all_frames * e2e_iters / e2e_s, "unit": "frame-iters/s", "h2d_bytes_per_step": int(h2d),
+                  "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s, "iterations_per_call": e2e_iters,
+                  "api": "smplpp_ik_solve_host (targets of every frame in, theta / attachments / status / residual out), "
+                         "page-locked host arrays", "frames_ok": int((st_h == 0).sum()),
+                  "mean_residual_m": float(res_h[st_h == 0].mean())}
 
     # (2) MoSh++ with the VPoser latent prior (configs[3]): D = 44, decoder + 63x32 Jacobian in the step
     optv = api.ik_options(enable_vposer=1)
@@ -115,8 +180,12 @@ def run(dev, rank, world, max_over_ranks, barrier, frames: int = 16384, iters: i
         tasks.shared_beta_step(optv, xv3, sbeta_v, vw4, prob["target"], pos_task_weight=prob["valid"])
 
     ms = time_steps(step_shared_vposer, max(3, iters // 2), 2, barrier, max_over_ranks, dev)
+    ach_v = (FLOPS_DIRECT + FLOPS_VPOSER_JAC) * frames / (ms * 1e-3) / 1e12
     out["shared_beta_vposer"] = {"value": all_frames / (ms * 1e-3), "ms_per_iter": ms, "unknowns_per_frame": 44,
-                                 "finite": bool(torch.isfinite(xv3).all().item() and torch.isfinite(sbeta_v).all().item())}
+                                 "finite": bool(torch.isfinite(xv3).all().item() and torch.isfinite(sbeta_v).all().item()),
+                                 "algorithmic_tflops": ach_v,
+                                 "note": "configs[3]: the per-frame part and the shared-beta system are pinned against the "
+                                         "compiled reference / a dense fp64 solve in tests/test_ik_configs_gpu.py"}
     # (4) projection of the task points onto the posed mesh + re-seated face / weights (node.cpp:970-1001):
     # full forward pass of a block of frames, then smplpp_closest_points (41 points x 13776 faces per frame)
     rb = min(frames, 4096)
@@ -135,12 +204,17 @@ def run(dev, rank, world, max_over_ranks, barrier, frames: int = 16384, iters: i
     return out
 
 
+def kernel_names():
+    return ("ik_jacobian_kernel", "ik_solve_kernel")
+
+
 def cpu_reference_ik(frames: int = 2, iters: int = 2):
     """Reference CPU path (oracle/_ref harness restating node.cpp:753-968 on the compiled reference objects):
     frame-iterations/s on a bounded sample."""
     from oracle import ref_lib
     params = synth.make_smpl_params(0)
     _, face_idx, vw = synth.make_marker_tasks(params)
+    ref_lib.set_num_threads(os.cpu_count() or 1)
     ref = ref_lib.RefSMPL(ref_lib.model_json_path(0))
     gt = synth.make_motion(frames + 1, 20)
     beta = np.zeros(10, np.float32)
@@ -154,5 +228,6 @@ def cpu_reference_ik(frames: int = 2, iters: int = 2):
             r = ref.ik_iteration(x, beta, face_idx, w, tgt, normal_task_weight=0.0, phi_limit=0.0, normal_offset=0.015)
             x, w = r["theta_state"], r["vertex_weights"]
     dt = time.perf_counter() - t0
-    return frames * iters / dt, ref_lib.get_num_threads(), "%d frames x %d iterations, 41 markers, direct theta (D=75)" % (
-        frames, iters)
+    return frames * iters / dt, ref_lib.get_num_threads(), (
+        "unmodified reference objects (oracle/_ref, libtorch CPU autograd rows) + node.cpp:753-968 restated: %d frames x %d "
+        "iterations, 41 markers, direct theta (D=75), 15 mm normal offset" % (frames, iters))

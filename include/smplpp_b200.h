@@ -271,6 +271,17 @@ int smplpp_ik_step(const smplpp_model_t * model, const smplpp_vposer_t * vposer,
                    float * e_out_dev, float * jac_out_dev, double * a_out_dev, double * b_out_dev,
                    double * delta_out_dev, void * workspace_dev, size_t workspace_bytes);
 
+/* `iterations` IK steps for B frames with HOST arrays (the mocap modes of node/node.cpp:645-1002 as one call: targets of
+ * every frame in, theta / re-weighted attachments / status out).  Copies in, iterates smplpp_ik_step on an internal
+ * stream, copies out, synchronises; bench.py's `ik.e2e` times this call.  Arrays as in smplpp_ik_step;
+ * beta_host is written back only with optimize_beta; residual_host (B, nullable) receives the mean over the valid
+ * markers of |e_m| at the last linearisation point (metres).  Not re-entrant per task-set handle. */
+int smplpp_ik_solve_host(const smplpp_model_t * model, const smplpp_vposer_t * vposer, smplpp_tasks_t * tasks,
+                         const smplpp_ik_options * opt, int64_t batch, int32_t iterations, float * theta_state_host,
+                         float * beta_host, int64_t beta_stride, float * vertex_weights_host,
+                         const float * target_pos_host, const float * pos_task_weight_host, int32_t * status_host,
+                         float * residual_host);
+
 /* Shared-beta stage (MoSh++ shape estimation over many frames).  Frames couple only through the
  * 10 shape unknowns, so the step is split around ONE all-reduce of 111 doubles:
  *   (1) smplpp_ik_shared_beta_reduce: per-frame normal equations with the beta columns, Schur complement
@@ -322,7 +333,8 @@ int64_t smplpp_c3d_point_count(const smplpp_c3d_t * c3d);   /* POINT:USED */
 double smplpp_c3d_frame_rate(const smplpp_c3d_t * c3d);     /* header().frameRate() */
 const char * smplpp_c3d_label(const smplpp_c3d_t * c3d, int64_t point); /* POINT:LABELS[point] */
 const char * smplpp_c3d_units(const smplpp_c3d_t * c3d);    /* POINT:UNITS */
-/* index of the first label that ends with `name` (node.cpp:580-594); the point count when there is none */
+/* index of the first POINT:LABELS value that ends with `name`; the length of that list when there is none
+ * (std::find_if + std::distance over valuesAsString(), node.cpp:580-594) */
 int64_t smplpp_c3d_find_label(const smplpp_c3d_t * c3d, const char * name);
 /* frames [first, first + count) -> xyz_host (count, points, 3), valid_host (count, points): 0 = point.isEmpty(),
  * whose coordinates are returned as 0 (node.cpp:682-683 zeroes the target of a missing marker) */

@@ -124,6 +124,11 @@ int solveBoxQp(const std::vector<double> & A,
     if(lo[i] == hi[i]) fixed[i] = 2;
   }
   std::vector<double> g(n);
+  // atMinimiser: the last step was a full, unblocked Newton step on the free variables, i.e. x minimises the
+  // objective on the current face up to rounding.  Re-solving there yields a step of rounding-noise size whose
+  // norm need not fall under any fixed threshold (cond(A) ~ 1e5 near convergence), so the multiplier test follows
+  // directly instead.
+  bool atMinimiser = false;
   for(int iter = 0; iter < 20 * n + 50; iter++)
   {
     for(int i = 0; i < n; i++)
@@ -138,7 +143,7 @@ int solveBoxQp(const std::vector<double> & A,
     int nf = static_cast<int>(freeIdx.size());
     std::vector<double> d(n, 0.0);
     double dmax = 0.0;
-    if(nf > 0)
+    if(nf > 0 && !atMinimiser)
     {
       std::vector<double> Aff(static_cast<size_t>(nf) * nf), rhs(nf);
       for(int r = 0; r < nf; r++)
@@ -156,7 +161,7 @@ int solveBoxQp(const std::vector<double> & A,
     }
     double xscale = 1.0;
     for(int i = 0; i < n; i++) xscale = std::max(xscale, std::abs(x[i]));
-    if(dmax <= 1e-14 * xscale)
+    if(atMinimiser || dmax <= 1e-14 * xscale)
     {
       // stationary on the current face: check multipliers of the bound-active variables
       int worst = -1;
@@ -174,6 +179,7 @@ int solveBoxQp(const std::vector<double> & A,
       }
       if(worst < 0) return 0;
       fixed[worst] = 0;
+      atMinimiser = false;
       continue;
     }
     double alpha = 1.0;
@@ -202,6 +208,7 @@ int solveBoxQp(const std::vector<double> & A,
       }
     }
     for(int i : freeIdx) x[i] += alpha * d[i];
+    atMinimiser = block < 0;
     if(block >= 0)
     {
       x[block] = blockSide > 0 ? hi[block] : lo[block];

@@ -382,18 +382,20 @@ def solve_box_qp(A: np.ndarray, b: np.ndarray, lo: np.ndarray, hi: np.ndarray) -
     x = np.clip(np.zeros(n), lo, hi)
     state = np.zeros(n, dtype=np.int64)  # 0 free, -1 lower, +1 upper, 2 pinned
     state[lo == hi] = 2
+    at_minimiser = False  # last step was a full unblocked Newton step: go straight to the multiplier test
     for _ in range(20 * n + 50):
         g = A @ x + b
         free = np.nonzero(state == 0)[0]
         d = np.zeros(n)
-        if free.size:
+        if free.size and not at_minimiser:
             d[free] = cholesky_solve_neg(A[np.ix_(free, free)], g[free])
-        if np.abs(d).max(initial=0.0) <= 1e-14 * max(1.0, np.abs(x).max(initial=0.0)):
+        if at_minimiser or np.abs(d).max(initial=0.0) <= 1e-14 * max(1.0, np.abs(x).max(initial=0.0)):
             viol = np.where(state == -1, -g, np.where(state == 1, g, 0.0))
             k = int(np.argmax(viol))
             if viol[k] <= 1e-12:
                 return x
             state[k] = 0
+            at_minimiser = False
             continue
         alpha, block, side = 1.0, -1, 0
         for i in free:
@@ -406,6 +408,7 @@ def solve_box_qp(A: np.ndarray, b: np.ndarray, lo: np.ndarray, hi: np.ndarray) -
                 if a < alpha:
                     alpha, block, side = a, i, -1
         x[free] += alpha * d[free]
+        at_minimiser = block < 0
         if block >= 0:
             x[block] = hi[block] if side > 0 else lo[block]
             state[block] = side

@@ -98,6 +98,21 @@ def rep_traffic(path: str) -> dict:
     return out
 
 
+def rep_l2(path: str) -> dict:
+    """L2 -> SM bytes per launch (l1tex__m_xbar2l1tex_read_bytes.sum): basis rows re-read from L2 show up here"""
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = [r for r in csv.reader(io.StringIO(raw)) if r and not r[0].startswith("==")]
+    hdr, units, body = rows[0], rows[1], rows[2:]
+    out = {}
+    key = "l1tex__m_xbar2l1tex_read_bytes.sum"
+    if key not in hdr:
+        return out
+    for r in body:
+        name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").split("<")[0]
+        out[name] = float(r[hdr.index(key)]) * unit_scale(units[hdr.index(key)])
+    return out
+
+
 def unit_scale(u: str) -> float:
     u = u.lower()
     return {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1.0)
@@ -121,17 +136,19 @@ def main():
     if reps is None:
         d = os.path.join(ROOT, "gpurun_out")
         reps = [os.path.join(d, f) for f in sorted(os.listdir(d)) if f.endswith(".ncu-rep")]
-    traffic = {}
+    traffic, l2 = {}, {}
     for rep in reps:
         name = os.path.splitext(os.path.basename(rep))[0]
         with open(os.path.join(ROOT, "profiles", "%s_%s.md" % (a.tag, name)), "w") as f:
             f.write(rep_md(rep, a.tag))
         traffic.update(rep_traffic(rep))
+        l2.update(rep_l2(rep))
     if traffic:
         # dram__bytes_read.sum + dram__bytes_write.sum per launch: what bench.py reports as roofline.traffic
         import json
         with open(os.path.join(ROOT, "profiles", "%s_traffic.json" % a.tag), "w") as f:
-            json.dump({"source": "ncu --set full --clock-control none, %s" % a.tag, "bytes_per_launch": traffic}, f, indent=1)
+            json.dump({"source": "ncu --set full --clock-control none, %s" % a.tag, "bytes_per_launch": traffic,
+                       "l2_to_sm_bytes_per_launch": l2}, f, indent=1)
     print("wrote profiles/%s_*" % a.tag)
 
 

@@ -893,6 +893,37 @@ class IkTaskSet:
                 _ptr(ws), C.c_size_t(ws.numel())))
         return (status, out) if outputs else status
 
+    def solve_host(self, opt: capi.IkOptions, iterations: int, theta_state: np.ndarray, beta: np.ndarray,
+                   vertex_weights: np.ndarray, target_pos: np.ndarray, pos_task_weight: Optional[np.ndarray] = None,
+                   want_residual: bool = True):
+        """smplpp_ik_solve_host: `iterations` IK steps for all frames with HOST arrays (numpy, pageable or page-locked);
+        theta_state (B,75|44), vertex_weights (B,n,3) (and beta with optimize_beta) are updated in place.
+        Returns (status (B,) int32, residual (B,) float32 or None)."""
+        b = theta_state.shape[0]
+        theta_dim = int(lib().smplpp_ik_theta_dim(C.byref(opt)))
+        for name, a, shape in (("theta_state", theta_state, (b, theta_dim)), ("vertex_weights", vertex_weights, (b, self.n, 3)),
+                               ("target_pos", target_pos, (b, self.n, 3))):
+            if not (isinstance(a, np.ndarray) and a.dtype == np.float32 and a.flags["C_CONTIGUOUS"] and a.shape == shape):
+                raise SmplppError("IkTask Error: %s must be a C-contiguous float32 array of shape %s" % (name, (shape,)))
+        if not (beta.dtype == np.float32 and beta.flags["C_CONTIGUOUS"]):
+            raise SmplppError("BlendShape Error: Failed to set beta!")
+        stride = 0 if beta.size == SHAPE_BASIS_DIM and b > 1 else SHAPE_BASIS_DIM
+        status = np.empty((b,), np.int32)
+        res = np.empty((b,), np.float32) if want_residual else None
+        pw = None
+        if pos_task_weight is not None:
+            pw = np.ascontiguousarray(pos_task_weight, dtype=np.float32)
+        vp = self.vposer.handle if (opt.enable_vposer and self.vposer is not None) else None
+
+        def p(a):
+            return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+        with torch.cuda.device(self.smpl.m__device):
+            check(lib().smplpp_ik_solve_host(self.smpl.handle, vp, self._h, C.byref(opt), C.c_int64(b), C.c_int32(iterations),
+                                             p(theta_state), p(beta), C.c_int64(stride), p(vertex_weights), p(target_pos),
+                                             p(pw), p(status), p(res)))
+        return status, res
+
     def shared_beta_step(self, opt: capi.IkOptions, theta_state: torch.Tensor, shared_beta: torch.Tensor,
                          vertex_weights: torch.Tensor, target_pos: torch.Tensor,
                          pos_task_weight: Optional[torch.Tensor] = None, process_group=None, return_reduced=False):

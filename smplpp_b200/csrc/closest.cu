@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(CP_THREADS, 2) closest_point_kernel(const CpPa
     const size_t o = static_cast<size_t>(f) * p.n + tid;
     p.face_out[o] = best_face;
     if(p.sqdist_out) p.sqdist_out[o] = best;
-    if(p.closest_out || p.weights_out)
+    if((p.closest_out || p.weights_out) && best_face != 0x7fffffff) // NaN points never beat the sentinel
     {
       const int i0 = p.faces[3 * best_face], i1 = p.faces[3 * best_face + 1], i2 = p.faces[3 * best_face + 2];
       const V3 a = {s_v[3 * i0], s_v[3 * i0 + 1], s_v[3 * i0 + 2]};
@@ -228,6 +228,7 @@ extern "C" int smplpp_closest_points(const smplpp_model_t * model, void * stream
   if(n_points < 1 || n_points > CP_THREADS)
     return fail(SMPLPP_ERR_INVALID, "IkTask", "Failed to project points onto the mesh! (1 .. 512 points per frame)");
   const ModelDev & d = model->d;
+  if(d.F < 1) return fail(SMPLPP_ERR_INVALID, "IkTask", "Failed to project points onto the mesh! (the model has no faces)");
   CpParams p;
   p.V = d.V;
   p.F = d.F;

@@ -1021,7 +1021,7 @@ __global__ void __launch_bounds__(c2::THREADS, 4) ik_solve_kernel(const IkSolveP
   double * colbuf = dstep + D; // D + 2: pivot column of block_cholesky (+ the next pivot at [N], N <= D + 1)
   int * state = reinterpret_cast<int *>(colbuf + D + 2); // D: 0 free, -1 at lower, +1 at upper, 2 pinned
   __shared__ double s_esq;
-  __shared__ int s_ok, s_flag, s_iter;
+  __shared__ int s_ok, s_flag, s_iter, s_atmin;
   __shared__ double s_red[c2::THREADS / 32];
 
   const int rows = 4 * p.n;
@@ -1266,7 +1266,7 @@ __global__ void __launch_bounds__(c2::THREADS, 4) ik_solve_kernel(const IkSolveP
       x[i] = 0.0;
       state[i] = 0;
     }
-    if(tid == 0) s_flag = 0, s_iter = 0;
+    if(tid == 0) s_flag = 0, s_iter = 0, s_atmin = 0;
     __syncthreads();
     auto lim = [&](int i) -> double {
       if(i < p.theta_dim) return INFINITY;
@@ -1313,7 +1313,10 @@ __global__ void __launch_bounds__(c2::THREADS, 4) ik_solve_kernel(const IkSolveP
           xmax = fmax(xmax, fabs(x[i]));
         }
         int flag = 0;
-        if(dmax <= 1e-14 * xmax)
+        // s_atmin: the previous step was a full, unblocked Newton step, so x already minimises the objective on the
+        // current face; the re-solved step is rounding noise (not necessarily below the threshold when A is
+        // ill-conditioned near convergence) and the multiplier test follows directly
+        if(s_atmin || dmax <= 1e-14 * xmax)
         {
           int worst = -1;
           double worst_val = 1e-12;
@@ -1326,6 +1329,7 @@ __global__ void __launch_bounds__(c2::THREADS, 4) ik_solve_kernel(const IkSolveP
             flag = 1; // optimal
           else
             state[worst] = 0;
+          s_atmin = 0;
         }
         else
         {
@@ -1349,6 +1353,7 @@ __global__ void __launch_bounds__(c2::THREADS, 4) ik_solve_kernel(const IkSolveP
           }
           for(int i = 0; i < D; i++)
             if(state[i] == 0) x[i] += alpha * dstep[i];
+          s_atmin = block < 0;
           if(block >= 0)
           {
             x[block] = side > 0 ? lim(block) : -lim(block);
@@ -1452,6 +1457,7 @@ __global__ void shared_beta_qp_kernel(const double * __restrict__ reduced, doubl
     st[i] = 0;
   }
   int status = 3;
+  bool atmin = false; // see ik_solve_kernel
   for(int iter = 0; iter < 20 * N + 50; iter++)
   {
     for(int i = 0; i < N; i++)
@@ -1501,8 +1507,9 @@ __global__ void shared_beta_qp_kernel(const double * __restrict__ reduced, doubl
     }
     double dmax = 0.0, xmax = 1.0;
     for(int i = 0; i < N; i++) dmax = fmax(dmax, fabs(d[i])), xmax = fmax(xmax, fabs(x[i]));
-    if(dmax <= 1e-14 * xmax)
+    if(atmin || dmax <= 1e-14 * xmax)
     {
+      atmin = false;
       int worst = -1;
       double wv = 1e-12;
       for(int i = 0; i < N; i++)
@@ -1537,6 +1544,7 @@ __global__ void shared_beta_qp_kernel(const double * __restrict__ reduced, doubl
       }
     for(int i = 0; i < N; i++)
       if(!st[i]) x[i] += alpha * d[i];
+    atmin = block < 0;
     if(block >= 0) x[block] = side * limit, st[block] = side;
   }
   for(int i = 0; i < N; i++) dbeta[i] = status == 0 ? x[i] : 0.0;
@@ -1740,6 +1748,15 @@ extern "C" int smplpp_tasks_create(const smplpp_model_t * model, int32_t n, cons
   t->sub.lbs_weight = const_cast<float *>(d.lbs_weight);
   t->sub.lbs_wsum = const_cast<float *>(d.lbs_wsum);
   t->sub.group_nj = nullptr, t->sub.group_joint = nullptr, t->sub.group_w = nullptr; // per-vertex slot path
+  // the tensor-core operands and the dense (V,24) weight table of the full model are indexed by FULL-model vertex ids:
+  // none of them may be reachable through the compact view (lbs_tc_usable() would otherwise accept an even nU >= 128
+  // and skin sub-vertex u with the weights of model vertex u)
+  t->sub.weights_dense = nullptr;
+  t->sub.basis_split[0] = t->sub.basis_split[1] = nullptr;
+  t->sub.basis_f16 = nullptr, t->sub.basis_img16 = nullptr;
+  t->sub.tc_ready = t->sub.tc2_ready = t->sub.tc3_ready = false;
+  t->sub.tc_tiles = t->sub.tc2_tiles = 0;
+  t->sub.faces = nullptr, t->sub.adj_offset = nullptr, t->sub.adj_faces = nullptr;
   t->sub_corner = t->sub;
   t->sub_corner.V = nCorner;
   t->h_sub_vert = sub_vert;
@@ -1751,6 +1768,7 @@ extern "C" int smplpp_tasks_create(const smplpp_model_t * model, int32_t n, cons
 extern "C" void smplpp_tasks_destroy(smplpp_tasks_t * t)
 {
   if(!t) return;
+  sb_release_host_solve(t);
   for(void * ptr : t->allocations) cudaFree(ptr);
   delete t;
 }

@@ -244,7 +244,18 @@ std::vector<T> cast_to(const std::vector<double> & v)
 const smplpp_json::Array * find(const smplpp_json & j, const char * key)
 {
   auto it = j.arrays.find(key);
-  return it == j.arrays.end() || it->second.ragged ? nullptr : &it->second;
+  if(it == j.arrays.end() || it->second.ragged) return nullptr;
+  // rectangular means data.size() == prod(shape): a mixed-depth array such as [[1,2],3] has consistent per-level counts
+  // (2 and 2) but only 3 values, and every consumer indexes data by the shape
+  const smplpp_json::Array & a = it->second;
+  size_t count = 1;
+  for(int64_t d : a.shape)
+  {
+    if(d < 0) return nullptr;
+    if(d != 0 && count > a.data.size() / static_cast<size_t>(d)) return nullptr;
+    count *= static_cast<size_t>(d);
+  }
+  return count == a.data.size() ? &a : nullptr;
 }
 } // namespace
 
@@ -387,7 +398,8 @@ struct smplpp_c3d
   float scale = 0.f;      // < 0: float32 data, else int16 * scale
   float rate = 0.f;
   size_t data_offset = 0;
-  std::vector<std::string> labels;
+  std::vector<std::string> labels;       // POINT:LABELS, LABELS2, ... padded to `points` (smplpp_c3d_label)
+  std::vector<std::string> labels_param; // the POINT:LABELS values exactly as stored (smplpp_c3d_find_label)
   std::string units;
 };
 
@@ -461,10 +473,12 @@ bool c3d_parameters(const std::string & b, size_t start, std::map<std::string, C
 
 double c3d_scalar(const std::string & b, const C3dParam & prm)
 {
+  // a truncated parameter section must not be read past the end of the file
+  const size_t need = prm.type == 4 ? 4 : (prm.type == 2 ? 2 : (prm.type == 1 ? 1 : 0));
+  if(need == 0 || prm.data_off > b.size() || b.size() - prm.data_off < need) return 0.0;
   if(prm.type == 4) return rd<float>(b, prm.data_off);
   if(prm.type == 2) return static_cast<uint16_t>(rd<int16_t>(b, prm.data_off)); // counts are stored unsigned
-  if(prm.type == 1) return static_cast<uint8_t>(b[prm.data_off]);
-  return 0.0;
+  return static_cast<uint8_t>(b[prm.data_off]);
 }
 
 void c3d_strings(const std::string & b, const C3dParam & prm, std::vector<std::string> & out)
@@ -514,6 +528,7 @@ extern "C" int smplpp_c3d_open(const char * path, smplpp_c3d_t ** out)
   if((it = prm.find("POINT:RATE")) != prm.end() && !(c->rate > 0.f)) c->rate = static_cast<float>(c3d_scalar(b, it->second));
   if((it = prm.find("POINT:SCALE")) != prm.end() && c->scale == 0.f) c->scale = static_cast<float>(c3d_scalar(b, it->second));
   if((it = prm.find("POINT:LABELS")) != prm.end()) c3d_strings(b, it->second, c->labels);
+  c->labels_param = c->labels; // what parameters().group("POINT").parameter("LABELS").valuesAsString() returns (node.cpp:582-583)
   for(int k = 2; k < 10; k++) // POINT:LABELS2 ... for more than 255 points
     if((it = prm.find("POINT:LABELS" + std::to_string(k))) != prm.end()) c3d_strings(b, it->second, c->labels);
   if((it = prm.find("POINT:UNITS")) != prm.end())
@@ -522,7 +537,7 @@ extern "C" int smplpp_c3d_open(const char * path, smplpp_c3d_t ** out)
     c3d_strings(b, it->second, u);
     if(!u.empty()) c->units = u[0];
   }
-  c->labels.resize(static_cast<size_t>(c->points)); // unnamed points keep an empty label
+  if(c->labels.size() < static_cast<size_t>(c->points)) c->labels.resize(static_cast<size_t>(c->points)); // unnamed points keep an empty label; never shrink
   if(data_block < 1 || c->points < 0 || c->frames < 0) return fail(SMPLPP_ERR_IO, "C3D", "inconsistent C3D header");
   c->data_offset = static_cast<size_t>(data_block - 1) * 512;
   const size_t word = c->scale < 0.f ? 4 : 2;
@@ -563,13 +578,14 @@ extern "C" const char * smplpp_c3d_units(const smplpp_c3d_t * c)
 extern "C" int64_t smplpp_c3d_find_label(const smplpp_c3d_t * c, const char * name)
 {
   if(!c || !name) return 0;
+  // std::find_if over the FULL POINT:LABELS value list, std::distance to end() when nothing matches (node.cpp:584-593)
   const size_t n = strlen(name);
-  for(size_t i = 0; i < c->labels.size(); i++)
+  for(size_t i = 0; i < c->labels_param.size(); i++)
   {
-    const std::string & s = c->labels[i];
+    const std::string & s = c->labels_param[i];
     if(s.size() >= n && s.compare(s.size() - n, n, name) == 0) return static_cast<int64_t>(i);
   }
-  return static_cast<int64_t>(c->labels.size());
+  return static_cast<int64_t>(c->labels_param.size());
 }
 
 // frames [first, first + count) -> xyz (count, points, 3) and valid (count, points): 1 when the point exists
@@ -822,6 +838,8 @@ bool npz_read(const std::string & b, smplpp_json & out, std::string & err)
     const int method = rd<uint16_t>(b, pos + 10);
     uint64_t csize = rd<uint32_t>(b, pos + 20), usize = rd<uint32_t>(b, pos + 24), lho = rd<uint32_t>(b, pos + 42);
     const int nlen = rd<uint16_t>(b, pos + 28), xlen = rd<uint16_t>(b, pos + 30), clen = rd<uint16_t>(b, pos + 32);
+    // every offset below comes from the archive itself: nothing is read before it is checked against the file size
+    if(pos + 46 + static_cast<size_t>(nlen) + xlen + clen > b.size()) return err = "corrupt central directory entry", false;
     std::string name(b.data() + pos + 46, nlen);
     // zip64 extended information (header id 1): the fields that are 0xFFFFFFFF above, in order
     size_t x = pos + 46 + nlen;
@@ -829,41 +847,60 @@ bool npz_read(const std::string & b, smplpp_json & out, std::string & err)
     while(x + 4 <= xend)
     {
       const int id = rd<uint16_t>(b, x), sz = rd<uint16_t>(b, x + 2);
+      if(x + 4 + static_cast<size_t>(sz) > xend) return err = "corrupt extra field of " + name, false;
       if(id == 1)
       {
         size_t q = x + 4;
-        if(usize == 0xFFFFFFFFu) usize = rd<uint64_t>(b, q), q += 8;
-        if(csize == 0xFFFFFFFFu) csize = rd<uint64_t>(b, q), q += 8;
-        if(lho == 0xFFFFFFFFu) lho = rd<uint64_t>(b, q), q += 8;
+        const size_t qend = x + 4 + sz;
+        auto take64 = [&](uint64_t & dst) -> bool {
+          if(q + 8 > qend) return false;
+          dst = rd<uint64_t>(b, q), q += 8;
+          return true;
+        };
+        if(usize == 0xFFFFFFFFu && !take64(usize)) return err = "truncated zip64 field of " + name, false;
+        if(csize == 0xFFFFFFFFu && !take64(csize)) return err = "truncated zip64 field of " + name, false;
+        if(lho == 0xFFFFFFFFu && !take64(lho)) return err = "truncated zip64 field of " + name, false;
       }
       x += 4 + sz;
     }
     pos = xend + clen;
     if(name.size() < 4 || name.compare(name.size() - 4, 4, ".npy") != 0) continue;
     if(method != 0) return err = "compressed .npz members are not supported (np.savez writes them stored): " + name, false;
-    if(lho + 30 > b.size() || rd<uint32_t>(b, lho) != 0x04034b50u) return err = "corrupt local header of " + name, false;
+    if(lho > b.size() || b.size() - lho < 30 || rd<uint32_t>(b, lho) != 0x04034b50u)
+      return err = "corrupt local header of " + name, false;
     const size_t data = lho + 30 + rd<uint16_t>(b, lho + 26) + rd<uint16_t>(b, lho + 28);
-    if(data + usize > b.size() || usize < 12) return err = "truncated member " + name, false;
+    if(data > b.size() || usize > b.size() - data || usize < 12) return err = "truncated member " + name, false;
     // .npy: magic, version, header length, python dict literal
     if(memcmp(b.data() + data, "\x93NUMPY", 6) != 0) return err = "not a .npy member: " + name, false;
     const int major = static_cast<uint8_t>(b[data + 6]);
     const size_t hlen = major >= 2 ? rd<uint32_t>(b, data + 8) : rd<uint16_t>(b, data + 8);
     const size_t hoff = data + (major >= 2 ? 12 : 10);
-    if(hoff + hlen > data + usize) return err = "truncated .npy header of " + name, false;
+    if(hlen > usize || hoff + hlen > data + usize) return err = "truncated .npy header of " + name, false;
     const std::string hdr(b.data() + hoff, hlen);
+    constexpr size_t npos = std::string::npos;
     auto after = [&](const char * key) -> size_t {
       const size_t k = hdr.find(key);
-      return k == std::string::npos ? k : hdr.find(':', k) + 1;
+      if(k == npos) return npos;
+      const size_t c = hdr.find(':', k);
+      return c == npos ? npos : c + 1;
     };
     size_t p = after("'descr'");
-    if(p == std::string::npos) return err = "no descr in " + name, false;
-    const size_t q1 = hdr.find('\'', p), q2 = hdr.find('\'', q1 + 1);
+    if(p == npos) return err = "no descr in " + name, false;
+    const size_t q1 = hdr.find('\'', p);
+    const size_t q2 = q1 == npos ? npos : hdr.find('\'', q1 + 1);
+    if(q2 == npos) return err = "malformed descr in " + name, false;
     const std::string descr = hdr.substr(q1 + 1, q2 - q1 - 1);
+    if(descr.size() < 3) return err = "unsupported dtype " + descr + " of " + name, false;
     p = after("'fortran_order'");
-    if(p != std::string::npos && hdr.compare(hdr.find_first_not_of(' ', p), 4, "True") == 0)
-      return err = "Fortran-ordered array " + name + " is not supported", false;
+    if(p != npos)
+    {
+      const size_t v = hdr.find_first_not_of(' ', p);
+      if(v != npos && hdr.compare(v, 4, "True") == 0) return err = "Fortran-ordered array " + name + " is not supported", false;
+    }
     p = after("'shape'");
-    const size_t s1 = hdr.find('(', p), s2 = hdr.find(')', s1);
+    const size_t s1 = p == npos ? npos : hdr.find('(', p);
+    const size_t s2 = s1 == npos ? npos : hdr.find(')', s1);
+    if(s2 == npos) return err = "no shape in " + name, false;
     smplpp_json::Array a;
     {
       const char * c = hdr.c_str() + s1 + 1;
@@ -873,17 +910,24 @@ bool npz_read(const std::string & b, smplpp_json & out, std::string & err)
         char * stop = nullptr;
         const long long v = strtoll(c, &stop, 10);
         if(stop == c) break;
+        if(v < 0) return err = "negative dimension in " + name, false;
         a.shape.push_back(v);
         c = stop;
         while(c < cend && (*c == ',' || *c == ' ')) c++;
       }
     }
-    size_t count = 1;
-    for(int64_t d : a.shape) count *= static_cast<size_t>(d);
     const size_t payload = hoff + hlen;
-    const size_t esz = descr.size() >= 3 ? static_cast<size_t>(descr[2] - '0') : 0;
-    if((descr[0] != '<' && descr[0] != '|') || (esz != 4 && esz != 8) || payload + count * esz > data + usize)
+    const size_t esz = static_cast<size_t>(descr[2] - '0');
+    if((descr[0] != '<' && descr[0] != '|') || (esz != 4 && esz != 8) || descr.size() != 3)
       return err = "unsupported dtype " + descr + " of " + name, false;
+    const size_t avail = (data + usize - payload) / esz; // elements the member can hold: the product may not exceed it
+    size_t count = 1;
+    for(int64_t d : a.shape)
+    {
+      if(d != 0 && count > avail / static_cast<size_t>(d)) return err = "shape of " + name + " exceeds the member size", false;
+      count *= static_cast<size_t>(d);
+    }
+    if(count > avail) return err = "shape of " + name + " exceeds the member size", false;
     a.data.resize(count);
     for(size_t i = 0; i < count; i++)
     {
@@ -908,7 +952,14 @@ extern "C" int smplpp_npz_open(const char * path, smplpp_json_t ** out)
   std::string bytes, err;
   if(!path || !read_file(path, bytes)) return fail(SMPLPP_ERR_IO, "NPZ", "Cannot find the .npz file!");
   std::unique_ptr<smplpp_json> j(new smplpp_json());
-  if(!npz_read(bytes, *j, err)) return fail(SMPLPP_ERR_IO, "NPZ", "Cannot read the .npz file: " + err);
+  try
+  {
+    if(!npz_read(bytes, *j, err)) return fail(SMPLPP_ERR_IO, "NPZ", "Cannot read the .npz file: " + err);
+  }
+  catch(const std::exception & ex) // no C++ exception may cross the C boundary
+  {
+    return fail(SMPLPP_ERR_IO, "NPZ", std::string("Cannot read the .npz file: ") + ex.what());
+  }
   *out = j.release();
   return SMPLPP_OK;
 }

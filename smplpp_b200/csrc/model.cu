@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <memory>
 
 #include "forward.cuh"
 
@@ -62,7 +63,10 @@ extern "C" int smplpp_model_create(const smplpp_model_desc * desc, smplpp_model_
   const int V = static_cast<int>(desc->vertex_num);
   const int F = static_cast<int>(desc->face_num);
   const int Vpad = (V + 63) / 64 * 64;
-  auto m = new smplpp_model();
+  // owned by a guard until the very end: every early return below releases the device buffers allocated so far
+  // (smplpp_model_destroy is nullptr-safe member by member)
+  std::unique_ptr<smplpp_model, void (*)(smplpp_model *)> guard(new smplpp_model(), smplpp_model_destroy);
+  smplpp_model * m = guard.get();
   ModelDev & d = m->d;
   d.V = V;
   d.Vpad = Vpad;
@@ -239,7 +243,7 @@ extern "C" int smplpp_model_create(const smplpp_model_desc * desc, smplpp_model_
     if(tc2_prepare_model(d, mx) != SMPLPP_OK) return SMPLPP_ERR_CUDA;
     if(tc3_prepare_model(d) != SMPLPP_OK) return SMPLPP_ERR_CUDA;
   }
-  *out = m;
+  *out = guard.release();
   return SMPLPP_OK;
 }
 

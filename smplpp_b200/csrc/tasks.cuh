@@ -45,4 +45,14 @@ struct smplpp_tasks
   std::vector<int64_t> h_face_idx;
   std::vector<int32_t> h_sub_vert; // local -> global vertex id
   std::vector<int32_t> h_corner;
+  // smplpp_ik_solve_host (ik_host.cu): grow-only device buffers and the stream of the host-buffer call
+  struct HostSolve
+  {
+    cudaStream_t stream = nullptr;
+    void * buf = nullptr;
+    size_t buf_bytes = 0;
+    void * ws = nullptr;
+    size_t ws_bytes = 0;
+  } host;
 };
+void sb_release_host_solve(smplpp_tasks * t);

@@ -1,0 +1,185 @@
+"""Multi-frame, multi-iteration IK goldens at the BASELINE configs, produced by the UNMODIFIED reference sources
+(oracle/_ref: compiled src/*.cpp + the harness restating node/node.cpp:753-968) looped the way the node loops it.
+
+    python tests/golden/make_ref_golden_ik_configs.py        (about 10 minutes on 8 cores)
+
+Writes tests/golden/ref_ik_configs.npz:
+  c3_*    BASELINE configs[2] "MoSh direct": 8 frames x 30 iterations, theta + translation per frame (D = 75),
+          fixed beta, 15 mm normal offset, 3.4 % marker dropout, all frames from the common initial pose
+  c4_*    BASELINE configs[3] "MoSh++ VPoser": 4 frames x 10 iterations, D = 44 with the latent prior
+  body_*  the body stage (node.cpp:652-656, 695-700, 1349): ONE frame x 51 iterations, VPoser state, beta and phi
+          (+-0.04) from iteration 25, and after every iteration the projection of actualPos + tangents * dphi onto
+          the PRE-update mesh with the re-seated face / weights (node.cpp:949-1001; libigl is un-vendored, the
+          projection is the float64 restatement oracle/smpl_oracle.py:project_points_on_mesh)
+  sb_*    shared-beta stage inputs: per-frame e and J = [theta | beta] of 16 frames (direct and VPoser) at the
+          initial state, from which the tests build the dense block-arrow system in float64
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+from oracle import ref_lib  # noqa: E402
+from oracle import smpl_oracle as so  # noqa: E402
+from smplpp_b200 import synth  # noqa: E402
+
+MOTION = dict(normal_task_weight=0.0, phi_limit=0.0, normal_offset=0.015)
+
+
+def marker_residual(e, valid):
+    """mean over the valid markers of |e_m| (metres)"""
+    r = np.linalg.norm(e.reshape(-1, 4)[:, :3], axis=1)
+    return float(r[valid > 0].mean())
+
+
+def assemble(vp, x):
+    th = np.zeros((25, 3), np.float32)
+    th[0], th[1] = x[0:3], x[3:6]
+    th[2:23] = vp.forward(x[6:38].reshape(1, 32))[0]
+    th[23], th[24] = x[38:41], x[41:44]
+    return th
+
+
+def main():
+    t_start = time.time()
+    params = synth.make_smpl_params(0)
+    ref = ref_lib.RefSMPL(ref_lib.model_json_path(0))
+    vp = ref_lib.RefVPoser(ref_lib.vposer_json_path(1))
+    names, face_idx, vw0 = synth.make_marker_tasks(params)
+    faces0 = params.face_indices.astype(np.int64) - 1
+    n = len(names)
+    b0 = (np.random.default_rng(5).normal(size=10) * 0.5).astype(np.float32)
+    zeros = np.zeros((n, 3), np.float32)
+    out = dict(face_idx=face_idx, vertex_weights_in=vw0, beta=b0)
+
+    def markers_of(x, beta, vposer=None):
+        r = ref.ik_iteration(x, beta, face_idx, vw0, zeros, update_state=False, vposer=vposer, **MOTION)
+        return r["actual_pos"]
+
+    # ---------------- configs[2]: 8 frames x 30 iterations, direct ----------------
+    F3, K3 = 8, 30
+    gt = synth.make_motion(40, 20)[::5][:F3]
+    noise, valid = synth.make_marker_noise(F3, n, 21)
+    valid = valid.astype(np.float32)
+    x0 = synth.make_motion(40, 20)[2].reshape(-1)
+    target = np.stack([markers_of(gt[f].reshape(-1), b0) for f in range(F3)]) + noise
+    target[valid == 0] = 0.0  # node.cpp:682-683
+    th_traj = np.zeros((F3, K3, 75), np.float32)
+    res = np.zeros((F3, K3))
+    vw_out = np.zeros((F3, n, 3), np.float32)
+    for f in range(F3):
+        x, w = x0.copy(), vw0.copy()
+        for k in range(K3):
+            r = ref.ik_iteration(x, b0, face_idx, w, target[f], pos_task_weight=valid[f].astype(np.float64), **MOTION)
+            x, w = r["theta_state"], r["vertex_weights"]
+            th_traj[f, k], res[f, k] = x, marker_residual(r["e"], valid[f])
+        vw_out[f] = w
+        print("c3 frame %d: residual %.5f -> %.6f m  (%.0f s)" % (f, res[f, 0], res[f, -1], time.time() - t_start), flush=True)
+    out.update(c3_theta_in=x0, c3_target=target, c3_valid=valid, c3_theta_traj=th_traj, c3_residual=res,
+               c3_vertex_weights_out=vw_out, c3_theta_gt=gt.reshape(F3, 75))
+
+    # ---------------- configs[3]: 4 frames x 10 iterations, VPoser latent state ----------------
+    F4, K4 = 4, 10
+    rng = np.random.default_rng(32)
+    xg = np.zeros((F4, 44), np.float32)
+    xg[:, 0:6] = gt[:F4].reshape(F4, 75)[:, 0:6]
+    xg[:, 6:38] = rng.normal(size=(F4, 32)).astype(np.float32) * 0.6
+    xg[:, 38:44] = rng.normal(size=(F4, 6)).astype(np.float32) * 0.02
+    noise4, valid4 = synth.make_marker_noise(F4, n, 22)
+    valid4 = valid4.astype(np.float32)
+    target4 = np.stack([markers_of(xg[f], b0, vposer=vp) for f in range(F4)]) + noise4
+    target4[valid4 == 0] = 0.0
+    xv0 = np.zeros(44, np.float32)
+    xv0[0:6] = x0[0:6]
+    th4 = np.zeros((F4, K4, 44), np.float32)
+    res4 = np.zeros((F4, K4))
+    for f in range(F4):
+        x, w = xv0.copy(), vw0.copy()
+        for k in range(K4):
+            r = ref.ik_iteration(x, b0, face_idx, w, target4[f], pos_task_weight=valid4[f].astype(np.float64), vposer=vp,
+                                 **MOTION)
+            x, w = r["theta_state"], r["vertex_weights"]
+            th4[f, k], res4[f, k] = x, marker_residual(r["e"], valid4[f])
+        print("c4 frame %d: residual %.5f -> %.6f m  (%.0f s)" % (f, res4[f, 0], res4[f, -1], time.time() - t_start), flush=True)
+    out.update(c4_theta_in=xv0, c4_target=target4, c4_valid=valid4, c4_theta_traj=th4, c4_residual=res4, c4_state_gt=xg)
+
+    # ---------------- body stage: 1 frame x 51 iterations with projection + re-seat ----------------
+    KB = 51
+    xb_gt = xg[1].copy()
+    true_w = vw0
+    target_b = markers_of(xb_gt, b0, vposer=vp) + synth.make_marker_noise(1, n, 23)[0][0]
+    x = xv0.copy()
+    x[0:6] = xb_gt[0:6] + np.random.default_rng(33).normal(size=6).astype(np.float32) * 0.05
+    beta = np.zeros(10, np.float32)
+    w = np.full((n, 3), 1.0 / 3.0, np.float32)  # IkTask default vertexWeights_ (IkTask.h:74)
+    fidx = face_idx.copy()
+    tr = dict(theta=np.zeros((KB, 44), np.float32), beta=np.zeros((KB, 10), np.float32), face=np.zeros((KB, n), np.int64),
+              vw=np.zeros((KB, n, 3), np.float32), res=np.zeros(KB), point=np.zeros((KB, n, 3), np.float32),
+              closest=np.zeros((KB, n, 3)), vw_pre=np.zeros((KB, n, 3), np.float32))
+    for k in range(KB):
+        late = k >= 25  # node.cpp:655, 695
+        beta_pre, x_pre = beta.copy(), x.copy()
+        r = ref.ik_iteration(x, beta, fidx, w, target_b, normal_task_weight=0.0, phi_limit=0.04 if late else 0.0,
+                             normal_offset=0.015, optimize_beta=late, vposer=vp)
+        # node.cpp:970-1001 on the PRE-update mesh
+        verts = ref.forward(beta_pre.reshape(1, 10), assemble(vp, x_pre).reshape(1, 25, 3), want=("vertices",))["vertices"][0]
+        face_new, closest, _, w_new = so.project_points_on_mesh(verts, faces0, r["actual_pos"])
+        tr["vw_pre"][k] = r["vertex_weights"]
+        x, beta = r["theta_state"], r["beta"]
+        fidx, w = face_new.astype(np.int64), w_new.astype(np.float32)
+        tr["theta"][k], tr["beta"][k], tr["face"][k], tr["vw"][k] = x, beta, fidx, w
+        tr["res"][k], tr["point"][k], tr["closest"][k] = marker_residual(r["e"], np.ones(n)), r["actual_pos"], closest
+        if k % 5 == 0 or k == KB - 1:
+            print("body iter %d: residual %.5f m, faces changed so far %d  (%.0f s)"
+                  % (k, tr["res"][k], int((tr["face"][: k + 1] != face_idx[None]).any(0).sum()), time.time() - t_start), flush=True)
+    out.update(body_theta_in=tr["theta"][0] * 0 + 0, body_target=target_b, body_true_weights=true_w)
+    x_in = xv0.copy()
+    x_in[0:6] = xb_gt[0:6] + np.random.default_rng(33).normal(size=6).astype(np.float32) * 0.05
+    out["body_theta_in"] = x_in
+    for key, val in tr.items():
+        out["body_" + key] = val
+    out["body_beta_gt"] = b0
+    out["body_state_gt"] = xb_gt
+
+    # ---------------- shared-beta inputs: 16 frames, J = [theta | beta] and e at the initial state ----------------
+    FS = 16
+    gts = synth.make_motion(64, 24)[::4][:FS]
+    noise_s, valid_s = synth.make_marker_noise(FS, n, 25)
+    valid_s = valid_s.astype(np.float32)
+    beta_true = np.random.default_rng(6).normal(size=10).astype(np.float32)
+    tgt_s = np.stack([markers_of(gts[f].reshape(-1), beta_true) for f in range(FS)]) + noise_s
+    tgt_s[valid_s == 0] = 0.0
+    xs = gts.reshape(FS, 75) + np.random.default_rng(7).normal(size=(FS, 75)).astype(np.float32) * 0.02
+    beta0 = np.zeros(10, np.float32)
+    Jd = np.zeros((FS, 4 * n, 85), np.float32)
+    ed = np.zeros((FS, 4 * n))
+    for f in range(FS):
+        r = ref.ik_iteration(xs[f], beta0, face_idx, vw0, tgt_s[f], pos_task_weight=valid_s[f].astype(np.float64),
+                             optimize_beta=True, update_state=False, **MOTION)
+        Jd[f] = np.concatenate([r["J"][:, :75], r["J"][:, 75 + 2 * n:]], axis=1).astype(np.float32)
+        ed[f] = r["e"]
+    print("shared-beta direct rows done (%.0f s)" % (time.time() - t_start), flush=True)
+    xsv = np.zeros((FS, 44), np.float32)
+    xsv[:, 0:6] = xs[:, 0:6]
+    xsv[:, 6:38] = np.random.default_rng(8).normal(size=(FS, 32)).astype(np.float32) * 0.4
+    Jv = np.zeros((FS, 4 * n, 54), np.float32)
+    ev = np.zeros((FS, 4 * n))
+    for f in range(FS):
+        r = ref.ik_iteration(xsv[f], beta0, face_idx, vw0, tgt_s[f], pos_task_weight=valid_s[f].astype(np.float64),
+                             optimize_beta=True, update_state=False, vposer=vp, **MOTION)
+        Jv[f] = np.concatenate([r["J"][:, :44], r["J"][:, 44 + 2 * n:]], axis=1).astype(np.float32)
+        ev[f] = r["e"]
+    out.update(sb_target=tgt_s, sb_valid=valid_s, sb_theta_in=xs.astype(np.float32), sb_J=Jd, sb_e=ed,
+               sb_state_in=xsv, sb_J_vposer=Jv, sb_e_vposer=ev, sb_beta_true=beta_true)
+    path = os.path.join(OUT, "ref_ik_configs.npz")
+    np.savez_compressed(path, **out)
+    print("ref_ik_configs.npz", os.path.getsize(path) // 1024, "KiB in %.0f s" % (time.time() - t_start))
+
+
+if __name__ == "__main__":
+    main()

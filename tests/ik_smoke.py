@@ -1,8 +1,9 @@
-"""smoke() leg for the IK step: one frame, one iteration on cuda:0 checked against the oracle."""
+"""smoke() leg for the IK step (test infrastructure, called by __graft_entry__.smoke()): one frame, one iteration on
+cuda:0 checked against the oracle."""
 import numpy as np
 import torch
 
-from . import api, synth
+from smplpp_b200 import api, synth
 
 
 def run(params):

@@ -1,0 +1,194 @@
+"""GPU parity of the IK path at the BASELINE configs against multi-frame, multi-iteration goldens of the compiled
+reference (tests/golden/ref_ik_configs.npz, made by tests/golden/make_ref_golden_ik_configs.py):
+
+  configs[2]  MoSh direct: 8 frames x 30 iterations (node.cpp:753-968 looped), residual trajectory + final theta
+  configs[3]  MoSh++ VPoser: 4 frames x 10 iterations
+  shared-beta stage with 16 frames (direct and VPoser) against a dense float64 solve of the block-arrow system built
+  from the reference's per-frame Jacobians
+  the host-buffer call smplpp_ik_solve_host against the device loop
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, TOL_RESIDUAL_M
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+MOTION = dict(normal_task_weight=0.0, phi_limit=0.0, normal_offset=0.015, optimize_beta=0, enable_qp=1, enable_phi=0)
+
+
+def cu(a, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device="cuda:0").contiguous()
+
+
+@pytest.fixture(scope="module")
+def gc():
+    return dict(np.load(os.path.join(GOLDEN, "ref_ik_configs.npz")))
+
+
+@pytest.fixture(scope="module")
+def task_set(smpl_gpu, marker_tasks, vposer_params):
+    from smplpp_b200 import api
+    _, face_idx, _ = marker_tasks
+    return api.IkTaskSet(smpl_gpu, face_idx, vposer=api.VPoserDecoder(vposer_params))
+
+
+def marker_residual(e, valid):
+    r = np.linalg.norm(e.reshape(e.shape[0], -1, 4)[:, :, :3], axis=2)
+    return (r * valid).sum(1) / valid.sum(1)
+
+
+def run_trajectory(task_set, opt, x0, beta, vw0, target, valid, iters):
+    F = target.shape[0]
+    theta = cu(np.repeat(x0[None], F, axis=0))
+    vw = cu(np.repeat(vw0[None], F, axis=0))
+    beta_d, tgt, pw = cu(beta), cu(target), cu(valid)
+    res, traj = [], []
+    for _ in range(iters):
+        status, out = task_set.step(opt, theta, beta_d, vw, tgt, pos_task_weight=pw, outputs=True)
+        assert (status == 0).all()
+        res.append(marker_residual(out["e"].cpu().numpy(), valid))
+        traj.append(theta.cpu().numpy().copy())
+    return np.stack(res, 1), np.stack(traj, 1), vw.cpu().numpy()
+
+
+def test_config3_motion_30_iterations(task_set, gc):
+    """BASELINE configs[2]: residual of every frame at every iteration within 1e-4 m of the compiled reference's."""
+    from smplpp_b200 import api
+    opt = api.ik_options(**MOTION)
+    res, traj, vw = run_trajectory(task_set, opt, gc["c3_theta_in"], gc["beta"], gc["vertex_weights_in"], gc["c3_target"],
+                                   gc["c3_valid"], gc["c3_residual"].shape[1])
+    assert np.abs(res - gc["c3_residual"]).max() < TOL_RESIDUAL_M
+    # the state itself: identical arithmetic up to fp32 rounding, amplified by 30 Gauss-Newton steps
+    assert np.abs(traj[:, 0] - gc["c3_theta_traj"][:, 0]).max() < 2e-4
+    assert np.abs(traj[:, -1] - gc["c3_theta_traj"][:, -1]).max() < 5e-3
+    assert np.abs(vw - gc["c3_vertex_weights_out"]).max() < 5e-3
+    assert res[:, -1].max() < 0.25 * res[:, 0].min()
+
+
+def test_config4_vposer_10_iterations(task_set, gc):
+    """BASELINE configs[3] (per-frame part): VPoser latent state, decoder + its Jacobian inside the step."""
+    from smplpp_b200 import api
+    opt = api.ik_options(enable_vposer=1, **MOTION)
+    res, traj, _ = run_trajectory(task_set, opt, gc["c4_theta_in"], gc["beta"], gc["vertex_weights_in"], gc["c4_target"],
+                                  gc["c4_valid"], gc["c4_residual"].shape[1])
+    assert np.abs(res - gc["c4_residual"]).max() < TOL_RESIDUAL_M
+    assert np.abs(traj[:, 0] - gc["c4_theta_traj"][:, 0]).max() < 5e-4
+    assert np.abs(traj[:, -1] - gc["c4_theta_traj"][:, -1]).max() < 2e-2
+
+
+def test_solve_host_equals_device_loop(task_set, gc):
+    """smplpp_ik_solve_host (host arrays in / out, K iterations inside) == K calls of smplpp_ik_step."""
+    from smplpp_b200 import api
+    opt = api.ik_options(**MOTION)
+    K = 5
+    F = gc["c3_target"].shape[0]
+    res, traj, vw = run_trajectory(task_set, opt, gc["c3_theta_in"], gc["beta"], gc["vertex_weights_in"], gc["c3_target"],
+                                   gc["c3_valid"], K)
+    theta_h = np.repeat(gc["c3_theta_in"][None], F, axis=0).astype(f32)
+    vw_h = np.repeat(gc["vertex_weights_in"][None], F, axis=0).astype(f32)
+    status, r = task_set.solve_host(opt, K, theta_h, gc["beta"].astype(f32), vw_h, gc["c3_target"].astype(f32),
+                                    pos_task_weight=gc["c3_valid"].astype(f32))
+    assert (status == 0).all()
+    assert np.array_equal(theta_h, traj[:, -1])
+    assert np.array_equal(vw_h, vw)
+    assert np.abs(r - res[:, -1]).max() < 1e-6
+
+
+def dense_block_arrow(J, e, theta_dim, prior=None):
+    """Dense float64 normal equations of the shared-beta problem over F frames (unknowns [x_1 .. x_F | beta]):
+    A_ff = J_f'J_f + (1e-3 + |e_f|^2) I (+ VPoser prior), A_f,beta = J_f' J_beta, A_beta,beta = sum_f J_beta'J_beta +
+    (1e-3 + sum_f |e_f|^2) I, b likewise (node/node.cpp:884-904 per frame; SURVEY 8e for the coupling)."""
+    F = J.shape[0]
+    D = theta_dim
+    N = F * D + 10
+    A = np.zeros((N, N))
+    b = np.zeros(N)
+    e2_total = 0.0
+    for f in range(F):
+        Jf = J[f].astype(np.float64)
+        Af = Jf.T @ Jf
+        bf = Jf.T @ e[f]
+        e2 = float(e[f] @ e[f])
+        e2_total += e2
+        s = slice(f * D, (f + 1) * D)
+        A[s, s] = Af[:D, :D] + (np.float64(f32(1e-3)) + e2) * np.eye(D)
+        A[s, F * D:] = Af[:D, D:]
+        A[F * D:, s] = Af[D:, :D]
+        A[F * D:, F * D:] += Af[D:, D:]
+        b[s] = bf[:D]
+        b[F * D:] += bf[D:]
+        if prior is not None:
+            w, x = prior
+            A[s, s] += np.diag(w)
+            b[s] += w * x[f].astype(np.float64)
+    A[F * D:, F * D:] += (np.float64(f32(1e-3)) + e2_total) * np.eye(10)
+    return A, b
+
+
+@pytest.mark.parametrize("mode", ["direct", "vposer"])
+def test_shared_beta_16_frames_vs_dense_solve(task_set, gc, mode):
+    from oracle import smpl_oracle as so
+    from smplpp_b200 import api
+    vposer = mode == "vposer"
+    D = 44 if vposer else 75
+    J = gc["sb_J_vposer" if vposer else "sb_J"]
+    e = gc["sb_e_vposer" if vposer else "sb_e"]
+    x_in = gc["sb_state_in" if vposer else "sb_theta_in"].astype(f32)
+    F = J.shape[0]
+    prior = None
+    if vposer:
+        w = np.concatenate([np.zeros(6), np.full(32, np.float64(f32(1e-5))), np.full(6, np.float64(f32(1e3)))])
+        prior = (w, x_in)
+    A, b = dense_block_arrow(J, e, D, prior)
+    lo = np.full(A.shape[0], -np.inf)
+    hi = np.full(A.shape[0], np.inf)
+    lo[F * D:], hi[F * D:] = -0.5, 0.5
+    x = so.solve_box_qp(A, b, lo, hi)
+    opt = api.ik_options(enable_vposer=int(vposer), **MOTION)
+    theta = cu(x_in)
+    sbeta = cu(np.zeros(10, f32))
+    vw = cu(np.repeat(gc["vertex_weights_in"][None], F, axis=0))
+    status = task_set.shared_beta_step(opt, theta, sbeta, vw, cu(gc["sb_target"]), pos_task_weight=cu(gc["sb_valid"]))
+    assert (status == 0).all()
+    dbeta = sbeta.cpu().numpy().astype(np.float64)
+    dtheta = (theta.cpu().numpy() - x_in).astype(np.float64)
+    assert np.abs(dbeta - x[F * D:]).max() < 2e-4
+    assert np.abs(dtheta - x[:F * D].reshape(F, D)).max() < 5e-4
+    assert (np.abs(dbeta) <= 0.5 + 1e-6).all()
+
+
+def test_even_task_vertex_count_vs_oracle(smpl_gpu, oracle_model, marker_tasks):
+    """A task set whose vertex count is EVEN and >= 128: the compact sub-model must never reach the tensor-core
+    skinning kernel (which indexes the full model's dense weights)."""
+    from oracle import smpl_oracle as so
+    from smplpp_b200 import api, synth
+    _, face_idx, vw0 = marker_tasks
+    ts = None
+    for k in range(11, len(face_idx) + 1):
+        cand = api.IkTaskSet(smpl_gpu, face_idx[:k])
+        if cand.vertex_count >= 128 and cand.vertex_count % 2 == 0:
+            ts = cand
+            break
+    assert ts is not None, "no prefix of the marker list has an even vertex count >= 128"
+    n = ts.n
+    gt = synth.make_motion(12, 20)
+    beta = (np.random.default_rng(5).normal(size=10) * 0.5).astype(f32)
+    smpl_gpu.launch(beta, gt[9:10])
+    w0 = cu(vw0[None, :n])
+    target = ts.positions(smpl_gpu.getVertex(), w0, 0.015).contiguous()
+    opt = api.ik_options(skip_if_too_few=0, **MOTION)
+    theta, vw = cu(gt[:1].reshape(1, 75)), w0.clone()
+    status, out = ts.step(opt, theta, cu(beta), vw, target, outputs=True)
+    assert int(status[0]) == 0
+    tgt_h = target.cpu().numpy()[0]
+    tasks = [so.IkTask(int(face_idx[i]), target_pos=torch.as_tensor(tgt_h[i]), normal_task_weight=0.0, phi_limit=0.0,
+                       normal_offset=0.015, vertex_weights=torch.as_tensor(vw0[i])) for i in range(n)]
+    r = so.ik_iteration(oracle_model, tasks, gt[0].reshape(-1), beta)
+    assert np.abs(out["e"][0].cpu().numpy() - r.e).max() < 1e-5
+    J = out["J"][0].cpu().numpy()
+    assert np.abs(J - r.J).max() / np.abs(r.J).max() < 1e-4
+    assert np.abs(theta[0].cpu().numpy() - r.theta_state).max() < 2e-4
