@@ -271,6 +271,19 @@ int smplpp_ik_step(const smplpp_model_t * model, const smplpp_vposer_t * vposer,
                    float * e_out_dev, float * jac_out_dev, double * a_out_dev, double * b_out_dev,
                    double * delta_out_dev, void * workspace_dev, size_t workspace_bytes);
 
+/* The same step with PER-FRAME attachments: face_idx_dev (B, n) int32 holds IkTask::faceIdx_ of every (frame, task) as
+ * re-seated by the projection of node/node.cpp:993-1001 (smplpp_ik_reproject); the 1-ring topology of every attachment is
+ * gathered on the device.  dphi_out_dev (B, n, 2), nullable: the phi part of the step (node.cpp:955-958), which
+ * smplpp_ik_reproject consumes.  Workspace: smplpp_ik_faces_workspace_bytes. */
+size_t smplpp_ik_faces_workspace_bytes(const smplpp_tasks_t * tasks, const smplpp_ik_options * opt, int64_t batch);
+int smplpp_ik_step_faces(const smplpp_model_t * model, const smplpp_vposer_t * vposer, const smplpp_tasks_t * tasks,
+                         const smplpp_ik_options * opt, void * stream, int64_t batch, float * theta_state_dev,
+                         float * beta_dev, int64_t beta_stride, float * vertex_weights_dev, const int32_t * face_idx_dev,
+                         const float * target_pos_dev, const float * target_normal_dev, const float * pos_task_weight_dev,
+                         int32_t * status_dev, float * e_out_dev, float * jac_out_dev, double * a_out_dev,
+                         double * b_out_dev, double * delta_out_dev, float * dphi_out_dev, void * workspace_dev,
+                         size_t workspace_bytes);
+
 /* `iterations` IK steps for B frames with HOST arrays (the mocap modes of node/node.cpp:645-1002 as one call: targets of
  * every frame in, theta / re-weighted attachments / status out).  Copies in, iterates smplpp_ik_step on an internal
  * stream, copies out, synchronises; bench.py's `ik.e2e` times this call.  Arrays as in smplpp_ik_step;

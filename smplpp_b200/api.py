@@ -856,7 +856,8 @@ class IkTaskSet:
 
     def step(self, opt: capi.IkOptions, theta_state: torch.Tensor, beta: torch.Tensor, vertex_weights: torch.Tensor,
              target_pos: torch.Tensor, pos_task_weight: Optional[torch.Tensor] = None,
-             target_normal: Optional[torch.Tensor] = None, outputs: bool = False):
+             target_normal: Optional[torch.Tensor] = None, outputs: bool = False,
+             face_idx: Optional[torch.Tensor] = None, dphi_out: Optional[torch.Tensor] = None):
         """One IK iteration for all frames (node/node.cpp:753-968 per frame).  theta_state (B,75|44), beta
         ((B,10) or (10,) shared) and vertex_weights (B,n,3) are updated IN PLACE.  Returns status (B,) int32 and,
         with outputs=True, a dict of e (B,4n), J (B,4n,dim), A (B,dim,dim), b, delta in the reference layout."""
@@ -881,9 +882,24 @@ class IkTaskSet:
                        A=torch.empty((b, dim, dim), dtype=torch.float64, device=dev),
                        b=torch.empty((b, dim), dtype=torch.float64, device=dev),
                        delta=torch.empty((b, dim), dtype=torch.float64, device=dev))
+        vp = self.vposer.handle if (opt.enable_vposer and self.vposer is not None) else None
+        if face_idx is not None:
+            # per-frame attachments (IkTask::faceIdx_ after the projection step, node.cpp:993-1001)
+            if not (face_idx.is_cuda and face_idx.dtype == torch.int32 and face_idx.is_contiguous()
+                    and face_idx.shape == (b, self.n)):
+                raise SmplppError("IkTask Error: face_idx must be a contiguous int32 CUDA tensor of shape (B, %d)" % self.n)
+            need = lib().smplpp_ik_faces_workspace_bytes(self._h, C.byref(opt), C.c_int64(b))
+            ws = self._workspace(need)
+            with torch.cuda.device(dev):
+                check(lib().smplpp_ik_step_faces(
+                    self.smpl.handle, vp, self._h, C.byref(opt), _stream(dev), C.c_int64(b), _ptr(theta_state), _ptr(beta),
+                    C.c_int64(stride), _ptr(vertex_weights), _ptr(face_idx), _ptr(target_pos), _ptr(target_normal),
+                    _ptr(pos_task_weight), _ptr(status), _ptr(out["e"]) if out else None, _ptr(out["J"]) if out else None,
+                    _ptr(out["A"]) if out else None, _ptr(out["b"]) if out else None, _ptr(out["delta"]) if out else None,
+                    _ptr(dphi_out), _ptr(ws), C.c_size_t(ws.numel())))
+            return (status, out) if outputs else status
         need = lib().smplpp_ik_workspace_bytes(self._h, C.byref(opt), C.c_int64(b))
         ws = self._workspace(need)
-        vp = self.vposer.handle if (opt.enable_vposer and self.vposer is not None) else None
         with torch.cuda.device(dev):
             check(lib().smplpp_ik_step(
                 self.smpl.handle, vp, self._h, C.byref(opt), _stream(dev), C.c_int64(b), _ptr(theta_state), _ptr(beta),

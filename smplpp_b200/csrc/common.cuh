@@ -102,6 +102,7 @@ struct ModelDev
   int32_t * adj_faces = nullptr;
   // originals kept for the task builder and the generic module kernels
   float * weights_dense = nullptr; // (V, 24)
+  uint32_t * vert_jmask = nullptr; // (V) joints whose rotation moves the vertex (ancestor closure of its influences)
   // tcgen05 blend variant (blend_tc.cu): split basis [part hi|lo][tile][plane x|y|z][128][224] as bf16 ([0]) and
   // tf32-rounded fp32 ([1]) with their TMA tensor maps (CUtensorMap is 128 bytes, 64-byte aligned)
   void * basis_split[2] = {nullptr, nullptr};
@@ -130,6 +131,7 @@ struct smplpp_model
   std::vector<int32_t> h_adj_faces;
   std::vector<float> h_basis;        // (3V, 224) same row layout as d.basis (unpadded V)
   std::vector<float> h_weights;      // (V, 24)
+  std::vector<uint32_t> h_vert_jmask; // (V)
   std::vector<float> h_joint_template, h_joint_shape;
   // smplpp_forward_host: chunked, double-buffered pipeline (compute stream + copy stream)
   struct HostPipe

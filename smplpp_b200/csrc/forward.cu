@@ -10,6 +10,7 @@
 //   skinning            src/LinearBlendSkinning.cpp:445-553 (homogeneous divide kept, root translation added)
 #include "common.cuh"
 #include "forward.cuh"
+#include "ik2.cuh"
 #include "tc3_layout.cuh"
 #include "vposer.cuh"
 
@@ -937,6 +938,11 @@ extern "C" int smplpp_set_forward_variant(int variant)
   if(variant >= 200 && variant <= 202)
   {
     g_lbs_variant = variant - 200;
+    return SMPLPP_OK;
+  }
+  if(variant == 400 || variant == 401) // IK step: 400 fused kernel (default), 401 two-kernel predecessor (cross-check)
+  {
+    g_ik_variant = variant - 400;
     return SMPLPP_OK;
   }
   if(variant < 0 || variant > 6) return fail(SMPLPP_ERR_INVALID, "SMPL", "unknown forward variant");

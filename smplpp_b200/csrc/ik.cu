@@ -15,121 +15,12 @@
 
 #include "common.cuh"
 #include "forward.cuh"
+#include "ik2.cuh"
+#include "ik_math.cuh"
 #include "tasks.cuh"
 #include "vposer.cuh"
 
 using namespace sb;
-
-// ------------------------------------------------------------------------------------------------------------
-// small device helpers
-// ------------------------------------------------------------------------------------------------------------
-struct f3
-{
-  float x, y, z;
-};
-__device__ __forceinline__ f3 mk3(float x, float y, float z)
-{
-  f3 r;
-  r.x = x, r.y = y, r.z = z;
-  return r;
-}
-__device__ __forceinline__ f3 ld3(const float * p)
-{
-  return mk3(p[0], p[1], p[2]);
-}
-__device__ __forceinline__ f3 operator+(f3 a, f3 b)
-{
-  return mk3(a.x + b.x, a.y + b.y, a.z + b.z);
-}
-__device__ __forceinline__ f3 operator-(f3 a, f3 b)
-{
-  return mk3(a.x - b.x, a.y - b.y, a.z - b.z);
-}
-__device__ __forceinline__ f3 operator*(float s, f3 a)
-{
-  return mk3(s * a.x, s * a.y, s * a.z);
-}
-__device__ __forceinline__ float dot3(f3 a, f3 b)
-{
-  return a.x * b.x + a.y * b.y + a.z * b.z;
-}
-__device__ __forceinline__ f3 cross3(f3 a, f3 b)
-{
-  return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
-}
-__device__ __forceinline__ float norm3(f3 a)
-{
-  return sqrtf(dot3(a, a));
-}
-// torch::nn::functional::normalize: v / max(||v||, 1e-12); returns 1 / max(||v||, eps), negative when clamped
-__device__ __forceinline__ f3 normalize_inv(f3 a, float & inv)
-{
-  float n = norm3(a);
-  bool clamped = !(n > 1e-12f);
-  float i = 1.f / fmaxf(n, 1e-12f);
-  inv = clamped ? -i : i;
-  return i * a;
-}
-// derivative of normalize at output direction n (unit) applied to x: (x - n (n.x)) / |v|   (or x / eps when clamped)
-__device__ __forceinline__ f3 proj_apply(f3 n, float inv, f3 x)
-{
-  if(inv < 0.f) return (-inv) * x;
-  return inv * (x - dot3(n, x) * n);
-}
-// calcTriangleVertexWeights (include/smplpp/toolbox/GeometryUtils.h:42-52)
-__device__ __forceinline__ void triangle_weights(f3 pos, f3 v0, f3 v1, f3 v2, float * w)
-{
-  float a0 = norm3(cross3(v1 - pos, v2 - pos));
-  float a1 = norm3(cross3(v2 - pos, v0 - pos));
-  float a2 = norm3(cross3(v0 - pos, v1 - pos));
-  float s = a0 + a1 + a2;
-  w[0] = a0 / s, w[1] = a1 / s, w[2] = a2 / s;
-}
-
-// BlendShape::rodrigues (src/BlendShape.cpp:803-844) with the derivative of THAT formula (da/dtheta uses theta+eps)
-__device__ void rodrigues_grad(float x, float y, float z, float * R, float * dR /* [3][9] */)
-{
-  const float eps = 1e-8f;
-  float th[3] = {x, y, z};
-  float ax = x + eps, ay = y + eps, az = z + eps;
-  float a = sqrtf(ax * ax + ay * ay + az * az);
-  float inv_a = 1.f / a;
-  float u[3] = {x / a, y / a, z / a};
-  float s, c;
-  sincosf(a, &s, &c);
-  float oc = 1.f - c;
-  float uu = u[0] * u[0] + u[1] * u[1] + u[2] * u[2];
-  R[0] = 1.f + oc * (-(u[2] * u[2]) - u[1] * u[1]);
-  R[1] = s * (-u[2]) + oc * (u[1] * u[0]);
-  R[2] = s * u[1] + oc * (u[2] * u[0]);
-  R[3] = s * u[2] + oc * (u[0] * u[1]);
-  R[4] = 1.f + oc * (-(u[2] * u[2]) - u[0] * u[0]);
-  R[5] = s * (-u[0]) + oc * (u[2] * u[1]);
-  R[6] = s * (-u[1]) + oc * (u[0] * u[2]);
-  R[7] = s * u[0] + oc * (u[1] * u[2]);
-  R[8] = 1.f + oc * (-(u[1] * u[1]) - u[0] * u[0]);
-  const float K[9] = {0.f, -u[2], u[1], u[2], 0.f, -u[0], -u[1], u[0], 0.f};
-  float da[3] = {ax * inv_a, ay * inv_a, az * inv_a};
-#pragma unroll
-  for(int q = 0; q < 3; q++)
-  {
-    float du[3];
-#pragma unroll
-    for(int i = 0; i < 3; i++) du[i] = ((i == q) ? inv_a : 0.f) - u[i] * da[q] * inv_a;
-    (void)th;
-    const float dK[9] = {0.f, -du[2], du[1], du[2], 0.f, -du[0], -du[1], du[0], 0.f};
-    float udu = u[0] * du[0] + u[1] * du[1] + u[2] * du[2];
-#pragma unroll
-    for(int i = 0; i < 3; i++)
-#pragma unroll
-      for(int k = 0; k < 3; k++)
-      {
-        float K2 = u[i] * u[k] - ((i == k) ? uu : 0.f);
-        float dK2 = du[i] * u[k] + u[i] * du[k] - ((i == k) ? 2.f * udu : 0.f);
-        dR[q * 9 + i * 3 + k] = c * da[q] * K[i * 3 + k] + s * dK[i * 3 + k] + s * da[q] * K2 + oc * dK2;
-      }
-  }
-}
 
 // ------------------------------------------------------------------------------------------------------------
 // standalone helpers of the API
@@ -1761,6 +1652,28 @@ extern "C" int smplpp_tasks_create(const smplpp_model_t * model, int32_t n, cons
   t->sub_corner.V = nCorner;
   t->h_sub_vert = sub_vert;
   t->h_corner = corner;
+  // self-contained per-task records of the fused step (ik2.cu)
+  {
+    std::vector<TaskRec> recs(n);
+    int mp = 3, mi = 0, ml = 1;
+    for(int m = 0; m < n; m++)
+    {
+      if(build_task_rec_host(model, face_idx[m], recs[m]) != 0)
+      {
+        smplpp_tasks_destroy(t);
+        return fail(SMPLPP_ERR_INVALID, "IkTask", "the 1-ring of an attachment face exceeds the record limits (48 vertices / 48 faces)");
+      }
+      mp = std::max<int>(mp, recs[m].np), mi = std::max<int>(mi, recs[m].ni);
+      ml = std::max<int>(ml, __builtin_popcount(recs[m].jmask));
+    }
+    rc = upload_vec(t, &t->recs, recs);
+    if(rc != SMPLPP_OK)
+    {
+      smplpp_tasks_destroy(t);
+      return rc;
+    }
+    t->maxPairs = mp, t->maxItems = mi, t->maxLive = ml;
+  }
   *out = t;
   return SMPLPP_OK;
 }
@@ -1899,7 +1812,11 @@ IkLayout make_layout(const smplpp_tasks_t * tasks, const smplpp_ik_options * o, 
   L.off_vjac = L.vposer ? take(C * 63 * 32 * sizeof(float)) : 0;
   L.off_vaux = L.vposer ? take(C * vposer_tc_aux_floats() * sizeof(float)) : 0; // d1 | d2 | daa of the tensor-core Jacobian
   L.off_info = take(C * 2 * sizeof(int));
-  L.off_aws = L.qp_ws ? take(C * (static_cast<size_t>(L.D) * (L.D + 1) / 2) * sizeof(double)) : 0;
+  {
+    const Ik2Dims dm = ik2_dims(L.n, L.vposer, L.phi_cols > 0, L.beta_cols > 0);
+    const size_t per_frame = std::max<size_t>(static_cast<size_t>(L.D) * (L.D + 1) / 2, ik2_qp_ws_doubles(dm));
+    L.off_aws = L.qp_ws ? take(C * per_frame * sizeof(double)) : 0;
+  }
   L.off_schur = schur ? take(static_cast<size_t>(batch) * 111 * sizeof(double)) : 0;
   if(schur)
   {
@@ -2061,12 +1978,35 @@ extern "C" size_t smplpp_ik_workspace_bytes(const smplpp_tasks_t * tasks, const 
   return make_layout(tasks, opt, batch, false).total;
 }
 
-extern "C" int smplpp_ik_step(const smplpp_model_t * model, const smplpp_vposer_t * vposer, const smplpp_tasks_t * tasks,
-                              const smplpp_ik_options * opt, void * stream, int64_t batch, float * theta_state,
-                              float * beta, int64_t beta_stride, float * vertex_weights, const float * target_pos,
-                              const float * target_normal, const float * pos_task_weight, int32_t * status,
-                              float * e_out, float * jac_out, double * a_out, double * b_out, double * delta_out,
-                              void * workspace, size_t workspace_bytes)
+namespace
+{
+// theta (B, 75) fed to the forward pass: the state itself, or [trans | root | decoder(latent) | hands] with the decoder
+// Jacobian on the side (node.cpp:761-772)
+int assemble_theta(const smplpp_vposer_t * vposer, const IkLayout & L, cudaStream_t st, int B, float * theta_state, char * ws,
+                   const float ** theta75, const float ** vjac)
+{
+  *theta75 = theta_state;
+  *vjac = nullptr;
+  if(!L.vposer) return SMPLPP_OK;
+  float * theta = reinterpret_cast<float *>(ws + L.off_theta);
+  float * jac = reinterpret_cast<float *>(ws + L.off_vjac);
+  theta_assemble_kernel<<<(B * 12 + 127) / 128, 128, 0, st>>>(B, theta_state, theta);
+  SB_LAUNCHED();
+  int rc = launch_vposer_decode(vposer, st, B, theta_state + 6, 44, theta + 6, 75, jac, reinterpret_cast<float *>(ws + L.off_vaux));
+  if(rc != SMPLPP_OK) return rc;
+  *theta75 = theta;
+  *vjac = jac;
+  return SMPLPP_OK;
+}
+} // namespace
+
+// face_idx (B, n) int32, nullable: per-frame IkTask::faceIdx_ (re-seated by smplpp_ik_reproject); records_ws: B * n records
+static int ik_step_impl(const smplpp_model_t * model, const smplpp_vposer_t * vposer, const smplpp_tasks_t * tasks,
+                        const smplpp_ik_options * opt, void * stream, int64_t batch, float * theta_state, float * beta,
+                        int64_t beta_stride, float * vertex_weights, const int32_t * face_idx, const float * target_pos,
+                        const float * target_normal, const float * pos_task_weight, int32_t * status, float * e_out,
+                        float * jac_out, double * a_out, double * b_out, double * delta_out, float * dphi_out,
+                        void * workspace, size_t workspace_bytes)
 {
   if(!model || !tasks || !opt || batch < 1 || !theta_state || !beta || !vertex_weights || !target_pos || !status)
     return fail(SMPLPP_ERR_INVALID, "IkTask", "invalid IK step arguments!");
@@ -2074,10 +2014,48 @@ extern "C" int smplpp_ik_step(const smplpp_model_t * model, const smplpp_vposer_
   if(opt->optimize_beta && beta_stride == 0 && batch > 1)
     return fail(SMPLPP_ERR_INVALID, "IkTask", "per-frame beta optimisation needs per-frame beta (use the shared-beta stage)");
   const IkLayout L = make_layout(tasks, opt, batch, false);
-  if(!workspace || workspace_bytes < L.total) return fail(SMPLPP_ERR_INVALID, "IkTask", "IK workspace too small!");
+  const size_t rec_chunk = 4096; // frames per launch when every frame carries its own attachment records
+  const size_t rec_bytes = face_idx ? align_up(ik2_rec_bytes(std::min<int64_t>(batch, rec_chunk), L.n)) : 0;
+  if(!workspace || workspace_bytes < L.total + rec_bytes) return fail(SMPLPP_ERR_INVALID, "IkTask", "IK workspace too small!");
   cudaStream_t st = as_stream(stream);
   char * ws = align_up_ptr<char>(workspace);
   const int n = L.n;
+  if(g_ik_variant == 0 || face_idx)
+  {
+    TaskRec * recs = face_idx ? reinterpret_cast<TaskRec *>(ws + L.total) : nullptr;
+    const int64_t chunk = face_idx ? static_cast<int64_t>(rec_chunk) : L.chunk;
+    for(int64_t s = 0; s < batch; s += chunk)
+    {
+      const int B = static_cast<int>(std::min<int64_t>(chunk, batch - s));
+      Ik2Call c;
+      c.model = model, c.vposer = vposer, c.tasks = tasks, c.opt = opt, c.st = st, c.B = B, c.schur = false;
+      c.theta_state = theta_state + s * L.theta_dim;
+      int rc = assemble_theta(vposer, L, st, B, c.theta_state, ws, &c.theta75, &c.vjac);
+      if(rc != SMPLPP_OK) return rc;
+      c.beta = beta + s * beta_stride, c.beta_stride = beta_stride;
+      c.vertex_weights = vertex_weights + s * n * 3;
+      c.target_pos = target_pos + s * n * 3;
+      c.target_normal = target_normal ? target_normal + s * n * 3 : nullptr;
+      c.pos_task_weight = pos_task_weight ? pos_task_weight + s * n : nullptr;
+      if(face_idx)
+      {
+        rc = launch_task_topo(model->d, st, static_cast<long long>(B) * n, face_idx + s * n, recs);
+        if(rc != SMPLPP_OK) return rc;
+        c.frame_recs = recs;
+      }
+      c.status = status + s;
+      c.e_out = e_out ? e_out + s * 4 * n : nullptr;
+      c.j_out = jac_out ? jac_out + s * 4 * n * L.dim_ref : nullptr;
+      c.a_out = a_out ? a_out + s * L.dim_ref * L.dim_ref : nullptr;
+      c.b_out = b_out ? b_out + s * L.dim_ref : nullptr;
+      c.delta_out = delta_out ? delta_out + s * L.dim_ref : nullptr;
+      c.dphi_out = dphi_out ? dphi_out + s * 2 * n : nullptr;
+      c.a_ws = L.qp_ws ? reinterpret_cast<double *>(ws + L.off_aws) : nullptr;
+      rc = launch_ik_fused(c);
+      if(rc != SMPLPP_OK) return rc;
+    }
+    return SMPLPP_OK;
+  }
   for(int64_t s = 0; s < batch; s += L.chunk)
   {
     const int B = static_cast<int>(std::min<int64_t>(L.chunk, batch - s));
@@ -2117,6 +2095,37 @@ extern "C" int smplpp_ik_step(const smplpp_model_t * model, const smplpp_vposer_
   return SMPLPP_OK;
 }
 
+extern "C" int smplpp_ik_step(const smplpp_model_t * model, const smplpp_vposer_t * vposer, const smplpp_tasks_t * tasks,
+                              const smplpp_ik_options * opt, void * stream, int64_t batch, float * theta_state,
+                              float * beta, int64_t beta_stride, float * vertex_weights, const float * target_pos,
+                              const float * target_normal, const float * pos_task_weight, int32_t * status,
+                              float * e_out, float * jac_out, double * a_out, double * b_out, double * delta_out,
+                              void * workspace, size_t workspace_bytes)
+{
+  return ik_step_impl(model, vposer, tasks, opt, stream, batch, theta_state, beta, beta_stride, vertex_weights, nullptr,
+                      target_pos, target_normal, pos_task_weight, status, e_out, jac_out, a_out, b_out, delta_out, nullptr,
+                      workspace, workspace_bytes);
+}
+
+extern "C" size_t smplpp_ik_faces_workspace_bytes(const smplpp_tasks_t * tasks, const smplpp_ik_options * opt, int64_t batch)
+{
+  if(!tasks || !opt || batch < 1) return 0;
+  return make_layout(tasks, opt, batch, false).total + align_up(ik2_rec_bytes(std::min<int64_t>(batch, 4096), tasks->d.n)) + 256;
+}
+
+extern "C" int smplpp_ik_step_faces(const smplpp_model_t * model, const smplpp_vposer_t * vposer, const smplpp_tasks_t * tasks,
+                                    const smplpp_ik_options * opt, void * stream, int64_t batch, float * theta_state,
+                                    float * beta, int64_t beta_stride, float * vertex_weights, const int32_t * face_idx,
+                                    const float * target_pos, const float * target_normal, const float * pos_task_weight,
+                                    int32_t * status, float * e_out, float * jac_out, double * a_out, double * b_out,
+                                    double * delta_out, float * dphi_out, void * workspace, size_t workspace_bytes)
+{
+  if(!face_idx) return fail(SMPLPP_ERR_INVALID, "IkTask", "invalid IK step arguments! (face indices)");
+  return ik_step_impl(model, vposer, tasks, opt, stream, batch, theta_state, beta, beta_stride, vertex_weights, face_idx,
+                      target_pos, target_normal, pos_task_weight, status, e_out, jac_out, a_out, b_out, delta_out, dphi_out,
+                      workspace, workspace_bytes);
+}
+
 extern "C" size_t smplpp_ik_shared_beta_workspace_bytes(const smplpp_tasks_t * tasks, const smplpp_ik_options * opt,
                                                         int64_t batch)
 {
@@ -2142,7 +2151,25 @@ extern "C" int smplpp_ik_shared_beta_reduce(const smplpp_model_t * model, const 
   const int n = L.n;
   const int npiv = L.D - L.beta_cols;
   const size_t P = static_cast<size_t>(npiv) * (npiv + 1) / 2 + static_cast<size_t>(L.beta_cols + 1) * npiv;
-  for(int64_t s = 0; s < batch; s += L.chunk)
+  for(int64_t s = 0; s < batch && g_ik_variant == 0; s += L.chunk)
+  {
+    const int B = static_cast<int>(std::min<int64_t>(L.chunk, batch - s));
+    Ik2Call c;
+    c.model = model, c.vposer = vposer, c.tasks = tasks, c.opt = opt, c.st = st, c.B = B, c.schur = true;
+    c.theta_state = const_cast<float *>(theta_state) + s * L.theta_dim;
+    int rc = assemble_theta(vposer, L, st, B, c.theta_state, ws, &c.theta75, &c.vjac);
+    if(rc != SMPLPP_OK) return rc;
+    c.beta = const_cast<float *>(shared_beta), c.beta_stride = 0;
+    c.vertex_weights = vertex_weights + s * n * 3;
+    c.target_pos = target_pos + s * n * 3;
+    c.pos_task_weight = pos_task_weight ? pos_task_weight + s * n : nullptr;
+    c.status = status + s;
+    c.schur_out = reinterpret_cast<double *>(ws + L.off_schur) + s * 111;
+    c.factor_ws = reinterpret_cast<double *>(ws + L.off_factor) + s * P;
+    rc = launch_ik_fused(c);
+    if(rc != SMPLPP_OK) return rc;
+  }
+  for(int64_t s = 0; s < batch && g_ik_variant != 0; s += L.chunk)
   {
     const int B = static_cast<int>(std::min<int64_t>(L.chunk, batch - s));
     int rc = run_chunk(model, vposer, tasks, opt, L, st, B, const_cast<float *>(theta_state) + s * L.theta_dim,

@@ -78,10 +78,7 @@ extern "C" int smplpp_model_create(const smplpp_model_desc * desc, smplpp_model_
     int64_t p = desc->kinematic_tree[j];
     d.parent[j] = (j > 0 && p >= 0 && p < kJoints) ? static_cast<int>(p) : -1;
     if(j > 0 && (d.parent[j] < 0 || d.parent[j] >= j))
-    {
-      delete m;
-      return fail(SMPLPP_ERR_INVALID, "WorldTransformation", "Cannot transform bones locally!");
-    }
+      return fail(SMPLPP_ERR_INVALID, "WorldTransformation", "Cannot transform bones locally!"); // the guard frees m
   }
   d.max_depth = 0;
   for(int j = 0; j < kJoints; j++)
@@ -205,17 +202,27 @@ extern "C" int smplpp_model_create(const smplpp_model_desc * desc, smplpp_model_
     if(upload(&d.group_w, gw) != SMPLPP_OK) return SMPLPP_ERR_CUDA;
   }
   if(upload(&d.weights_dense, m->h_weights) != SMPLPP_OK) return SMPLPP_ERR_CUDA;
+  {
+    // per vertex: the joints whose rotation moves it = ancestor closure of its influencing joints (IK Jacobian sparsity)
+    uint32_t anc[kJoints];
+    for(int j = 0; j < kJoints; j++)
+    {
+      anc[j] = 0;
+      for(int k = j; k >= 0; k = d.parent[k]) anc[j] |= 1u << k;
+    }
+    m->h_vert_jmask.assign(V, 0u);
+    for(int v = 0; v < V; v++)
+      for(int j = 0; j < kJoints; j++)
+        if(m->h_weights[static_cast<size_t>(v) * kJoints + j] != 0.f) m->h_vert_jmask[v] |= anc[j];
+    if(upload(&d.vert_jmask, m->h_vert_jmask) != SMPLPP_OK) return SMPLPP_ERR_CUDA;
+  }
 
   // topology: 0-based faces + vertex -> adjacent faces (SMPL.cpp:619-640; uniform weights 1/deg)
   m->h_faces.resize(static_cast<size_t>(F) * 3);
   for(size_t i = 0; i < m->h_faces.size(); i++)
   {
     int32_t id = desc->face_indices[i] - 1;
-    if(id < 0 || id >= V)
-    {
-      delete m;
-      return fail(SMPLPP_ERR_INVALID, "SMPL", "Failed to get face indices!");
-    }
+    if(id < 0 || id >= V) return fail(SMPLPP_ERR_INVALID, "SMPL", "Failed to get face indices!"); // the guard frees m
     m->h_faces[i] = id;
   }
   m->h_adj_offset.assign(V + 1, 0);
@@ -264,6 +271,7 @@ extern "C" void smplpp_model_destroy(smplpp_model_t * m)
   cudaFree(d.adj_offset);
   cudaFree(d.adj_faces);
   cudaFree(d.weights_dense);
+  cudaFree(d.vert_jmask);
   tc_release_model(d);
   tc3_release_model(d);
   tc2_release_model(d);

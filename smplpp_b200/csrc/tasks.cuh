@@ -34,6 +34,29 @@ struct TasksDev
   const float * lbs_weight = nullptr;  // [kmax][nUpad]
   const float * lbs_wsum = nullptr;    // (nUpad)
 };
+// ---- fused IK step (ik2.cu): one self-contained topology record per task -------------------------------------------
+// Everything the step needs about ONE attachment face: its three corners, their 1-rings (SMPL::calcVertexNormal,
+// src/SMPL.cpp:527-535) and the distinct vertices ("pairs") these touch, as GLOBAL vertex ids of the model.  A task set
+// holds n of them (all frames share the topology); per-frame attachments (IkTask::faceIdx_ re-seated by the projection of
+// node/node.cpp:993-1001) are (B, n) records built on the device by task_topo_kernel.
+constexpr int kRecPairs = 48; // distinct vertices of a task: 3 corners + ring
+constexpr int kRecItems = 48; // (corner, adjacent face) items of a task = sum of the three corner valences
+struct alignas(16) TaskRec
+{
+  int32_t face;          // 0-based row of face_indices; < 0 marks a record that does not fit (valence too high)
+  uint32_t jmask;        // joints that move any pair (ancestor closure of the influencing joints)
+  uint32_t jmask_corner; // the same for the three corners only
+  uint8_t np;            // pairs; pairs 0..2 are corners 0..2 of the face (in face order)
+  uint8_t ni;            // items, ordered by corner
+  uint8_t nic[3];        // items per corner
+  uint8_t pad[3];
+  int32_t gv[kRecPairs];            // global vertex id of every pair
+  uint8_t item[kRecItems][4];       // pair-local ids of the adjacent face's vertices in face order; [3] = corner
+  uint8_t ref_off[kRecPairs + 1];   // CSR pair -> references
+  uint8_t refs[3 * kRecItems];      // item * 4 + slot (slot = position of the pair in the item's face)
+  uint8_t pad2[3];
+};
+static_assert(sizeof(TaskRec) == 608, "TaskRec layout");
 } // namespace sb
 
 struct smplpp_tasks
@@ -45,6 +68,9 @@ struct smplpp_tasks
   std::vector<int64_t> h_face_idx;
   std::vector<int32_t> h_sub_vert; // local -> global vertex id
   std::vector<int32_t> h_corner;
+  // fused IK step (ik2.cu)
+  const sb::TaskRec * recs = nullptr; // (n) device
+  int maxPairs = 0, maxItems = 0, maxLive = 0, maxPairsCorner = 3;
   // smplpp_ik_solve_host (ik_host.cu): grow-only device buffers and the stream of the host-buffer call
   struct HostSolve
   {

@@ -69,26 +69,41 @@ def main():
     x0 = synth.make_motion(40, 20)[2].reshape(-1)
     target = np.stack([markers_of(gt[f].reshape(-1), b0) for f in range(F3)]) + noise
     target[valid == 0] = 0.0  # node.cpp:682-683
-    th_traj = np.zeros((F3, K3, 75), np.float32)
-    res = np.zeros((F3, K3))
-    vw_out = np.zeros((F3, n, 3), np.float32)
-    for f in range(F3):
-        x, w = x0.copy(), vw0.copy()
-        for k in range(K3):
-            r = ref.ik_iteration(x, b0, face_idx, w, target[f], pos_task_weight=valid[f].astype(np.float64), **MOTION)
-            x, w = r["theta_state"], r["vertex_weights"]
-            th_traj[f, k], res[f, k] = x, marker_residual(r["e"], valid[f])
-        vw_out[f] = w
-        print("c3 frame %d: residual %.5f -> %.6f m  (%.0f s)" % (f, res[f, 0], res[f, -1], time.time() - t_start), flush=True)
+    def run_c3(frames):
+        th_traj = np.zeros((len(frames), K3, 75), np.float32)
+        res = np.zeros((len(frames), K3))
+        vw_traj = np.zeros((len(frames), K3, n, 3), np.float32)
+        for i, f in enumerate(frames):
+            x, w = x0.copy(), vw0.copy()
+            for k in range(K3):
+                r = ref.ik_iteration(x, b0, face_idx, w, target[f], pos_task_weight=valid[f].astype(np.float64), **MOTION)
+                x, w = r["theta_state"], r["vertex_weights"]
+                th_traj[i, k], res[i, k], vw_traj[i, k] = x, marker_residual(r["e"], valid[f]), w
+            print("c3 frame %d: residual %.5f -> %.6f m  (%.0f s)" % (f, res[i, 0], res[i, -1], time.time() - t_start), flush=True)
+        return th_traj, res, vw_traj
+
+    th_traj, res, vw_traj = run_c3(range(F3))
     out.update(c3_theta_in=x0, c3_target=target, c3_valid=valid, c3_theta_traj=th_traj, c3_residual=res,
-               c3_vertex_weights_out=vw_out, c3_theta_gt=gt.reshape(F3, 75))
+               c3_vertex_weights_traj=vw_traj, c3_theta_gt=gt.reshape(F3, 75))
+    # The same loop of the same compiled reference with ONE libtorch thread instead of all of them (another summation
+    # order inside at::matmul): how far two runs of the reference itself drift apart over 30 iterations.  The iteration
+    # is not contractive along weakly observed joints (damping 1e-3 only), so rounding differences grow; the GPU parity
+    # tests use this band for the free-running comparison and exact per-iteration (teacher-forced) checks otherwise.
+    alt_frames = [1, 4, 6]
+    nthreads = ref_lib.get_num_threads()
+    ref_lib.set_num_threads(1)
+    th_alt, res_alt, _ = run_c3(alt_frames)
+    ref_lib.set_num_threads(nthreads)
+    out.update(c3_alt_frames=np.asarray(alt_frames), c3_alt_theta_traj=th_alt, c3_alt_residual=res_alt)
+    print("reference vs itself (1 thread vs %d): max residual deviation %.3g m, max theta deviation %.3g"
+          % (nthreads, np.abs(res_alt - res[alt_frames]).max(), np.abs(th_alt - th_traj[alt_frames]).max()), flush=True)
 
     # ---------------- configs[3]: 4 frames x 10 iterations, VPoser latent state ----------------
     F4, K4 = 4, 10
     rng = np.random.default_rng(32)
     xg = np.zeros((F4, 44), np.float32)
     xg[:, 0:6] = gt[:F4].reshape(F4, 75)[:, 0:6]
-    xg[:, 6:38] = rng.normal(size=(F4, 32)).astype(np.float32) * 0.6
+    xg[:, 6:38] = rng.normal(size=(F4, 32)).astype(np.float32) * 0.15
     xg[:, 38:44] = rng.normal(size=(F4, 6)).astype(np.float32) * 0.02
     noise4, valid4 = synth.make_marker_noise(F4, n, 22)
     valid4 = valid4.astype(np.float32)
@@ -98,15 +113,17 @@ def main():
     xv0[0:6] = x0[0:6]
     th4 = np.zeros((F4, K4, 44), np.float32)
     res4 = np.zeros((F4, K4))
+    vw4 = np.zeros((F4, K4, n, 3), np.float32)
     for f in range(F4):
         x, w = xv0.copy(), vw0.copy()
         for k in range(K4):
             r = ref.ik_iteration(x, b0, face_idx, w, target4[f], pos_task_weight=valid4[f].astype(np.float64), vposer=vp,
                                  **MOTION)
             x, w = r["theta_state"], r["vertex_weights"]
-            th4[f, k], res4[f, k] = x, marker_residual(r["e"], valid4[f])
+            th4[f, k], res4[f, k], vw4[f, k] = x, marker_residual(r["e"], valid4[f]), w
         print("c4 frame %d: residual %.5f -> %.6f m  (%.0f s)" % (f, res4[f, 0], res4[f, -1], time.time() - t_start), flush=True)
-    out.update(c4_theta_in=xv0, c4_target=target4, c4_valid=valid4, c4_theta_traj=th4, c4_residual=res4, c4_state_gt=xg)
+    out.update(c4_theta_in=xv0, c4_target=target4, c4_valid=valid4, c4_theta_traj=th4, c4_residual=res4,
+               c4_vertex_weights_traj=vw4, c4_state_gt=xg)
 
     # ---------------- body stage: 1 frame x 51 iterations with projection + re-seat ----------------
     KB = 51
