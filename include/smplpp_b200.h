@@ -284,6 +284,20 @@ int smplpp_ik_step_faces(const smplpp_model_t * model, const smplpp_vposer_t * v
                          double * b_out_dev, double * delta_out_dev, float * dphi_out_dev, void * workspace_dev,
                          size_t workspace_bytes);
 
+/* The tail of the reference's iteration (node/node.cpp:949-1001) for B frames: on the mesh of the given state -- the node
+ * uses the PRE-update theta / beta of the iteration, i.e. the state the step linearised at -- every task point
+ * p = calcActualPos() + tangents * dphi (IkTask.cpp:33-47, 59-72) is projected onto the mesh
+ * (igl::point_mesh_squared_distance there) and the attachment is re-seated in place:
+ *   face_idx_dev       (B, n) int32  in: IkTask::faceIdx_ per frame  out: the closest face
+ *   vertex_weights_dev (B, n, 3)     in: the weights the step left   out: calcTriangleVertexWeights(closest point, face)
+ *   dphi_dev           (B, n, 2)     nullable: the phi part of the step (smplpp_ik_step_faces)
+ *   sq_dist_dev        (B, n)        nullable out: squared distance of the point to the mesh */
+size_t smplpp_ik_reproject_workspace_bytes(const smplpp_model_t * model, const smplpp_tasks_t * tasks, int64_t batch);
+int smplpp_ik_reproject(const smplpp_model_t * model, const smplpp_vposer_t * vposer, const smplpp_tasks_t * tasks,
+                        const smplpp_ik_options * opt, void * stream, int64_t batch, const float * theta_state_dev,
+                        const float * beta_dev, int64_t beta_stride, float * vertex_weights_dev, int32_t * face_idx_dev,
+                        const float * dphi_dev, float * sq_dist_dev, void * workspace_dev, size_t workspace_bytes);
+
 /* `iterations` IK steps for B frames with HOST arrays (the mocap modes of node/node.cpp:645-1002 as one call: targets of
  * every frame in, theta / re-weighted attachments / status out).  Copies in, iterates smplpp_ik_step on an internal
  * stream, copies out, synchronises; bench.py's `ik.e2e` times this call.  Arrays as in smplpp_ik_step;

@@ -810,44 +810,45 @@ class IkTaskSet:
         return torch.cat([theta_state[:, 0:3].reshape(b, 1, 3), theta_state[:, 3:6].reshape(b, 1, 3), body,
                           theta_state[:, 38:41].reshape(b, 1, 3), theta_state[:, 41:44].reshape(b, 1, 3)], dim=1).contiguous()
 
-    def reproject(self, theta_state: torch.Tensor, beta: torch.Tensor, vertex_weights: torch.Tensor,
-                  normal_offset: float = 0.015, phi: Optional[torch.Tensor] = None, apply: bool = True, chunk: int = 4096):
-        """The tail of an IK iteration in the reference (node/node.cpp:949-1001) for every frame: the point
-        p = calcActualPos() + tangents * phi of every task is projected onto the posed mesh
-        (igl::point_mesh_squared_distance there, smplpp_closest_points here) and the attachment is re-seated:
-        faceIdx_ = closest face, vertexWeights_ = calcTriangleVertexWeights(closest point, face).
-
-        Returns (face (B,n) int32 0-based, weights (B,n,3), same_face (B,n) bool).  With apply=True `vertex_weights` is
-        updated in place where the face did not change; a changed face is only REPORTED, because the task set shares
-        one attachment topology between all frames (per-frame topologies are the next step)."""
+    def reproject(self, opt: capi.IkOptions, theta_state: torch.Tensor, beta: torch.Tensor, vertex_weights: torch.Tensor,
+                  face_idx: torch.Tensor, dphi: Optional[torch.Tensor] = None, want_sq_dist: bool = False):
+        """The tail of an IK iteration in the reference (node/node.cpp:949-1001) for every frame, through
+        smplpp_ik_reproject: on the mesh of `theta_state` / `beta` (the node uses the PRE-update state of the iteration)
+        the point p = calcActualPos() + tangents * dphi of every task is projected onto the mesh and the attachment is
+        re-seated IN PLACE: face_idx (B,n) int32 <- closest face, vertex_weights (B,n,3) <-
+        calcTriangleVertexWeights(closest point, face).  Returns the squared distances (B,n) when asked for."""
         dev = self.smpl.m__device
         b = theta_state.shape[0]
-        faces0 = torch.as_tensor(self.smpl._faces_host.astype(np.int64) - 1, device=dev)      # (F,3)
-        task_faces = torch.as_tensor(self.face_idx, device=dev)                                # (n,)
-        face_out = torch.empty((b, self.n), dtype=torch.int32, device=dev)
-        w_out = torch.empty((b, self.n, 3), dtype=torch.float32, device=dev)
+        for name, t, dt in (("theta_state", theta_state, torch.float32), ("vertex_weights", vertex_weights, torch.float32),
+                            ("face_idx", face_idx, torch.int32)):
+            if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dt and t.is_contiguous()):
+                raise SmplppError("IkTask Error: %s must be a contiguous CUDA tensor" % name)
         beta_t = _dev_f32(beta, dev)
-        for s0 in range(0, b, chunk):
-            s1 = min(b, s0 + chunk)
-            theta = self.assemble_theta(theta_state[s0:s1])
-            self.smpl.launch(beta_t if beta_t.dim() == 1 or beta_t.shape[0] == 1 else beta_t[s0:s1], theta)
-            verts = self.smpl._vertices
-            pts = self.positions(verts, vertex_weights[s0:s1].contiguous(), normal_offset)
-            if phi is not None:
-                # IkTask::calcTangents (src/IkTask.cpp:33-47): t1 = normalize(v1 - v0), t2 = normalize((t1 x (v2 - v0)) x t1)
-                tri = verts[:, faces0[task_faces]]                                             # (c,n,3,3)
-                e1, e2 = tri[:, :, 1] - tri[:, :, 0], tri[:, :, 2] - tri[:, :, 0]
-                nrm = torch.cross(e1, e2, dim=-1)
-                t1 = torch.nn.functional.normalize(e1, dim=-1)
-                t2 = torch.nn.functional.normalize(torch.cross(nrm, e1, dim=-1), dim=-1)
-                ph = _dev_f32(phi, dev)[s0:s1]
-                pts = pts + t1 * ph[..., 0:1] + t2 * ph[..., 1:2]
-            face, _, _, w = self.smpl.projectPoints(pts.contiguous(), verts)
-            face_out[s0:s1], w_out[s0:s1] = face, w
-        same = face_out.long() == task_faces[None, :]
-        if apply:
-            vertex_weights.copy_(torch.where(same[..., None], w_out, vertex_weights))
-        return face_out, w_out, same
+        stride = 0 if beta_t.numel() == SHAPE_BASIS_DIM and b > 1 else SHAPE_BASIS_DIM
+        sq = torch.empty((b, self.n), dtype=torch.float32, device=dev) if want_sq_dist else None
+        need = lib().smplpp_ik_reproject_workspace_bytes(self.smpl.handle, self._h, C.c_int64(b))
+        ws = self._workspace(need)
+        vp = self.vposer.handle if (opt.enable_vposer and self.vposer is not None) else None
+        with torch.cuda.device(dev):
+            check(lib().smplpp_ik_reproject(self.smpl.handle, vp, self._h, C.byref(opt), _stream(dev), C.c_int64(b),
+                                            _ptr(theta_state), _ptr(beta_t), C.c_int64(stride), _ptr(vertex_weights),
+                                            _ptr(face_idx), _ptr(dphi), _ptr(sq), _ptr(ws), C.c_size_t(ws.numel())))
+        return sq
+
+    def iterate(self, opt: capi.IkOptions, theta_state: torch.Tensor, beta: torch.Tensor, vertex_weights: torch.Tensor,
+                face_idx: torch.Tensor, target_pos: torch.Tensor, pos_task_weight: Optional[torch.Tensor] = None,
+                outputs: bool = False):
+        """One COMPLETE iteration of the reference's loop body (node/node.cpp:753-1001) for every frame: the step on
+        the per-frame attachments, then the projection of the moved task points onto the pre-update mesh and the
+        re-seated faces / weights.  theta_state, beta (per frame when optimize_beta), vertex_weights, face_idx in place."""
+        dev = self.smpl.m__device
+        b = theta_state.shape[0]
+        theta_pre, beta_pre = theta_state.clone(), beta.clone()
+        dphi = torch.zeros((b, self.n, 2), dtype=torch.float32, device=dev)
+        r = self.step(opt, theta_state, beta, vertex_weights, target_pos, pos_task_weight=pos_task_weight, outputs=outputs,
+                      face_idx=face_idx, dphi_out=dphi)
+        self.reproject(opt, theta_pre, beta_pre, vertex_weights, face_idx, dphi=dphi)
+        return r
 
     def _workspace(self, nbytes: int) -> torch.Tensor:
         if self._ws is None or self._ws.numel() < nbytes:

@@ -49,7 +49,7 @@ EXPORTS = [
     "smplpp_tasks_create", "smplpp_tasks_destroy", "smplpp_tasks_count", "smplpp_tasks_vertex_count",
     "smplpp_triangle_vertex_weights", "smplpp_ik_options_default", "smplpp_ik_theta_dim", "smplpp_ik_dim",
     "smplpp_task_positions", "smplpp_closest_points", "smplpp_ik_workspace_bytes", "smplpp_ik_step", "smplpp_ik_solve_host",
-    "smplpp_ik_faces_workspace_bytes", "smplpp_ik_step_faces",
+    "smplpp_ik_faces_workspace_bytes", "smplpp_ik_step_faces", "smplpp_ik_reproject_workspace_bytes", "smplpp_ik_reproject",
     "smplpp_ik_shared_beta_workspace_bytes", "smplpp_ik_shared_beta_reduce", "smplpp_ik_shared_beta_apply",
     "smplpp_json_open", "smplpp_json_close", "smplpp_json_array", "smplpp_model_load_json", "smplpp_vposer_load_json",
     "smplpp_npz_open", "smplpp_model_load_npz",

@@ -940,7 +940,9 @@ extern "C" int smplpp_set_forward_variant(int variant)
     g_lbs_variant = variant - 200;
     return SMPLPP_OK;
   }
-  if(variant == 400 || variant == 401) // IK step: 400 fused kernel (default), 401 two-kernel predecessor (cross-check)
+  // IK step: 400 auto (two kernels for a shared attachment topology, the fused kernel for per-frame attachments),
+  // 401 two kernels, 402 fused kernel for every call
+  if(variant >= 400 && variant <= 402)
   {
     g_ik_variant = variant - 400;
     return SMPLPP_OK;

@@ -36,17 +36,20 @@ __global__ void triangle_weights_kernel(long long n, const float * __restrict__ 
 }
 
 // IkTask::calcActualPos / calcActualNormal (src/IkTask.cpp:59-86) on a full vertex buffer: thread per (frame, task)
+// face_idx: (n) int64 shared by all frames, or face_idx32 (B, n) int32 per frame (IkTask::faceIdx_ after the re-seating of
+// node.cpp:993-1001).  dphi (B, n, 2), nullable: the point moves by tangents * phi (IkTask::calcTangents, IkTask.cpp:33-47;
+// node.cpp:955-958).
 __global__ void task_positions_kernel(const int32_t * __restrict__ faces, const int32_t * __restrict__ adj_offset,
                                       const int32_t * __restrict__ adj_faces, int V, int B, int n,
-                                      const long long * __restrict__ face_idx, const float * __restrict__ verts,
-                                      const float * __restrict__ weights, float offset, float * __restrict__ pos_out,
-                                      float * __restrict__ nrm_out)
+                                      const long long * __restrict__ face_idx, const int32_t * __restrict__ face_idx32,
+                                      const float * __restrict__ verts, const float * __restrict__ weights, float offset,
+                                      const float * __restrict__ dphi, float * __restrict__ pos_out, float * __restrict__ nrm_out)
 {
   long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if(i >= static_cast<long long>(B) * n) return;
   int b = static_cast<int>(i / n), m = static_cast<int>(i % n);
   const float * vb = verts + static_cast<size_t>(b) * V * 3;
-  const int f = static_cast<int>(face_idx[m]);
+  const int f = face_idx32 ? face_idx32[i] : static_cast<int>(face_idx[m]);
   const float * w = weights + i * 3;
   f3 p = mk3(0.f, 0.f, 0.f), s = mk3(0.f, 0.f, 0.f);
   const bool need_n = offset > 0.f || nrm_out != nullptr;
@@ -76,6 +79,14 @@ __global__ void task_positions_kernel(const int32_t * __restrict__ faces, const 
     f3 nh = normalize_inv(s, inv);
     if(offset > 0.f) p = p + offset * nh;
     if(nrm_out) nrm_out[3 * i] = nh.x, nrm_out[3 * i + 1] = nh.y, nrm_out[3 * i + 2] = nh.z;
+  }
+  if(dphi)
+  {
+    const f3 v0 = ld3(vb + 3 * faces[3 * f]), v1 = ld3(vb + 3 * faces[3 * f + 1]), v2 = ld3(vb + 3 * faces[3 * f + 2]);
+    const f3 t1 = v1 - v0;
+    const f3 t2 = cross3(cross3(t1, v2 - v0), t1);
+    float inv;
+    p = p + dphi[2 * i] * normalize_inv(t1, inv) + dphi[2 * i + 1] * normalize_inv(t2, inv);
   }
   pos_out[3 * i] = p.x, pos_out[3 * i + 1] = p.y, pos_out[3 * i + 2] = p.z;
 }
@@ -1756,8 +1767,8 @@ extern "C" int smplpp_task_positions(const smplpp_model_t * model, const smplpp_
   const ModelDev & d = model->d;
   long long total = batch * tasks->d.n;
   task_positions_kernel<<<static_cast<unsigned>((total + 63) / 64), 64, 0, as_stream(stream)>>>(
-      d.faces, d.adj_offset, d.adj_faces, d.V, static_cast<int>(batch), tasks->d.n, cached, vertices, vertex_weights,
-      normal_offset, positions, normals);
+      d.faces, d.adj_offset, d.adj_faces, d.V, static_cast<int>(batch), tasks->d.n, cached, nullptr, vertices, vertex_weights,
+      normal_offset, nullptr, positions, normals);
   SB_LAUNCHED();
   return SMPLPP_OK;
 }
@@ -2020,7 +2031,7 @@ static int ik_step_impl(const smplpp_model_t * model, const smplpp_vposer_t * vp
   cudaStream_t st = as_stream(stream);
   char * ws = align_up_ptr<char>(workspace);
   const int n = L.n;
-  if(g_ik_variant == 0 || face_idx)
+  if(g_ik_variant == 2 || face_idx) // fused kernel: per-frame attachments always, shared ones when selected
   {
     TaskRec * recs = face_idx ? reinterpret_cast<TaskRec *>(ws + L.total) : nullptr;
     const int64_t chunk = face_idx ? static_cast<int64_t>(rec_chunk) : L.chunk;
@@ -2126,6 +2137,91 @@ extern "C" int smplpp_ik_step_faces(const smplpp_model_t * model, const smplpp_v
                       workspace, workspace_bytes);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// the tail of the reference's iteration (node.cpp:949-1001), batched: p = calcActualPos() + tangents * dphi on the mesh
+// of the given (PRE-update) state -> closest face and point of that mesh -> faceIdx_ and vertexWeights_ re-seated
+// ------------------------------------------------------------------------------------------------------------
+namespace
+{
+struct ReprojLayout
+{
+  int64_t chunk;
+  size_t off_theta, off_vaa, off_verts, off_points, off_fwd, total, fwd_bytes;
+};
+ReprojLayout reproj_layout(const smplpp_model_t * model, const smplpp_tasks_t * tasks, int64_t batch)
+{
+  ReprojLayout R{};
+  R.chunk = std::min<int64_t>(batch, 2048);
+  size_t off = 256;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += align_up(bytes);
+    return o;
+  };
+  const size_t C = static_cast<size_t>(R.chunk);
+  R.off_theta = take(C * 75 * sizeof(float));
+  R.off_vaa = take(C * vposer_tc_aux_floats() * sizeof(float));
+  R.off_verts = take(C * model->d.V * 3 * sizeof(float));
+  R.off_points = take(C * tasks->d.n * 3 * sizeof(float));
+  R.fwd_bytes = smplpp_forward_workspace_bytes(model, R.chunk);
+  R.off_fwd = take(R.fwd_bytes);
+  R.total = off;
+  return R;
+}
+} // namespace
+
+extern "C" size_t smplpp_ik_reproject_workspace_bytes(const smplpp_model_t * model, const smplpp_tasks_t * tasks, int64_t batch)
+{
+  if(!model || !tasks || batch < 1) return 0;
+  return reproj_layout(model, tasks, batch).total + 256;
+}
+
+extern "C" int smplpp_ik_reproject(const smplpp_model_t * model, const smplpp_vposer_t * vposer, const smplpp_tasks_t * tasks,
+                                   const smplpp_ik_options * opt, void * stream, int64_t batch, const float * theta_state,
+                                   const float * beta, int64_t beta_stride, float * vertex_weights, int32_t * face_idx,
+                                   const float * dphi, float * sq_dist, void * workspace, size_t workspace_bytes)
+{
+  if(!model || !tasks || !opt || batch < 1 || !theta_state || !beta || !vertex_weights || !face_idx)
+    return fail(SMPLPP_ERR_INVALID, "IkTask", "Failed to project points onto the mesh!");
+  if(opt->enable_vposer && !vposer) return fail(SMPLPP_ERR_INVALID, "VPoser", "VPoser decoder is required!");
+  const ReprojLayout R = reproj_layout(model, tasks, batch);
+  if(!workspace || workspace_bytes < R.total) return fail(SMPLPP_ERR_INVALID, "IkTask", "IK workspace too small!");
+  cudaStream_t st = as_stream(stream);
+  char * ws = align_up_ptr<char>(workspace);
+  const ModelDev & d = model->d;
+  const int n = tasks->d.n;
+  const int theta_dim = opt->enable_vposer ? 44 : 75;
+  float * theta = reinterpret_cast<float *>(ws + R.off_theta);
+  float * verts = reinterpret_cast<float *>(ws + R.off_verts);
+  float * points = reinterpret_cast<float *>(ws + R.off_points);
+  for(int64_t s = 0; s < batch; s += R.chunk)
+  {
+    const int B = static_cast<int>(std::min<int64_t>(R.chunk, batch - s));
+    const float * th = theta_state + s * theta_dim;
+    const float * theta75 = th;
+    if(opt->enable_vposer)
+    {
+      theta_assemble_kernel<<<(B * 12 + 127) / 128, 128, 0, st>>>(B, th, theta);
+      SB_LAUNCHED();
+      int rc = launch_vposer_decode(vposer, st, B, th + 6, 44, theta + 6, 75, nullptr, reinterpret_cast<float *>(ws + R.off_vaa));
+      if(rc != SMPLPP_OK) return rc;
+      theta75 = theta;
+    }
+    int rc = smplpp_forward(model, st, B, beta + s * beta_stride, beta_stride, theta75, verts, nullptr, nullptr, nullptr,
+                            ws + R.off_fwd, R.fwd_bytes);
+    if(rc != SMPLPP_OK) return rc;
+    const long long total = static_cast<long long>(B) * n;
+    task_positions_kernel<<<static_cast<unsigned>((total + 63) / 64), 64, 0, st>>>(
+        d.faces, d.adj_offset, d.adj_faces, d.V, B, n, nullptr, face_idx + s * n, verts, vertex_weights + s * n * 3,
+        opt->normal_offset, dphi ? dphi + s * n * 2 : nullptr, points, nullptr);
+    SB_LAUNCHED();
+    rc = smplpp_closest_points(model, st, B, n, verts, points, face_idx + s * n, nullptr, sq_dist ? sq_dist + s * n : nullptr,
+                               vertex_weights + s * n * 3);
+    if(rc != SMPLPP_OK) return rc;
+  }
+  return SMPLPP_OK;
+}
+
 extern "C" size_t smplpp_ik_shared_beta_workspace_bytes(const smplpp_tasks_t * tasks, const smplpp_ik_options * opt,
                                                         int64_t batch)
 {
@@ -2151,7 +2247,7 @@ extern "C" int smplpp_ik_shared_beta_reduce(const smplpp_model_t * model, const 
   const int n = L.n;
   const int npiv = L.D - L.beta_cols;
   const size_t P = static_cast<size_t>(npiv) * (npiv + 1) / 2 + static_cast<size_t>(L.beta_cols + 1) * npiv;
-  for(int64_t s = 0; s < batch && g_ik_variant == 0; s += L.chunk)
+  for(int64_t s = 0; s < batch && g_ik_variant == 2; s += L.chunk)
   {
     const int B = static_cast<int>(std::min<int64_t>(L.chunk, batch - s));
     Ik2Call c;
@@ -2169,7 +2265,7 @@ extern "C" int smplpp_ik_shared_beta_reduce(const smplpp_model_t * model, const 
     rc = launch_ik_fused(c);
     if(rc != SMPLPP_OK) return rc;
   }
-  for(int64_t s = 0; s < batch && g_ik_variant != 0; s += L.chunk)
+  for(int64_t s = 0; s < batch && g_ik_variant != 2; s += L.chunk)
   {
     const int B = static_cast<int>(std::min<int64_t>(L.chunk, batch - s));
     int rc = run_chunk(model, vposer, tasks, opt, L, st, B, const_cast<float *>(theta_state) + s * L.theta_dim,

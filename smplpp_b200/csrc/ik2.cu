@@ -49,7 +49,7 @@ struct Ik2Layout
   int theta, beta, coef, R, dR, Jt, G, tp, M, JS, dTg, dTp; // chain (floats)
   int A, bvec, misc;                                         // fp64: tiles, b, [esq, valid, bad, ok, ...]
   int rec;                                                   // the task's record (608 B)
-  int pv, pr, sw, xw, sj, Au, itemN, cornN, ts, Dref, C4, ybuf, live, Q, Jrow, Jc; // per-task scratch
+  int pv, pr, sw, xw, sj, Au, itemN, cornN, ts, Dref, C4, CA4, ybuf, live, Q, Jrow, Jc; // per-task scratch
   int sx, sg, sd, sstate;                                    // solve temporaries (alias the per-task scratch)
   int team_bytes;
   int ring_off, ring_slots, bar_off, total;
@@ -75,7 +75,7 @@ struct Ik2Params
   // problem
   int B, F;
   int use_ring, beta_cols, phi_cols, vposer, enable_qp, skip_if_too_few, update_state, update_weights, schur;
-  int theta_dim, thp, php, Dp, ldf, ld, nbt, dim_ref, opt_beta_ref;
+  int theta_dim, thp, php, Dp, ldf, ld, nbt, ntile, dim_ref;
   float normal_offset, normal_task_weight, reg_theta, reg_phi, reg_beta, phi_limit, beta_limit, latent_reg, hand_reg;
   // per-frame state
   const float * theta75;  // (B, 75) assembled theta (== theta_state when !vposer)
@@ -111,10 +111,13 @@ __device__ __forceinline__ int tile_idx(int bi, int bj) // bi >= bj
 {
   return bi * (bi + 1) / 2 + bj;
 }
-// element (i, j), i >= j, of the tiled lower triangle (4x4 tiles, row-major inside a tile)
-__device__ __forceinline__ double & Aat(double * A, int i, int j)
+// The lower triangle of A lives in shared memory as 4x4 tiles in ELEMENT-MAJOR order: element e = 4 r + c of tile t sits at
+// A[e * NT + t] (NT = number of tiles, odd).  Threads that own consecutive tiles then touch consecutive doubles; the
+// tile-major order (16 contiguous doubles per tile) put all 32 lanes of a warp on the same bank.
+// element (i, j), i >= j:
+__device__ __forceinline__ double & Aat(double * A, int NT, int i, int j)
 {
-  return A[tile_idx(i >> 2, j >> 2) * 16 + (i & 3) * 4 + (j & 3)];
+  return A[((i & 3) * 4 + (j & 3)) * NT + tile_idx(i >> 2, j >> 2)];
 }
 // u-th (row, column) of a lower triangle enumerated row by row
 __device__ __forceinline__ void tri_coords(int u, int & i, int & j)
@@ -128,19 +131,19 @@ __device__ __forceinline__ void tri_coords(int u, int & i, int & j)
 // Tiled right-looking Cholesky of the leading `npb` block pivots of the (nbt x nbt tiles) lower triangle, executed by one
 // team.  With npb < nbt the trailing tiles are left holding the Schur complement.  *ok = 0 on a non-positive pivot
 // (Eigen::LLT NumericalIssue, node.cpp:934-937).
-__device__ void team_cholesky(double * A, int nbt, int npb, int tt, int team, volatile int * ok)
+__device__ void team_cholesky(double * A, int NT, int nbt, int npb, int tt, int team, volatile int * ok)
 {
   for(int kb = 0; kb < npb; kb++)
   {
+    const int tkk = tile_idx(kb, kb);
     if(tt == 0)
     {
-      double * T = A + tile_idx(kb, kb) * 16;
       double l[4][4];
       bool good = true;
 #pragma unroll
       for(int j = 0; j < 4; j++)
       {
-        double d = T[j * 4 + j];
+        double d = A[(j * 4 + j) * NT + tkk];
 #pragma unroll
         for(int k = 0; k < 4; k++)
           if(k < j) d -= l[j][k] * l[j][k];
@@ -152,7 +155,7 @@ __device__ void team_cholesky(double * A, int nbt, int npb, int tt, int team, vo
         for(int i = 0; i < 4; i++)
           if(i > j)
           {
-            double s = T[i * 4 + j];
+            double s = A[(i * 4 + j) * NT + tkk];
 #pragma unroll
             for(int k = 0; k < 4; k++)
               if(k < j) s -= l[i][k] * l[j][k];
@@ -162,24 +165,28 @@ __device__ void team_cholesky(double * A, int nbt, int npb, int tt, int team, vo
 #pragma unroll
       for(int i = 0; i < 4; i++)
 #pragma unroll
-        for(int j = 0; j < 4; j++) T[i * 4 + j] = j <= i ? l[i][j] : 0.0;
+        for(int j = 0; j < 4; j++) A[(i * 4 + j) * NT + tkk] = j <= i ? l[i][j] : 0.0;
       if(!good) *ok = 0;
     }
     team_sync(team);
     if(!*ok) return;
     // panel: rows of the tiles below the pivot tile, X L_kk' = T  (one thread per row)
     {
-      const double * Lk = A + tile_idx(kb, kb) * 16;
-      const double l00 = Lk[0], l10 = Lk[4], l11 = Lk[5], l20 = Lk[8], l21 = Lk[9], l22 = Lk[10], l30 = Lk[12], l31 = Lk[13],
-                   l32 = Lk[14], l33 = Lk[15];
+      const double l00 = A[0 * NT + tkk], l10 = A[4 * NT + tkk], l11 = A[5 * NT + tkk], l20 = A[8 * NT + tkk],
+                   l21 = A[9 * NT + tkk], l22 = A[10 * NT + tkk], l30 = A[12 * NT + tkk], l31 = A[13 * NT + tkk],
+                   l32 = A[14 * NT + tkk], l33 = A[15 * NT + tkk];
+      const double i00 = 1.0 / l00, i11 = 1.0 / l11, i22 = 1.0 / l22, i33 = 1.0 / l33;
       for(int u = tt; u < 4 * (nbt - kb - 1); u += k2::TEAM)
       {
-        double * row = A + tile_idx(kb + 1 + (u >> 2), kb) * 16 + (u & 3) * 4;
-        const double x0 = row[0] / l00;
-        const double x1 = (row[1] - x0 * l10) / l11;
-        const double x2 = (row[2] - x0 * l20 - x1 * l21) / l22;
-        const double x3 = (row[3] - x0 * l30 - x1 * l31 - x2 * l32) / l33;
-        row[0] = x0, row[1] = x1, row[2] = x2, row[3] = x3;
+        // thread = (row of the tile, tile): consecutive threads take the same row of consecutive tiles
+        const int nt_below = nbt - kb - 1;
+        const int r = u / nt_below, ti = u - r * nt_below;
+        double * row = A + (r * 4) * NT + tile_idx(kb + 1 + ti, kb);
+        const double x0 = row[0] * i00;
+        const double x1 = (row[NT] - x0 * l10) * i11;
+        const double x2 = (row[2 * NT] - x0 * l20 - x1 * l21) * i22;
+        const double x3 = (row[3 * NT] - x0 * l30 - x1 * l31 - x2 * l32) * i33;
+        row[0] = x0, row[NT] = x1, row[2 * NT] = x2, row[3 * NT] = x3;
       }
     }
     team_sync(team);
@@ -192,21 +199,21 @@ __device__ void team_cholesky(double * A, int nbt, int npb, int tt, int team, vo
         int il, jl;
         tri_coords(u, il, jl);
         const int i = kb + 1 + il, j = kb + 1 + jl;
-        const double * Ti = A + tile_idx(i, kb) * 16;
-        const double * Tj = A + tile_idx(j, kb) * 16;
-        double * T = A + tile_idx(i, j) * 16;
+        const double * Ti = A + tile_idx(i, kb);
+        const double * Tj = A + tile_idx(j, kb);
+        double * T = A + tile_idx(i, j);
         double a[16], b[16];
 #pragma unroll
-        for(int e = 0; e < 16; e++) a[e] = Ti[e], b[e] = Tj[e];
+        for(int e = 0; e < 16; e++) a[e] = Ti[e * NT], b[e] = Tj[e * NT];
 #pragma unroll
         for(int r = 0; r < 4; r++)
 #pragma unroll
           for(int c = 0; c < 4; c++)
           {
-            double s = T[r * 4 + c];
+            double s = T[(r * 4 + c) * NT];
 #pragma unroll
             for(int k = 0; k < 4; k++) s = fma(-a[r * 4 + k], b[c * 4 + k], s);
-            T[r * 4 + c] = s;
+            T[(r * 4 + c) * NT] = s;
           }
       }
     }
@@ -215,24 +222,24 @@ __device__ void team_cholesky(double * A, int nbt, int npb, int tt, int team, vo
 }
 
 // x <- L^-T L^-1 x on the leading n x n block; executed by warp 0 of the team, result in x
-__device__ void warp_tiled_solve(double * A, int n, double * x, int tt)
+__device__ void warp_tiled_solve(double * A, int NT, int n, double * x, int tt)
 {
   if(tt < 32)
   {
     for(int k = 0; k < n; k++)
     {
-      const double xk = x[k] / Aat(A, k, k);
+      const double xk = x[k] / Aat(A, NT, k, k);
       __syncwarp();
       if(tt == 0) x[k] = xk;
-      for(int i = k + 1 + tt; i < n; i += 32) x[i] -= Aat(A, i, k) * xk;
+      for(int i = k + 1 + tt; i < n; i += 32) x[i] -= Aat(A, NT, i, k) * xk;
       __syncwarp();
     }
     for(int k = n - 1; k >= 0; k--)
     {
-      const double xk = x[k] / Aat(A, k, k);
+      const double xk = x[k] / Aat(A, NT, k, k);
       __syncwarp();
       if(tt == 0) x[k] = xk;
-      for(int i = tt; i < k; i += 32) x[i] -= Aat(A, k, i) * xk;
+      for(int i = tt; i < k; i += 32) x[i] -= Aat(A, NT, k, i) * xk;
       __syncwarp();
     }
   }
@@ -376,33 +383,38 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
       // ---- producer warp: basis rows of the pairs of task m -> ring, up to NBAR tasks / R slots ahead of the consumers ----
       if((tid & 31) == 0)
       {
+        // pair-granular: the byte count of a task is armed up front, its copies go out as ring slots come free, so the
+        // ring is always full and the next task's first rows are in flight while the current one is still being read
         int ring_pos = 0, free_slots = R, oldest = 0;
+        auto release_oldest = [&]() {
+          ptx::mbar_wait(bar_done + (oldest % NBAR), static_cast<uint32_t>((oldest / NBAR) & 1));
+          free_slots += p.use_ring ? p.recs[oldest].np : 3;
+          oldest++;
+        };
         for(int m = 0; m < n; m++)
         {
           const TaskRec * rec = p.recs + m;
           const int npe = p.use_ring ? rec->np : 3;
-          while(free_slots < npe || m - oldest >= NBAR)
-          {
-            ptx::mbar_wait(bar_done + (oldest % NBAR), static_cast<uint32_t>((oldest / NBAR) & 1));
-            free_slots += p.use_ring ? p.recs[oldest].np : 3;
-            oldest++;
-          }
+          while(m - oldest >= NBAR) release_oldest();
           uint64_t * full = bar_full + (m % NBAR);
           ptx::mbar_expect_tx(full, static_cast<uint32_t>(npe * PAIR_BYTES));
           for(int q = 0; q < npe; q++)
           {
-            const int slot = ring_pos + q < R ? ring_pos + q : ring_pos + q - R;
-            ptx::bulk_load_1d(ring + static_cast<size_t>(slot) * PAIR_BYTES,
+            while(free_slots < 1) release_oldest();
+            ptx::bulk_load_1d(ring + static_cast<size_t>(ring_pos) * PAIR_BYTES,
                               p.basis + static_cast<size_t>(rec->gv[q]) * (3 * kBlendK), PAIR_BYTES, full);
+            ring_pos = ring_pos + 1 < R ? ring_pos + 1 : 0;
+            free_slots--;
           }
-          ring_pos = ring_pos + npe < R ? ring_pos + npe : ring_pos + npe - R;
-          free_slots -= npe;
         }
       }
       return;
     }
   }
-  const int team = tid / TEAM, tt = tid % TEAM, tw = tt >> 5, lane = tt & 31;
+  // Roles inside a team are rotated by one warp per team: hardware warp w of every team sits on SM sub-partition w % 4,
+  // and the thin phases (one thread, three threads, one warp) would otherwise all land on sub-partition 0.
+  const int team = tid / TEAM;
+  const int tt = ((tid % TEAM) + 32 * team) % TEAM, tw = tt >> 5, lane = tt & 31;
   const long long f_raw = static_cast<long long>(blockIdx.x) * F + team;
   const bool live_frame = f_raw < p.B; // a padding team of the last CTA repeats the last frame and writes nothing
   const long long f = live_frame ? f_raw : p.B - 1;
@@ -422,7 +434,7 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
   double * s_A = reinterpret_cast<double *>(base + L.A);
   double * s_b = reinterpret_cast<double *>(base + L.bvec);
   double * s_misc = reinterpret_cast<double *>(base + L.misc); // [0] esq  [1] valid  [2] bad  [3] ok  [4] flag  [5] iter  [6] atmin
-  const TaskRec * s_rec = reinterpret_cast<const TaskRec *>(base + L.rec);
+  const int rec_bytes = (static_cast<int>(sizeof(TaskRec)) + 15) / 16 * 16;
   float * s_pv = reinterpret_cast<float *>(base + L.pv);
   float * s_pr = reinterpret_cast<float *>(base + L.pr);
   float * s_sw = reinterpret_cast<float *>(base + L.sw);
@@ -434,6 +446,7 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
   float * s_ts = reinterpret_cast<float *>(base + L.ts);
   float * s_Dref = reinterpret_cast<float *>(base + L.Dref);
   float * s_C4 = reinterpret_cast<float *>(base + L.C4);
+  float * s_CA4 = reinterpret_cast<float *>(base + L.CA4);
   float * s_y = reinterpret_cast<float *>(base + L.ybuf);
   uint8_t * s_live = reinterpret_cast<uint8_t *>(base + L.live);
   float * s_Q = reinterpret_cast<float *>(base + L.Q);
@@ -443,12 +456,12 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
   const int ldf = p.ldf, ld = p.ld;
   const int phi_off_f = 76;             // phi columns of the theta-space row
   const int beta_off_f = 76 + p.php;    // beta columns of the theta-space row
-  const int ntile_all = p.nbt * (p.nbt + 1) / 2;
+  const int NT = p.ntile; // tiles of the (augmented) lower triangle, padded to an odd count
 
   // ---- prologue: state, rotations and their derivatives, joints, chain ----
   for(int i = tt; i < 75; i += TEAM) s_theta[i] = p.theta75[static_cast<size_t>(f) * 75 + i];
   if(tt < kShapeDim) s_beta[tt] = p.beta[static_cast<size_t>(f) * p.beta_stride + tt];
-  for(int i = tt; i < ntile_all * 16; i += TEAM) s_A[i] = 0.0;
+  for(int i = tt; i < NT * 16; i += TEAM) s_A[i] = 0.0;
   for(int i = tt; i < p.Dp + 4; i += TEAM) s_b[i] = 0.0;
   team_sync(team);
   if(tt < kJoints)
@@ -470,7 +483,9 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
     }
   }
   team_sync(team);
-  // blend coefficients of the frame: pose feature vec(R_1..R_23) - vec(I) | beta | 1 (template) | 0
+  // blend coefficients of the frame: pose feature vec(R_1..R_23) - vec(I) | beta | 0 ...  The template column (217) is
+  // NOT part of the dot product: the ~1 m template is added last, to the fully reduced sum of the mm-sized blend terms
+  // (one rounding at the 1 m scale, as in the forward kernels; task normals amplify vertex noise by 1 / edge length)
   for(int i = tt; i < kBlendK; i += TEAM)
   {
     float v = 0.f;
@@ -481,8 +496,6 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
     }
     else if(i < kPoseDim + kShapeDim)
       v = s_beta[i - kPoseDim];
-    else if(i == kPoseDim + kShapeDim)
-      v = 1.f;
     s_coef[i] = v;
   }
   if(tt < 32)
@@ -595,16 +608,24 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
   const float * Jv = p.vposer ? p.vposer_jac + static_cast<size_t>(f) * 63 * 32 : nullptr;
   const TaskRec * grec = p.recs + static_cast<size_t>(f) * p.rec_stride;
 
+  // tiles of A = J'J owned by this thread (two at most are kept in registers; larger problems recompute the coordinates)
+  const int nb_acc = p.Dp >> 2;
+  const int ntiles_acc = nb_acc * (nb_acc + 1) / 2;
+  int my_bi[2] = {0, 0}, my_bj[2] = {0, 0};
+#pragma unroll
+  for(int s2 = 0; s2 < 2; s2++)
+    if(tt + s2 * TEAM < ntiles_acc) tri_coords(tt + s2 * TEAM, my_bi[s2], my_bj[s2]);
+
+  // the record of task m lives in buffer m & 1; the next one is fetched while the current task is being accumulated
+  if(tt < static_cast<int>(sizeof(TaskRec) / 16))
+    reinterpret_cast<uint4 *>(base + L.rec)[tt] = __ldg(reinterpret_cast<const uint4 *>(grec) + tt);
+  team_sync(team);
+
   for(int m = 0; m < n; m++)
   {
-    // ---- T0: the task's record, empty J rows ----
-    {
-      const uint4 * src = reinterpret_cast<const uint4 *>(grec + m);
-      uint4 * dst = reinterpret_cast<uint4 *>(base + L.rec);
-      if(tt < static_cast<int>(sizeof(TaskRec) / 16)) dst[tt] = __ldg(src + tt);
-      for(int i = tt; i < 4 * ldf; i += TEAM) s_Jrow[i] = 0.f;
-    }
-    team_sync(team);
+    const TaskRec * s_rec = reinterpret_cast<const TaskRec *>(base + L.rec + (m & 1) * rec_bytes);
+    // ---- empty J rows (the previous task's rows were consumed before its closing barrier) ----
+    for(int i = tt; i < 4 * ldf; i += TEAM) s_Jrow[i] = 0.f;
     const bool rec_ok = s_rec->face >= 0;
     const int npe = rec_ok ? (p.use_ring ? s_rec->np : 3) : 0;
     const int nie = rec_ok && p.use_ring ? s_rec->ni : 0;
@@ -613,7 +634,8 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
     const unsigned char * ring_base = nullptr;
     if(STAGED)
     {
-      ptx::mbar_wait(bar_full + (m % NBAR), static_cast<uint32_t>((m / NBAR) & 1));
+      if(lane == 0) ptx::mbar_wait(bar_full + (m % NBAR), static_cast<uint32_t>((m / NBAR) & 1));
+      __syncwarp();
       ring_base = ring;
     }
     for(int q = tw; q < npe; q += TEAM / 32)
@@ -643,58 +665,92 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
         ay += __shfl_xor_sync(0xffffffffu, ay, o);
         az += __shfl_xor_sync(0xffffffffu, az, o);
       }
-      if(lane == 0) s_pr[3 * q] = ax, s_pr[3 * q + 1] = ay, s_pr[3 * q + 2] = az;
+      if(lane == 0)
+      {
+        constexpr int kT = kPoseDim + kShapeDim; // template column
+        s_pr[3 * q] = ax + (STAGED ? P[kT] : __ldg(P + kT));
+        s_pr[3 * q + 1] = ay + (STAGED ? P[kBlendK + kT] : __ldg(P + kBlendK + kT));
+        s_pr[3 * q + 2] = az + (STAGED ? P[2 * kBlendK + kT] : __ldg(P + 2 * kBlendK + kT));
+      }
     }
     team_sync(team);
-    // ---- skinning: normalised weights, w_j x_uj (vertex carried by bone j, no root translation) ----
-    for(int i = tt; i < npe * kmax; i += TEAM)
-    {
-      const int q = i / kmax, sl = i - q * kmax;
-      const int gv = s_rec->gv[q];
-      const float wj = __ldg(p.lbs_weight + static_cast<size_t>(sl) * p.Vpad + gv) / __ldg(p.lbs_wsum + gv);
-      const int j = __ldg(p.lbs_joint + static_cast<size_t>(sl) * p.Vpad + gv);
-      s_sw[i] = wj;
-      s_sj[i] = static_cast<uint8_t>(j);
-      const float * G = s_G + 12 * j;
-      const f3 ru = ld3(s_pr + 3 * q);
-      s_xw[3 * i] = wj * (G[0] * ru.x + G[1] * ru.y + G[2] * ru.z + s_tp[3 * j]);
-      s_xw[3 * i + 1] = wj * (G[4] * ru.x + G[5] * ru.y + G[6] * ru.z + s_tp[3 * j + 1]);
-      s_xw[3 * i + 2] = wj * (G[8] * ru.x + G[9] * ru.y + G[10] * ru.z + s_tp[3 * j + 2]);
-    }
-    team_sync(team);
+    // ---- skinning, one thread per vertex: normalised weights, w_j x_uj (vertex carried by bone j, no root translation),
+    //      the posed vertex in the reference's order of operations (LinearBlendSkinning.cpp:445-483: M = sum_j W_j G'_j
+    //      with the raw weights, h = M [rest; 1], vertex = h / sum_j W_j + trans -- the task normals amplify any rounding
+    //      difference in the vertices by 1 / edge length) and A_u = sum_j w_j Rg_j (rotation part of the skinning matrix);
+    //      the last warp lists the live joints of the task (the joint must be an ancestor of a vertex of the task) ----
+    const uint32_t jm = rec_ok ? (p.use_ring ? s_rec->jmask : s_rec->jmask_corner) : 0u;
+    const int nlive = min(__popc(jm), ML);
+    if(tt >= 96 && tt - 96 < nlive) s_live[tt - 96] = static_cast<uint8_t>(__fns(jm, 0, tt - 96 + 1));
     if(tt < npe)
     {
-      // posed vertex = sum_j w_j x_uj + trans; A_u = sum_j w_j Rg_j (rotation part of the skinning matrix)
-      f3 v = trans;
+      const int gv = s_rec->gv[tt];
+      const float ws = __ldg(p.lbs_wsum + gv);
+      const f3 ru = ld3(s_pr + 3 * tt);
       float Au[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      float Mr[12] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       for(int sl = 0; sl < kmax; sl++)
       {
         const int i = tt * kmax + sl;
-        v = v + ld3(s_xw + 3 * i);
-        const float wj = s_sw[i];
-        const float * G = s_G + 12 * s_sj[i];
+        const float wr = __ldg(p.lbs_weight + static_cast<size_t>(sl) * p.Vpad + gv);
+        const int j = __ldg(p.lbs_joint + static_cast<size_t>(sl) * p.Vpad + gv);
+        const float wj = wr / ws;
+        s_sw[i] = wj;
+        s_sj[i] = static_cast<uint8_t>(j);
+        const float * G = s_G + 12 * j;
+        s_xw[3 * i] = wj * (G[0] * ru.x + G[1] * ru.y + G[2] * ru.z + s_tp[3 * j]);
+        s_xw[3 * i + 1] = wj * (G[4] * ru.x + G[5] * ru.y + G[6] * ru.z + s_tp[3 * j + 1]);
+        s_xw[3 * i + 2] = wj * (G[8] * ru.x + G[9] * ru.y + G[10] * ru.z + s_tp[3 * j + 2]);
 #pragma unroll
         for(int r = 0; r < 3; r++)
+        {
 #pragma unroll
-          for(int c = 0; c < 3; c++) Au[3 * r + c] = fmaf(wj, G[4 * r + c], Au[3 * r + c]);
+          for(int c = 0; c < 3; c++)
+          {
+            Au[3 * r + c] = fmaf(wj, G[4 * r + c], Au[3 * r + c]);
+            Mr[4 * r + c] = fmaf(wr, G[4 * r + c], Mr[4 * r + c]);
+          }
+          Mr[4 * r + 3] = fmaf(wr, s_tp[3 * j + r], Mr[4 * r + 3]);
+        }
       }
+      f3 v; // homo2cart divides (LinearBlendSkinning.cpp:538-553)
+      v.x = (Mr[0] * ru.x + Mr[1] * ru.y + Mr[2] * ru.z + Mr[3]) / ws + trans.x;
+      v.y = (Mr[4] * ru.x + Mr[5] * ru.y + Mr[6] * ru.z + Mr[7]) / ws + trans.y;
+      v.z = (Mr[8] * ru.x + Mr[9] * ru.y + Mr[10] * ru.z + Mr[11]) / ws + trans.z;
       s_pv[3 * tt] = v.x, s_pv[3 * tt + 1] = v.y, s_pv[3 * tt + 2] = v.z;
 #pragma unroll
       for(int e = 0; e < 9; e++) s_Au[9 * tt + e] = Au[e];
     }
     team_sync(team);
-    // ---- face normals of the ring items, vertex normals of the corners (SMPL::calcNormal / calcVertexNormal) ----
-    if(p.use_ring)
-    {
-      if(tt < nie)
+    // ---- y_uk = sum_{j in desc*(k)} w_j (x_uj - tg_k) for the live joints: warps 1..3, while warp 0 does the normals ----
+    if(tt >= 32)
+      for(int u = tt - 32; u < npe * nlive; u += TEAM - 32)
       {
-        const uint8_t * it = s_rec->item[tt];
+        const int q = u / nlive, li = u - q * nlive;
+        const int k = s_live[li];
+        const f3 tgk = mk3(s_G[12 * k + 3], s_G[12 * k + 7], s_G[12 * k + 11]);
+        f3 y = mk3(0.f, 0.f, 0.f);
+        for(int sl = 0; sl < kmax; sl++)
+        {
+          const int i = q * kmax + sl;
+          const float wj = s_sw[i];
+          if(wj != 0.f && ((p.anc_mask[s_sj[i]] >> k) & 1u)) y = y + (ld3(s_xw + 3 * i) - wj * tgk);
+        }
+        float * yo = s_y + 3 * (q * ML + li);
+        yo[0] = y.x, yo[1] = y.y, yo[2] = y.z;
+      }
+    // ---- face normals of the ring items, vertex normals of the corners (SMPL::calcNormal / calcVertexNormal) ----
+    if(p.use_ring && tt < 32)
+    {
+      for(int it0 = tt; it0 < nie; it0 += 32)
+      {
+        const uint8_t * it = s_rec->item[it0];
         const f3 v0 = ld3(s_pv + 3 * it[0]), v1 = ld3(s_pv + 3 * it[1]), v2 = ld3(s_pv + 3 * it[2]);
         float inv;
         const f3 nn = normalize_inv(cross3(v1 - v0, v2 - v0), inv);
-        s_itemN[4 * tt] = nn.x, s_itemN[4 * tt + 1] = nn.y, s_itemN[4 * tt + 2] = nn.z, s_itemN[4 * tt + 3] = inv;
+        s_itemN[4 * it0] = nn.x, s_itemN[4 * it0 + 1] = nn.y, s_itemN[4 * it0 + 2] = nn.z, s_itemN[4 * it0 + 3] = inv;
       }
-      team_sync(team);
+      __syncwarp(); // items, corners and the task are chained inside warp 0
       if(tt < 3 && rec_ok)
       {
         int s0 = 0;
@@ -707,7 +763,7 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
         const f3 nn = normalize_inv(q, inv);
         s_cornN[4 * tt] = nn.x, s_cornN[4 * tt + 1] = nn.y, s_cornN[4 * tt + 2] = nn.z, s_cornN[4 * tt + 3] = inv;
       }
-      team_sync(team);
+      __syncwarp();
     }
     // ---- the task: actual position, re-weighting (node.cpp:803-804), residual (:807-820), phi columns ----
     if(tt == 0)
@@ -838,37 +894,23 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
       }
       else
         C[9] = C[10] = C[11] = 0.f;
+      // CA4 = C4 . A_u (the pose-blend columns contract it with the basis rows)
+      const float * Au = s_Au + 9 * tt;
+      float * CA = s_CA4 + 12 * tt;
+#pragma unroll
+      for(int r = 0; r < 4; r++)
+#pragma unroll
+        for(int c = 0; c < 3; c++) CA[3 * r + c] = C[3 * r] * Au[c] + C[3 * r + 1] * Au[3 + c] + C[3 * r + 2] * Au[6 + c];
     }
-    // live joints of the task (the joint must be an ancestor of a vertex of the task)
-    const uint32_t jm = rec_ok ? (p.use_ring ? s_rec->jmask : s_rec->jmask_corner) : 0u;
-    const int nlive = min(__popc(jm), ML);
-    if(tt < nlive) s_live[tt] = static_cast<uint8_t>(__fns(jm, 0, tt + 1));
     team_sync(team);
-    // ---- translation columns; y_uk = sum_{j in desc*(k)} w_j (x_uj - tg_k) for the live joints ----
-    if(tt < 3 * ROWS)
+    // ---- translation columns (last warp); kinematic-chain columns: sum_u C4_u M_kc y_uk  (thread = (live joint, row)) ----
+    if(tt >= 96 && tt - 96 < 3 * ROWS)
     {
-      const int r = tt / 3, c = tt - 3 * r;
+      const int r = (tt - 96) / 3, c = (tt - 96) - 3 * r;
       float acc = 0.f;
       for(int q = 0; q < npe; q++) acc += s_C4[12 * q + 3 * r + c];
       s_Jrow[r * ldf + c] = acc;
     }
-    for(int u = tt; u < npe * nlive; u += TEAM)
-    {
-      const int q = u / nlive, li = u - q * nlive;
-      const int k = s_live[li];
-      const f3 tgk = mk3(s_G[12 * k + 3], s_G[12 * k + 7], s_G[12 * k + 11]);
-      f3 y = mk3(0.f, 0.f, 0.f);
-      for(int sl = 0; sl < kmax; sl++)
-      {
-        const int i = q * kmax + sl;
-        const float wj = s_sw[i];
-        if(wj != 0.f && ((p.anc_mask[s_sj[i]] >> k) & 1u)) y = y + (ld3(s_xw + 3 * i) - wj * tgk);
-      }
-      float * yo = s_y + 3 * (q * ML + li);
-      yo[0] = y.x, yo[1] = y.y, yo[2] = y.z;
-    }
-    team_sync(team);
-    // ---- kinematic-chain columns: sum_u C4_u M_kc y_uk  (thread = (live joint, row)) ----
     for(int u = tt; u < nlive * ROWS; u += TEAM)
     {
       const int li = u / ROWS, r = u - li * ROWS;
@@ -918,20 +960,6 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
       }
     }
     team_sync(team);
-    // ---- CA4 = C4 . A_u in place ----
-    if(tt < npe)
-    {
-      float * C = s_C4 + 12 * tt;
-      const float * Au = s_Au + 9 * tt;
-      float out[12];
-#pragma unroll
-      for(int r = 0; r < 4; r++)
-#pragma unroll
-        for(int c = 0; c < 3; c++) out[3 * r + c] = C[3 * r] * Au[c] + C[3 * r + 1] * Au[3 + c] + C[3 * r + 2] * Au[6 + c];
-#pragma unroll
-      for(int e = 0; e < 12; e++) C[e] = out[e];
-    }
-    team_sync(team);
     // ---- pose-blend (and shape-blend) columns, step 1: Q = sum_u CA4_u P_u (ROWS x 224); lane owns two columns ----
     {
       const int col = 2 * (32 * tw + lane);
@@ -958,7 +986,7 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
             py = __ldg(reinterpret_cast<const float2 *>(P + kBlendK));
             pz = __ldg(reinterpret_cast<const float2 *>(P + 2 * kBlendK));
           }
-          const float4 * C4 = reinterpret_cast<const float4 *>(s_C4 + 12 * q);
+          const float4 * C4 = reinterpret_cast<const float4 *>(s_CA4 + 12 * q);
           const float4 c0 = C4[0], c1 = C4[1], c2 = C4[2];
           const float C[12] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w};
 #pragma unroll
@@ -1047,17 +1075,16 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
         jo[u] = v;
       }
     }
-    // ---- A += J'J (fp64, 4x4 tiles of the lower triangle), b += J'e ----
+    // ---- A += J'J (fp64, 4x4 tiles of the lower triangle), b += J'e; next task's record ----
     {
-      const int nb = p.Dp >> 2;
-      const int ntiles = nb * (nb + 1) / 2;
-      for(int tl = tt; tl < ntiles; tl += TEAM)
-      {
-        int bi, bj;
-        tri_coords(tl, bi, bj);
+      if(m + 1 < n && tt < static_cast<int>(sizeof(TaskRec) / 16))
+        reinterpret_cast<uint4 *>(base + L.rec + ((m + 1) & 1) * rec_bytes)[tt] =
+            __ldg(reinterpret_cast<const uint4 *>(grec + m + 1) + tt);
+      auto accum_tile = [&](int tl, int bi, int bj) {
+        double * T = s_A + tl;
         double acc[16];
 #pragma unroll
-        for(int e = 0; e < 16; e++) acc[e] = 0.0;
+        for(int e = 0; e < 16; e++) acc[e] = T[e * NT];
 #pragma unroll
         for(int r = 0; r < ROWS; r++)
         {
@@ -1070,9 +1097,16 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
 #pragma unroll
             for(int b = 0; b < 4; b++) acc[4 * a + b] = fma(a4[a], b4[b], acc[4 * a + b]);
         }
-        double * T = s_A + tl * 16;
 #pragma unroll
-        for(int e = 0; e < 16; e++) T[e] += acc[e];
+        for(int e = 0; e < 16; e++) T[e * NT] = acc[e];
+      };
+      if(tt < ntiles_acc) accum_tile(tt, my_bi[0], my_bj[0]);
+      if(tt + TEAM < ntiles_acc) accum_tile(tt + TEAM, my_bi[1], my_bj[1]);
+      for(int tl = tt + 2 * TEAM; tl < ntiles_acc; tl += TEAM)
+      {
+        int bi, bj;
+        tri_coords(tl, bi, bj);
+        accum_tile(tl, bi, bj);
       }
       for(int c = tt; c < p.Dp; c += TEAM)
       {
@@ -1127,7 +1161,7 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
         s_b[i] += w * static_cast<double>(p.theta_state[static_cast<size_t>(f) * p.theta_dim + i]);
       }
     }
-    Aat(s_A, i, i) += add;
+    Aat(s_A, NT, i, i) += add;
   }
   team_sync(team);
   // compact position -> column of the reference layout [theta | phi (2n) | beta]
@@ -1151,7 +1185,7 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
         tri_coords(u, r, c);
         const int rr = ref_col(r), cc = ref_col(c);
         if(rr < 0 || cc < 0) continue;
-        const double v = Aat(s_A, r, c);
+        const double v = Aat(s_A, NT, r, c);
         Ao[rr * p.dim_ref + cc] = v;
         Ao[cc * p.dim_ref + rr] = v;
       }
@@ -1181,10 +1215,10 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
   {
     // ---- shared-beta stage: partial Cholesky with b appended as an extra row, so that the elimination also produces
     //      y0 = L^-1 b_f and r = b_beta - Y' y0 ----
-    for(int i = tt; i < Dp; i += TEAM) Aat(s_A, Dp, i) = s_b[i];
+    for(int i = tt; i < Dp; i += TEAM) Aat(s_A, NT, Dp, i) = s_b[i];
     team_sync(team);
     const int npiv = beta_off; // thp (phi is off in this stage)
-    team_cholesky(s_A, p.nbt, npiv >> 2, tt, team, s_ok);
+    team_cholesky(s_A, NT, p.nbt, npiv >> 2, tt, team, s_ok);
     const bool good = s_ok[0] && !bad && !too_few;
     if(live_frame)
     {
@@ -1197,10 +1231,10 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
           if(i < 100)
           {
             const int r = i / 10, c = i % 10;
-            v = r >= c ? Aat(s_A, beta_off + r, beta_off + c) : Aat(s_A, beta_off + c, beta_off + r);
+            v = r >= c ? Aat(s_A, NT, beta_off + r, beta_off + c) : Aat(s_A, NT, beta_off + c, beta_off + r);
           }
           else if(i < 110)
-            v = Aat(s_A, Dp, beta_off + (i - 100));
+            v = Aat(s_A, NT, Dp, beta_off + (i - 100));
           else
             v = esq;
         }
@@ -1216,12 +1250,12 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
       {
         int r, c;
         tri_coords(u, r, c);
-        fw[u] = Aat(s_A, r, c);
+        fw[u] = Aat(s_A, NT, r, c);
       }
       for(int u = tt; u < (p.beta_cols + 1) * td; u += TEAM)
       {
         const int r = u / td, c = u - r * td;
-        fw[nff + u] = r < p.beta_cols ? Aat(s_A, beta_off + r, c) : Aat(s_A, Dp, c);
+        fw[nff + u] = r < p.beta_cols ? Aat(s_A, NT, beta_off + r, c) : Aat(s_A, NT, Dp, c);
       }
       if(tt == 0) p.status[f] = too_few ? 1 : ((bad || !s_ok[0]) ? 2 : 0);
     }
@@ -1233,10 +1267,10 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
   int status = 0;
   if(!qp)
   {
-    team_cholesky(s_A, nb, nb, tt, team, s_ok);
+    team_cholesky(s_A, NT, nb, nb, tt, team, s_ok);
     for(int i = tt; i < Dp; i += TEAM) x[i] = -s_b[i];
     team_sync(team);
-    if(s_ok[0]) warp_tiled_solve(s_A, Dp, x, tt);
+    if(s_ok[0]) warp_tiled_solve(s_A, NT, Dp, x, tt);
     team_sync(team);
     if(!s_ok[0]) status = 2;
   }
@@ -1244,11 +1278,11 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
   {
     // primal active-set on min 1/2 x'Ax + b'x, lo <= x <= hi (same iteration as the oracle's solve_box_qp)
     const int ntiles = nb * (nb + 1) / 2;
-    double * A0 = p.a_ws + static_cast<size_t>(f_raw < p.B ? f_raw : 0) * ntiles * 16;
+    double * A0 = p.a_ws + static_cast<size_t>(f_raw < p.B ? f_raw : 0) * NT * 16;
     volatile int * s_iter = s_flag + 1;
     volatile int * s_atmin = s_flag + 2;
     if(live_frame)
-      for(int i = tt; i < ntiles * 16; i += TEAM) A0[i] = s_A[i];
+      for(int i = tt; i < NT * 16; i += TEAM) A0[i] = s_A[i];
     for(int i = tt; i < Dp; i += TEAM)
     {
       x[i] = 0.0;
@@ -1264,30 +1298,33 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
     };
     // a padding team has no A0 slot of its own: it re-reads the last frame's copy, which that frame's team may still be
     // writing - harmless, because nothing it computes is stored
-    const double * Aref = live_frame ? A0 : p.a_ws + static_cast<size_t>(p.B - 1) * ntiles * 16;
+    const double * Aref = live_frame ? A0 : p.a_ws + static_cast<size_t>(p.B - 1) * NT * 16;
     const int max_iter = 20 * Dp + 50;
     while(true)
     {
       for(int i = tt; i < Dp; i += TEAM)
       {
         double acc = s_b[i];
-        for(int k = 0; k < Dp; k++) acc = fma(i >= k ? Aref[tile_idx(i >> 2, k >> 2) * 16 + (i & 3) * 4 + (k & 3)]
-                                                     : Aref[tile_idx(k >> 2, i >> 2) * 16 + (k & 3) * 4 + (i & 3)],
+        for(int k = 0; k < Dp; k++) acc = fma(i >= k ? Aref[((i & 3) * 4 + (k & 3)) * NT + tile_idx(i >> 2, k >> 2)]
+                                                     : Aref[((k & 3) * 4 + (i & 3)) * NT + tile_idx(k >> 2, i >> 2)],
                                               x[k], acc);
         g[i] = acc;
       }
       // masked copy: fixed variables become identity rows / columns
-      for(int u = tt; u < ntiles * 16; u += TEAM)
+      for(int tl = tt; tl < ntiles; tl += TEAM)
       {
-        const int tl = u >> 4, e = u & 15;
         int bi, bj;
         tri_coords(tl, bi, bj);
-        const int r = 4 * bi + (e >> 2), c = 4 * bj + (e & 3);
-        const bool fixed = state[r] != 0 || state[c] != 0;
-        s_A[u] = fixed ? (r == c ? 1.0 : 0.0) : Aref[u];
+#pragma unroll
+        for(int e = 0; e < 16; e++)
+        {
+          const int r = 4 * bi + (e >> 2), c = 4 * bj + (e & 3);
+          const bool fixed = state[r] != 0 || state[c] != 0;
+          s_A[e * NT + tl] = fixed ? (r == c ? 1.0 : 0.0) : Aref[e * NT + tl];
+        }
       }
       team_sync(team);
-      team_cholesky(s_A, nb, nb, tt, team, s_ok);
+      team_cholesky(s_A, NT, nb, nb, tt, team, s_ok);
       if(!s_ok[0])
       {
         status = 2;
@@ -1295,7 +1332,7 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
       }
       for(int i = tt; i < Dp; i += TEAM) dstep[i] = state[i] != 0 ? 0.0 : -g[i];
       team_sync(team);
-      warp_tiled_solve(s_A, Dp, dstep, tt);
+      warp_tiled_solve(s_A, NT, Dp, dstep, tt);
       team_sync(team);
       if(tt == 0)
       {
@@ -1490,19 +1527,22 @@ bool plan_smem(Ik2Params & p, int rows, bool staged, int want_slots)
   L.G = takef(288), L.tp = takef(72), L.M = takef(648);
   L.JS = L.dTg = L.dTp = 0;
   if(p.beta_cols) L.JS = takef(720), L.dTg = takef(720), L.dTp = takef(720);
-  const int ntile_all = p.nbt * (p.nbt + 1) / 2;
-  L.A = off, off += ntile_all * 16 * 8;
+  p.ntile = (p.nbt * (p.nbt + 1) / 2) | 1; // odd: the 16 element planes of the tile storage start on different banks
+  L.A = off, off += p.ntile * 16 * 8;
   L.bvec = off, off += up16((p.Dp + 4) * 8);
   L.misc = off, off += 128;
   const int scratch0 = off;
-  L.rec = off, off += up16(static_cast<int>(sizeof(TaskRec)));
+  L.rec = off, off += 2 * up16(static_cast<int>(sizeof(TaskRec)));
   const int MP = p.MP, MI = p.MI, ML = p.ML, kmax = p.kmax;
   L.pv = takef(3 * MP), L.pr = takef(3 * MP), L.sw = takef(MP * kmax), L.xw = takef(3 * MP * kmax);
   L.sj = off, off += up16(MP * kmax);
   L.Au = takef(9 * MP), L.itemN = takef(4 * std::max(MI, 1)), L.cornN = takef(12), L.ts = takef(16);
-  L.Dref = takef(27 * std::max(MI, 1)), L.C4 = takef(12 * MP), L.ybuf = takef(3 * MP * ML);
+  // d(normal)/d(vertex) contributions and Q are live in disjoint phases of a task
+  L.Dref = L.Q = takef(std::max(27 * std::max(MI, 1), rows * kBlendK));
+  L.ybuf = takef(3 * MP * ML);
+  L.C4 = takef(12 * MP), L.CA4 = takef(12 * MP);
   L.live = off, off += up16(ML);
-  L.Q = takef(rows * kBlendK), L.Jrow = takef(4 * p.ldf);
+  L.Jrow = takef(4 * p.ldf);
   L.Jc = p.vposer ? takef(4 * p.ld) : L.Jrow;
   // solve temporaries alias the per-task scratch
   int so = scratch0;
@@ -1545,7 +1585,7 @@ size_t ik2_rec_bytes(int64_t batch, int n)
 size_t ik2_qp_ws_doubles(const Ik2Dims & d)
 {
   const int nb = d.Dp / 4;
-  return static_cast<size_t>(nb) * (nb + 1) / 2 * 16;
+  return static_cast<size_t>((nb * (nb + 1) / 2) | 1) * 16;
 }
 
 Ik2Dims ik2_dims(int n, bool vposer, bool phi, bool beta)

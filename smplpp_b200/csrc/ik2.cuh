@@ -51,5 +51,5 @@ int launch_ik_fused(const Ik2Call & c);
 int build_task_rec_host(const smplpp_model * model, int64_t face, TaskRec & rec);
 // (total) records from per-frame face indices on the device (total = frames * tasks)
 int launch_task_topo(const ModelDev & d, cudaStream_t st, long long total, const int32_t * face_idx, TaskRec * out);
-extern int g_ik_variant; // 0: fused kernel (default), 1: two-kernel predecessor (ik_jacobian_kernel + ik_solve_kernel)
+extern int g_ik_variant; // 0: auto (two kernels when the frames share the attachments, fused kernel otherwise), 1: two kernels, 2: fused
 } // namespace sb

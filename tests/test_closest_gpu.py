@@ -123,10 +123,11 @@ def test_reproject_vs_oracle(smpl_gpu, oracle_model, marker_tasks, params, vpose
     phi = (rng.uniform(-0.01, 0.01, (B, n, 2)).astype(np.float32)) if with_phi else None
     w = torch.as_tensor(np.repeat(vw[None], B, axis=0), device="cuda:0").contiguous()
     state = torch.as_tensor(theta.reshape(B, 75), device="cuda:0").contiguous()
-    w_before = w.clone()
-    face, wn, same = tasks.reproject(state, torch.as_tensor(beta_shared, device="cuda:0"), w, 0.015,
-                                     phi=None if phi is None else torch.as_tensor(phi, device="cuda:0"))
-    face, wn, same = face.cpu().numpy(), wn.cpu().numpy(), same.cpu().numpy()
+    fidx = torch.as_tensor(np.repeat(face_idx[None].astype(np.int32), B, axis=0), device="cuda:0").contiguous()
+    opt = api.ik_options(normal_offset=0.015)
+    tasks.reproject(opt, state, torch.as_tensor(beta_shared, device="cuda:0"), w, fidx,
+                    dphi=None if phi is None else torch.as_tensor(phi, device="cuda:0"))
+    face, wn = fidx.cpu().numpy(), w.cpu().numpy()
     agree = 0
     with torch.no_grad():
         r = so.smpl_launch(oracle_model, torch.as_tensor(np.repeat(beta_shared[None], B, 0)), torch.as_tensor(theta))
@@ -148,8 +149,6 @@ def test_reproject_vs_oracle(smpl_gpu, oracle_model, marker_tasks, params, vpose
                     # weights are 1 / edge-length conditioned: compare the point they reproduce
                     got = (wn[b, m][:, None] * v64[faces0[face[b, m]]]).sum(0)
                     assert np.abs(got - o_closest[m]).max() < 1e-5
-                assert same[b, m] == (face[b, m] == face_idx[m])
     assert agree >= 0.95 * B * n
-    # applied in place exactly where the face did not change
-    w_after = w.cpu().numpy()
-    assert np.array_equal(w_after[same], wn[same]) and np.array_equal(w_after[~same], w_before.cpu().numpy()[~same])
+    # on this mesh the 15 mm offset point often lands on another face: the re-seating must actually move attachments
+    assert (face != face_idx[None]).any()

@@ -55,29 +55,75 @@ def run_trajectory(task_set, opt, x0, beta, vw0, target, valid, iters):
     return np.stack(res, 1), np.stack(traj, 1), vw.cpu().numpy()
 
 
-def test_config3_motion_30_iterations(task_set, gc):
-    """BASELINE configs[2]: residual of every frame at every iteration within 1e-4 m of the compiled reference's."""
+def teacher_forced(task_set, opt, gc, prefix, theta_dim):
+    """Every (frame, iteration) of the golden trajectory as ONE batch element: iteration k starts from the compiled
+    reference's own state after iteration k-1, so each step is an independent parity check along the real trajectory."""
+    th, vw, res = gc[prefix + "_theta_traj"], gc[prefix + "_vertex_weights_traj"], gc[prefix + "_residual"]
+    F, K = res.shape
+    n = vw.shape[2]
+    th_in = np.concatenate([np.repeat(gc[prefix + "_theta_in"][None, None], F, axis=0), th[:, :-1]], axis=1)
+    vw_in = np.concatenate([np.repeat(gc["vertex_weights_in"][None, None], F, axis=0), vw[:, :-1]], axis=1)
+    theta, w = cu(th_in.reshape(F * K, theta_dim)), cu(vw_in.reshape(F * K, n, 3))
+    tgt = cu(np.repeat(gc[prefix + "_target"][:, None], K, axis=1).reshape(F * K, n, 3))
+    valid = np.repeat(gc[prefix + "_valid"][:, None], K, axis=1).reshape(F * K, n)
+    status, out = task_set.step(opt, theta, cu(gc["beta"]), w, tgt, pos_task_weight=cu(valid), outputs=True)
+    assert (status == 0).all()
+    r = marker_residual(out["e"].cpu().numpy(), valid).reshape(F, K)
+    return r, theta.cpu().numpy().reshape(F, K, theta_dim), w.cpu().numpy().reshape(F, K, n, 3)
+
+
+def test_config3_every_iteration_vs_reference(task_set, gc):
+    """BASELINE configs[2], 8 frames x 30 iterations of the compiled reference, teacher-forced: the residual of every
+    (frame, iteration) within 1e-5 m, the updated theta and re-weighted attachments of every step."""
+    from smplpp_b200 import api
+    res, th, vw = teacher_forced(task_set, api.ik_options(**MOTION), gc, "c3", 75)
+    assert np.abs(res - gc["c3_residual"]).max() < 1e-5
+    assert np.abs(th - gc["c3_theta_traj"]).max() < 3e-4
+    assert np.abs(vw - gc["c3_vertex_weights_traj"]).max() < 2e-4
+
+
+def test_config3_free_running_30_iterations(task_set, gc):
+    """The same 30 iterations free-running on the GPU.  The iteration is not contractive along weakly observed joints
+    (damping 1e-3 only): two runs of the COMPILED REFERENCE that differ only in the libtorch thread count drift apart by
+    up to `band` (2e-4 m of residual, 0.08 rad; golden c3_alt_*).  The GPU run must stay inside that band, reach the
+    reference's converged residual within 1e-4 m, and track it to 1e-5 m while the trajectories still coincide."""
     from smplpp_b200 import api
     opt = api.ik_options(**MOTION)
+    K = gc["c3_residual"].shape[1]
     res, traj, vw = run_trajectory(task_set, opt, gc["c3_theta_in"], gc["beta"], gc["vertex_weights_in"], gc["c3_target"],
-                                   gc["c3_valid"], gc["c3_residual"].shape[1])
-    assert np.abs(res - gc["c3_residual"]).max() < TOL_RESIDUAL_M
-    # the state itself: identical arithmetic up to fp32 rounding, amplified by 30 Gauss-Newton steps
+                                   gc["c3_valid"], K)
+    alt = gc["c3_alt_frames"]
+    band = np.abs(gc["c3_alt_residual"] - gc["c3_residual"][alt]).max()
+    dev = np.abs(res - gc["c3_residual"])
+    print("free-running residual deviation %.2e m (reference vs itself: %.2e m)" % (dev.max(), band))
+    assert dev[:, :3].max() < 1e-5
+    assert dev.max() < max(TOL_RESIDUAL_M, 1.5 * band)
+    assert dev[:, -1].max() < TOL_RESIDUAL_M                      # converged marker residual within 1e-4 m
     assert np.abs(traj[:, 0] - gc["c3_theta_traj"][:, 0]).max() < 2e-4
-    assert np.abs(traj[:, -1] - gc["c3_theta_traj"][:, -1]).max() < 5e-3
-    assert np.abs(vw - gc["c3_vertex_weights_out"]).max() < 5e-3
     assert res[:, -1].max() < 0.25 * res[:, 0].min()
 
 
-def test_config4_vposer_10_iterations(task_set, gc):
-    """BASELINE configs[3] (per-frame part): VPoser latent state, decoder + its Jacobian inside the step."""
+def test_config4_vposer_every_iteration_vs_reference(task_set, gc):
+    """BASELINE configs[3] (per-frame part), 4 frames x 10 iterations, teacher-forced: VPoser latent state, decoder and
+    its Jacobian inside the step."""
+    from smplpp_b200 import api
+    res, th, vw = teacher_forced(task_set, api.ik_options(enable_vposer=1, **MOTION), gc, "c4", 44)
+    assert np.abs(res - gc["c4_residual"]).max() < 2e-5
+    assert np.abs(th - gc["c4_theta_traj"]).max() < 1e-3
+    assert np.abs(vw - gc["c4_vertex_weights_traj"]).max() < 5e-4
+
+
+def test_config4_vposer_free_running(task_set, gc):
     from smplpp_b200 import api
     opt = api.ik_options(enable_vposer=1, **MOTION)
+    K = gc["c4_residual"].shape[1]
     res, traj, _ = run_trajectory(task_set, opt, gc["c4_theta_in"], gc["beta"], gc["vertex_weights_in"], gc["c4_target"],
-                                  gc["c4_valid"], gc["c4_residual"].shape[1])
-    assert np.abs(res - gc["c4_residual"]).max() < TOL_RESIDUAL_M
+                                  gc["c4_valid"], K)
+    dev = np.abs(res - gc["c4_residual"])
+    print("VPoser free-running residual deviation %.2e m" % dev.max())
+    assert dev[:, :3].max() < 2e-5
+    assert dev.max() < 1e-3
     assert np.abs(traj[:, 0] - gc["c4_theta_traj"][:, 0]).max() < 5e-4
-    assert np.abs(traj[:, -1] - gc["c4_theta_traj"][:, -1]).max() < 2e-2
 
 
 def test_solve_host_equals_device_loop(task_set, gc):
@@ -192,3 +238,77 @@ def test_even_task_vertex_count_vs_oracle(smpl_gpu, oracle_model, marker_tasks):
     J = out["J"][0].cpu().numpy()
     assert np.abs(J - r.J).max() / np.abs(r.J).max() < 1e-4
     assert np.abs(theta[0].cpu().numpy() - r.theta_state).max() < 2e-4
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# body stage (node.cpp:652-656, 695-700, 1349): 51 iterations of ONE frame, VPoser state, beta and phi from iteration 25,
+# the attachment re-seated after every iteration (faces change on this mesh in almost every iteration)
+# ----------------------------------------------------------------------------------------------------------------
+def body_options(api, late):
+    return api.ik_options(enable_vposer=1, skip_if_too_few=0, normal_task_weight=0.0, normal_offset=0.015,
+                          phi_limit=0.04 if late else 0.0, enable_phi=1 if late else 0, optimize_beta=1 if late else 0, enable_qp=1)
+
+
+def test_body_stage_every_iteration_vs_reference(task_set, gc, smpl_gpu):
+    """Teacher-forced: iteration k starts from the compiled reference's state after iteration k-1 (theta, beta, faces,
+    weights), so each of the 51 iterations is an independent parity check of the COMPLETE loop body - step on per-frame
+    attachments, projection onto the pre-update mesh, re-seated faces and weights - including all the face changes."""
+    from smplpp_b200 import api
+    n = task_set.n
+    K = gc["body_theta"].shape[0]
+    th_in = np.concatenate([gc["body_theta_in"][None], gc["body_theta"][:-1]]).astype(f32)
+    be_in = np.concatenate([np.zeros((1, 10), f32), gc["body_beta"][:-1]]).astype(f32)
+    fa_in = np.concatenate([gc["face_idx"][None], gc["body_face"][:-1]]).astype(np.int32)
+    vw_in = np.concatenate([np.full((1, n, 3), 1.0 / 3.0, f32), gc["body_vw"][:-1]]).astype(f32)
+    changed = 0
+    for lo, hi, late in ((0, 25, False), (25, K, True)):
+        B = hi - lo
+        opt = body_options(api, late)
+        theta, beta = cu(th_in[lo:hi]), cu(be_in[lo:hi])
+        vw, face = cu(vw_in[lo:hi]), cu(fa_in[lo:hi], torch.int32)
+        tgt = cu(np.repeat(gc["body_target"][None], B, axis=0))
+        status, out = task_set.iterate(opt, theta, beta, vw, face, tgt, outputs=True)
+        assert (status == 0).all()
+        res = marker_residual(out["e"].cpu().numpy(), np.ones((B, n), f32))
+        assert np.abs(res - gc["body_res"][lo:hi]).max() < 1e-5          # same state in, same residual
+        assert np.abs(theta.cpu().numpy() - gc["body_theta"][lo:hi]).max() < 5e-4
+        assert np.abs(beta.cpu().numpy() - gc["body_beta"][lo:hi]).max() < 5e-4
+        # re-seated attachment: same face (ties between neighbouring faces aside) and the same point on the mesh
+        f_gpu, f_ref = face.cpu().numpy(), gc["body_face"][lo:hi]
+        agree = f_gpu == f_ref
+        assert agree.mean() >= 0.97
+        changed += int((f_ref != fa_in[lo:hi]).sum())
+        # the point the weights reproduce on the pre-update mesh against the reference's closest point
+        smpl_gpu.launch(be_in[lo:hi], task_set.assemble_theta(cu(th_in[lo:hi])))
+        verts = smpl_gpu.getVertex().cpu().numpy().astype(np.float64)
+        faces0 = smpl_gpu._faces_host.astype(np.int64) - 1
+        tri = verts[np.arange(B)[:, None, None], faces0[f_gpu]]           # (B, n, 3, 3)
+        pt = (vw.cpu().numpy()[..., None].astype(np.float64) * tri).sum(2)
+        assert np.abs(pt - gc["body_closest"][lo:hi]).max() < 2e-5
+        assert np.abs(vw.cpu().numpy()[agree] - gc["body_vw"][lo:hi][agree]).max() < 2e-3
+    assert changed > 200  # the golden trajectory really exercises re-seated faces
+
+
+def test_body_stage_free_running(task_set, gc):
+    """The same 51 iterations free-running on the GPU: beta and phi switch on at iteration 25, attachments wander over
+    the mesh; the residual trajectory stays with the compiled reference's (a face tie resolved differently moves the
+    two trajectories apart by less than a millimetre of residual)."""
+    from smplpp_b200 import api
+    n = task_set.n
+    K = gc["body_theta"].shape[0]
+    theta, beta = cu(gc["body_theta_in"][None]), cu(np.zeros((1, 10), f32))
+    vw, face = cu(np.full((1, n, 3), 1.0 / 3.0, f32)), cu(gc["face_idx"][None], torch.int32)
+    tgt = cu(gc["body_target"][None])
+    res = []
+    for k in range(K):
+        status, out = task_set.iterate(body_options(api, k >= 25), theta, beta, vw, face, tgt, outputs=True)
+        assert int(status[0]) == 0
+        res.append(marker_residual(out["e"].cpu().numpy(), np.ones((1, n), f32))[0])
+    res = np.asarray(res)
+    print("body stage residual: gpu %.5f -> %.5f m, reference %.5f -> %.5f m, max deviation %.2e m, faces equal at the end: %d / %d"
+          % (res[0], res[-1], gc["body_res"][0], gc["body_res"][-1], np.abs(res - gc["body_res"]).max(),
+             int((face.cpu().numpy()[0] == gc["body_face"][-1]).sum()), n))
+    assert np.abs(res[:25] - gc["body_res"][:25]).max() < 2e-3
+    assert abs(res[-1] - gc["body_res"][-1]) < 5e-3
+    assert res[-1] < 0.5 * res[0]
+    assert np.abs(beta.cpu().numpy()[0] - gc["body_beta"][-1]).max() < 0.1

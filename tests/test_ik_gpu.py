@@ -87,7 +87,11 @@ def test_ik_step_vs_reference_golden(task_set, golden_ik, mode):
     e, J = out["e"][0].cpu().numpy(), out["J"][0].cpu().numpy()
     Jref = g[mode + "_J"]
     assert np.abs(e - g[mode + "_e"]).max() < (2e-5 if mode == "interactive" else TOL_VERTEX_M)
-    assert np.abs(J - Jref).max() / np.abs(Jref).max() <= TOL_JACOBIAN_REL
+    rows = np.arange(J.shape[0])
+    err_pos = np.abs(J - Jref)[rows % 4 != 3].max() / np.abs(Jref).max()
+    err_nrm = np.abs(J - Jref)[rows % 4 == 3].max() / np.abs(Jref).max()
+    print("%s: Jacobian relative error, position rows %.3g, normal rows %.3g" % (mode, err_pos, err_nrm))
+    assert np.abs(J - Jref).max() / np.abs(Jref).max() <= TOL_JACOBIAN_REL, (err_pos, err_nrm)
     # per-block relative error too (theta / phi / beta columns have different scales)
     for lo, hi in ((0, 3), (3, 75), (75, 75 + 2 * n), (75 + 2 * n, J.shape[1])):
         if hi > lo and np.abs(Jref[:, lo:hi]).max() > 0:
