@@ -71,8 +71,18 @@ def test_triangle_vertex_weights_property():
     assert np.abs(np.einsum("ni,nik->nk", got, tri) - pos).max() < 1e-3
 
 
+@pytest.fixture(params=[401, 402], ids=["two_kernels", "fused_kernel"])
+def ik_variant(request):
+    """Both implementations of the step on a shared attachment topology: ik_jacobian_kernel + ik_solve_kernel (the
+    default there) and the fused kernel (the only one for per-frame attachments)."""
+    from smplpp_b200 import capi
+    capi.check(capi.lib().smplpp_set_forward_variant(request.param))
+    yield request.param
+    capi.check(capi.lib().smplpp_set_forward_variant(400))
+
+
 @pytest.mark.parametrize("mode", list(MODES))
-def test_ik_step_vs_reference_golden(task_set, golden_ik, mode):
+def test_ik_step_vs_reference_golden(task_set, golden_ik, mode, ik_variant):
     from smplpp_b200 import api
     g = golden_ik
     n = task_set.n
@@ -113,7 +123,7 @@ def test_ik_step_vs_reference_golden(task_set, golden_ik, mode):
     assert np.abs(A - A_chk).max() < 1e-9 * max(1.0, np.abs(A_chk).max())
 
 
-def test_ik_step_vposer_vs_reference_golden(task_set, golden_ik):
+def test_ik_step_vposer_vs_reference_golden(task_set, golden_ik, ik_variant):
     from smplpp_b200 import api
     g = golden_ik
     n = task_set.n
@@ -183,7 +193,7 @@ def test_ik_skip_and_missing_markers(task_set, marker_tasks, smpl_gpu):
     assert not np.array_equal(theta[0].cpu().numpy(), x0[0])
 
 
-def test_shared_beta_single_frame_equals_joint_qp(task_set, oracle_model, marker_tasks, golden_ik):
+def test_shared_beta_single_frame_equals_joint_qp(task_set, oracle_model, marker_tasks, golden_ik, ik_variant):
     """With ONE frame the shared-beta stage (Schur complement + 10-dim box QP + back-substitution) must equal
     the reference's joint QP over [theta | beta] with |dbeta| <= 0.5 (phi pinned)."""
     from oracle import smpl_oracle as so
@@ -205,7 +215,7 @@ def test_shared_beta_single_frame_equals_joint_qp(task_set, oracle_model, marker
     assert np.abs(theta[0].cpu().numpy() - r.theta_state).max() < 2e-4
 
 
-def test_shared_beta_many_frames_kkt(task_set, marker_tasks, smpl_gpu):
+def test_shared_beta_many_frames_kkt(task_set, marker_tasks, smpl_gpu, ik_variant):
     """Many frames: the reduced 111 doubles are a deterministic sum, the solve satisfies the box-QP KKT
     conditions, and two identical runs agree bitwise."""
     from smplpp_b200 import api, synth
