@@ -309,6 +309,12 @@ int smplpp_ik_solve_host(const smplpp_model_t * model, const smplpp_vposer_t * v
                          const float * target_pos_host, const float * pos_task_weight_host, int32_t * status_host,
                          float * residual_host);
 
+/* IkTask::calcTangents (src/IkTask.cpp:33-47) batched: vertices (B,V,3) -> tangents (B,n,3,2) like IkTask::tangents_
+ * (column 0 = normalize(v1 - v0), column 1 = normalize(normal x (v1 - v0))); face_idx_dev (B,n) int32 nullable = the
+ * faces of the task set */
+int smplpp_task_tangents(const smplpp_model_t * model, const smplpp_tasks_t * tasks, void * stream, int64_t batch,
+                         const float * vertices_dev, const int32_t * face_idx_dev, float * tangents_dev);
+
 /* Shared-beta stage (MoSh++ shape estimation over many frames).  Frames couple only through the
  * 10 shape unknowns, so the step is split around ONE all-reduce of 111 doubles:
  *   (1) smplpp_ik_shared_beta_reduce: per-frame normal equations with the beta columns, Schur complement
@@ -330,6 +336,56 @@ int smplpp_ik_shared_beta_apply(const smplpp_tasks_t * tasks, const smplpp_ik_op
                                 int64_t batch, float * theta_state_dev, float * shared_beta_dev,
                                 const int32_t * status_dev, const double * reduced_dev, void * workspace_dev,
                                 size_t workspace_bytes);
+
+/* The three calls above as ONE, with the collective inside (smplpp_shared_beta_step(..., ncclComm_t)):
+ * reduce -> ncclAllReduce(sum) of the 111 doubles on `stream` over `nccl_comm` (an ncclComm_t passed as void*; NULL on a
+ * single GPU) -> apply.  reduced_dev (111 doubles) is caller-owned scratch that also returns the summed message.  NCCL is
+ * resolved at run time (the process's own ncclAllReduce when a framework loaded it, else libnccl.so.2, or the library
+ * named by SMPLPP_NCCL_LIB): libsmplpp_b200.so itself links only the CUDA runtime. */
+int smplpp_ik_shared_beta_step(const smplpp_model_t * model, const smplpp_vposer_t * vposer, const smplpp_tasks_t * tasks,
+                               const smplpp_ik_options * opt, void * stream, int64_t batch, float * theta_state_dev,
+                               float * shared_beta_dev, float * vertex_weights_dev, const float * target_pos_dev,
+                               const float * pos_task_weight_dev, int32_t * status_dev, double * reduced_dev,
+                               void * nccl_comm, void * workspace_dev, size_t workspace_bytes);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * The motion stage of the mocap mode as one call (node/node.cpp:509-535 MocapBody.yaml, :571-595 label matching,
+ * :667-691 targets, :785 skip rule, :1369-1407 loop, scripts/convertRosbagToText.py motion text).
+ * The reference walks the frames serially with ONE iteration per frame, warm-started from the previous frame after 31
+ * warm-up iterations on the first frame.  Here all frames are solved at once: `warmup_iterations` on the first frame of
+ * the range give the common start (state, attachments), then every frame gets `iterations` steps; with reproject != 0
+ * every step is the full loop body (projection onto the pre-update mesh, faces / weights re-seated per frame).
+ *   opt                  enable_vposer, regularisation, normal_offset ...; the motion-stage settings (phi pinned, fixed
+ *                        beta) are forced as the node does (node.cpp:558-560, 699)
+ *   initial_state_host   (theta_dim) g_theta at start (node.cpp:377-410)
+ *   first_frame, frame_count  range of C3D frames (frame_count 0 = to the end)
+ *   theta75_out_host     (frames, 75)  theta of every frame, VPoser states decoded (node.cpp:1374-1391); nullable
+ *   status_out_host      (frames)      0 solved, 1 skipped (fewer than half of the markers), 2 / 3 numerical; nullable
+ *   residual_out_host    (frames)      mean |e_m| over the valid markers at the last linearisation point; nullable
+ *   motion_text_path     nullable: 75 values per line and frame
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct smplpp_mocap_summary
+{
+  int64_t frames, markers, solved, skipped, failed;
+  double mean_residual, max_residual; /* over the solved frames, metres */
+} smplpp_mocap_summary;
+
+int smplpp_solve_mocap_motion(const smplpp_model_t * model, const smplpp_vposer_t * vposer, const char * c3d_path,
+                              const char * mocap_body_yaml_path, const smplpp_ik_options * opt, int32_t warmup_iterations,
+                              int32_t iterations, int32_t reproject, const float * initial_state_host, int64_t first_frame,
+                              int64_t frame_count, float * theta75_out_host, int32_t * status_out_host,
+                              float * residual_out_host, const char * motion_text_path, smplpp_mocap_summary * summary);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Device memory for callers that link nothing but this C ABI (the header-only C++ facade has no CUDA headers).
+ * smplpp_copy_to_host synchronises `stream`; smplpp_copy_to_device only enqueues (pageable sources are staged by the
+ * runtime before it returns).
+ * ------------------------------------------------------------------------------------------------------- */
+int smplpp_device_alloc(void ** out_dev, size_t bytes);
+void smplpp_device_free(void * ptr_dev);
+int smplpp_copy_to_device(void * dst_dev, const void * src_host, size_t bytes, void * stream);
+int smplpp_copy_to_host(void * dst_host, const void * src_dev, size_t bytes, void * stream);
+int smplpp_stream_synchronize(void * stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Data formats on either side of the path (host only)

@@ -1006,3 +1006,26 @@ class IkTask:
     def calcActualNormal(self) -> torch.Tensor:
         v = self.smpl_._vertices[:1]
         return self._set.positions(v, self.vertexWeights_.view(1, 1, 3), 0.0, want_normals=True)[1][0, 0]
+
+
+def solve_mocap_motion(smpl: SMPL, vposer: Optional[VPoserDecoder], c3d_path: str, body_yaml_path: str, opt: capi.IkOptions,
+                       initial_state, warmup_iterations: int = 31, iterations: int = 1, reproject: bool = False,
+                       first_frame: int = 0, frame_count: int = 0, motion_text_path: Optional[str] = None) -> dict:
+    """smplpp_solve_mocap_motion: the motion stage of the mocap mode (node/node.cpp:509-535, 571-595, 667-691, 785,
+    1369-1407) as one call - C3D file + MocapBody.yaml in, theta (frames,75), status, residual and a summary out."""
+    c3d = C3D(c3d_path)
+    frames = c3d.frames - first_frame if frame_count <= 0 else min(frame_count, c3d.frames - first_frame)
+    theta = np.empty((frames, 75), np.float32)
+    status = np.empty((frames,), np.int32)
+    res = np.empty((frames,), np.float32)
+    summ = capi.MocapSummary()
+    init = np.ascontiguousarray(initial_state, dtype=np.float32).reshape(-1)
+    vp = vposer.handle if (opt.enable_vposer and vposer is not None) else None
+    with torch.cuda.device(smpl.m__device):
+        check(lib().smplpp_solve_mocap_motion(
+            smpl.handle, vp, c3d_path.encode(), body_yaml_path.encode(), C.byref(opt), C.c_int32(warmup_iterations),
+            C.c_int32(iterations), C.c_int32(int(reproject)), init.ctypes.data_as(C.c_void_p), C.c_int64(first_frame),
+            C.c_int64(frame_count), theta.ctypes.data_as(C.c_void_p), status.ctypes.data_as(C.c_void_p),
+            res.ctypes.data_as(C.c_void_p), motion_text_path.encode() if motion_text_path else None, C.byref(summ)))
+    return dict(theta=theta.reshape(frames, 25, 3), status=status, residual=res,
+                summary={k: getattr(summ, k) for k, _ in capi.MocapSummary._fields_})

@@ -26,6 +26,11 @@ class VposerDesc(C.Structure):
     _fields_ = [("w0", c_f32p), ("b0", c_f32p), ("w3", c_f32p), ("b3", c_f32p), ("w5", c_f32p), ("b5", c_f32p)]
 
 
+class MocapSummary(C.Structure):
+    _fields_ = [("frames", C.c_int64), ("markers", C.c_int64), ("solved", C.c_int64), ("skipped", C.c_int64),
+                ("failed", C.c_int64), ("mean_residual", C.c_double), ("max_residual", C.c_double)]
+
+
 class IkOptions(C.Structure):
     _fields_ = [
         ("enable_vposer", C.c_int32), ("optimize_beta", C.c_int32), ("enable_qp", C.c_int32),
@@ -51,6 +56,8 @@ EXPORTS = [
     "smplpp_task_positions", "smplpp_closest_points", "smplpp_ik_workspace_bytes", "smplpp_ik_step", "smplpp_ik_solve_host",
     "smplpp_ik_faces_workspace_bytes", "smplpp_ik_step_faces", "smplpp_ik_reproject_workspace_bytes", "smplpp_ik_reproject",
     "smplpp_ik_shared_beta_workspace_bytes", "smplpp_ik_shared_beta_reduce", "smplpp_ik_shared_beta_apply",
+    "smplpp_ik_shared_beta_step", "smplpp_task_tangents", "smplpp_solve_mocap_motion",
+    "smplpp_device_alloc", "smplpp_device_free", "smplpp_copy_to_device", "smplpp_copy_to_host", "smplpp_stream_synchronize",
     "smplpp_json_open", "smplpp_json_close", "smplpp_json_array", "smplpp_model_load_json", "smplpp_vposer_load_json",
     "smplpp_npz_open", "smplpp_model_load_npz",
     "smplpp_c3d_open", "smplpp_c3d_close", "smplpp_c3d_frame_count", "smplpp_c3d_point_count", "smplpp_c3d_frame_rate",

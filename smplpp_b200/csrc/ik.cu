@@ -91,6 +91,26 @@ __global__ void task_positions_kernel(const int32_t * __restrict__ faces, const 
   pos_out[3 * i] = p.x, pos_out[3 * i + 1] = p.y, pos_out[3 * i + 2] = p.z;
 }
 
+// IkTask::calcTangents (src/IkTask.cpp:33-47): t1 = normalize(v1 - v0), t2 = normalize(((v1 - v0) x (v2 - v0)) x (v1 - v0));
+// out (B, n, 3, 2) like IkTask::tangents_ (columns are the two tangents)
+__global__ void task_tangents_kernel(const int32_t * __restrict__ faces, int V, int B, int n,
+                                     const long long * __restrict__ face_idx, const int32_t * __restrict__ face_idx32,
+                                     const float * __restrict__ verts, float * __restrict__ out)
+{
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if(i >= static_cast<long long>(B) * n) return;
+  const int b = static_cast<int>(i / n), m = static_cast<int>(i % n);
+  const float * vb = verts + static_cast<size_t>(b) * V * 3;
+  const int f = face_idx32 ? face_idx32[i] : static_cast<int>(face_idx[m]);
+  const f3 v0 = ld3(vb + 3 * faces[3 * f]), v1 = ld3(vb + 3 * faces[3 * f + 1]), v2 = ld3(vb + 3 * faces[3 * f + 2]);
+  const f3 t1r = v1 - v0;
+  const f3 t2r = cross3(cross3(t1r, v2 - v0), t1r);
+  float inv;
+  const f3 t1 = normalize_inv(t1r, inv), t2 = normalize_inv(t2r, inv);
+  float * o = out + 6 * i;
+  o[0] = t1.x, o[1] = t2.x, o[2] = t1.y, o[3] = t2.y, o[4] = t1.z, o[5] = t2.z;
+}
+
 // VPoser state (B,44) -> theta rows 0,1 and 23,24 (node.cpp:761-772); rows 2..22 are written by the decoder
 __global__ void theta_assemble_kernel(int B, const float * __restrict__ state, float * __restrict__ theta)
 {
@@ -1754,21 +1774,40 @@ extern "C" int smplpp_task_positions(const smplpp_model_t * model, const smplpp_
     return fail(SMPLPP_ERR_INVALID, "IkTask", "invalid task tensors!");
   // face indices on the device: reuse a small upload per call site is avoided by caching in the handle
   smplpp_tasks * t = const_cast<smplpp_tasks *>(tasks);
-  static thread_local const long long * cached = nullptr;
-  static thread_local const smplpp_tasks * cached_for = nullptr;
-  if(cached_for != tasks)
+  if(!t->face_idx_dev)
   {
-    const long long * ptr = nullptr;
     std::vector<long long> tmp(t->h_face_idx.begin(), t->h_face_idx.end());
-    if(upload_vec(t, &ptr, tmp) != SMPLPP_OK) return SMPLPP_ERR_CUDA;
-    cached = ptr;
-    cached_for = tasks;
+    if(upload_vec(t, &t->face_idx_dev, tmp) != SMPLPP_OK) return SMPLPP_ERR_CUDA;
   }
+  const long long * cached = t->face_idx_dev;
   const ModelDev & d = model->d;
   long long total = batch * tasks->d.n;
   task_positions_kernel<<<static_cast<unsigned>((total + 63) / 64), 64, 0, as_stream(stream)>>>(
       d.faces, d.adj_offset, d.adj_faces, d.V, static_cast<int>(batch), tasks->d.n, cached, nullptr, vertices, vertex_weights,
       normal_offset, nullptr, positions, normals);
+  SB_LAUNCHED();
+  return SMPLPP_OK;
+}
+
+extern "C" int smplpp_task_tangents(const smplpp_model_t * model, const smplpp_tasks_t * tasks, void * stream, int64_t batch,
+                                    const float * vertices, const int32_t * face_idx, float * tangents)
+{
+  if(!model || !tasks || batch < 1 || !vertices || !tangents) return fail(SMPLPP_ERR_INVALID, "IkTask", "invalid task tensors!");
+  smplpp_tasks * t = const_cast<smplpp_tasks *>(tasks);
+  const long long * shared = nullptr;
+  if(!face_idx)
+  {
+    if(!t->face_idx_dev)
+    {
+      std::vector<long long> tmp(t->h_face_idx.begin(), t->h_face_idx.end());
+      if(upload_vec(t, &t->face_idx_dev, tmp) != SMPLPP_OK) return SMPLPP_ERR_CUDA;
+    }
+    shared = t->face_idx_dev;
+  }
+  const ModelDev & d = model->d;
+  const long long total = batch * tasks->d.n;
+  task_tangents_kernel<<<static_cast<unsigned>((total + 63) / 64), 64, 0, as_stream(stream)>>>(
+      d.faces, d.V, static_cast<int>(batch), tasks->d.n, shared, face_idx, vertices, tangents);
   SB_LAUNCHED();
   return SMPLPP_OK;
 }

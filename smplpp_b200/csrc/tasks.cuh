@@ -70,6 +70,7 @@ struct smplpp_tasks
   std::vector<int32_t> h_corner;
   // fused IK step (ik2.cu)
   const sb::TaskRec * recs = nullptr; // (n) device
+  const long long * face_idx_dev = nullptr; // (n) device copy of the attachment faces (smplpp_task_positions / _tangents)
   int maxPairs = 0, maxItems = 0, maxLive = 0, maxPairsCorner = 3;
   // smplpp_ik_solve_host (ik_host.cu): grow-only device buffers and the stream of the host-buffer call
   struct HostSolve

@@ -1,0 +1,108 @@
+"""The mocap-motion driver behind the C ABI (smplpp_solve_mocap_motion) on a synthetic 'sample_walk-shaped' C3D file:
+3163 frames at 120 Hz, 49 points of which 41 carry the task names as label suffixes, float32 records, 3.4 % of the
+markers missing (negative residual word) and a stretch of frames with fewer than half of the markers (SURVEY Appendix C;
+BASELINE configs[2]).  The markers come from the synthetic model, so the solver has something it can fit."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from c3d_writer import write_c3d  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+FRAMES = 3163
+
+
+@pytest.fixture(scope="module")
+def walk(tmp_path_factory, smpl_gpu, marker_tasks, params):
+    from smplpp_b200 import api, synth
+    names, face_idx, vw = marker_tasks
+    n = len(names)
+    d = tmp_path_factory.mktemp("mocap")
+    gt = synth.make_motion(FRAMES, 20)
+    beta = (np.random.default_rng(5).normal(size=10) * 0.5).astype(f32)
+    tasks = api.IkTaskSet(smpl_gpu, face_idx)
+    markers = np.empty((FRAMES, n, 3), f32)
+    w = torch.as_tensor(np.repeat(vw[None], 1024, axis=0), device="cuda:0").contiguous()
+    for s in range(0, FRAMES, 1024):
+        e = min(FRAMES, s + 1024)
+        smpl_gpu.launch(beta, gt[s:e])
+        markers[s:e] = tasks.positions(smpl_gpu.getVertex(), w[: e - s], 0.015).cpu().numpy()
+    noise, valid = synth.make_marker_noise(FRAMES, n, 21)
+    markers += noise
+    valid[1500:1520, : n - 12] = False        # 20 frames with only 12 of 41 markers: skipped (node.cpp:785)
+    # 49 points like the real file: the 41 markers with a subject prefix + 8 unlabelled trajectories, shuffled
+    rng = np.random.default_rng(3)
+    perm = rng.permutation(49)
+    xyz = np.zeros((FRAMES, 49, 3), f32)
+    ok = np.zeros((FRAMES, 49), bool)
+    labels = [""] * 49
+    for i in range(49):
+        p = perm[i]
+        if i < n:
+            xyz[:, p], ok[:, p], labels[p] = markers[:, i], valid[:, i], "Subject01:" + names[i]
+        else:
+            xyz[:, p], ok[:, p], labels[p] = rng.normal(size=(FRAMES, 3)), True, "*%d" % (i - n)
+    c3d = str(d / "walk.c3d")
+    write_c3d(c3d, xyz, ok, labels, rate=120.0)
+    yaml = str(d / "MocapBody.yaml")
+    api.write_mocap_body(yaml, beta, names, face_idx, vw)
+    return dict(c3d=c3d, yaml=yaml, gt=gt, valid=valid, dir=d)
+
+
+@pytest.mark.parametrize("reproject", [False, True], ids=["step_only", "full_loop_body"])
+def test_solve_mocap_motion_direct(walk, smpl_gpu, reproject):
+    """All 3163 frames, direct theta (D = 75): warm-up on frame 0, then 12 iterations per frame."""
+    from smplpp_b200 import api, synth
+    opt = api.ik_options(enable_vposer=0)
+    x0 = synth.make_motion(FRAMES, 20)[0].reshape(-1) + np.random.default_rng(1).normal(size=75).astype(f32) * 0.05
+    txt = str(walk["dir"] / ("motion_%d.txt" % int(reproject)))
+    frames = FRAMES if not reproject else 512
+    r = api.solve_mocap_motion(smpl_gpu, None, walk["c3d"], walk["yaml"], opt, x0, warmup_iterations=31, iterations=12,
+                               reproject=reproject, frame_count=frames, motion_text_path=txt)
+    s = r["summary"]
+    assert s["frames"] == frames and s["markers"] == 41
+    skipped = np.nonzero(r["status"] == 1)[0]
+    if not reproject:
+        assert skipped.tolist() == list(range(1500, 1520)) and s["skipped"] == 20
+    assert s["failed"] == 0 and s["solved"] == frames - len(skipped)
+    assert np.isfinite(r["theta"]).all()
+    # 1 mm marker noise: the fit ends at the noise level (without the re-seating the attachments are the file's own)
+    assert s["mean_residual"] < (2.5e-3 if not reproject else 2e-2)
+    assert np.array_equal(api.read_motion_text(txt).reshape(frames, 25, 3), r["theta"])
+    if not reproject:
+        # the recovered motion is the ground truth up to the weakly observed joints: compare where markers see it
+        ok = r["status"] == 0
+        assert np.abs(r["theta"][ok][:, 0] - walk["gt"][:frames][ok][:, 0]).max() < 0.02   # root translation
+        assert np.median(np.abs(r["theta"][ok][:, 1:5] - walk["gt"][:frames][ok][:, 1:5])) < 0.02
+
+
+def test_solve_mocap_motion_vposer(walk, smpl_gpu, vposer_params):
+    """VPoser state (the mode the node forces for mocap, node.cpp:316-322): runs through, decoded theta out."""
+    from smplpp_b200 import api, synth
+    vp = api.VPoserDecoder(vposer_params)
+    opt = api.ik_options(enable_vposer=1)
+    x0 = np.zeros(44, f32)
+    x0[:6] = synth.make_motion(FRAMES, 20)[0].reshape(-1)[:6]
+    r = api.solve_mocap_motion(smpl_gpu, vp, walk["c3d"], walk["yaml"], opt, x0, warmup_iterations=10, iterations=4,
+                               frame_count=600)
+    s = r["summary"]
+    assert s["frames"] == 600 and s["failed"] == 0 and s["solved"] == 600
+    assert np.isfinite(r["theta"]).all() and np.isfinite(r["residual"]).all()
+    # hands are pinned by the 1e3 prior (node.cpp:900)
+    assert np.abs(r["theta"][:, 23:25]).max() < 1e-2
+
+
+def test_solve_mocap_motion_errors(walk, smpl_gpu, tmp_path):
+    from smplpp_b200 import api
+    opt = api.ik_options()
+    with pytest.raises(api.SmplppError):
+        api.solve_mocap_motion(smpl_gpu, None, str(tmp_path / "missing.c3d"), walk["yaml"], opt, np.zeros(75, f32))
+    bad = str(tmp_path / "Body.yaml")
+    api.write_mocap_body(bad, np.zeros(10, f32), ["NOPE"], np.array([5], np.int64), np.full((1, 3), 1 / 3, f32))
+    with pytest.raises(api.SmplppError, match="NOPE"):
+        api.solve_mocap_motion(smpl_gpu, None, walk["c3d"], bad, opt, np.zeros(75, f32))
