@@ -217,6 +217,8 @@ def main():
                          "step long enough for the clock sampler and the driver's consistency check)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ik", action="store_true")
+    ap.add_argument("--no-config4", action="store_true", help="skip the 2^20-frame strong-scaling IK leg (BASELINE configs[4])")
+    ap.add_argument("--config4-frames", type=int, default=1 << 20)
     ap.add_argument("--ik-frames-total", type=int, default=0,
                     help="BASELINE configs[4]: total mocap frames of the IK leg, sharded over the ranks as contiguous "
                          "blocks (default 0 = 16384 frames per GPU)")
@@ -462,6 +464,11 @@ def main():
                               frames_total=args.ik_frames_total)
         else:
             ik = bench_ik.run(dev, rank, world, max_over_ranks, barrier)
+        if not args.no_config4:
+            # BASELINE configs[4]: 2^20 frames over the N ranks (strong scaling), NCCL all-reduce of the shared-beta blocks,
+            # final gather of theta
+            torch.cuda.empty_cache()
+            ik["config4"] = bench_ik.run_config4(dev, rank, world, max_over_ranks, barrier, frames_total=args.config4_frames)
 
     clocks.__exit__(None, None, None)
     line = {
@@ -494,6 +501,12 @@ def main():
         for k in ("mosh_direct", "moshpp_vposer", "shared_beta", "shared_beta_vposer"):
             if k in ik:
                 line["ik_" + k] = ik[k]["value"]
+        if "config4" in ik:
+            c4 = ik["config4"]
+            line["ik_config4_frames_total"] = c4["frames_total"]
+            line["ik_config4_mosh_direct"] = c4["mosh_direct"]["value"]
+            line["ik_config4_shared_beta"] = c4["shared_beta"]["value"]
+            line["ik_config4_gather_s"] = c4["final_gather"]["seconds"]
         if "roofline" in ik:
             r = ik["roofline"]
             roofline.update(ik_bound=r["bound"], ik_achieved=r["achieved"], ik_peak=r["peak"], ik_unit=r["unit"],

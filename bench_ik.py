@@ -45,15 +45,17 @@ def make_problem(smpl, tasks, frames: int, seed: int, dev):
     rng = np.random.default_rng(seed)
     # per-frame random poses around the walking clip statistics (cheap to generate for millions of frames)
     base = synth.make_motion(min(frames, 4096), seed)
-    reps = (frames + base.shape[0] - 1) // base.shape[0]
-    gt = np.tile(base, (reps, 1, 1))[:frames].copy()
-    gt[:, 2:] += rng.normal(scale=0.02, size=(frames, 23, 3)).astype(np.float32)
     beta = (rng.normal(size=10) * 0.5).astype(np.float32)
-    w0 = torch.as_tensor(np.repeat(vw0[None], frames, axis=0), device=dev).contiguous()
+    w0 = torch.as_tensor(vw0[None], device=dev).repeat(frames, 1, 1).contiguous()
     target = torch.empty((frames, n, 3), dtype=torch.float32, device=dev)
-    for s in range(0, frames, 4096):
+    gt = None
+    for s in range(0, frames, 4096):  # chunk by chunk: a million frames never exist as one host array
         e = min(frames, s + 4096)
-        smpl.launch(beta, gt[s:e])
+        chunk = base[: e - s].copy()
+        chunk[:, 2:] += rng.normal(scale=0.02, size=(e - s, 23, 3)).astype(np.float32)
+        if gt is None:
+            gt = chunk
+        smpl.launch(beta, chunk)
         target[s:e] = tasks.positions(smpl._vertices, w0[s:e], 0.015)
     gen = torch.Generator(device=dev).manual_seed(seed)
     target += 1e-3 * torch.randn(target.shape, generator=gen, device=dev)
@@ -202,6 +204,55 @@ def run(dev, rank, world, max_over_ranks, barrier, frames: int = 16384, iters: i
                         "vertex_bytes_read_gbs": rb * 82680 / (ms * 1e-3) / 1e9}
     out["value"] = out["mosh_direct"]["value"]
     return out
+
+
+def run_config4(dev, rank, world, max_over_ranks, barrier, frames_total: int = 1 << 20, iters: int = 2):
+    """BASELINE configs[4]: `frames_total` synthetic mocap frames sharded over the ranks as contiguous blocks (strong
+    scaling).  Per-frame IK steps need no exchange; the shared-beta stage all-reduces 111 doubles per iteration (NCCL over
+    NVLink when world > 1); the per-frame state is gathered on every rank at the end (parallel.gather_frames)."""
+    from smplpp_b200 import parallel
+    start, frames = parallel.frame_block(frames_total, rank, world)
+    params = synth.make_smpl_params(0)
+    smpl = api.SMPL(params, device=dev)
+    _, face_idx, _ = synth.make_marker_tasks(params)
+    tasks = api.IkTaskSet(smpl, face_idx)
+    prob = make_problem(smpl, tasks, frames, 22 + rank, dev)
+    opt = api.ik_options()
+    theta, vw = prob["x0"].clone(), prob["w0"].clone()
+
+    def step_direct():
+        tasks.step(opt, theta, prob["beta"], vw, prob["target"], pos_task_weight=prob["valid"])
+
+    ms_direct = time_steps(step_direct, iters, 1, barrier, max_over_ranks, dev)
+    sbeta = torch.zeros(10, dtype=torch.float32, device=dev)
+    th2, vw2 = prob["x0"].clone(), prob["w0"].clone()
+
+    def step_shared():
+        tasks.shared_beta_step(opt, th2, sbeta, vw2, prob["target"], pos_task_weight=prob["valid"])
+
+    ms_shared = time_steps(step_shared, iters, 1, barrier, max_over_ranks, dev)
+    # every rank solved the same 10-dim problem from the same all-reduced message: identical betas
+    beta_spread = 0.0
+    if world > 1:
+        import torch.distributed as dist
+        lo, hi = sbeta.clone(), sbeta.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        beta_spread = float((hi - lo).abs().max().item())
+    barrier()
+    t0 = time.perf_counter()
+    full = parallel.gather_frames(th2, frames_total)
+    torch.cuda.synchronize()
+    gather_s = max_over_ranks(time.perf_counter() - t0)
+    ok = bool(full.shape[0] == frames_total and torch.isfinite(full).all().item())
+    return {"frames_total": frames_total, "frames_this_rank": frames, "scaling": "strong", "unit": "frame-iters/s",
+            "mosh_direct": {"value": frames_total / (ms_direct * 1e-3), "ms_per_iter": ms_direct},
+            "shared_beta": {"value": frames_total / (ms_shared * 1e-3), "ms_per_iter": ms_shared,
+                            "collective": "all_reduce(sum) of 111 float64 per iteration (NCCL)" if world > 1 else "none (1 GPU)",
+                            "beta_spread_over_ranks": beta_spread},
+            "final_gather": {"seconds": gather_s, "bytes": int(frames_total * 75 * 4), "gathered_rows": int(full.shape[0]),
+                             "finite": ok, "collective": "all_gather over NCCL" if world > 1 else "none (1 GPU)"},
+            "value": frames_total / (ms_direct * 1e-3)}
 
 
 def kernel_names():
