@@ -10,8 +10,8 @@ SEL='test_forward_vs_reference_golden or test_model_skinning_vs_oracle or test_i
 : > gpurun_out/sanitize_summary.txt
 for tool in memcheck racecheck synccheck; do
   extra=""
-  [ "$tool" == "racecheck" ] && extra="--racecheck-report all"
-  timeout ${SANITIZE_TIMEOUT:-900} compute-sanitizer --tool $tool $extra --error-exitcode 99 --print-limit 20 \
+  [ "$tool" == "racecheck" ] && extra="--racecheck-report analysis"
+  timeout ${SANITIZE_TIMEOUT:-900} compute-sanitizer --tool $tool $extra --error-exitcode 99 --print-limit 400 \
       python -m pytest tests -m gpu -x -q -k "$SEL" > gpurun_out/sanitize_$tool.log 2>&1
   rc=$?
   errs=$(grep -c "========= \(Error\|ERROR\|Invalid\|Race\|Barrier error\|Warning: Race\)" gpurun_out/sanitize_$tool.log)

@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsmplpp_b200.so")
+# SMPLPP_B200_LIB: an instrumented build of the same library (scripts/build_dbg.sh), for kernel phase timers
+LIB_PATH = os.environ.get("SMPLPP_B200_LIB") or os.path.join(HERE, "libsmplpp_b200.so")
 
 c_f32p = C.POINTER(C.c_float)
 c_f64p = C.POINTER(C.c_double)

@@ -1698,6 +1698,12 @@ extern "C" int smplpp_tasks_create(const smplpp_model_t * model, int32_t n, cons
       ml = std::max<int>(ml, __builtin_popcount(recs[m].jmask));
     }
     rc = upload_vec(t, &t->recs, recs);
+    if(rc == SMPLPP_OK && md.kmax <= 4)
+    {
+      std::vector<TaskSkin> skins(n);
+      for(int m = 0; m < n; m++) build_task_skin_host(model, recs[m], skins[m]);
+      rc = upload_vec(t, &t->skins, skins);
+    }
     if(rc != SMPLPP_OK)
     {
       smplpp_tasks_destroy(t);
@@ -2065,7 +2071,8 @@ static int ik_step_impl(const smplpp_model_t * model, const smplpp_vposer_t * vp
     return fail(SMPLPP_ERR_INVALID, "IkTask", "per-frame beta optimisation needs per-frame beta (use the shared-beta stage)");
   const IkLayout L = make_layout(tasks, opt, batch, false);
   const size_t rec_chunk = 4096; // frames per launch when every frame carries its own attachment records
-  const size_t rec_bytes = face_idx ? align_up(ik2_rec_bytes(std::min<int64_t>(batch, rec_chunk), L.n)) : 0;
+  const size_t rec_only = face_idx ? align_up(ik2_rec_bytes(std::min<int64_t>(batch, rec_chunk), L.n)) : 0;
+  const size_t rec_bytes = face_idx ? rec_only + align_up(ik2_skin_bytes(std::min<int64_t>(batch, rec_chunk), L.n)) : 0;
   if(!workspace || workspace_bytes < L.total + rec_bytes) return fail(SMPLPP_ERR_INVALID, "IkTask", "IK workspace too small!");
   cudaStream_t st = as_stream(stream);
   char * ws = align_up_ptr<char>(workspace);
@@ -2073,6 +2080,7 @@ static int ik_step_impl(const smplpp_model_t * model, const smplpp_vposer_t * vp
   if(g_ik_variant == 2 || face_idx) // fused kernel: per-frame attachments always, shared ones when selected
   {
     TaskRec * recs = face_idx ? reinterpret_cast<TaskRec *>(ws + L.total) : nullptr;
+    TaskSkin * skins = face_idx ? reinterpret_cast<TaskSkin *>(ws + L.total + rec_only) : nullptr;
     const int64_t chunk = face_idx ? static_cast<int64_t>(rec_chunk) : L.chunk;
     for(int64_t s = 0; s < batch; s += chunk)
     {
@@ -2089,9 +2097,10 @@ static int ik_step_impl(const smplpp_model_t * model, const smplpp_vposer_t * vp
       c.pos_task_weight = pos_task_weight ? pos_task_weight + s * n : nullptr;
       if(face_idx)
       {
-        rc = launch_task_topo(model->d, st, static_cast<long long>(B) * n, face_idx + s * n, recs);
+        rc = launch_task_topo(model->d, st, static_cast<long long>(B) * n, face_idx + s * n, recs, skins);
         if(rc != SMPLPP_OK) return rc;
         c.frame_recs = recs;
+        c.frame_skins = skins;
       }
       c.status = status + s;
       c.e_out = e_out ? e_out + s * 4 * n : nullptr;
@@ -2160,7 +2169,8 @@ extern "C" int smplpp_ik_step(const smplpp_model_t * model, const smplpp_vposer_
 extern "C" size_t smplpp_ik_faces_workspace_bytes(const smplpp_tasks_t * tasks, const smplpp_ik_options * opt, int64_t batch)
 {
   if(!tasks || !opt || batch < 1) return 0;
-  return make_layout(tasks, opt, batch, false).total + align_up(ik2_rec_bytes(std::min<int64_t>(batch, 4096), tasks->d.n)) + 256;
+  return make_layout(tasks, opt, batch, false).total + align_up(ik2_rec_bytes(std::min<int64_t>(batch, 4096), tasks->d.n))
+         + align_up(ik2_skin_bytes(std::min<int64_t>(batch, 4096), tasks->d.n)) + 256;
 }
 
 extern "C" int smplpp_ik_step_faces(const smplpp_model_t * model, const smplpp_vposer_t * vposer, const smplpp_tasks_t * tasks,

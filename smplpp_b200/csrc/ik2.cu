@@ -49,7 +49,7 @@ struct Ik2Layout
   int theta, beta, coef, R, dR, Jt, G, tp, M, JS, dTg, dTp; // chain (floats)
   int A, bvec, misc;                                         // fp64: tiles, b, [esq, valid, bad, ok, ...]
   int rec;                                                   // the task's record (608 B)
-  int pv, pr, sw, xw, sj, Au, itemN, cornN, ts, Dref, C4, CA4, ybuf, live, Q, Jrow, Jc; // per-task scratch
+  int tin, skin, pv, pr, sw, xw, sj, Au, itemN, cornN, ts, Dref, C4, CA4, ybuf, live, Q, Jrow, Jc; // per-task scratch
   int sx, sg, sd, sstate;                                    // solve temporaries (alias the per-task scratch)
   int team_bytes;
   int ring_off, ring_slots, bar_off, total;
@@ -70,6 +70,7 @@ struct Ik2Params
   const float * joint_shape;
   // topology
   const TaskRec * recs;
+  const TaskSkin * skins; // skinning rows of the records (kmax <= 4), else null: read from the model arrays
   long long rec_stride; // records per frame: 0 = shared by all frames
   int n, MP, MI, ML;
   // problem
@@ -98,11 +99,28 @@ struct Ik2Params
   double * a_ws;      // (B, ntiles * 16) copy of A for the active-set QP
   double * schur_out; // (B, 111)
   double * factor_ws; // (B, P)
+  long long * dbg_cycles; // (32) phase timer of the debug build
 };
 
 // ------------------------------------------------------------------------------------------------------------
 // device helpers
 // ------------------------------------------------------------------------------------------------------------
+// Phase timer of the task loop (debug builds only: -DSMPLPP_IK2_DBG): team 0 of CTA 0 accumulates the cycles between
+// consecutive barriers of the task loop into p.dbg_cycles[phase].
+#ifdef SMPLPP_IK2_DBG
+#define IK2_STAMP(k)                                                                \
+  do                                                                                \
+  {                                                                                 \
+    if(blockIdx.x == 0 && team == 0 && tt == 0 && p.dbg_cycles)                     \
+    {                                                                               \
+      const long long now = clock64();                                              \
+      p.dbg_cycles[k] += now - dbg_last;                                            \
+      dbg_last = now;                                                               \
+    }                                                                               \
+  } while(0)
+#else
+#define IK2_STAMP(k)
+#endif
 __device__ __forceinline__ void team_sync(int team)
 {
   asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(k2::TEAM) : "memory");
@@ -221,27 +239,45 @@ __device__ void team_cholesky(double * A, int NT, int nbt, int npb, int tt, int 
   }
 }
 
-// x <- L^-T L^-1 x on the leading n x n block; executed by warp 0 of the team, result in x
+// x <- L^-T L^-1 x on the leading n x n block (n a multiple of 4); executed by warp 0 of the team, result in x.
+// Blocked by the 4x4 tiles: every lane solves the diagonal tile redundantly in registers (no exchange inside a block),
+// then the lanes update the remaining rows; one warp barrier per block instead of two per unknown.
 __device__ void warp_tiled_solve(double * A, int NT, int n, double * x, int tt)
 {
-  if(tt < 32)
+  if(tt >= 32) return;
+  const int nb = n >> 2;
+  for(int kb = 0; kb < nb; kb++)
   {
-    for(int k = 0; k < n; k++)
+    const double * Tk = A + tile_idx(kb, kb);
+    const double x0 = x[4 * kb] / Tk[0];
+    const double x1 = (x[4 * kb + 1] - Tk[4 * NT] * x0) / Tk[5 * NT];
+    const double x2 = (x[4 * kb + 2] - Tk[8 * NT] * x0 - Tk[9 * NT] * x1) / Tk[10 * NT];
+    const double x3 = (x[4 * kb + 3] - Tk[12 * NT] * x0 - Tk[13 * NT] * x1 - Tk[14 * NT] * x2) / Tk[15 * NT];
+    __syncwarp();
+    if(tt == 0) x[4 * kb] = x0, x[4 * kb + 1] = x1, x[4 * kb + 2] = x2, x[4 * kb + 3] = x3;
+    for(int i = 4 * (kb + 1) + tt; i < n; i += 32)
     {
-      const double xk = x[k] / Aat(A, NT, k, k);
-      __syncwarp();
-      if(tt == 0) x[k] = xk;
-      for(int i = k + 1 + tt; i < n; i += 32) x[i] -= Aat(A, NT, i, k) * xk;
-      __syncwarp();
+      const double * row = A + ((i & 3) * 4) * NT + tile_idx(i >> 2, kb);
+      x[i] -= row[0] * x0 + row[NT] * x1 + row[2 * NT] * x2 + row[3 * NT] * x3;
     }
-    for(int k = n - 1; k >= 0; k--)
+    __syncwarp();
+  }
+  for(int kb = nb - 1; kb >= 0; kb--)
+  {
+    const double * Tk = A + tile_idx(kb, kb);
+    const double x3 = x[4 * kb + 3] / Tk[15 * NT];
+    const double x2 = (x[4 * kb + 2] - Tk[14 * NT] * x3) / Tk[10 * NT];
+    const double x1 = (x[4 * kb + 1] - Tk[9 * NT] * x2 - Tk[13 * NT] * x3) / Tk[5 * NT];
+    const double x0 = (x[4 * kb] - Tk[4 * NT] * x1 - Tk[8 * NT] * x2 - Tk[12 * NT] * x3) / Tk[0];
+    __syncwarp();
+    if(tt == 0) x[4 * kb] = x0, x[4 * kb + 1] = x1, x[4 * kb + 2] = x2, x[4 * kb + 3] = x3;
+    for(int i = tt; i < 4 * kb; i += 32)
     {
-      const double xk = x[k] / Aat(A, NT, k, k);
-      __syncwarp();
-      if(tt == 0) x[k] = xk;
-      for(int i = tt; i < k; i += 32) x[i] -= Aat(A, NT, k, i) * xk;
-      __syncwarp();
+      // L(4 kb + c, i): tile (kb, i >> 2), element (c, i & 3)
+      const double * col = A + (i & 3) * NT + tile_idx(kb, i >> 2);
+      x[i] -= col[0] * x0 + col[4 * NT] * x1 + col[8 * NT] * x2 + col[12 * NT] * x3;
     }
+    __syncwarp();
   }
 }
 
@@ -251,7 +287,10 @@ __device__ void warp_tiled_solve(double * A, int NT, int n, double * x, int tt)
 __global__ void __launch_bounds__(128) task_topo_kernel(long long total, const int32_t * __restrict__ face_idx, int F,
                                                         const int32_t * __restrict__ faces, const int32_t * __restrict__ adj_offset,
                                                         const int32_t * __restrict__ adj_faces,
-                                                        const uint32_t * __restrict__ vert_jmask, TaskRec * __restrict__ out)
+                                                        const uint32_t * __restrict__ vert_jmask, TaskRec * __restrict__ out,
+                                                        TaskSkin * __restrict__ skins, const uint8_t * __restrict__ lbs_joint,
+                                                        const float * __restrict__ lbs_weight, const float * __restrict__ lbs_wsum,
+                                                        int Vpad, int kmax)
 {
   __shared__ TaskRec s_rec[4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -348,6 +387,20 @@ __global__ void __launch_bounds__(128) task_topo_kernel(long long total, const i
   uint4 * dst = reinterpret_cast<uint4 *>(out + id);
   const uint4 * src = reinterpret_cast<const uint4 *>(&r);
   for(int i = lane; i < static_cast<int>(sizeof(TaskRec) / 16); i += 32) dst[i] = src[i];
+  if(skins)
+  {
+    TaskSkin & sk = skins[id];
+    const int npp = bad ? 0 : np;
+    for(int i = lane; i < kRecPairs * 4; i += 32)
+    {
+      const int q = i >> 2, sl = i & 3;
+      const bool on = q < npp && sl < kmax;
+      const int gv = on ? r.gv[q] : 0;
+      sk.w[q][sl] = on ? lbs_weight[static_cast<size_t>(sl) * Vpad + gv] : 0.f;
+      sk.j[q][sl] = on ? lbs_joint[static_cast<size_t>(sl) * Vpad + gv] : 0;
+    }
+    for(int q = lane; q < kRecPairs; q += 32) sk.ws[q] = q < npp ? lbs_wsum[r.gv[q]] : 1.f;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -434,7 +487,6 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
   double * s_A = reinterpret_cast<double *>(base + L.A);
   double * s_b = reinterpret_cast<double *>(base + L.bvec);
   double * s_misc = reinterpret_cast<double *>(base + L.misc); // [0] esq  [1] valid  [2] bad  [3] ok  [4] flag  [5] iter  [6] atmin
-  const int rec_bytes = (static_cast<int>(sizeof(TaskRec)) + 15) / 16 * 16;
   float * s_pv = reinterpret_cast<float *>(base + L.pv);
   float * s_pr = reinterpret_cast<float *>(base + L.pr);
   float * s_sw = reinterpret_cast<float *>(base + L.sw);
@@ -452,6 +504,7 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
   float * s_Q = reinterpret_cast<float *>(base + L.Q);
   float * s_Jrow = reinterpret_cast<float *>(base + L.Jrow);
   float * s_Jc = reinterpret_cast<float *>(base + L.Jc);
+  float * s_tin = reinterpret_cast<float *>(base + L.tin);
   const int kmax = p.kmax, ML = p.ML;
   const int ldf = p.ldf, ld = p.ld;
   const int phi_off_f = 76;             // phi columns of the theta-space row
@@ -600,6 +653,16 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
   }
   team_sync(team);
 
+  // per-task inputs of the frame (attachment weights, target, marker weight, target normal): fetched once, coalesced,
+  // instead of by one thread per task with the full global latency on the critical path of every task
+  for(int i = tt; i < 3 * n; i += TEAM)
+  {
+    s_tin[i] = p.vertex_weights[static_cast<size_t>(f) * 3 * n + i];
+    s_tin[3 * n + i] = p.target_pos[static_cast<size_t>(f) * 3 * n + i];
+    if(ROWS == 4) s_tin[7 * n + i] = p.target_normal ? p.target_normal[static_cast<size_t>(f) * 3 * n + i] : (i % 3 == 2 ? 1.f : 0.f);
+  }
+  for(int i = tt; i < n; i += TEAM) s_tin[6 * n + i] = p.pos_task_weight ? p.pos_task_weight[static_cast<size_t>(f) * n + i] : 1.f;
+  team_sync(team);
   // thread 0 of the team carries the frame's scalars through the task loop
   double esq = 0.0;
   int valid = 0, bad = 0;
@@ -617,13 +680,20 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
     if(tt + s2 * TEAM < ntiles_acc) tri_coords(tt + s2 * TEAM, my_bi[s2], my_bj[s2]);
 
   // the record of task m lives in buffer m & 1; the next one is fetched while the current task is being accumulated
+  const TaskSkin * gskin = p.skins ? p.skins + static_cast<size_t>(f) * p.rec_stride : nullptr;
+  const int skin_bytes = static_cast<int>(sizeof(TaskSkin));
   if(tt < static_cast<int>(sizeof(TaskRec) / 16))
     reinterpret_cast<uint4 *>(base + L.rec)[tt] = __ldg(reinterpret_cast<const uint4 *>(grec) + tt);
+  if(gskin && tt >= 32 && tt - 32 < skin_bytes / 16)
+    reinterpret_cast<uint4 *>(base + L.skin)[tt - 32] = __ldg(reinterpret_cast<const uint4 *>(gskin) + (tt - 32));
   team_sync(team);
 
+#ifdef SMPLPP_IK2_DBG
+  long long dbg_last = clock64();
+#endif
   for(int m = 0; m < n; m++)
   {
-    const TaskRec * s_rec = reinterpret_cast<const TaskRec *>(base + L.rec + (m & 1) * rec_bytes);
+    const TaskRec * s_rec = reinterpret_cast<const TaskRec *>(base + L.rec);
     // ---- empty J rows (the previous task's rows were consumed before its closing barrier) ----
     for(int i = tt; i < 4 * ldf; i += TEAM) s_Jrow[i] = 0.f;
     const bool rec_ok = s_rec->face >= 0;
@@ -674,6 +744,7 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
       }
     }
     team_sync(team);
+    IK2_STAMP(0);
     // ---- skinning, one thread per vertex: normalised weights, w_j x_uj (vertex carried by bone j, no root translation),
     //      the posed vertex in the reference's order of operations (LinearBlendSkinning.cpp:445-483: M = sum_j W_j G'_j
     //      with the raw weights, h = M [rest; 1], vertex = h / sum_j W_j + trans -- the task normals amplify any rounding
@@ -685,15 +756,16 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
     if(tt < npe)
     {
       const int gv = s_rec->gv[tt];
-      const float ws = __ldg(p.lbs_wsum + gv);
+      const TaskSkin * s_skin = reinterpret_cast<const TaskSkin *>(base + L.skin);
+      const float ws = gskin ? s_skin->ws[tt] : __ldg(p.lbs_wsum + gv);
       const f3 ru = ld3(s_pr + 3 * tt);
       float Au[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       float Mr[12] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       for(int sl = 0; sl < kmax; sl++)
       {
         const int i = tt * kmax + sl;
-        const float wr = __ldg(p.lbs_weight + static_cast<size_t>(sl) * p.Vpad + gv);
-        const int j = __ldg(p.lbs_joint + static_cast<size_t>(sl) * p.Vpad + gv);
+        const float wr = gskin ? s_skin->w[tt][sl] : __ldg(p.lbs_weight + static_cast<size_t>(sl) * p.Vpad + gv);
+        const int j = gskin ? s_skin->j[tt][sl] : __ldg(p.lbs_joint + static_cast<size_t>(sl) * p.Vpad + gv);
         const float wj = wr / ws;
         s_sw[i] = wj;
         s_sj[i] = static_cast<uint8_t>(j);
@@ -722,6 +794,7 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
       for(int e = 0; e < 9; e++) s_Au[9 * tt + e] = Au[e];
     }
     team_sync(team);
+    IK2_STAMP(1);
     // ---- y_uk = sum_{j in desc*(k)} w_j (x_uj - tg_k) for the live joints: warps 1..3, while warp 0 does the normals ----
     if(tt >= 32)
       for(int u = tt - 32; u < npe * nlive; u += TEAM - 32)
@@ -774,7 +847,7 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
         v[c] = rec_ok ? ld3(s_pv + 3 * c) : mk3(0.f, 0.f, 0.f);
         nc[c] = p.use_ring ? ld3(s_cornN + 4 * c) : mk3(0.f, 0.f, 0.f);
       }
-      const float w[3] = {p.vertex_weights[3 * fm], p.vertex_weights[3 * fm + 1], p.vertex_weights[3 * fm + 2]};
+      const float w[3] = {s_tin[3 * m], s_tin[3 * m + 1], s_tin[3 * m + 2]};
       f3 pos = w[0] * v[0] + w[1] * v[1] + w[2] * v[2];
       float inv_s = 0.f;
       if(p.use_ring && p.normal_offset > 0.f)
@@ -787,9 +860,9 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
       if(p.use_ring) nh = normalize_inv(wn[0] * nc[0] + wn[1] * nc[1] + wn[2] * nc[2], inv_s);
       f3 pn = wn[0] * v[0] + wn[1] * v[1] + wn[2] * v[2];
       if(p.normal_offset > 0.f) pn = pn + p.normal_offset * nh;
-      const float posw = p.pos_task_weight ? p.pos_task_weight[fm] : 1.f;
-      const f3 tgt = ld3(p.target_pos + 3 * fm);
-      const f3 nt = p.target_normal ? ld3(p.target_normal + 3 * fm) : mk3(0.f, 0.f, 1.f);
+      const float posw = s_tin[6 * n + m];
+      const f3 tgt = ld3(s_tin + 3 * n + 3 * m);
+      const f3 nt = ROWS == 4 ? ld3(s_tin + 7 * n + 3 * m) : mk3(0.f, 0.f, 1.f);
       float e[4] = {posw * (pn.x - tgt.x), posw * (pn.y - tgt.y), posw * (pn.z - tgt.z),
                     p.normal_task_weight > 0.f ? p.normal_task_weight * (dot3(nh, nt) + 1.f) : 0.f};
       if(!rec_ok) e[0] = e[1] = e[2] = e[3] = CUDART_NAN_F; // attachment outside the record limits: numerical-issue status
@@ -837,6 +910,7 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
       }
     }
     team_sync(team);
+    IK2_STAMP(2);
     // ---- d(normal) / d(vertex): one thread per (item, slot) reference, then a fixed-order sum per pair ----
     if(p.use_ring)
     {
@@ -864,6 +938,7 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
         }
       }
       team_sync(team);
+    IK2_STAMP(3);
     }
     // ---- C4 = d(residual rows) / d(vertex) (4 x 3) per pair ----
     if(tt < npe)
@@ -903,6 +978,7 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
         for(int c = 0; c < 3; c++) CA[3 * r + c] = C[3 * r] * Au[c] + C[3 * r + 1] * Au[3 + c] + C[3 * r + 2] * Au[6 + c];
     }
     team_sync(team);
+    IK2_STAMP(4);
     // ---- translation columns (last warp); kinematic-chain columns: sum_u C4_u M_kc y_uk  (thread = (live joint, row)) ----
     if(tt >= 96 && tt - 96 < 3 * ROWS)
     {
@@ -960,6 +1036,7 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
       }
     }
     team_sync(team);
+    IK2_STAMP(5);
     // ---- pose-blend (and shape-blend) columns, step 1: Q = sum_u CA4_u P_u (ROWS x 224); lane owns two columns ----
     {
       const int col = 2 * (32 * tw + lane);
@@ -1007,6 +1084,7 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
       }
     }
     team_sync(team);
+    IK2_STAMP(6);
     // ---- step 2: J[r][3 + 3k + c] += sum_e Q[r][9(k-1)+e] dvec(R_k)/dtheta_kc [e];  beta columns += Q[r][207 + i] ----
     for(int u = tt; u < 69 * ROWS; u += TEAM)
     {
@@ -1026,6 +1104,7 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
         s_Jrow[r * ldf + beta_off_f + ib] += s_Q[r * kBlendK + kPoseDim + ib];
       }
     team_sync(team);
+    IK2_STAMP(7);
     // ---- VPoser: contract the 63 body columns with d(axis-angle)/d(latent) (node.cpp:761-772) ----
     const float * Jsrc = s_Jrow;
     if(p.vposer)
@@ -1054,6 +1133,7 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
       }
       Jsrc = s_Jc;
       team_sync(team);
+    IK2_STAMP(8);
     }
     // ---- the task's rows in the reference layout (the "Jacobian getter") ----
     if(p.j_out && live_frame)
@@ -1078,8 +1158,9 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
     // ---- A += J'J (fp64, 4x4 tiles of the lower triangle), b += J'e; next task's record ----
     {
       if(m + 1 < n && tt < static_cast<int>(sizeof(TaskRec) / 16))
-        reinterpret_cast<uint4 *>(base + L.rec + ((m + 1) & 1) * rec_bytes)[tt] =
-            __ldg(reinterpret_cast<const uint4 *>(grec + m + 1) + tt);
+        reinterpret_cast<uint4 *>(base + L.rec)[tt] = __ldg(reinterpret_cast<const uint4 *>(grec + m + 1) + tt);
+      if(m + 1 < n && gskin && tt >= 48 && tt - 48 < skin_bytes / 16)
+        reinterpret_cast<uint4 *>(base + L.skin)[tt - 48] = __ldg(reinterpret_cast<const uint4 *>(gskin + m + 1) + (tt - 48));
       auto accum_tile = [&](int tl, int bi, int bj) {
         double * T = s_A + tl;
         double acc[16];
@@ -1117,13 +1198,16 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
       }
     }
     team_sync(team);
+    IK2_STAMP(9);
   }
 
+  IK2_STAMP(30);
   // =========================================================================================================
   // normal equations complete: damping, prior, solve, update  (node.cpp:887-968)
   // =========================================================================================================
   if(tt == 0) s_misc[0] = esq, s_misc[1] = valid, s_misc[2] = bad, s_misc[3] = 1.0;
   team_sync(team);
+    IK2_STAMP(10);
   esq = s_misc[0];
   valid = static_cast<int>(s_misc[1]);
   bad = static_cast<int>(s_misc[2]);
@@ -1403,6 +1487,7 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
     }
     team_sync(team);
   }
+  IK2_STAMP(31);
   if(bad) status = 2;
   if(status == 0 && too_few) status = 1;
   if(!live_frame) return;
@@ -1498,10 +1583,40 @@ int build_task_rec_host(const smplpp_model * model, int64_t face, TaskRec & r)
   return 0;
 }
 
-int launch_task_topo(const ModelDev & d, cudaStream_t st, long long total, const int32_t * face_idx, TaskRec * out)
+void build_task_skin_host(const smplpp_model * model, const TaskRec & rec, TaskSkin & sk)
+{
+  std::memset(&sk, 0, sizeof(sk));
+  for(int q = 0; q < kRecPairs; q++) sk.ws[q] = 1.f;
+  for(int q = 0; q < rec.np; q++)
+  {
+    const int v = rec.gv[q];
+    int k = 0;
+    float sum = 0.f;
+    for(int j = 0; j < kJoints; j++)
+    {
+      const float w = model->h_weights[static_cast<size_t>(v) * kJoints + j];
+      sum += w; // joint order, as lbs_wsum
+      if(w != 0.f && k < 4)
+      {
+        sk.w[q][k] = w;
+        sk.j[q][k] = static_cast<uint8_t>(j);
+        k++;
+      }
+    }
+    sk.ws[q] = sum;
+  }
+}
+
+size_t ik2_skin_bytes(int64_t batch, int n)
+{
+  return static_cast<size_t>(batch) * n * sizeof(TaskSkin);
+}
+
+int launch_task_topo(const ModelDev & d, cudaStream_t st, long long total, const int32_t * face_idx, TaskRec * out, TaskSkin * skins)
 {
   task_topo_kernel<<<static_cast<unsigned>((total + 3) / 4), 128, 0, st>>>(total, face_idx, d.F, d.faces, d.adj_offset, d.adj_faces,
-                                                                         d.vert_jmask, out);
+                                                                         d.vert_jmask, out, d.kmax <= 4 ? skins : nullptr,
+                                                                         d.lbs_joint, d.lbs_weight, d.lbs_wsum, d.Vpad, d.kmax);
   SB_LAUNCHED();
   return SMPLPP_OK;
 }
@@ -1531,12 +1646,27 @@ bool plan_smem(Ik2Params & p, int rows, bool staged, int want_slots)
   L.A = off, off += p.ntile * 16 * 8;
   L.bvec = off, off += up16((p.Dp + 4) * 8);
   L.misc = off, off += 128;
+  L.tin = takef((rows == 4 ? 10 : 7) * p.n);
   const int scratch0 = off;
-  L.rec = off, off += 2 * up16(static_cast<int>(sizeof(TaskRec)));
+  L.rec = off, off += up16(static_cast<int>(sizeof(TaskRec)));
+  L.skin = off, off += p.skins ? static_cast<int>(sizeof(TaskSkin)) : 0;
   const int MP = p.MP, MI = p.MI, ML = p.ML, kmax = p.kmax;
+  // theta, beta, R and Jt (1504 B) are only read by the prologue: the small per-task arrays reuse that space when they fit
+  {
+    int dead = L.theta;
+    const int dead_end = L.coef; // theta | beta
+    auto take_dead = [&](int bytes, int & field) {
+      if(dead + up16(bytes) <= dead_end)
+        field = dead, dead += up16(bytes);
+      else
+        field = off, off += up16(bytes);
+    };
+    take_dead(16 * 4, L.ts);
+    take_dead(12 * 4, L.cornN);
+    take_dead(MP * kmax, L.sj);
+  }
   L.pv = takef(3 * MP), L.pr = takef(3 * MP), L.sw = takef(MP * kmax), L.xw = takef(3 * MP * kmax);
-  L.sj = off, off += up16(MP * kmax);
-  L.Au = takef(9 * MP), L.itemN = takef(4 * std::max(MI, 1)), L.cornN = takef(12), L.ts = takef(16);
+  L.Au = takef(9 * MP), L.itemN = takef(4 * std::max(MI, 1));
   // d(normal)/d(vertex) contributions and Q are live in disjoint phases of a task
   L.Dref = L.Q = takef(std::max(27 * std::max(MI, 1), rows * kBlendK));
   L.ybuf = takef(3 * MP * ML);
@@ -1620,6 +1750,7 @@ int launch_ik_fused(const Ik2Call & c)
   p.joint_template = md.joint_template, p.joint_shape = md.joint_shape;
   const bool per_frame = c.frame_recs != nullptr;
   p.recs = per_frame ? c.frame_recs : t->recs;
+  p.skins = md.kmax <= 4 ? (per_frame ? c.frame_skins : t->skins) : nullptr;
   p.rec_stride = per_frame ? t->d.n : 0;
   p.n = t->d.n;
   const bool vposer = o->enable_vposer != 0;
@@ -1648,6 +1779,30 @@ int launch_ik_fused(const Ik2Call & c)
   p.pos_task_weight = c.pos_task_weight, p.vposer_jac = c.vjac;
   p.status = c.status, p.e_out = c.e_out, p.j_out = c.j_out, p.a_out = c.a_out, p.b_out = c.b_out, p.delta_out = c.delta_out;
   p.dphi_out = c.dphi_out, p.a_ws = c.a_ws, p.schur_out = c.schur_out, p.factor_ws = c.factor_ws;
+  p.dbg_cycles = nullptr;
+#ifdef SMPLPP_IK2_DBG
+  {
+    static long long * dbg = nullptr;
+    if(!dbg)
+    {
+      cudaMalloc(&dbg, 32 * sizeof(long long));
+      cudaMemset(dbg, 0, 32 * sizeof(long long));
+    }
+    long long h[32];
+    cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    long long tot = 0;
+    for(int i = 0; i < 32; i++) tot += h[i];
+    if(tot > 0)
+    {
+      fprintf(stderr, "ik2 phase cycles (previous launch, team 0 of CTA 0):");
+      for(int i = 0; i < 32; i++)
+        if(h[i]) fprintf(stderr, " [%d] %lld", i, h[i]);
+      fprintf(stderr, " total %lld\n", tot);
+    }
+    cudaMemset(dbg, 0, 32 * sizeof(long long));
+    p.dbg_cycles = dbg;
+  }
+#endif
   const int rows = o->normal_task_weight > 0.f ? 4 : 3;
   const bool staged = !per_frame;
   if(!plan_smem(p, rows, staged, 3 * p.MP))

@@ -35,6 +35,7 @@ struct Ik2Call
   const float * pos_task_weight = nullptr;
   const float * vjac = nullptr;          // (B, 63, 32) decoder Jacobian
   const TaskRec * frame_recs = nullptr;  // (B, n) per-frame attachments; null: the task set's records
+  const TaskSkin * frame_skins = nullptr; // (B, n) skinning rows of frame_recs (models with <= 4 influences), else null
   int32_t * status = nullptr;
   float * e_out = nullptr;
   float * j_out = nullptr;
@@ -49,7 +50,10 @@ struct Ik2Call
 int launch_ik_fused(const Ik2Call & c);
 // one record from the host copies of the model topology; -1 when the 1-rings exceed the record limits
 int build_task_rec_host(const smplpp_model * model, int64_t face, TaskRec & rec);
+void build_task_skin_host(const smplpp_model * model, const TaskRec & rec, TaskSkin & skin); // model kmax <= 4
 // (total) records from per-frame face indices on the device (total = frames * tasks)
-int launch_task_topo(const ModelDev & d, cudaStream_t st, long long total, const int32_t * face_idx, TaskRec * out);
+// skins (nullable): also the skinning rows of every record (d.kmax <= 4)
+int launch_task_topo(const ModelDev & d, cudaStream_t st, long long total, const int32_t * face_idx, TaskRec * out, TaskSkin * skins);
+size_t ik2_skin_bytes(int64_t batch, int n);
 extern int g_ik_variant; // 0: auto (two kernels when the frames share the attachments, fused kernel otherwise), 1: two kernels, 2: fused
 } // namespace sb

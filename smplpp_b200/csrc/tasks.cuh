@@ -57,6 +57,15 @@ struct alignas(16) TaskRec
   uint8_t pad2[3];
 };
 static_assert(sizeof(TaskRec) == 608, "TaskRec layout");
+// skinning rows of the pairs of a record (models with at most 4 influences per vertex, i.e. SMPL): fetched with the
+// record, so that the skinning phase of a task starts without a dependent chain of global loads
+struct alignas(16) TaskSkin
+{
+  float w[kRecPairs][4];   // raw weights W[v, j] of the (up to) four influences
+  float ws[kRecPairs];     // sum_j W[v, j] (the homogeneous coordinate)
+  uint8_t j[kRecPairs][4]; // joints
+};
+static_assert(sizeof(TaskSkin) == 1152, "TaskSkin layout");
 } // namespace sb
 
 struct smplpp_tasks
@@ -70,6 +79,7 @@ struct smplpp_tasks
   std::vector<int32_t> h_corner;
   // fused IK step (ik2.cu)
   const sb::TaskRec * recs = nullptr; // (n) device
+  const sb::TaskSkin * skins = nullptr; // (n) device, null when the model has more than 4 influences per vertex
   const long long * face_idx_dev = nullptr; // (n) device copy of the attachment faces (smplpp_task_positions / _tangents)
   int maxPairs = 0, maxItems = 0, maxLive = 0, maxPairsCorner = 3;
   // smplpp_ik_solve_host (ik_host.cu): grow-only device buffers and the stream of the host-buffer call
