@@ -36,6 +36,18 @@ METRICS = [
     "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__warps_eligible.avg.per_cycle_active",
     "l1tex__m_xbar2l1tex_read_bytes.sum", "l1tex__m_l1tex2xbar_write_bytes_mem_global_op_tma_st.sum",
     "lts__t_sectors_op_read.sum", "lts__t_sectors_op_write.sum",
+    # shared-memory side of the tensor-core kernels: UMMA operand reads (tc data pipe), LSU wavefronts, data-bank load
+    "l1tex__data_pipe_tc_wavefronts_mem_shared.sum", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__data_bank_reads.avg.pct_of_peak_sustained_elapsed", "l1tex__data_bank_writes.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__data_bank_reads.max.pct_of_peak_sustained_elapsed", "l1tex__data_bank_writes.max.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed_pipe_tc.sum.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tmem.sum.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_uniform.sum.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
 ]
 
 

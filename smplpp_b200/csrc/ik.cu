@@ -903,27 +903,54 @@ __device__ void block_cholesky(double * L, double * col, int N, int npiv, int ti
   }
 }
 
-// x <- L^-T L^-1 x for the leading n x n block, executed by warp 0 (other threads idle); result in x
+// x <- L^-T L^-1 x for the leading n x n block, executed by warp 0 (other threads idle); result in x.  Four unknowns per
+// step: every lane solves the 4x4 diagonal block redundantly in registers, then the lanes update the other rows.
 __device__ void warp_chol_solve(const double * L, int n, double * x, int tid)
 {
-  if(tid < 32)
+  if(tid >= 32) return;
+  for(int k0 = 0; k0 < n; k0 += 4)
   {
-    for(int k = 0; k < n; k++)
+    const int bs = min(4, n - k0);
+    double xs[4] = {0.0, 0.0, 0.0, 0.0};
+    for(int c = 0; c < bs; c++)
     {
-      double xk = x[k] / L[tri_idx(k, k)];
-      __syncwarp();
-      if(tid == 0) x[k] = xk;
-      for(int i = k + 1 + tid; i < n; i += 32) x[i] -= L[tri_idx(i, k)] * xk;
-      __syncwarp();
+      double v = x[k0 + c];
+      for(int k = 0; k < c; k++) v -= L[tri_idx(k0 + c, k0 + k)] * xs[k];
+      xs[c] = v / L[tri_idx(k0 + c, k0 + c)];
     }
-    for(int k = n - 1; k >= 0; k--)
+    __syncwarp();
+    if(tid == 0)
+      for(int c = 0; c < bs; c++) x[k0 + c] = xs[c];
+    for(int i = k0 + bs + tid; i < n; i += 32)
     {
-      double xk = x[k] / L[tri_idx(k, k)];
-      __syncwarp();
-      if(tid == 0) x[k] = xk;
-      for(int i = tid; i < k; i += 32) x[i] -= L[tri_idx(k, i)] * xk;
-      __syncwarp();
+      const double * row = L + tri_idx(i, k0);
+      double v = x[i];
+      for(int c = 0; c < bs; c++) v -= row[c] * xs[c];
+      x[i] = v;
     }
+    __syncwarp();
+  }
+  const int last = (n - 1) / 4 * 4;
+  for(int k0 = last; k0 >= 0; k0 -= 4)
+  {
+    const int bs = min(4, n - k0);
+    double xs[4] = {0.0, 0.0, 0.0, 0.0};
+    for(int c = bs - 1; c >= 0; c--)
+    {
+      double v = x[k0 + c];
+      for(int k = c + 1; k < bs; k++) v -= L[tri_idx(k0 + k, k0 + c)] * xs[k];
+      xs[c] = v / L[tri_idx(k0 + c, k0 + c)];
+    }
+    __syncwarp();
+    if(tid == 0)
+      for(int c = 0; c < bs; c++) x[k0 + c] = xs[c];
+    for(int i = tid; i < k0; i += 32)
+    {
+      double v = x[i];
+      for(int c = 0; c < bs; c++) v -= L[tri_idx(k0 + c, i)] * xs[c];
+      x[i] = v;
+    }
+    __syncwarp();
   }
 }
 
