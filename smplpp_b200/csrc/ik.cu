@@ -658,122 +658,123 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
   }
   __syncthreads();
   // ---- P5d: pose-blend (and shape-blend) columns: Q_m = sum_u CA4_u P_u (ROWS x 218), J += Q_m dvec(R_k)/dtheta.
-  //      Warp w works for joint group g = w & 3 on the tasks of parity w >> 2.  Every lane owns TWO basis columns: set A
-  //      = joints 6g+1..6g+3, set B = joints 6g+4..6g+6 (27 lanes x 9 columns each; group 3's set B also holds the 10
-  //      shape columns in lanes 18..27), so that the pair's vertex id, its 12 C4 floats and the loop overhead are
-  //      paid once per 18 FMAs instead of once per 9.  The 9-term contraction per (joint, axis) is a segmented shuffle
-  //      reduction: no block barrier per task. ----
+  //      One warp per task; every lane owns SEVEN CONSECUTIVE basis columns (7 x 32 = 224), so a pair costs 7 16-byte
+  //      loads + 3 broadcast loads for 21 * ROWS FMAs (the version this replaces gave a lane two scattered columns: 18
+  //      FMAs per pair and a segmented 4-level shuffle reduction per (row, axis) that cost as much as the contraction).
+  //      The 9 columns of a joint span two or three neighbouring lanes: every lane forms the partial sums of the (at most
+  //      two) joints its columns touch, the first lane of a joint collects the pieces of its one or two right neighbours
+  //      with two shuffles per value - a fixed order, so results stay bitwise reproducible. ----
   {
     const int warp = tid >> 5, lane = tid & 31;
     const int bcol = 75 + p.phi_cols;
-    const int g = warp & 3, parity = warp >> 2;
-    const int e = lane % 9;
-    int kk[2] = {6 * g + 1 + lane / 9, 6 * g + 4 + lane / 9}, dd[2] = {-1, -1}, ib = -1;
-#pragma unroll
-    for(int sset = 0; sset < 2; sset++)
-      if(lane < 27 && kk[sset] < kJoints) dd[sset] = 9 * (kk[sset] - 1) + e;
-    if(g == 3 && lane >= 18 && lane < 18 + kShapeDim && p.beta_cols) ib = lane - 18, dd[1] = kPoseDim + ib;
-    const bool joint_lane[2] = {dd[0] >= 0, dd[1] >= 0 && ib < 0};
-    float dv[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-#pragma unroll
-    for(int sset = 0; sset < 2; sset++)
-      if(joint_lane[sset])
-        dv[sset][0] = s_dR[27 * kk[sset] + e], dv[sset][1] = s_dR[27 * kk[sset] + 9 + e], dv[sset][2] = s_dR[27 * kk[sset] + 18 + e];
-    // lanes without a column in a set read column 0 (always valid) and their products are dropped
-    const int da = dd[0] >= 0 ? dd[0] : 0, db = dd[1] >= 0 ? dd[1] : 0;
-    for(int m = parity; m < n; m += 2)
+    const int c_first = 7 * lane;                      // first owned column
+    // joints touched: slot A holds the joint of the first column, slot B the next one when the lane reaches into it
+    const int kA = c_first < kPoseDim ? c_first / 9 + 1 : 0;
+    const int endA = 9 * kA;                           // first column behind joint kA
+    const int kB = (kA > 0 && endA < c_first + 7 && endA < kPoseDim) ? kA + 1 : 0;
+    // the joint this lane collects: the one whose first column lies in [c_first, c_first + 7)
+    int kOwn = 0;
+    if(c_first < kPoseDim)
     {
-      float qa[ROWS], qb[ROWS];
+      const int kk = (c_first + 8) / 9 + 1;            // first joint starting at or after c_first
+      if(9 * (kk - 1) < c_first + 7 && kk < kJoints) kOwn = kk;
+    }
+    const bool ownIsA = kOwn != 0 && kOwn == kA;       // the joint starts exactly at the lane's first column
+    const int span = kOwn ? (9 * (kOwn - 1) + 8) / 7 - lane : 0; // lanes to the right holding the rest of the joint (1 or 2)
+    // derivative entries of the owned columns: dv[i][c] = d vec(R_k)[e] / d theta_kc
+    float dv[7][3];
 #pragma unroll
-      for(int r = 0; r < ROWS; r++) qa[r] = qb[r] = 0.f;
+    for(int i = 0; i < 7; i++)
+    {
+      const int d = c_first + i;
+      const bool on = d < kPoseDim;
+      const int k = on ? d / 9 + 1 : 1, e = on ? d % 9 : 0;
+#pragma unroll
+      for(int c = 0; c < 3; c++) dv[i][c] = on ? s_dR[27 * k + 9 * c + e] : 0.f;
+    }
+    for(int m = warp; m < n; m += THREADS / 32)
+    {
+      float qacc[ROWS][7];
+#pragma unroll
+      for(int r = 0; r < ROWS; r++)
+#pragma unroll
+        for(int i = 0; i < 7; i++) qacc[r][i] = 0.f;
       const int p0 = t.pair_off[m];
       const int np = p.use_ring ? t.pair_off[m + 1] - p0 : 3;
-      // the rigid part of these entries was written by an earlier phase: fetch it now so that the global round trip
-      // overlaps the contraction (ncu: the dependent read-modify-write at the end of every task was 30 % of the samples)
-      // (only ~1/3 of the (task, joint) entries have a rigid part: the others are known to be zero from the joint mask)
       const uint32_t jmask = p.use_ring ? t.task_joint_mask[m] : t.task_joint_mask_corner[m];
-      float jprev[2][ROWS][3];
-#pragma unroll
-      for(int sset = 0; sset < 2; sset++)
-        if(joint_lane[sset] && e == 0)
-        {
-          const bool live = (jmask >> kk[sset]) & 1u;
-#pragma unroll
-          for(int r = 0; r < ROWS; r++)
-#pragma unroll
-            for(int c = 0; c < 3; c++) jprev[sset][r][c] = live ? Jf[(4 * m + r) * p.ldfull + 3 + 3 * kk[sset] + c] : 0.f;
-        }
+      // the rigid part of the owned joint was written by P5b: fetch it now, the round trip overlaps the contraction
+      float jprev[ROWS][3];
+      if(kOwn)
       {
-        // basis rows come from L2 (~300 cycles): two pairs x two columns per trip keep four 16-byte loads in flight
-        constexpr int UQ = 2;
-        int q = 0;
-        for(; q + UQ <= np; q += UQ)
-        {
-          float4 ba[UQ], bb[UQ];
-#pragma unroll
-          for(int i = 0; i < UQ; i++)
-          {
-            const float4 * row = t.basis4 + static_cast<size_t>(t.pair_vert[p0 + q + i]) * kBlendK;
-            ba[i] = __ldg(row + da), bb[i] = __ldg(row + db); // x, y, z rows of a column in one load
-          }
-#pragma unroll
-          for(int i = 0; i < UQ; i++)
-          {
-            // the 12 floats of a pair are warp-uniform: three 16-byte broadcast loads
-            const float4 * C4 = reinterpret_cast<const float4 *>(s_C4 + 12 * (p0 + q + i));
-            const float4 c0 = C4[0], c1 = C4[1], c2 = C4[2];
-            const float C[12] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w};
-#pragma unroll
-            for(int r = 0; r < ROWS; r++)
-            {
-              qa[r] = fmaf(C[3 * r], ba[i].x, fmaf(C[3 * r + 1], ba[i].y, fmaf(C[3 * r + 2], ba[i].z, qa[r])));
-              qb[r] = fmaf(C[3 * r], bb[i].x, fmaf(C[3 * r + 1], bb[i].y, fmaf(C[3 * r + 2], bb[i].z, qb[r])));
-            }
-          }
-        }
-        for(; q < np; q++)
-        {
-          const float4 * row = t.basis4 + static_cast<size_t>(t.pair_vert[p0 + q]) * kBlendK;
-          const float4 ba = __ldg(row + da), bb = __ldg(row + db);
-          const float * C = s_C4 + 12 * (p0 + q);
-#pragma unroll
-          for(int r = 0; r < ROWS; r++)
-          {
-            qa[r] = fmaf(C[3 * r], ba.x, fmaf(C[3 * r + 1], ba.y, fmaf(C[3 * r + 2], ba.z, qa[r])));
-            qb[r] = fmaf(C[3 * r], bb.x, fmaf(C[3 * r + 1], bb.y, fmaf(C[3 * r + 2], bb.z, qb[r])));
-          }
-        }
-      }
-#pragma unroll
-      for(int sset = 0; sset < 2; sset++)
-      {
-        float val[ROWS][3];
+        const bool live = (jmask >> kOwn) & 1u;
 #pragma unroll
         for(int r = 0; r < ROWS; r++)
 #pragma unroll
-          for(int c = 0; c < 3; c++)
-          {
-            float v = (sset == 0 ? qa[r] : qb[r]) * dv[sset][c]; // dv = 0 on lanes without a joint column in this set
-#pragma unroll
-            for(int o = 1; o < 16; o <<= 1)
-            {
-              const float other = __shfl_down_sync(0xffffffffu, v, o);
-              if(e + o < 9) v += other;
-            }
-            val[r][c] = v;
-          }
-        if(joint_lane[sset] && e == 0)
-        {
-#pragma unroll
-          for(int r = 0; r < ROWS; r++)
-#pragma unroll
-            for(int c = 0; c < 3; c++) Jf[(4 * m + r) * p.ldfull + 3 + 3 * kk[sset] + c] = jprev[sset][r][c] + val[r][c];
-        }
+          for(int c = 0; c < 3; c++) jprev[r][c] = live ? Jf[(4 * m + r) * p.ldfull + 3 + 3 * kOwn + c] : 0.f;
       }
-      if(ib >= 0)
+      for(int q = 0; q < np; q++)
+      {
+        const float4 * row = t.basis4 + static_cast<size_t>(t.pair_vert[p0 + q]) * kBlendK + c_first;
+        float4 b[7];
+#pragma unroll
+        for(int i = 0; i < 7; i++) b[i] = __ldg(row + i);
+        const float4 * C4 = reinterpret_cast<const float4 *>(s_C4 + 12 * (p0 + q));
+        const float4 c0 = C4[0], c1 = C4[1], c2 = C4[2];
+        const float C[12] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w};
+#pragma unroll
+        for(int r = 0; r < ROWS; r++)
+#pragma unroll
+          for(int i = 0; i < 7; i++)
+            qacc[r][i] = fmaf(C[3 * r], b[i].x, fmaf(C[3 * r + 1], b[i].y, fmaf(C[3 * r + 2], b[i].z, qacc[r][i])));
+      }
+      // partial sums of the two touched joints over the owned columns
+      float pa[ROWS][3], pb[ROWS][3];
+#pragma unroll
+      for(int r = 0; r < ROWS; r++)
+#pragma unroll
+        for(int c = 0; c < 3; c++)
+        {
+          float sa = 0.f, sb2 = 0.f;
+#pragma unroll
+          for(int i = 0; i < 7; i++)
+          {
+            const float v = qacc[r][i] * dv[i][c]; // dv = 0 on columns that are no pose feature
+            if(c_first + i < endA)
+              sa += v;
+            else
+              sb2 += v;
+          }
+          pa[r][c] = sa, pb[r][c] = sb2;
+        }
+#pragma unroll
+      for(int r = 0; r < ROWS; r++)
+#pragma unroll
+        for(int c = 0; c < 3; c++)
+        {
+          const float n1 = __shfl_down_sync(0xffffffffu, pa[r][c], 1);
+          const float n2 = __shfl_down_sync(0xffffffffu, pa[r][c], 2);
+          if(kOwn)
+          {
+            float v = ownIsA ? pa[r][c] : pb[r][c];
+            v += n1;
+            if(span == 2) v += n2;
+            Jf[(4 * m + r) * p.ldfull + 3 + 3 * kOwn + c] = jprev[r][c] + v;
+          }
+        }
+      (void)kB;
+      // shape-blend columns 207..216 -> beta columns
+      if(p.beta_cols)
       {
 #pragma unroll
-        for(int r = 0; r < ROWS; r++) Jf[(4 * m + r) * p.ldfull + bcol + ib] += qb[r];
+        for(int i = 0; i < 7; i++)
+        {
+          const int ib = c_first + i - kPoseDim;
+          if(ib >= 0 && ib < kShapeDim)
+          {
+#pragma unroll
+            for(int r = 0; r < ROWS; r++) Jf[(4 * m + r) * p.ldfull + bcol + ib] += qacc[r][i];
+          }
+        }
       }
     }
   }
