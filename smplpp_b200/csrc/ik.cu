@@ -658,33 +658,34 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
   }
   __syncthreads();
   // ---- P5d: pose-blend (and shape-blend) columns: Q_m = sum_u CA4_u P_u (ROWS x 218), J += Q_m dvec(R_k)/dtheta.
-  //      One warp per task; every lane owns SEVEN CONSECUTIVE basis columns (7 x 32 = 224), so a pair costs 7 16-byte
-  //      loads + 3 broadcast loads for 21 * ROWS FMAs (the version this replaces gave a lane two scattered columns: 18
-  //      FMAs per pair and a segmented 4-level shuffle reduction per (row, axis) that cost as much as the contraction).
-  //      The 9 columns of a joint span two or three neighbouring lanes: every lane forms the partial sums of the (at most
-  //      two) joints its columns touch, the first lane of a joint collects the pieces of its one or two right neighbours
-  //      with two shuffles per value - a fixed order, so results stay bitwise reproducible. ----
+  //      One warp per task; lanes 0..27 own EIGHT CONSECUTIVE basis columns each (8 x 28 = 224) of the K-major x / y / z
+  //      rows of a vertex: a pair costs 6 16-byte loads + 3 broadcast loads for 24 * ROWS FMAs, and exactly the 2688
+  //      bytes of the three rows cross L2 (the (x, y, z, 0) float4-per-column layout moved 3584; at 16384 frames this
+  //      phase runs at the L2 -> SM bandwidth, so bytes are time).  The version before gave a lane two scattered columns:
+  //      18 FMAs per pair and a segmented 4-level shuffle reduction per (row, axis) that cost as much as the contraction.
+  //      The 9 columns of a joint always span exactly two neighbouring lanes: every lane forms the partial sums of the two
+  //      joints its columns touch, the lane holding a joint's first column adds its right neighbour's piece (one shuffle
+  //      per value) - a fixed order, so results stay bitwise reproducible. ----
   {
     const int warp = tid >> 5, lane = tid & 31;
     const int bcol = 75 + p.phi_cols;
-    const int c_first = 7 * lane;                      // first owned column
-    // joints touched: slot A holds the joint of the first column, slot B the next one when the lane reaches into it
+    const int c_first = 8 * lane;                      // first owned column (lanes 28..31 own none)
+    const bool has_cols = c_first < kBlendK;
+    // slot A: the joint of the first column; slot B: the next joint, which the lane reaches into
     const int kA = c_first < kPoseDim ? c_first / 9 + 1 : 0;
     const int endA = 9 * kA;                           // first column behind joint kA
-    const int kB = (kA > 0 && endA < c_first + 7 && endA < kPoseDim) ? kA + 1 : 0;
-    // the joint this lane collects: the one whose first column lies in [c_first, c_first + 7)
+    // the joint this lane completes: the one whose first column lies in [c_first, c_first + 8)
     int kOwn = 0;
     if(c_first < kPoseDim)
     {
       const int kk = (c_first + 8) / 9 + 1;            // first joint starting at or after c_first
-      if(9 * (kk - 1) < c_first + 7 && kk < kJoints) kOwn = kk;
+      if(9 * (kk - 1) < c_first + 8 && kk < kJoints) kOwn = kk;
     }
     const bool ownIsA = kOwn != 0 && kOwn == kA;       // the joint starts exactly at the lane's first column
-    const int span = kOwn ? (9 * (kOwn - 1) + 8) / 7 - lane : 0; // lanes to the right holding the rest of the joint (1 or 2)
     // derivative entries of the owned columns: dv[i][c] = d vec(R_k)[e] / d theta_kc
-    float dv[7][3];
+    float dv[8][3];
 #pragma unroll
-    for(int i = 0; i < 7; i++)
+    for(int i = 0; i < 8; i++)
     {
       const int d = c_first + i;
       const bool on = d < kPoseDim;
@@ -694,11 +695,11 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
     }
     for(int m = warp; m < n; m += THREADS / 32)
     {
-      float qacc[ROWS][7];
+      float qacc[ROWS][8];
 #pragma unroll
       for(int r = 0; r < ROWS; r++)
 #pragma unroll
-        for(int i = 0; i < 7; i++) qacc[r][i] = 0.f;
+        for(int i = 0; i < 8; i++) qacc[r][i] = 0.f;
       const int p0 = t.pair_off[m];
       const int np = p.use_ring ? t.pair_off[m + 1] - p0 : 3;
       const uint32_t jmask = p.use_ring ? t.task_joint_mask[m] : t.task_joint_mask_corner[m];
@@ -712,23 +713,26 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
 #pragma unroll
           for(int c = 0; c < 3; c++) jprev[r][c] = live ? Jf[(4 * m + r) * p.ldfull + 3 + 3 * kOwn + c] : 0.f;
       }
-      for(int q = 0; q < np; q++)
-      {
-        const float4 * row = t.basis4 + static_cast<size_t>(t.pair_vert[p0 + q]) * kBlendK + c_first;
-        float4 b[7];
+      if(has_cols)
+        for(int q = 0; q < np; q++)
+        {
+          const float * row = t.basis + static_cast<size_t>(3 * t.pair_vert[p0 + q]) * kBlendK + c_first;
+          const float4 x0 = __ldg(reinterpret_cast<const float4 *>(row)), x1 = __ldg(reinterpret_cast<const float4 *>(row + 4));
+          const float4 y0 = __ldg(reinterpret_cast<const float4 *>(row + kBlendK)), y1 = __ldg(reinterpret_cast<const float4 *>(row + kBlendK + 4));
+          const float4 z0 = __ldg(reinterpret_cast<const float4 *>(row + 2 * kBlendK)), z1 = __ldg(reinterpret_cast<const float4 *>(row + 2 * kBlendK + 4));
+          const float bx[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+          const float by[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+          const float bz[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+          const float4 * C4 = reinterpret_cast<const float4 *>(s_C4 + 12 * (p0 + q));
+          const float4 c0 = C4[0], c1 = C4[1], c2 = C4[2];
+          const float C[12] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w};
 #pragma unroll
-        for(int i = 0; i < 7; i++) b[i] = __ldg(row + i);
-        const float4 * C4 = reinterpret_cast<const float4 *>(s_C4 + 12 * (p0 + q));
-        const float4 c0 = C4[0], c1 = C4[1], c2 = C4[2];
-        const float C[12] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w};
+          for(int r = 0; r < ROWS; r++)
 #pragma unroll
-        for(int r = 0; r < ROWS; r++)
-#pragma unroll
-          for(int i = 0; i < 7; i++)
-            qacc[r][i] = fmaf(C[3 * r], b[i].x, fmaf(C[3 * r + 1], b[i].y, fmaf(C[3 * r + 2], b[i].z, qacc[r][i])));
-      }
-      // partial sums of the two touched joints over the owned columns
-      float pa[ROWS][3], pb[ROWS][3];
+            for(int i = 0; i < 8; i++)
+              qacc[r][i] = fmaf(C[3 * r], bx[i], fmaf(C[3 * r + 1], by[i], fmaf(C[3 * r + 2], bz[i], qacc[r][i])));
+        }
+      // partial sums of the two touched joints over the owned columns, combined with the right neighbour's slot A
 #pragma unroll
       for(int r = 0; r < ROWS; r++)
 #pragma unroll
@@ -736,7 +740,7 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
         {
           float sa = 0.f, sb2 = 0.f;
 #pragma unroll
-          for(int i = 0; i < 7; i++)
+          for(int i = 0; i < 8; i++)
           {
             const float v = qacc[r][i] * dv[i][c]; // dv = 0 on columns that are no pose feature
             if(c_first + i < endA)
@@ -744,29 +748,14 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
             else
               sb2 += v;
           }
-          pa[r][c] = sa, pb[r][c] = sb2;
+          const float n1 = __shfl_down_sync(0xffffffffu, sa, 1);
+          if(kOwn) Jf[(4 * m + r) * p.ldfull + 3 + 3 * kOwn + c] = jprev[r][c] + ((ownIsA ? sa : sb2) + n1);
         }
-#pragma unroll
-      for(int r = 0; r < ROWS; r++)
-#pragma unroll
-        for(int c = 0; c < 3; c++)
-        {
-          const float n1 = __shfl_down_sync(0xffffffffu, pa[r][c], 1);
-          const float n2 = __shfl_down_sync(0xffffffffu, pa[r][c], 2);
-          if(kOwn)
-          {
-            float v = ownIsA ? pa[r][c] : pb[r][c];
-            v += n1;
-            if(span == 2) v += n2;
-            Jf[(4 * m + r) * p.ldfull + 3 + 3 * kOwn + c] = jprev[r][c] + v;
-          }
-        }
-      (void)kB;
       // shape-blend columns 207..216 -> beta columns
       if(p.beta_cols)
       {
 #pragma unroll
-        for(int i = 0; i < 7; i++)
+        for(int i = 0; i < 8; i++)
         {
           const int ib = c_first + i - kPoseDim;
           if(ib >= 0 && ib < kShapeDim)
