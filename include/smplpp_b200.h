@@ -337,7 +337,7 @@ int smplpp_ik_shared_beta_apply(const smplpp_tasks_t * tasks, const smplpp_ik_op
                                 const int32_t * status_dev, const double * reduced_dev, void * workspace_dev,
                                 size_t workspace_bytes);
 
-/* The three calls above as ONE, with the collective inside (smplpp_shared_beta_step(..., ncclComm_t)):
+/* The three calls above as ONE, with the collective inside (the shared-beta step taking an ncclComm_t):
  * reduce -> ncclAllReduce(sum) of the 111 doubles on `stream` over `nccl_comm` (an ncclComm_t passed as void*; NULL on a
  * single GPU) -> apply.  reduced_dev (111 doubles) is caller-owned scratch that also returns the summed message.  NCCL is
  * resolved at run time (the process's own ncclAllReduce when a framework loaded it, else libnccl.so.2, or the library
