@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "forward.cuh"
 #include "ik2.cuh"
+#include "ik_solve.cuh"
 #include "tc3_layout.cuh"
 #include "vposer.cuh"
 
@@ -945,6 +946,13 @@ extern "C" int smplpp_set_forward_variant(int variant)
   if(variant >= 400 && variant <= 402)
   {
     g_ik_variant = variant - 400;
+    return SMPLPP_OK;
+  }
+  // normal equations + solve of the two-kernel IK path: 410 auto (fp64 tensor-core kernel where the shape allows),
+  // 411 the scalar ik_solve_kernel always
+  if(variant == 410 || variant == 411)
+  {
+    g_solve_variant = variant - 410;
     return SMPLPP_OK;
   }
   if(variant < 0 || variant > 6) return fail(SMPLPP_ERR_INVALID, "SMPL", "unknown forward variant");

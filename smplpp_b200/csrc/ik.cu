@@ -17,6 +17,7 @@
 #include "forward.cuh"
 #include "ik2.cuh"
 #include "ik_math.cuh"
+#include "ik_solve.cuh"
 #include "tasks.cuh"
 #include "vposer.cuh"
 
@@ -813,32 +814,6 @@ namespace c2
 constexpr int THREADS = 256;
 }
 
-struct IkSolveParams
-{
-  int B, n, rows_per_task; // rows actually populated per task (3 or 4)
-  int theta_dim, phi_cols, beta_cols, D; // D = theta_dim + phi_cols + beta_cols (compact)
-  int ld;                  // row stride of J
-  int rows_off;            // byte offset of the row staging area [2][4][ld] floats in the dynamic shared memory
-  int vposer, enable_qp, skip_if_too_few, update_state;
-  int schur;               // shared-beta stage: eliminate only the first D - beta_cols pivots
-  float reg_theta, reg_phi, reg_beta, phi_limit, beta_limit, latent_reg, hand_reg;
-  const float * J;   // (B, 4n, ld)
-  const float * e;   // (B, 4n)
-  const int * frame_info;
-  float * theta_state; // (B, theta_dim) in/out
-  float * beta;        // (B, 10) in/out when beta_cols && !schur
-  long long beta_stride;
-  int * status;        // (B)
-  // optional outputs in the reference layout dim_ref = theta_dim + 2n + (beta ? 10 : 0)
-  int dim_ref;
-  double * a_out;
-  double * b_out;
-  double * delta_out;
-  double * a_ws;       // (B, D(D+1)/2) preserved A for the active-set QP (null when no bound can bind)
-  // shared-beta stage
-  double * schur_out;  // (B, 111): S (10x10 row-major) | r (10) | ||e||^2
-  double * factor_ws;  // (B, P) packed factor rows kept for the apply step
-};
 
 __device__ __forceinline__ int tri_idx(int i, int j) // i >= j
 {
@@ -2163,6 +2138,10 @@ static int ik_step_impl(const smplpp_model_t * model, const smplpp_vposer_t * vp
     sp.delta_out = delta_out ? delta_out + s * L.dim_ref : nullptr;
     const size_t smem = solve_smem_bytes(L, false);
     sp.rows_off = static_cast<int>(solve_rows_off(L, false));
+    bool handled = false;
+    rc = launch_ik_solve_mma(sp, st, &handled); // J'J on the fp64 tensor cores where the problem shape allows
+    if(rc != SMPLPP_OK) return rc;
+    if(handled) continue;
     if(smem > 227 * 1024) return fail(SMPLPP_ERR_INVALID, "IkTask", "IK problem too large for one CTA per frame");
     SB_CUDA(cudaFuncSetAttribute(ik_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     ik_solve_kernel<<<B, solve_block_threads(L.D), smem, st>>>(sp);
@@ -2346,6 +2325,10 @@ extern "C" int smplpp_ik_shared_beta_reduce(const smplpp_model_t * model, const 
     sp.factor_ws = reinterpret_cast<double *>(ws + L.off_factor) + s * P;
     const size_t smem = solve_smem_bytes(L, true);
     sp.rows_off = static_cast<int>(solve_rows_off(L, true));
+    bool handled = false;
+    rc = launch_ik_solve_mma(sp, st, &handled);
+    if(rc != SMPLPP_OK) return rc;
+    if(handled) continue;
     SB_CUDA(cudaFuncSetAttribute(ik_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     ik_solve_kernel<<<B, solve_block_threads(L.D), smem, st>>>(sp);
     SB_LAUNCHED();

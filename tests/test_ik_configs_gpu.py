@@ -187,12 +187,16 @@ def dense_block_arrow(J, e, theta_dim, prior=None):
     return A, b
 
 
-@pytest.fixture(params=[401, 402], ids=["two_kernels", "fused_kernel"])
+@pytest.fixture(params=[(401, 410), (401, 411), (402, 410)], ids=["two_kernels", "two_kernels_scalar_solve", "fused_kernel"])
 def ik_variant(request):
     from smplpp_b200 import capi
-    capi.check(capi.lib().smplpp_set_forward_variant(request.param))
-    yield request.param
+    # 401 / 402: ik_jacobian_kernel + solve kernel / fused kernel; 410 / 411: ik_solve_mma_kernel (fp64 tensor cores, the
+    # default where the problem shape allows) / the scalar ik_solve_kernel
+    capi.check(capi.lib().smplpp_set_forward_variant(request.param[0]))
+    capi.check(capi.lib().smplpp_set_forward_variant(request.param[1]))
+    yield request.param[0]
     capi.check(capi.lib().smplpp_set_forward_variant(400))
+    capi.check(capi.lib().smplpp_set_forward_variant(410))
 
 
 @pytest.mark.parametrize("mode", ["direct", "vposer"])
