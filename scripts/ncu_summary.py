@@ -57,7 +57,7 @@ def launches_md(path: str, tag: str) -> str:
     for r in rows:
         if r.get("Metric Name") != "gpu__time_duration.sum":
             continue
-        k = r["Kernel Name"].split("(")[0].replace("void ", "")
+        k = r["Kernel Name"].split("(")[0].replace("void ", "").replace("<unnamed>::", "")
         a = agg.setdefault(k, [0, 0.0, r["Grid Size"], r["Block Size"]])
         a[0] += 1
         a[1] += float(r["Metric Value"])
@@ -79,7 +79,7 @@ def rep_md(path: str, tag: str) -> str:
     hdr, units, body = rows[0], rows[1], rows[2:]
     out = ["# %s — `ncu --set full --clock-control none` capture: %s" % (tag, os.path.basename(path)), ""]
     for r in body:
-        name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "")
+        name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").replace("<unnamed>::", "")
         out += ["## `%s`" % name, "", "| metric | value | unit |", "|---|---:|---|"]
         for m in METRICS:
             if m in hdr:
@@ -103,7 +103,7 @@ def rep_traffic(path: str) -> dict:
     hdr, units, body = rows[0], rows[1], rows[2:]
     out = {}
     for r in body:
-        name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").split("<")[0]
+        name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").replace("<unnamed>::", "").split("<")[0]
         rd = float(r[hdr.index("dram__bytes_read.sum")]) * unit_scale(units[hdr.index("dram__bytes_read.sum")])
         wr = float(r[hdr.index("dram__bytes_write.sum")]) * unit_scale(units[hdr.index("dram__bytes_write.sum")])
         out[name] = rd + wr
@@ -120,7 +120,7 @@ def rep_l2(path: str) -> dict:
     if key not in hdr:
         return out
     for r in body:
-        name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").split("<")[0]
+        name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").replace("<unnamed>::", "").split("<")[0]
         out[name] = float(r[hdr.index(key)]) * unit_scale(units[hdr.index(key)])
     return out
 
