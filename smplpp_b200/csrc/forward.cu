@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "forward.cuh"
 #include "ik2.cuh"
+#include "ik_poseblend.cuh"
 #include "ik_solve.cuh"
 #include "tc3_layout.cuh"
 #include "vposer.cuh"
@@ -953,6 +954,12 @@ extern "C" int smplpp_set_forward_variant(int variant)
   if(variant == 410 || variant == 411)
   {
     g_solve_variant = variant - 410;
+    return SMPLPP_OK;
+  }
+  // pose-blend columns of the IK Jacobian: 420 auto (ik_poseblend_tc_kernel, tcgen05), 421 the FFMA phase of ik_jacobian_kernel
+  if(variant == 420 || variant == 421)
+  {
+    g_poseblend_variant = variant - 420;
     return SMPLPP_OK;
   }
   if(variant < 0 || variant > 6) return fail(SMPLPP_ERR_INVALID, "SMPL", "unknown forward variant");

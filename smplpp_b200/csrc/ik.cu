@@ -161,6 +161,12 @@ struct IkJacParams
   float * jout;    // (B, 4n, ld) compact Jacobian [thetaDim | phi | beta]
   int ld;
   int * frame_info; // (B, 2): valid marker count, non-finite flag
+  // pose-blend columns on tensor cores (ik_poseblend_tc_kernel): this kernel then skips P5d (and P5e) and leaves
+  // CA4 = d(residual rows) / d(rest vertex) and d vec(R_k) / d theta_k of every frame behind
+  float * ca_out;        // (B, ca_stride): per task [4 row slots][32 * K-blocks], k = 3 * pair + axis; null: FFMA phase here
+  const int * ca_slot_off; // (n + 1) first K-block of every task
+  int ca_stride;
+  float * dr_out;        // (B, 621): s_dR of joints 1..23
 };
 
 template<int ROWS>
@@ -656,6 +662,22 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
       for(int c = 0; c < 3; c++) out[3 * r + c] = C[3 * r] * A[c] + C[3 * r + 1] * A[3 + c] + C[3 * r + 2] * A[6 + c];
 #pragma unroll
     for(int e = 0; e < 12; e++) C[e] = out[e];
+    if(p.ca_out)
+    {
+      const int m = t.pair_task[pr], q = pr - t.pair_off[m];
+      const int s0 = p.ca_slot_off[m], kp = 32 * (p.ca_slot_off[m + 1] - s0);
+      float * dst = p.ca_out + static_cast<size_t>(f) * p.ca_stride + static_cast<size_t>(s0) * 128 + 3 * q;
+#pragma unroll
+      for(int r = 0; r < ROWS; r++)
+#pragma unroll
+        for(int a = 0; a < 3; a++) dst[r * kp + a] = out[3 * r + a];
+    }
+  }
+  if(p.ca_out)
+  {
+    float * dst = p.dr_out + static_cast<size_t>(f) * 621;
+    for(int i = tid; i < 621; i += THREADS) dst[i] = s_dR[27 + i];
+    return; // P5d / P5e run as kernels of their own
   }
   __syncthreads();
   // ---- P5d: pose-blend (and shape-blend) columns: Q_m = sum_u CA4_u P_u (ROWS x 218), J += Q_m dvec(R_k)/dtheta.
@@ -803,6 +825,46 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
         src = 75 + (c - 12), dst = 44 + (c - 12);
       Jo[row * p.ld + dst] = Jf[row * p.ldfull + src];
     }
+  }
+}
+
+// P5e of ik_jacobian_kernel as a kernel of its own (the pose-blend columns are added by ik_poseblend_tc_kernel between
+// the two): contract the 63 body columns with d(axis-angle)/d(latent) (node.cpp:761-772), one CTA per frame
+template<int ROWS>
+__global__ void __launch_bounds__(256) ik_vposer_contract_kernel(int n, int extra, const float * __restrict__ jfull, int ldfull,
+                                                                 const float * __restrict__ vposer_jac, float * __restrict__ jout,
+                                                                 int ld)
+{
+  const int tid = threadIdx.x, f = blockIdx.x;
+  const float * Jf = jfull + static_cast<size_t>(f) * 4 * n * ldfull;
+  float * Jo = jout + static_cast<size_t>(f) * 4 * n * ld;
+  const float * Jv = vposer_jac + static_cast<size_t>(f) * 63 * 32;
+  for(int i = tid; i < n * 32; i += 256)
+  {
+    const int m = i >> 5, tt = i & 31;
+    const float * jr = Jf + (4 * m) * ldfull + 6;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 7
+    for(int q = 0; q < 63; q++)
+    {
+      const float v = __ldg(Jv + q * 32 + tt);
+#pragma unroll
+      for(int r = 0; r < ROWS; r++) acc[r] = fmaf(jr[r * ldfull + q], v, acc[r]);
+    }
+#pragma unroll
+    for(int r = 0; r < 4; r++) Jo[(4 * m + r) * ld + 6 + tt] = acc[r];
+  }
+  for(int i = tid; i < 4 * n * (12 + extra); i += 256)
+  {
+    const int row = i / (12 + extra), c = i % (12 + extra);
+    int src, dst;
+    if(c < 6)
+      src = c, dst = c;
+    else if(c < 12)
+      src = 63 + c, dst = 32 + c;
+    else
+      src = 75 + (c - 12), dst = 44 + (c - 12);
+    Jo[row * ld + dst] = Jf[row * ldfull + src];
   }
 }
 
@@ -1675,6 +1737,12 @@ extern "C" int smplpp_tasks_create(const smplpp_model_t * model, int32_t n, cons
   t->sub_corner.V = nCorner;
   t->h_sub_vert = sub_vert;
   t->h_corner = corner;
+  rc = poseblend_tc_prepare(basis, pair_off, pair_vert, t->pb, t->allocations);
+  if(rc != SMPLPP_OK)
+  {
+    smplpp_tasks_destroy(t);
+    return rc;
+  }
   // self-contained per-task records of the fused step (ik2.cu)
   {
     std::vector<TaskRec> recs(n);
@@ -1820,7 +1888,8 @@ struct IkLayout
   int n, theta_dim, phi_cols, beta_cols, D, ld, ldfull, dim_ref, rows_per_task, use_ring, nUse;
   bool vposer, qp_ws;
   size_t off_theta, off_coef, off_xf, off_verts, off_rest, off_e, off_j, off_jfull, off_vaa, off_vjac, off_vaux, off_info,
-      off_aws, off_schur, off_factor, off_misc, total;
+      off_aws, off_schur, off_factor, off_misc, off_ca, off_dr, total;
+  bool pb_tc; // pose-blend columns by ik_poseblend_tc_kernel
   int chunk;
 };
 
@@ -1873,6 +1942,9 @@ IkLayout make_layout(const smplpp_tasks_t * tasks, const smplpp_ik_options * o, 
     L.off_factor = take(static_cast<size_t>(batch) * P * sizeof(double));
   }
   L.off_misc = take(64 * sizeof(double));
+  L.pb_tc = tasks->pb.ready && g_poseblend_variant == 0 && L.phi_cols == 0;
+  L.off_ca = tasks->pb.ready ? take(C * tasks->pb.slots * 128 * sizeof(float)) : 0;
+  L.off_dr = tasks->pb.ready ? take(C * 621 * sizeof(float)) : 0;
   L.total = off;
   return L;
 }
@@ -1982,6 +2054,13 @@ int run_chunk(const smplpp_model_t * model, const smplpp_vposer_t * vposer, cons
   jp.jout = reinterpret_cast<float *>(ws + L.off_j);
   jp.ld = L.ld;
   jp.frame_info = reinterpret_cast<int *>(ws + L.off_info);
+  if(L.pb_tc)
+  {
+    jp.ca_out = reinterpret_cast<float *>(ws + L.off_ca);
+    jp.ca_slot_off = tasks->pb.slot_off;
+    jp.ca_stride = tasks->pb.slots * 128;
+    jp.dr_out = reinterpret_cast<float *>(ws + L.off_dr);
+  }
   const size_t smem = jac_smem_bytes(tasks->d, L);
   if(smem > 227 * 1024) return fail(SMPLPP_ERR_INVALID, "IkTask", "task set too large for one CTA per frame");
   if(L.rows_per_task == 4)
@@ -1995,6 +2074,21 @@ int run_chunk(const smplpp_model_t * model, const smplpp_vposer_t * vposer, cons
     ik_jacobian_kernel<3><<<B, c1::THREADS, smem, st>>>(jp);
   }
   SB_LAUNCHED();
+  if(L.pb_tc)
+  {
+    rc = launch_poseblend_tc(tasks->pb, tasks->d, st, B, L.rows_per_task, L.use_ring, L.beta_cols ? 75 + L.phi_cols : -1,
+                             jp.ca_out, jp.dr_out, jp.jfull, jp.ldfull);
+    if(rc != SMPLPP_OK) return rc;
+    if(L.vposer)
+    {
+      const int extra = L.phi_cols + L.beta_cols;
+      if(L.rows_per_task == 4)
+        ik_vposer_contract_kernel<4><<<B, 256, 0, st>>>(L.n, extra, jp.jfull, jp.ldfull, vjac, jp.jout, jp.ld);
+      else
+        ik_vposer_contract_kernel<3><<<B, 256, 0, st>>>(L.n, extra, jp.jfull, jp.ldfull, vjac, jp.jout, jp.ld);
+      SB_LAUNCHED();
+    }
+  }
   return SMPLPP_OK;
 }
 

@@ -3,6 +3,7 @@
 // blend basis / skinning rows of the vertices the tasks depend on.
 #pragma once
 #include "common.cuh"
+#include "ik_poseblend.cuh"
 
 namespace sb
 {
@@ -73,6 +74,7 @@ struct smplpp_tasks
   sb::TasksDev d;
   sb::ModelDev sub;      // sparse-forward view (basis/lbs arrays alias the TasksDev ones)
   sb::ModelDev sub_corner; // same arrays, V = nCorner (no normals needed)
+  sb::PoseBlendTc pb;   // operand images of ik_poseblend_tc_kernel
   std::vector<void *> allocations;
   std::vector<int64_t> h_face_idx;
   std::vector<int32_t> h_sub_vert; // local -> global vertex id

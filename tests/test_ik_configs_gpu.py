@@ -92,20 +92,27 @@ def test_config3_every_iteration_vs_reference(task_set, gc, ik_variant):
 def test_config3_free_running_30_iterations(task_set, gc):
     """The same 30 iterations free-running on the GPU.  The iteration is not contractive along weakly observed joints
     (damping 1e-3 only): two runs of the COMPILED REFERENCE that differ only in the libtorch thread count drift apart by
-    up to `band` (2e-4 m of residual, 0.08 rad; golden c3_alt_*).  The GPU run must stay inside that band, reach the
-    reference's converged residual within 1e-4 m, and track it to 1e-5 m while the trajectories still coincide."""
+    up to `band` (2e-4 m of residual, 0.08 rad; golden c3_alt_*).  Frame 4 shows what that means: its residual bounces
+    between 1.49 and 1.67 mm from iteration 8 on before it drops into the converged 1.46 mm, and rounding decides when -
+    iteration 19 in the reference run, 27 in its other-thread-count twin, 19 / 30 in the two GPU variants of the pose-blend
+    columns (scripts/diag_pb.py).  The GPU run must stay inside the band during the 30 iterations, track the reference to
+    1e-5 m while the trajectories still coincide, and - run on until every frame has settled - reach the reference's
+    converged residual within 1e-4 m."""
     from smplpp_b200 import api
     opt = api.ik_options(**MOTION)
     K = gc["c3_residual"].shape[1]
     res, traj, vw = run_trajectory(task_set, opt, gc["c3_theta_in"], gc["beta"], gc["vertex_weights_in"], gc["c3_target"],
-                                   gc["c3_valid"], K)
+                                   gc["c3_valid"], 2 * K)
     alt = gc["c3_alt_frames"]
     band = np.abs(gc["c3_alt_residual"] - gc["c3_residual"][alt]).max()
-    dev = np.abs(res - gc["c3_residual"])
-    print("free-running residual deviation %.2e m (reference vs itself: %.2e m)" % (dev.max(), band))
+    dev = np.abs(res[:, :K] - gc["c3_residual"])
+    conv = np.abs(res[:, -1] - gc["c3_residual"][:, -1])
+    print("free-running residual deviation %.2e m (reference vs itself: %.2e m), converged residual deviation %.2e m"
+          % (dev.max(), band, conv.max()))
     assert dev[:, :3].max() < 1e-5
     assert dev.max() < max(TOL_RESIDUAL_M, 1.5 * band)
-    assert dev[:, -1].max() < TOL_RESIDUAL_M                      # converged marker residual within 1e-4 m
+    assert conv.max() < TOL_RESIDUAL_M                            # converged marker residual within 1e-4 m
+    assert np.abs(res[:, -1] - res[:, -5]).max() < 1e-5           # ... and it IS converged
     assert np.abs(traj[:, 0] - gc["c3_theta_traj"][:, 0]).max() < 2e-4
     assert res[:, -1].max() < 0.25 * res[:, 0].min()
 
@@ -187,16 +194,17 @@ def dense_block_arrow(J, e, theta_dim, prior=None):
     return A, b
 
 
-@pytest.fixture(params=[(401, 410), (401, 411), (402, 410)], ids=["two_kernels", "two_kernels_scalar_solve", "fused_kernel"])
+@pytest.fixture(params=[(401, 410, 420), (401, 411, 421), (402, 410, 420)], ids=["two_kernels", "two_kernels_ffma_variants", "fused_kernel"])
 def ik_variant(request):
     from smplpp_b200 import capi
     # 401 / 402: ik_jacobian_kernel + solve kernel / fused kernel; 410 / 411: ik_solve_mma_kernel (fp64 tensor cores, the
-    # default where the problem shape allows) / the scalar ik_solve_kernel
-    capi.check(capi.lib().smplpp_set_forward_variant(request.param[0]))
-    capi.check(capi.lib().smplpp_set_forward_variant(request.param[1]))
+    # default where the problem shape allows) / the scalar ik_solve_kernel; 420 / 421: pose-blend columns of J by
+    # ik_poseblend_tc_kernel (tcgen05, the default) / by the FFMA phase of ik_jacobian_kernel
+    for v in request.param:
+        capi.check(capi.lib().smplpp_set_forward_variant(v))
     yield request.param[0]
-    capi.check(capi.lib().smplpp_set_forward_variant(400))
-    capi.check(capi.lib().smplpp_set_forward_variant(410))
+    for v in (400, 410, 420):
+        capi.check(capi.lib().smplpp_set_forward_variant(v))
 
 
 @pytest.mark.parametrize("mode", ["direct", "vposer"])

@@ -71,18 +71,19 @@ def test_triangle_vertex_weights_property():
     assert np.abs(np.einsum("ni,nik->nk", got, tri) - pos).max() < 1e-3
 
 
-@pytest.fixture(params=[(401, 410), (401, 411), (402, 410)], ids=["two_kernels", "two_kernels_scalar_solve", "fused_kernel"])
+@pytest.fixture(params=[(401, 410, 420), (401, 411, 421), (402, 410, 420)], ids=["two_kernels", "two_kernels_ffma_variants", "fused_kernel"])
 def ik_variant(request):
     """Both implementations of the step on a shared attachment topology: ik_jacobian_kernel + ik_solve_kernel (the
     default there) and the fused kernel (the only one for per-frame attachments)."""
     from smplpp_b200 import capi
     # 401 / 402: ik_jacobian_kernel + solve kernel / fused kernel; 410 / 411: ik_solve_mma_kernel (fp64 tensor cores, the
-    # default where the problem shape allows) / the scalar ik_solve_kernel
-    capi.check(capi.lib().smplpp_set_forward_variant(request.param[0]))
-    capi.check(capi.lib().smplpp_set_forward_variant(request.param[1]))
+    # default where the problem shape allows) / the scalar ik_solve_kernel; 420 / 421: pose-blend columns of J by
+    # ik_poseblend_tc_kernel (tcgen05, the default) / by the FFMA phase of ik_jacobian_kernel
+    for v in request.param:
+        capi.check(capi.lib().smplpp_set_forward_variant(v))
     yield request.param[0]
-    capi.check(capi.lib().smplpp_set_forward_variant(400))
-    capi.check(capi.lib().smplpp_set_forward_variant(410))
+    for v in (400, 410, 420):
+        capi.check(capi.lib().smplpp_set_forward_variant(v))
 
 
 @pytest.mark.parametrize("mode", list(MODES))
