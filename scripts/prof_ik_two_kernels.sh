@@ -15,4 +15,4 @@ for _ in range(3):
     tasks.step(opt, theta, prob["beta"], vw, prob["target"], pos_task_weight=prob["valid"])
 torch.cuda.synchronize()
 PY
-ncu --set full --clock-control none --import-source on -k regex:"ik_jacobian|ik_solve" -s 2 -c 2 -o gpurun_out/prof_ik1 -f python /tmp/prof_ik1.py > gpurun_out/ncu_ik1.log 2>&1; tail -1 gpurun_out/ncu_ik1.log
+ncu --set full --clock-control none --import-source on -k regex:"ik_jacobian|ik_solve|ik_poseblend" -s 3 -c 3 -o gpurun_out/prof_ik1 -f python /tmp/prof_ik1.py > gpurun_out/ncu_ik1.log 2>&1; tail -1 gpurun_out/ncu_ik1.log

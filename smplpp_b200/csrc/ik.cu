@@ -456,8 +456,11 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
     s_xw[3 * i + 1] = wj * (G[4] * ru.x + G[5] * ru.y + G[6] * ru.z + s_tp[3 * j + 1]);
     s_xw[3 * i + 2] = wj * (G[8] * ru.x + G[9] * ru.y + G[10] * ru.z + s_tp[3 * j + 2]);
   }
-  for(int pr = tid; pr < t.nPairs; pr += THREADS)
+  // pairs in the order of decreasing reference count (pair_order): the lanes of a warp then run the same number of trips
+  // (a corner is referenced by ~12 ring faces, a ring-only vertex by ~3: in pair order a warp ran at 1/3 efficiency)
+  for(int ip = tid; ip < t.nPairs; ip += THREADS)
   {
+    const int pr = t.pair_order[ip];
     const int m = t.pair_task[pr];
     const int q = pr - t.pair_off[m];
     float * C = s_C4 + 12 * pr;
@@ -471,28 +474,44 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
     float D[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if(p.use_ring)
     {
+      // d nh / d v = sum over the corners c, over the ring faces g of c that contain v:
+      //   (w_c / deg_c) P(nh) P(n_c) P(n_g) [a]x      (P(n) x = (x - n (n.x)) / |unnormalised n|, a = the opposite edge)
+      // the references of a pair are ordered by face and the faces by corner: P(n_g) [a]x is summed per corner first, the
+      // two outer projections are applied once per (pair, corner)
       const f3 nh = mk3(ts[3], ts[4], ts[5]);
       const float inv_s = ts[6];
-      for(int rf = t.pair_ref_off[pr]; rf < t.pair_ref_off[pr + 1]; rf++)
+      int rf = t.pair_ref_off[pr];
+      const int rf_end = t.pair_ref_off[pr + 1];
+      int c = 0;
+      while(rf < rf_end)
       {
-        const int it = t.pair_refs[rf] >> 2, slot = t.pair_refs[rf] & 3;
-        // corner index of the item: items of (m, c) are contiguous
-        int c = 0;
+        int it = t.pair_refs[rf] >> 2;
         while(it >= t.item_off[3 * m + c + 1]) c++;
         const int ci = 3 * m + c;
-        const float wg = 1.f / static_cast<float>(t.item_off[ci + 1] - t.item_off[ci]);
-        const float scale = ts[c] * wg;
-        f3 v0 = ld3(s_verts + 3 * t.item_verts[3 * it]), v1 = ld3(s_verts + 3 * t.item_verts[3 * it + 1]),
-           v2 = ld3(s_verts + 3 * t.item_verts[3 * it + 2]);
-        f3 e1 = v1 - v0, e2 = v2 - v0;
-        f3 a = slot == 0 ? (e2 - e1) : (slot == 1 ? mk3(-e2.x, -e2.y, -e2.z) : e1);
-        const f3 ng = ld3(s_itemN + 4 * it), nci = ld3(s_cornN + 4 * ci);
-        const float inv_g = s_itemN[4 * it + 3], inv_q = s_cornN[4 * ci + 3];
-        const f3 ax[3] = {mk3(0.f, a.z, -a.y), mk3(-a.z, 0.f, a.x), mk3(a.y, -a.x, 0.f)}; // a x e_c
+        const int it_end = t.item_off[ci + 1];
+        f3 S[3] = {mk3(0.f, 0.f, 0.f), mk3(0.f, 0.f, 0.f), mk3(0.f, 0.f, 0.f)};
+        do
+        {
+          const int slot = t.pair_refs[rf] & 3;
+          f3 v0 = ld3(s_verts + 3 * t.item_verts[3 * it]), v1 = ld3(s_verts + 3 * t.item_verts[3 * it + 1]),
+             v2 = ld3(s_verts + 3 * t.item_verts[3 * it + 2]);
+          f3 e1 = v1 - v0, e2 = v2 - v0;
+          f3 a = slot == 0 ? (e2 - e1) : (slot == 1 ? mk3(-e2.x, -e2.y, -e2.z) : e1);
+          const f3 ng = ld3(s_itemN + 4 * it);
+          const float inv_g = s_itemN[4 * it + 3];
+          const f3 ax[3] = {mk3(0.f, a.z, -a.y), mk3(-a.z, 0.f, a.x), mk3(a.y, -a.x, 0.f)}; // a x e_c
+#pragma unroll
+          for(int cc = 0; cc < 3; cc++) S[cc] = S[cc] + proj_apply(ng, inv_g, ax[cc]);
+          rf++;
+          if(rf < rf_end) it = t.pair_refs[rf] >> 2;
+        } while(rf < rf_end && it < it_end);
+        const float scale = ts[c] / static_cast<float>(it_end - t.item_off[ci]);
+        const f3 nci = ld3(s_cornN + 4 * ci);
+        const float inv_q = s_cornN[4 * ci + 3];
 #pragma unroll
         for(int cc = 0; cc < 3; cc++)
         {
-          f3 y = proj_apply(nh, inv_s, proj_apply(nci, inv_q, proj_apply(ng, inv_g, ax[cc])));
+          f3 y = proj_apply(nh, inv_s, proj_apply(nci, inv_q, S[cc]));
           D[cc] += scale * y.x, D[3 + cc] += scale * y.y, D[6 + cc] += scale * y.z;
         }
       }
@@ -1695,6 +1714,15 @@ extern "C" int smplpp_tasks_create(const smplpp_model_t * model, int32_t n, cons
   if(rc == SMPLPP_OK) rc = upload_vec(t, &d.pair_task, pair_task);
   if(rc == SMPLPP_OK) rc = upload_vec(t, &d.pair_ref_off, pair_ref_off);
   if(rc == SMPLPP_OK) rc = upload_vec(t, &d.pair_refs, pair_refs);
+  if(rc == SMPLPP_OK)
+  {
+    std::vector<int32_t> order(nPairs);
+    for(int i = 0; i < nPairs; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+      return pair_ref_off[a + 1] - pair_ref_off[a] > pair_ref_off[b + 1] - pair_ref_off[b];
+    });
+    rc = upload_vec(t, &d.pair_order, order);
+  }
   if(rc == SMPLPP_OK) rc = upload_vec(t, &d.task_joint_mask, mask_all);
   if(rc == SMPLPP_OK) rc = upload_vec(t, &d.task_joint_mask_corner, mask_corner);
   if(rc == SMPLPP_OK) rc = upload_vec(t, &d.basis, basis);

@@ -71,6 +71,15 @@ struct Params
   int ld;
 };
 
+__device__ __forceinline__ void red_add_v2(float * addr, float a, float b)
+{
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float * addr, float a, float b, float c, float d)
+{
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 template<int G>
 __device__ __forceinline__ void epilogue_task(const Params & p, uint32_t taddr, const float * dr, float * jrow, bool live)
 {
@@ -105,10 +114,25 @@ __device__ __forceinline__ void epilogue_task(const Params & p, uint32_t taddr, 
     }
   }
   if(!live) return;
+  // J row + 3 + 3 K0 .. : 36 (G = 0, columns 6..41) or 33 (G = 1, columns 42..74) consecutive floats of a 16-byte aligned
+  // row (ld % 4 == 0): two leading floats, then 16-byte vector reductions (one L2 transaction per 4 values instead of 4)
+  float o[3 * NK + 3];
 #pragma unroll
   for(int k = 0; k < NK; k++)
 #pragma unroll
-    for(int c = 0; c < 3; c++) atomicAdd(jrow + 3 + 3 * (K0 + k) + c, acc[k][c] * p.out_scale);
+    for(int c = 0; c < 3; c++) o[3 * k + c] = acc[k][c] * p.out_scale;
+  float * dst = jrow + 3 + 3 * K0; // column 6 or 42: 8 bytes past a 16-byte boundary
+  red_add_v2(dst, o[0], o[1]);
+  constexpr int NV4 = (3 * NK - 2) / 4; // G = 0: 8 (columns 8..39), G = 1: 7 (columns 44..71)
+#pragma unroll
+  for(int i = 0; i < NV4; i++) red_add_v4(dst + 2 + 4 * i, o[2 + 4 * i], o[3 + 4 * i], o[4 + 4 * i], o[5 + 4 * i]);
+  if(G == 0)
+    red_add_v2(dst + 34, o[34], o[35]);
+  else
+  {
+    red_add_v2(dst + 30, o[30], o[31]);
+    atomicAdd(dst + 32, o[32]);
+  }
   if(G == 1 && p.beta_col >= 0)
   {
 #pragma unroll
@@ -229,56 +253,81 @@ __global__ void __launch_bounds__(pbtc::THREADS, 1) ik_poseblend_tc_kernel(const
     const int L = (bw & 3) * 32 + lane, fl = L >> 2, r = L & 3;
     const bool live = f0 + fl < p.B && r < p.rows;
     const float * ca_f = p.ca + static_cast<size_t>(f0 + fl) * p.ca_stride;
-    int it = 0;
-    for(int m = 0; m < p.n; m++)
-    {
-      const int s0 = __ldg(p.slot_off + m), nkb_all = __ldg(p.slot_off + m + 1) - s0, nkb = p.use_ring ? nkb_all : 1;
-      const int np = p.use_ring ? __ldg(p.pair_off + m + 1) - __ldg(p.pair_off + m) : 3;
+    // K-block `it` of the whole sequence -> (task, K-block in task): this group's K-blocks are it = gb, gb + 2, ...; the
+    // loads of the next one are in flight while the current one is converted and stored
+    int m_nx = 0, kb_nx = 0, it_nx = 0;
+    auto advance = [&](int steps) { // move the cursor `steps` K-blocks on; m_nx = p.n at the end
+      while(steps > 0 && m_nx < p.n)
+      {
+        const int nkb = task_kb(m_nx);
+        if(kb_nx + steps < nkb)
+        {
+          kb_nx += steps, it_nx += steps, steps = 0;
+        }
+        else
+        {
+          const int adv = nkb - kb_nx;
+          steps -= adv, it_nx += adv, kb_nx = 0, m_nx++;
+        }
+      }
+    };
+    float4 nxt[8];
+    auto prefetch = [&]() {
+      if(m_nx >= p.n) return;
+      const int s0 = __ldg(p.slot_off + m_nx), nkb_all = __ldg(p.slot_off + m_nx + 1) - s0;
+      const int np = p.use_ring ? __ldg(p.pair_off + m_nx + 1) - __ldg(p.pair_off + m_nx) : 3;
       const int kvalid = 3 * np;
       const float * row = ca_f + static_cast<size_t>(s0) * 128 + r * (32 * nkb_all);
-      for(int kb = 0; kb < nkb; kb++, it++)
+#pragma unroll
+      for(int c = 0; c < 8; c++)
       {
-        if((it & 1) != gb) continue;
-        const int s = it % SLOTS;
-        float x[32];
-#pragma unroll
-        for(int c = 0; c < 8; c++)
-        {
-          const int k = 32 * kb + 4 * c;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if(live && k < kvalid) v = __ldg(reinterpret_cast<const float4 *>(row + k));
-          x[4 * c] = v.x, x[4 * c + 1] = k + 1 < kvalid ? v.y : 0.f, x[4 * c + 2] = k + 2 < kvalid ? v.z : 0.f,
-                x[4 * c + 3] = k + 3 < kvalid ? v.w : 0.f;
-        }
-        uint4 hi[4], lo[4];
-#pragma unroll
-        for(int c = 0; c < 4; c++)
-        {
-          uint32_t h[4], l[4];
-#pragma unroll
-          for(int e = 0; e < 4; e++)
-          {
-            const float a = fminf(fmaxf(x[8 * c + 2 * e], -6.0e4f), 6.0e4f), b = fminf(fmaxf(x[8 * c + 2 * e + 1], -6.0e4f), 6.0e4f);
-            const float ah = __half2float(__float2half_rn(a)), bh = __half2float(__float2half_rn(b));
-            h[e] = skin::pack_half2(ah, bh);
-            l[e] = skin::pack_half2(a - ah, b - bh);
-          }
-          hi[c] = make_uint4(h[0], h[1], h[2], h[3]);
-          lo[c] = make_uint4(l[0], l[1], l[2], l[3]);
-        }
-        ptx::mbar_wait(&empty[s], ((it / SLOTS) & 1) ^ 1);
-        uint8_t * dst = smem + s * SLOT + 2 * B_PART;
-#pragma unroll
-        for(int c = 0; c < 4; c++)
-        {
-          const uint32_t o = static_cast<uint32_t>(L * ROWB + c * 16);
-          *reinterpret_cast<uint4 *>(dst + swz64(o)) = hi[c];
-          *reinterpret_cast<uint4 *>(dst + swz64(A_PART + o)) = lo[c];
-        }
-        ptx::fence_proxy_async(); // generic-proxy stores -> visible to the tensor core's async-proxy reads
-        __syncwarp();
-        if(lane == 0) ptx::mbar_arrive(&full_a[s]);
+        const int k = 32 * kb_nx + 4 * c;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if(live && k < kvalid) v = __ldg(reinterpret_cast<const float4 *>(row + k));
+        if(k + 1 >= kvalid) v.y = 0.f;
+        if(k + 2 >= kvalid) v.z = 0.f;
+        if(k + 3 >= kvalid) v.w = 0.f;
+        nxt[c] = v;
       }
+    };
+    advance(gb);
+    prefetch();
+    while(m_nx < p.n)
+    {
+      const int it = it_nx, s = it % SLOTS;
+      float x[32];
+#pragma unroll
+      for(int c = 0; c < 8; c++) x[4 * c] = nxt[c].x, x[4 * c + 1] = nxt[c].y, x[4 * c + 2] = nxt[c].z, x[4 * c + 3] = nxt[c].w;
+      advance(2);
+      prefetch();
+      uint4 hi[4], lo[4];
+#pragma unroll
+      for(int c = 0; c < 4; c++)
+      {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for(int e = 0; e < 4; e++)
+        {
+          const float a = fminf(fmaxf(x[8 * c + 2 * e], -6.0e4f), 6.0e4f), b = fminf(fmaxf(x[8 * c + 2 * e + 1], -6.0e4f), 6.0e4f);
+          const float ah = __half2float(__float2half_rn(a)), bh = __half2float(__float2half_rn(b));
+          h[e] = skin::pack_half2(ah, bh);
+          l[e] = skin::pack_half2(a - ah, b - bh);
+        }
+        hi[c] = make_uint4(h[0], h[1], h[2], h[3]);
+        lo[c] = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+      ptx::mbar_wait(&empty[s], ((it / SLOTS) & 1) ^ 1);
+      uint8_t * dst = smem + s * SLOT + 2 * B_PART;
+#pragma unroll
+      for(int c = 0; c < 4; c++)
+      {
+        const uint32_t o = static_cast<uint32_t>(L * ROWB + c * 16);
+        *reinterpret_cast<uint4 *>(dst + swz64(o)) = hi[c];
+        *reinterpret_cast<uint4 *>(dst + swz64(A_PART + o)) = lo[c];
+      }
+      ptx::fence_proxy_async(); // generic-proxy stores -> visible to the tensor core's async-proxy reads
+      __syncwarp();
+      if(lane == 0) ptx::mbar_arrive(&full_a[s]);
     }
   }
   else if(warp >= CTRL_WARPS + BUILD_WARPS)

@@ -26,6 +26,7 @@ struct TasksDev
   const int32_t * pair_task = nullptr;    // (nPairs) owning task
   const int32_t * pair_ref_off = nullptr; // (nPairs + 1) CSR pair -> references
   const int32_t * pair_refs = nullptr;    // item * 4 + slot (slot = position of the vertex in the item's face)
+  const int32_t * pair_order = nullptr;   // (nPairs) pairs by decreasing reference count (balanced warps in ik_jacobian_kernel)
   const uint32_t * task_joint_mask = nullptr; // (n) joints that move any vertex of the task (corners only: bit 24+)
   const uint32_t * task_joint_mask_corner = nullptr; // (n) same, restricted to the three corners
   // compact model rows of the nU vertices (same layouts as ModelDev, V -> nU)
