@@ -81,23 +81,26 @@ __device__ __forceinline__ void red_add_v4(float * addr, float a, float b, float
 }
 
 template<int G>
-__device__ __forceinline__ void epilogue_task(const Params & p, uint32_t taddr, const float * dr, float * jrow, bool live)
+__device__ __forceinline__ void epilogue_task(const Params & p, uint32_t taddr, uint32_t dr, float * jrow, bool live)
 {
-  // G = 0: columns [0, 108) = joints 1..12; G = 1: columns [108, 224) = joints 13..23, then 10 shape columns
-  constexpr int C0 = G == 0 ? 0 : 96, C1 = G == 0 ? 112 : 224; // chunks of 16 columns that cover the range
+  // G = 0: columns [0, 108) = joints 1..12; G = 1: columns [108, 224) = joints 13..23, then 10 shape columns.
+  // dr: SHARED-space address of this frame's derivative table (explicit ld.shared: through a generic pointer the compiler
+  // emitted LD.E + R2UR pairs, 27 % of the kernel's stall samples)
+  constexpr int C0 = G == 0 ? 0 : 96, C1 = G == 0 ? 128 : 224; // chunks of 32 columns that cover the range
   constexpr int K0 = G == 0 ? 1 : 13, NK = G == 0 ? 12 : 11;
   float acc[NK][3];
 #pragma unroll
   for(int k = 0; k < NK; k++) acc[k][0] = acc[k][1] = acc[k][2] = 0.f;
   float shp[kShapeDim];
 #pragma unroll
-  for(int ch = C0; ch < C1; ch += 16)
+  for(int ch = C0; ch < C1; ch += 32)
   {
-    float v[16];
+    float v[32];
     ptx::tmem_ld_x16(taddr + ch, v);
+    ptx::tmem_ld_x16(taddr + ch + 16, v + 16);
     ptx::tmem_ld_wait();
 #pragma unroll
-    for(int i = 0; i < 16; i++)
+    for(int i = 0; i < 32; i++)
     {
       const int d = ch + i;
       if(d < kPoseDim)
@@ -106,7 +109,7 @@ __device__ __forceinline__ void epilogue_task(const Params & p, uint32_t taddr, 
         if(k >= K0 && k < K0 + NK)
         {
 #pragma unroll
-          for(int c = 0; c < 3; c++) acc[k - K0][c] = fmaf(v[i], dr[27 * (k - 1) + 9 * c + e], acc[k - K0][c]);
+          for(int c = 0; c < 3; c++) acc[k - K0][c] = fmaf(v[i], ptx::lds32(dr + 4 * (27 * (k - 1) + 9 * c + e)), acc[k - K0][c]);
         }
       }
       else if(G == 1 && d < kPoseDim + kShapeDim)
@@ -337,7 +340,7 @@ __global__ void __launch_bounds__(pbtc::THREADS, 1) ik_poseblend_tc_kernel(const
     const int L = q * 32 + lane, fl = L >> 2, r = L & 3;
     const bool live = f0 + fl < p.B && r < p.rows;
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const float * dr = s_dr + fl * DR;
+    const uint32_t dr = ptx::smem_u32(s_dr + fl * DR);
     float * jf = p.J + (static_cast<size_t>(f0 + fl) * 4 * p.n + r) * p.ld;
     for(int m = 0; m < p.n; m++)
     {
