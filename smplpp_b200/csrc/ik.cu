@@ -212,9 +212,8 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
     for(int i = tid; i < 3 * p.nUse; i += THREADS) s_verts[i] = gv[i], s_rest[i] = gr[i];
     for(int i = tid; i < p.nUse * t.kmax; i += THREADS)
     {
-      const int u = i / t.kmax, sl = i % t.kmax;
-      s_sw[i] = t.lbs_weight[static_cast<size_t>(sl) * t.nUpad + u] / t.lbs_wsum[u];
-      s_sj[i] = t.lbs_joint[static_cast<size_t>(sl) * t.nUpad + u];
+      s_sw[i] = t.sw_norm[i]; // W[u, slot] / sum_j W[u, j], [u][slot] like the shared-memory copy
+      s_sj[i] = t.sj_flat[i];
     }
   }
   __syncthreads();
@@ -458,8 +457,11 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
   }
   // pairs in the order of decreasing reference count (pair_order): the lanes of a warp then run the same number of trips
   // (a corner is referenced by ~12 ring faces, a ring-only vertex by ~3: in pair order a warp ran at 1/3 efficiency)
-  for(int ip = tid; ip < t.nPairs; ip += THREADS)
+  for(int ip0 = 0, round = 0; ip0 < t.nPairs; ip0 += THREADS, round++)
   {
+    // odd rounds run backwards: the warp that had the heaviest vertices of one round gets the lightest of the next
+    const int ip = ip0 + ((round & 1) ? THREADS - 1 - tid : tid);
+    if(ip >= t.nPairs) continue;
     const int pr = t.pair_order[ip];
     const int m = t.pair_task[pr];
     const int q = pr - t.pair_off[m];
@@ -570,9 +572,16 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
     }
   }
   __syncthreads();
-  for(int ia = tid; ia < s_nact; ia += THREADS)
+  // two neighbouring lanes share a live (task, joint) pair: each sums half of the task's vertices (everything up to the
+  // entries of J is linear in the per-vertex terms), the even lane adds the odd lane's result and stores.  330 live pairs
+  // are 1.3 rounds of 256 threads; 660 half items are 2.6 rounds of half the length.
+  const int nact2 = 2 * s_nact;
+  for(int ia0 = 0; ia0 < nact2; ia0 += THREADS)
   {
-    const int i = s_act[ia];
+    const int ia = ia0 + tid;
+    const bool on = ia < nact2;
+    const int half = ia & 1;
+    const int i = s_act[on ? ia >> 1 : 0];
     const int m = i / kJoints, k = i % kJoints;
     float out[4][3];
 #pragma unroll
@@ -586,7 +595,8 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
       const int p0 = t.pair_off[m];
       const int np = p.use_ring ? t.pair_off[m + 1] - p0 : 3;
       const f3 tgk = mk3(s_G[12 * k + 3], s_G[12 * k + 7], s_G[12 * k + 11]);
-      for(int q = 0; q < np; q++)
+      const int q0 = on ? (half ? (np + 1) >> 1 : 0) : 0, q1 = on ? (half ? np : (np + 1) >> 1) : 0;
+      for(int q = q0; q < q1; q++)
       {
         const int u = t.pair_vert[p0 + q];
         f3 y = mk3(0.f, 0.f, 0.f);
@@ -624,7 +634,11 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
 #pragma unroll
     for(int r = 0; r < 4; r++)
 #pragma unroll
-      for(int c = 0; c < 3; c++) Jf[(4 * m + r) * p.ldfull + 3 + 3 * k + c] = out[r][c];
+      for(int c = 0; c < 3; c++)
+      {
+        out[r][c] += __shfl_xor_sync(0xffffffffu, out[r][c], 1);
+        if(on && !half) Jf[(4 * m + r) * p.ldfull + 3 + 3 * k + c] = out[r][c];
+      }
   }
   // ---- P5c: beta columns, rigid part: sum_u C4_u sum_j wn_j d t'_j / d beta_i ----
   if(p.beta_cols)
@@ -1739,6 +1753,19 @@ extern "C" int smplpp_tasks_create(const smplpp_model_t * model, int32_t n, cons
   if(rc == SMPLPP_OK) rc = upload_vec(t, &d.lbs_joint, lj);
   if(rc == SMPLPP_OK) rc = upload_vec(t, &d.lbs_weight, lw);
   if(rc == SMPLPP_OK) rc = upload_vec(t, &d.lbs_wsum, ws);
+  if(rc == SMPLPP_OK)
+  {
+    std::vector<float> swn(static_cast<size_t>(nU) * kmax);
+    std::vector<uint8_t> sjf(static_cast<size_t>(nU) * kmax);
+    for(int u = 0; u < nU; u++)
+      for(int sl = 0; sl < kmax; sl++)
+      {
+        swn[static_cast<size_t>(u) * kmax + sl] = lw[static_cast<size_t>(sl) * nUpad + u] / ws[u];
+        sjf[static_cast<size_t>(u) * kmax + sl] = lj[static_cast<size_t>(sl) * nUpad + u];
+      }
+    rc = upload_vec(t, &d.sw_norm, swn);
+    if(rc == SMPLPP_OK) rc = upload_vec(t, &d.sj_flat, sjf);
+  }
   if(rc != SMPLPP_OK)
   {
     smplpp_tasks_destroy(t);

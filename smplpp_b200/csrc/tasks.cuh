@@ -35,6 +35,8 @@ struct TasksDev
   const uint8_t * lbs_joint = nullptr; // [kmax][nUpad]
   const float * lbs_weight = nullptr;  // [kmax][nUpad]
   const float * lbs_wsum = nullptr;    // (nUpad)
+  const float * sw_norm = nullptr;     // (nU, kmax) W[u, slot] / sum_j W[u, j]: the layout ik_jacobian_kernel keeps in shared memory
+  const uint8_t * sj_flat = nullptr;   // (nU, kmax) joint of the slot
 };
 // ---- fused IK step (ik2.cu): one self-contained topology record per task -------------------------------------------
 // Everything the step needs about ONE attachment face: its three corners, their 1-rings (SMPL::calcVertexNormal,
