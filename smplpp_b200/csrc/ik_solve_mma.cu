@@ -5,8 +5,8 @@
 // into 8x8 tiles of the lower triangle; a warp owns every fourth tile (column-major order) and keeps their accumulators
 // in REGISTERS as mma.m8n8k4.f64 C fragments for the whole kernel: four live rows of J are one k-step, so a chunk of four
 // rows costs every lane NB loads + NB conversions and the warp NT/4 DMMAs (the scalar kernel: 8 loads, 8 conversions and
-// 16 DFMAs per thread and row, 3.0 G warp instructions per 16384 frames, 63 % issue-bound).  The rows arrive through a
-// three-stage cp.async ring.  Cholesky is right-looking over 8-wide panels: the owners of column p store their tiles to
+// 16 DFMAs per thread and row, 3.0 G warp instructions per 16384 frames, 63 % issue-bound).  The rows arrive through an
+// eight-stage cp.async ring.  Cholesky is right-looking over 8-wide panels: the owners of column p store their tiles to
 // shared memory, the owner of the diagonal tile factors it with warp shuffles, one thread per row solves the panel against
 // it, and every warp applies the rank-8 update to its own register tiles with two DMMAs per tile.  Because the right-hand
 // side is row D of the matrix, the forward substitution falls out of the elimination (L[D][k] = (L^-1 b)[k]) and only the
@@ -27,7 +27,7 @@ namespace
 {
 constexpr int NW = 4;
 constexpr int THREADS = NW * 32;
-constexpr int NSTAGE = 3;
+constexpr int NSTAGE = 8; // 7 chunks of 1.4 KB in flight per CTA: the J rows come from HBM, two chunks in flight left the loop latency-bound
 
 constexpr int col_start(int NB, int j) // index of tile (j, j) in the column-major list of lower-triangular tiles
 {
@@ -239,12 +239,12 @@ __device__ __forceinline__ void solve_body(const IkSolveParams & p, unsigned cha
   double acc[TPW][2];
 #pragma unroll
   for(int k = 0; k < TPW; k++) acc[k][0] = acc[k][1] = 0.0;
-  issue(0, 0);
-  issue(1, 1);
+#pragma unroll
+  for(int c = 0; c < NSTAGE - 1; c++) issue(c, c);
   int buf = 0;
   for(int c = 0; c < nchunks; c++)
   {
-    cp_async_wait<1>();
+    cp_async_wait<NSTAGE - 2>();
     if(fixer)
     {
       const int l = 4 * c + q_ld;
@@ -253,7 +253,7 @@ __device__ __forceinline__ void solve_body(const IkSolveParams & p, unsigned cha
       for(int cc = D + 1; cc < ld; cc++) row[cc] = 0.f;
     }
     cta_sync();
-    issue(c + 2, buf == 0 ? 2 : buf - 1);
+    issue(c + NSTAGE - 1, buf == 0 ? NSTAGE - 1 : buf - 1);
     const float * st = stage + (buf * 4 + t) * LDS + g;
     double v[NB];
 #pragma unroll
@@ -268,7 +268,7 @@ __device__ __forceinline__ void solve_body(const IkSolveParams & p, unsigned cha
           }
         },
         ks);
-    buf = buf == 2 ? 0 : buf + 1;
+    buf = buf == NSTAGE - 1 ? 0 : buf + 1;
   }
   // ---- |e|^2 = element (D, D) ----
   for_each_k(
