@@ -39,6 +39,19 @@ def ncu_counter(kernel: str, key: str):
     return None, None
 
 
+def ncu_counter_sum(kernels, key: str):
+    """sum of a per-launch counter over the kernels of one IK iteration, from the newest capture that holds all of them"""
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")), reverse=True):
+        try:
+            with open(path) as f:
+                t = json.load(f).get(key, {})
+            if all(k in t for k in kernels):
+                return float(sum(t[k] for k in kernels)), os.path.basename(path)
+        except Exception:
+            continue
+    return None, None
+
+
 def make_problem(smpl, tasks, frames: int, seed: int, dev):
     _, _, vw0 = synth.make_marker_tasks(smpl._params)
     n = tasks.n
@@ -112,9 +125,10 @@ def run(dev, rank, world, max_over_ranks, barrier, frames: int = 16384, iters: i
     out["mosh_direct"]["frames_ok"] = int((status == 0).sum().item())
     # roofline of the IK step: CUDA-core fp32 work (not HBM, not tensor) per SURVEY 8(d)
     ach = FLOPS_DIRECT * frames / (ms * 1e-3) / 1e12
-    l2b, l2src = ncu_counter(kernel_names()[0], "l2_to_sm_bytes_per_launch")
-    drb, _ = ncu_counter(kernel_names()[0], "bytes_per_launch")
-    out["roofline"] = {"kernel": " + ".join(kernel_names()), "bound": "fp32 (CUDA-core FFMA / issue; neither hbm nor tensor)",
+    l2b, l2src = ncu_counter_sum(kernel_names(), "l2_to_sm_bytes_per_launch")
+    drb, _ = ncu_counter_sum(kernel_names(), "bytes_per_launch")
+    out["roofline"] = {"kernel": " + ".join(kernel_names()),
+                       "bound": "fp32 (CUDA-core FFMA / issue and latency; the fp16 / fp64 tensor-pipe parts are minor; neither hbm nor tensor)",
                        "achieved": ach, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach / FP32_PEAK_TFLOPS,
                        "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz (MEASURED_PEAKS.json has no fp32 figure)",
                        "algorithmic_flops_per_frame_iter": FLOPS_DIRECT, "ms_per_launch": ms, "frames_per_launch": frames,
@@ -256,7 +270,7 @@ def run_config4(dev, rank, world, max_over_ranks, barrier, frames_total: int = 1
 
 
 def kernel_names():
-    return ("ik_jacobian_kernel", "ik_solve_kernel")
+    return ("ik_jacobian_kernel", "ik_poseblend_tc_kernel", "ik_solve_mma_kernel")
 
 
 def cpu_reference_ik(frames: int = 2, iters: int = 2):
