@@ -126,7 +126,8 @@ __global__ void theta_assemble_kernel(int B, const float * __restrict__ state, f
 // ------------------------------------------------------------------------------------------------------------
 namespace c1
 {
-constexpr int THREADS = 256;
+constexpr int THREADS = 256;    // FFMA pose-blend phase inside the kernel (125 registers)
+constexpr int THREADS_TC = 384; // pose-blend columns left to ik_poseblend_tc_kernel (80 registers)
 constexpr int TS = 16; // floats of per-task scratch
 }
 
@@ -169,10 +170,12 @@ struct IkJacParams
   float * dr_out;        // (B, 621): s_dR of joints 1..23
 };
 
-template<int ROWS>
-__global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJacParams p)
+// TC: the pose-blend columns are left to ik_poseblend_tc_kernel (P5d / P5e are not even compiled in: 125 -> fewer registers)
+template<int ROWS, bool TC>
+__global__ void __launch_bounds__(TC ? c1::THREADS_TC : c1::THREADS, 2) ik_jacobian_kernel(const IkJacParams p)
 {
-  using namespace c1;
+  using c1::TS;
+  constexpr int THREADS = TC ? c1::THREADS_TC : c1::THREADS;
   extern __shared__ __align__(16) float sm[];
   const int tid = threadIdx.x;
   const int f = blockIdx.x;
@@ -207,9 +210,8 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
   for(int i = tid; i < 75; i += THREADS) s_theta[i] = p.theta[static_cast<size_t>(f) * 75 + i];
   if(tid < kShapeDim) s_beta[tid] = p.beta[static_cast<size_t>(f) * p.beta_stride + tid];
   {
-    const float * gv = p.verts + static_cast<size_t>(f) * p.nUse * 3;
     const float * gr = p.rest + static_cast<size_t>(f) * p.nUse * 3;
-    for(int i = tid; i < 3 * p.nUse; i += THREADS) s_verts[i] = gv[i], s_rest[i] = gr[i];
+    for(int i = tid; i < 3 * p.nUse; i += THREADS) s_rest[i] = gr[i];
     for(int i = tid; i < p.nUse * t.kmax; i += THREADS)
     {
       s_sw[i] = t.sw_norm[i]; // W[u, slot] / sum_j W[u, j], [u][slot] like the shared-memory copy
@@ -281,6 +283,29 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
     }
   }
   __syncthreads();
+  // ---- skinning of the task vertices (LinearBlendSkinning.cpp:445-553 on the ~480 rows the tasks touch): the terms
+  //      wn_j x_uj = (W[u,j] / sum W) (Rg_j rest_u + t'_j) are what the chain columns need anyway (P5b), their sum over
+  //      the influences plus the root translation is the posed vertex - no skinning launch, no vertex round trip ----
+  for(int u = tid; u < p.nUse; u += THREADS)
+  {
+    const f3 ru = ld3(s_rest + 3 * u);
+    f3 v = mk3(s_theta[0], s_theta[1], s_theta[2]);
+    f3 acc = mk3(0.f, 0.f, 0.f);
+    for(int sl = 0; sl < t.kmax; sl++)
+    {
+      const int i = u * t.kmax + sl;
+      const int j = s_sj[i];
+      const float wj = s_sw[i];
+      const float * G = s_G + 12 * j;
+      const f3 x = mk3(wj * (G[0] * ru.x + G[1] * ru.y + G[2] * ru.z + s_tp[3 * j]),
+                       wj * (G[4] * ru.x + G[5] * ru.y + G[6] * ru.z + s_tp[3 * j + 1]),
+                       wj * (G[8] * ru.x + G[9] * ru.y + G[10] * ru.z + s_tp[3 * j + 2]));
+      s_xw[3 * i] = x.x, s_xw[3 * i + 1] = x.y, s_xw[3 * i + 2] = x.z;
+      acc = acc + x;
+    }
+    v = v + acc;
+    s_verts[3 * u] = v.x, s_verts[3 * u + 1] = v.y, s_verts[3 * u + 2] = v.z;
+  }
   // ---- P2b: M_kc = Rg_parent(k) dR_kc Rg_k^T  (d x_j / d theta_kc = M_kc (x_j - tg_k)) ----
   if(tid < 72)
   {
@@ -339,6 +364,7 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
             s_dTg[(3 * j + r) * kShapeDim + i] - (G[4 * r] * js[0] + G[4 * r + 1] * js[1] + G[4 * r + 2] * js[2]);
     }
   }
+  __syncthreads(); // posed vertices complete
   // ---- P4 / G1: face normals of the ring items ----
   if(p.use_ring)
   {
@@ -444,17 +470,6 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
   }
   __syncthreads();
   // ---- G4: per (task, vertex) pair: C4 = d(residual rows) / d(vertex)  (ROWS x 3); also wn_j * x_uj ----
-  for(int i = tid; i < p.nUse * t.kmax; i += THREADS)
-  {
-    const int u = i / t.kmax;
-    const int j = s_sj[i];
-    const float wj = s_sw[i];
-    const float * G = s_G + 12 * j;
-    const f3 ru = ld3(s_rest + 3 * u);
-    s_xw[3 * i] = wj * (G[0] * ru.x + G[1] * ru.y + G[2] * ru.z + s_tp[3 * j]);
-    s_xw[3 * i + 1] = wj * (G[4] * ru.x + G[5] * ru.y + G[6] * ru.z + s_tp[3 * j + 1]);
-    s_xw[3 * i + 2] = wj * (G[8] * ru.x + G[9] * ru.y + G[10] * ru.z + s_tp[3 * j + 2]);
-  }
   // pairs in the order of decreasing reference count (pair_order): the lanes of a warp then run the same number of trips
   // (a corner is referenced by ~12 ring faces, a ring-only vertex by ~3: in pair order a warp ran at 1/3 efficiency)
   for(int ip0 = 0, round = 0; ip0 < t.nPairs; ip0 += THREADS, round++)
@@ -695,7 +710,7 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
       for(int c = 0; c < 3; c++) out[3 * r + c] = C[3 * r] * A[c] + C[3 * r + 1] * A[3 + c] + C[3 * r + 2] * A[6 + c];
 #pragma unroll
     for(int e = 0; e < 12; e++) C[e] = out[e];
-    if(p.ca_out)
+    if constexpr(TC)
     {
       const int m = t.pair_task[pr], q = pr - t.pair_off[m];
       const int s0 = p.ca_slot_off[m], kp = 32 * (p.ca_slot_off[m + 1] - s0);
@@ -706,12 +721,14 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
         for(int a = 0; a < 3; a++) dst[r * kp + a] = out[3 * r + a];
     }
   }
-  if(p.ca_out)
+  if constexpr(TC)
   {
     float * dst = p.dr_out + static_cast<size_t>(f) * 621;
     for(int i = tid; i < 621; i += THREADS) dst[i] = s_dR[27 + i];
     return; // P5d / P5e run as kernels of their own
   }
+  else
+  {
   __syncthreads();
   // ---- P5d: pose-blend (and shape-blend) columns: Q_m = sum_u CA4_u P_u (ROWS x 218), J += Q_m dvec(R_k)/dtheta.
   //      One warp per task; lanes 0..27 own EIGHT CONSECUTIVE basis columns each (8 x 28 = 224) of the K-major x / y / z
@@ -859,6 +876,7 @@ __global__ void __launch_bounds__(c1::THREADS, 2) ik_jacobian_kernel(const IkJac
       Jo[row * p.ld + dst] = Jf[row * p.ldfull + src];
     }
   }
+  } // !TC
 }
 
 // P5e of ik_jacobian_kernel as a kernel of its own (the pose-blend columns are added by ik_poseblend_tc_kernel between
@@ -2070,8 +2088,7 @@ int run_chunk(const smplpp_model_t * model, const smplpp_vposer_t * vposer, cons
   if(rc != SMPLPP_OK) return rc;
   // skinning WITHOUT the root translation is what the chain derivatives need (x_uj), the translation is added
   // back analytically: vertices = skinned + trans.  launch_lbs with root = theta row 0.
-  rc = launch_lbs(sub, st, B, rest, xf, true, theta_in, 75, verts);
-  if(rc != SMPLPP_OK) return rc;
+  (void)verts; // the task vertices are skinned inside ik_jacobian_kernel
 
   IkJacParams jp{};
   jp.topo = make_topo(md);
@@ -2118,16 +2135,16 @@ int run_chunk(const smplpp_model_t * model, const smplpp_vposer_t * vposer, cons
   }
   const size_t smem = jac_smem_bytes(tasks->d, L);
   if(smem > 227 * 1024) return fail(SMPLPP_ERR_INVALID, "IkTask", "task set too large for one CTA per frame");
+  auto launch = [&](auto kernel) -> int {
+    SB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kernel<<<B, L.pb_tc ? c1::THREADS_TC : c1::THREADS, smem, st>>>(jp);
+    return SMPLPP_OK;
+  };
   if(L.rows_per_task == 4)
-  {
-    SB_CUDA(cudaFuncSetAttribute(ik_jacobian_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    ik_jacobian_kernel<4><<<B, c1::THREADS, smem, st>>>(jp);
-  }
+    rc = L.pb_tc ? launch(ik_jacobian_kernel<4, true>) : launch(ik_jacobian_kernel<4, false>);
   else
-  {
-    SB_CUDA(cudaFuncSetAttribute(ik_jacobian_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    ik_jacobian_kernel<3><<<B, c1::THREADS, smem, st>>>(jp);
-  }
+    rc = L.pb_tc ? launch(ik_jacobian_kernel<3, true>) : launch(ik_jacobian_kernel<3, false>);
+  if(rc != SMPLPP_OK) return rc;
   SB_LAUNCHED();
   if(L.pb_tc)
   {
