@@ -167,7 +167,7 @@ struct IkJacParams
   float * ca_out;        // (B, ca_stride): per task [4 row slots][32 * K-blocks], k = 3 * pair + axis; null: FFMA phase here
   const int * ca_slot_off; // (n + 1) first K-block of every task
   int ca_stride;
-  float * dr_out;        // (B, 621): s_dR of joints 1..23
+  float * dr_out;        // (B, 23, 28): s_dR of joints 1..23, rows padded to 16 bytes
 };
 
 // TC: the pose-blend columns are left to ik_poseblend_tc_kernel (P5d / P5e are not even compiled in: 125 -> fewer registers)
@@ -723,8 +723,12 @@ __global__ void __launch_bounds__(TC ? c1::THREADS_TC : c1::THREADS, 2) ik_jacob
   }
   if constexpr(TC)
   {
-    float * dst = p.dr_out + static_cast<size_t>(f) * 621;
-    for(int i = tid; i < 621; i += THREADS) dst[i] = s_dR[27 + i];
+    float * dst = p.dr_out + static_cast<size_t>(f) * 644; // [23 joints][28]: 27 entries + one pad (16-byte rows)
+    for(int i = tid; i < 644; i += THREADS)
+    {
+      const int k = i / 28, e = i - 28 * k;
+      dst[i] = e < 27 ? s_dR[27 * (k + 1) + e] : 0.f;
+    }
     return; // P5d / P5e run as kernels of their own
   }
   else
@@ -2017,7 +2021,7 @@ IkLayout make_layout(const smplpp_tasks_t * tasks, const smplpp_ik_options * o, 
   L.off_misc = take(64 * sizeof(double));
   L.pb_tc = tasks->pb.ready && g_poseblend_variant == 0 && L.phi_cols == 0;
   L.off_ca = tasks->pb.ready ? take(C * tasks->pb.slots * 128 * sizeof(float)) : 0;
-  L.off_dr = tasks->pb.ready ? take(C * 621 * sizeof(float)) : 0;
+  L.off_dr = tasks->pb.ready ? take(C * 644 * sizeof(float)) : 0;
   L.total = off;
   return L;
 }

@@ -41,7 +41,9 @@ constexpr int B_PART = NCOL * ROWB;      // 14336
 constexpr int A_PART = 128 * ROWB;       // 8192
 constexpr int SLOT = 2 * B_PART + 2 * A_PART; // 45056: [P hi | P lo | CA hi | CA lo] of one K-block
 constexpr int SLOTS = 3;
-constexpr int DR = 27 * (kJoints - 1);   // 621: d vec(R_k) / d theta_kc of joints 1..23 (odd => conflict-free rows)
+constexpr int DRJ = 28;                  // per joint: 27 entries d vec(R_k)[e] / d theta_kc at [9 c + e], padded to 7 float4
+constexpr int DR = DRJ * (kJoints - 1);  // 644 floats per frame (4 mod 32: the 8 frames of a warp read 16 bytes each from
+                                         // different banks)
 constexpr int OFF_DR = SLOTS * SLOT;
 constexpr int OFF_BAR = OFF_DR + FPB * DR * 4;
 constexpr int SMEM_BYTES = 1024 + OFF_BAR + 256;
@@ -65,7 +67,7 @@ struct Params
   const int * pair_off;        // (n + 1)
   const uint8_t * img;         // [K-block][hi | lo][224][64 B]
   const float * ca;            // (B, ca_stride): per task [4 row slots][32 * K-blocks]
-  const float * dr;            // (B, 621)
+  const float * dr;            // (B, 23, 28)
   float out_scale;             // 2^-basis_exp
   float * J;                   // (B, 4 n, ld)
   int ld;
@@ -85,22 +87,23 @@ __device__ __forceinline__ void epilogue_task(const Params & p, uint32_t taddr, 
 {
   // G = 0: columns [0, 108) = joints 1..12; G = 1: columns [108, 224) = joints 13..23, then 10 shape columns.
   // dr: SHARED-space address of this frame's derivative table (explicit ld.shared: through a generic pointer the compiler
-  // emitted LD.E + R2UR pairs, 27 % of the kernel's stall samples)
-  constexpr int C0 = G == 0 ? 0 : 96, C1 = G == 0 ? 128 : 224; // chunks of 32 columns that cover the range
+  // emitted LD.E + R2UR pairs, 27 % of the kernel's stall samples; seven 16-byte loads per joint: with one 4-byte load per
+  // entry the epilogue ran at the issue rate of the shared-memory pipe)
+  constexpr int C0 = G == 0 ? 0 : 96, C1 = G == 0 ? 112 : 224; // chunks of 16 columns that cover the range
   constexpr int K0 = G == 0 ? 1 : 13, NK = G == 0 ? 12 : 11;
   float acc[NK][3];
 #pragma unroll
   for(int k = 0; k < NK; k++) acc[k][0] = acc[k][1] = acc[k][2] = 0.f;
   float shp[kShapeDim];
+  float jd[DRJ]; // derivative entries of the joint whose columns are being read
 #pragma unroll
-  for(int ch = C0; ch < C1; ch += 32)
+  for(int ch = C0; ch < C1; ch += 16)
   {
-    float v[32];
+    float v[16];
     ptx::tmem_ld_x16(taddr + ch, v);
-    ptx::tmem_ld_x16(taddr + ch + 16, v + 16);
     ptx::tmem_ld_wait();
 #pragma unroll
-    for(int i = 0; i < 32; i++)
+    for(int i = 0; i < 16; i++)
     {
       const int d = ch + i;
       if(d < kPoseDim)
@@ -108,8 +111,17 @@ __device__ __forceinline__ void epilogue_task(const Params & p, uint32_t taddr, 
         const int k = d / 9 + 1, e = d % 9;
         if(k >= K0 && k < K0 + NK)
         {
+          if(e == 0)
+          {
 #pragma unroll
-          for(int c = 0; c < 3; c++) acc[k - K0][c] = fmaf(v[i], ptx::lds32(dr + 4 * (27 * (k - 1) + 9 * c + e)), acc[k - K0][c]);
+            for(int q = 0; q < DRJ / 4; q++)
+            {
+              const float4 t4 = ptx::lds128(dr + 4 * (DRJ * (k - 1) + 4 * q));
+              jd[4 * q] = t4.x, jd[4 * q + 1] = t4.y, jd[4 * q + 2] = t4.z, jd[4 * q + 3] = t4.w;
+            }
+          }
+#pragma unroll
+          for(int c = 0; c < 3; c++) acc[k - K0][c] = fmaf(v[i], jd[9 * c + e], acc[k - K0][c]);
         }
       }
       else if(G == 1 && d < kPoseDim + kShapeDim)
@@ -190,6 +202,12 @@ __global__ void __launch_bounds__(pbtc::THREADS, 1) ik_poseblend_tc_kernel(const
   // K-blocks of task m that carry data: all of them with the 1-rings, the first one (3 corners = 9 values) without
   auto task_kb = [&](int m) { return p.use_ring ? __ldg(p.slot_off + m + 1) - __ldg(p.slot_off + m) : 1; };
 
+  // registers: 96 per thread at launch (640 threads); the control warps and the builders hand some back, the epilogue
+  // warps (36 accumulators + 28 derivative entries + 16 TMEM words live) take 128
+  // (setmaxnreg inside the role branches: ptxas only honours it there)
+  if(warp < CTRL_WARPS)
+  {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if(warp == 0)
   {
     if(ptx::elect_one())
@@ -249,8 +267,10 @@ __global__ void __launch_bounds__(pbtc::THREADS, 1) ik_poseblend_tc_kernel(const
       }
     }
   }
-  else if(warp >= CTRL_WARPS && warp < CTRL_WARPS + BUILD_WARPS)
+  } // control warps
+  else if(warp < CTRL_WARPS + BUILD_WARPS)
   {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
     // ---- CA_m K-blocks: thread = row (frame fl, row slot r); group gb builds every other K-block ----
     const int bw = warp - CTRL_WARPS, gb = bw >> 2;
     const int L = (bw & 3) * 32 + lane, fl = L >> 2, r = L & 3;
@@ -333,8 +353,9 @@ __global__ void __launch_bounds__(pbtc::THREADS, 1) ik_poseblend_tc_kernel(const
       if(lane == 0) ptx::mbar_arrive(&full_a[s]);
     }
   }
-  else if(warp >= CTRL_WARPS + BUILD_WARPS)
+  else
   {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
     // ---- epilogue: thread = TMEM lane L = 4 fl + r ----
     const int ew = warp - CTRL_WARPS - BUILD_WARPS, ge = ew >> 2, q = warp & 3;
     const int L = q * 32 + lane, fl = L >> 2, r = L & 3;
