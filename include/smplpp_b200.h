@@ -245,6 +245,19 @@ int smplpp_closest_points(const smplpp_model_t * model, void * stream, int64_t b
                           const float * vertices_dev, const float * points_dev, int32_t * face_idx_dev,
                           float * closest_dev, float * sq_dist_dev, float * vertex_weights_dev);
 
+/* Sweep grid of ONE posed mesh (replaces node/node.cpp:1023-1073 and toolbox/GridUtils.hpp:28-63; igl::winding_number is
+ * un-vendored: generalized winding number = sum of the signed solid angles of the faces / 4 pi):
+ *   smplpp_sweep_grid_bounds   vertices (V, 3) device -> grid_idx_min[3] = getGridIdxFloor(min corner),
+ *                              grid_num[3] = getGridIdxCeil(max corner) - grid_idx_min + 1   (host arrays; synchronises)
+ *   smplpp_sweep_grid_winding  winding number (optional) and occupancy (optional, 1 where winding > 0.5, node.cpp:1056) of
+ *                              the grid points 0.025 * (grid_idx_min + (ix, iy, iz)), ix outermost / iz innermost like the
+ *                              reference's loop (node.cpp:1038-1048); both outputs hold grid_num[0]*[1]*[2] entries (device) */
+int smplpp_sweep_grid_bounds(const smplpp_model_t * model, void * stream, const float * vertices_dev, int32_t * grid_idx_min,
+                             int32_t * grid_num);
+int smplpp_sweep_grid_winding(const smplpp_model_t * model, void * stream, const float * vertices_dev,
+                              const int32_t * grid_idx_min, const int32_t * grid_num, float * winding_dev,
+                              uint8_t * occupied_dev);
+
 /* One IK iteration for B independent frames (replaces node/node.cpp:753-968 per frame):
  *   theta assembly (+VPoser) -> sparse forward on the task vertices -> tangents + re-weighting (:803-804) ->
  *   residual e (:807-820) -> analytic Jacobian J (what the one-hot backward rows of :823-873 yield) ->

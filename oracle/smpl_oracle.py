@@ -607,3 +607,44 @@ def forward_numpy(model: SmplModel, beta: np.ndarray, theta: np.ndarray, chunk: 
             for o, t in zip(outs, (r.vertices, r.joints, r.rest_shape, r.transforms)):
                 o.append(t.numpy())
     return tuple(np.concatenate(o, 0) for o in outs)
+
+
+def sweep_grid_points(verts: np.ndarray):
+    """toolbox/GridUtils.hpp:28-63 + node/node.cpp:1031-1049: grid_idx_min = floor(min corner / GRID_SCALE), grid_num from
+    ceil(max corner / GRID_SCALE) (float positions divided by float(0.025)), and the grid points float(0.025) * index in the
+    reference's loop order (x outermost, z innermost), as float64 (N, 3)."""
+    v32 = np.asarray(verts, dtype=np.float32)
+    gs32 = np.float32(0.025)
+    lo = np.floor(v32.min(0) / gs32).astype(np.int32)
+    hi = np.ceil(v32.max(0) / gs32).astype(np.int32)
+    num = hi - lo + 1
+    ix, iy, iz = np.meshgrid(np.arange(num[0]), np.arange(num[1]), np.arange(num[2]), indexing="ij")
+    idx = np.stack([ix, iy, iz], -1).reshape(-1, 3) + lo[None]
+    return lo, num, (gs32 * idx.astype(np.float32)).astype(np.float64)
+
+
+def winding_number(verts: np.ndarray, faces0: np.ndarray, pts: np.ndarray):
+    """Generalized winding number of a triangle mesh at pts (N, 3): sum of the signed solid angles of the faces / 4 pi
+    (Van Oosterom & Strackee 1983; what igl::winding_number evaluates, node/node.cpp:1052 - libigl is un-vendored)."""
+    v = np.asarray(verts, dtype=np.float32).astype(np.float64)
+    A, B, C = v[faces0[:, 0]], v[faces0[:, 1]], v[faces0[:, 2]]
+    pts = np.asarray(pts, dtype=np.float64)
+    w = np.zeros(len(pts))
+    for s in range(0, len(pts), 256):  # chunks keep the (points, faces, 3) temporaries small
+        p = pts[s:s + 256, None, :]
+        a, b, c = A[None] - p, B[None] - p, C[None] - p
+        la, lb, lc = np.linalg.norm(a, axis=2), np.linalg.norm(b, axis=2), np.linalg.norm(c, axis=2)
+        det = np.einsum("pfi,pfi->pf", a, np.cross(b, c))
+        den = la * lb * lc + np.einsum("pfi,pfi->pf", a, b) * lc + np.einsum("pfi,pfi->pf", b, c) * la \
+            + np.einsum("pfi,pfi->pf", c, a) * lb
+        w[s:s + 256] = (2.0 * np.arctan2(det, den)).sum(1) / (4.0 * np.pi)
+    return w
+
+
+def sweep_grid(verts: np.ndarray, faces0: np.ndarray):
+    """node/node.cpp:1023-1073 for one frame: the 2.5 cm grid around the mesh and the winding number of every grid point
+    (float64 inside).  Returns (grid_idx_min (3,), grid_num (3,), winding (nx, ny, nz)); a cell is occupied where
+    winding > 0.5 (node.cpp:1056).  NOTE: the reference stores libigl's result in an Eigen::VectorXi (node.cpp:1051) -
+    whether libigl rounds or truncates into it cannot be checked here, so the oracle keeps the real number."""
+    lo, num, pts = sweep_grid_points(verts)
+    return lo, num, winding_number(verts, faces0, pts).reshape(num[0], num[1], num[2])

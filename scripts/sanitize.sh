@@ -2,11 +2,12 @@
 # compute-sanitizer pass over a reduced-size subset of the GPU tests (the reference relies on ASan-less gtests;
 # the hand-rolled mbarrier / TMEM / TMA pipelines here need their own race and bounds checks).
 #   memcheck  : out-of-bounds / misaligned global + shared accesses
-#   racecheck : shared-memory hazards (the cp.async.bulk ring of the fused IK kernel, the stage rings of the tcgen05 kernels)
+#   racecheck : shared-memory hazards (the cp.async.bulk ring of the fused IK kernel, the stage rings of the tcgen05 kernels,
+#               the cp.async ring / tile storage of ik_solve_mma_kernel, the operand ring of ik_poseblend_tc_kernel)
 #   synccheck : divergent / invalid barrier use (named barriers per frame team)
 # Output: gpurun_out/sanitize_<tool>.log and a one-line-per-tool summary gpurun_out/sanitize_summary.txt
 mkdir -p gpurun_out
-SEL='test_forward_vs_reference_golden or test_model_skinning_vs_oracle or test_ik_step_vs_reference_golden or test_ik_step_vposer or test_shared_beta_single or test_closest_points_vs_oracle or test_decoder_vs_reference_golden or test_body_stage_every_iteration'
+SEL='test_forward_vs_reference_golden or test_model_skinning_vs_oracle or test_ik_step_vs_reference_golden or test_ik_step_vposer or test_shared_beta_single or test_closest_points_vs_oracle or test_decoder_vs_reference_golden or test_body_stage_every_iteration or test_config4_vposer_every_iteration or test_shared_beta_16_frames or test_sweep_grid_bounds'
 : > gpurun_out/sanitize_summary.txt
 for tool in memcheck racecheck synccheck; do
   extra=""

@@ -262,6 +262,27 @@ class SMPL:
                                               C.c_void_p(face.data_ptr()), _ptr(closest), _ptr(sq), _ptr(w)))
         return face, closest, sq, w
 
+    def sweepGrid(self, vertices: Optional[torch.Tensor] = None, index: int = 0):
+        """Sweep-grid occupancy of one posed mesh (node/node.cpp:1023-1073): the 2.5 cm grid around the mesh of batch
+        element `index` and the winding number of every grid point.  Returns (grid_idx_min (3,) int32, grid_num (3,)
+        int32, winding (nx, ny, nz) float32, occupied (nx, ny, nz) bool); grid point (ix, iy, iz) sits at
+        0.025 * (grid_idx_min + (ix, iy, iz))."""
+        dev = self.m__device
+        if vertices is None:
+            self._launched("LinearBlendSknning Error: Failed to get vertices of new pose!")
+            vertices = self._vertices
+        v = _dev_f32(vertices, dev)
+        v = (v[index] if v.dim() == 3 else v).contiguous()
+        lo, num = (C.c_int32 * 3)(), (C.c_int32 * 3)()
+        with torch.cuda.device(dev):
+            check(lib().smplpp_sweep_grid_bounds(self.handle, _stream(dev), _ptr(v), lo, num))
+            total = num[0] * num[1] * num[2]
+            w = torch.empty(total, dtype=torch.float32, device=dev)
+            occ = torch.empty(total, dtype=torch.uint8, device=dev)
+            check(lib().smplpp_sweep_grid_winding(self.handle, _stream(dev), _ptr(v), lo, num, _ptr(w), C.c_void_p(occ.data_ptr())))
+        shape = (num[0], num[1], num[2])
+        return np.array(list(lo), np.int32), np.array(list(num), np.int32), w.view(shape), occ.view(shape).bool()
+
     def setVertPath(self, path: str):
         self.m__vertPath = path
 

@@ -82,7 +82,10 @@ __device__ __forceinline__ double dneg(double a) // sign flip on the integer pip
   return __hiloint2double(__double2hiint(a) ^ 0x80000000, __double2loint(a));
 }
 
-__device__ __forceinline__ void cta_sync()
+// The kernel body exists once per warp of the CTA (static register indices): one out-of-line barrier, so that the four
+// warps arrive at the SAME instruction (compute-sanitizer's synccheck reports warps that meet at a named barrier from
+// different code addresses as divergent).
+__device__ __noinline__ void cta_sync()
 {
   asm volatile("bar.sync 1, %0;\n" ::"n"(THREADS) : "memory");
 }
@@ -137,6 +140,7 @@ __device__ __forceinline__ void diag_factor(double * tile, int npl, double * inv
       }
     }
   }
+  __syncwarp(); // lanes 8..31 have read the rows that lanes 0..7 overwrite
   if(lane < 8)
   {
 #pragma unroll

@@ -225,3 +225,19 @@ def test_oracle_mesh_projection_properties(params):
     assert face_v[0] == incident.min() and sq_v[0] == 0.0
     assert np.abs(closest_v[0] - verts[vid]).max() == 0.0
     assert np.abs((w_v[0][:, None] * verts[faces0[face_v[0]]]).sum(0) - verts[vid]).max() < 1e-12
+
+
+def test_sweep_grid_oracle_on_a_cube():
+    """Winding number of a closed cube: 1 inside, 0 outside, 1/2 on a face, and the grid bounds of GridUtils.hpp."""
+    from oracle import smpl_oracle as so
+    c = np.array([[x, y, z] for x in (0.0, 1.0) for y in (0.0, 1.0) for z in (0.0, 1.0)]) * 0.1 + np.array([0.013, -0.06, 0.2])
+    faces = np.array([[0, 1, 3], [0, 3, 2], [4, 6, 7], [4, 7, 5], [0, 4, 5], [0, 5, 1], [2, 3, 7], [2, 7, 6], [0, 2, 6], [0, 6, 4],
+                      [1, 5, 7], [1, 7, 3]])
+    lo, num, w = so.sweep_grid(c, faces)
+    assert np.array_equal(lo, [0, -3, 8]) and np.array_equal(lo + num - 1, [5, 2, 12])
+    pts = 0.025 * (np.stack(np.meshgrid(*[np.arange(n) for n in num], indexing="ij"), -1) + lo)
+    inside = ((pts > c.min(0) + 1e-6) & (pts < c.max(0) - 1e-6)).all(-1)
+    outside = ((pts < c.min(0) - 1e-6) | (pts > c.max(0) + 1e-6)).any(-1)
+    sign = 1.0 if w[inside].mean() > 0 else -1.0  # orientation of the hand-written faces
+    assert inside.sum() >= 27 and np.abs(sign * w[inside] - 1.0).max() < 1e-9
+    assert np.abs(w[outside]).max() < 1e-9
