@@ -395,7 +395,7 @@ bool encode_kmajor(CUtensorMap * out, bool tf32, void * base, uint64_t rows, uin
 
 namespace sb
 {
-int g_tc_grid_order = 1;
+std::atomic<int> g_tc_grid_order{1};
 
 bool tc_blend_available()
 {

@@ -20,8 +20,8 @@ using namespace sb;
 
 namespace sb
 {
-int g_forward_variant = 0;
-int g_lbs_variant = 2;
+std::atomic<int> g_forward_variant{0};
+std::atomic<int> g_lbs_variant{2};
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -54,10 +54,10 @@ int launch_lbs_tma(const ModelDev & d, cudaStream_t st, int B, const float * res
 bool lbs_tc_usable(const ModelDev & d, const float * rest, const float * out, const float * xforms);
 int launch_lbs_tc(const ModelDev & d, cudaStream_t st, int B, const float * rest, const float * xforms, int xf_floats,
                   const float * root, int root_stride, float * out);
-extern int g_lbs_variant; // 0: FFMA TMA pipeline when usable, 1: FFMA register-pipelined kernel, 2: tcgen05 (default)
+extern std::atomic<int> g_lbs_variant; // 0: FFMA TMA pipeline when usable, 1: FFMA register-pipelined kernel, 2: tcgen05 (default)
 // frees the streams, events and buffers of smplpp_forward_host (host_pipe.cu)
 void release_host_pipe(smplpp_model * m);
 
-extern int g_forward_variant;
-extern int g_tc_grid_order; // 1: frame tiles fastest in the tcgen05 kernel's grid (CTAs in flight share the basis tile)
+extern std::atomic<int> g_forward_variant;
+extern std::atomic<int> g_tc_grid_order; // 1: frame tiles fastest in the tcgen05 kernel's grid (CTAs in flight share the basis tile)
 } // namespace sb

@@ -1522,7 +1522,7 @@ __global__ void __launch_bounds__(k2::MAXF * k2::TEAM + 32, 1) ik_fused_kernel(c
 // ------------------------------------------------------------------------------------------------------------
 namespace sb
 {
-int g_ik_variant = 0;
+std::atomic<int> g_ik_variant{0};
 
 int build_task_rec_host(const smplpp_model * model, int64_t face, TaskRec & r)
 {

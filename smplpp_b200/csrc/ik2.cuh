@@ -55,5 +55,5 @@ void build_task_skin_host(const smplpp_model * model, const TaskRec & rec, TaskS
 // skins (nullable): also the skinning rows of every record (d.kmax <= 4)
 int launch_task_topo(const ModelDev & d, cudaStream_t st, long long total, const int32_t * face_idx, TaskRec * out, TaskSkin * skins);
 size_t ik2_skin_bytes(int64_t batch, int n);
-extern int g_ik_variant; // 0: auto (two kernels when the frames share the attachments, fused kernel otherwise), 1: two kernels, 2: fused
+extern std::atomic<int> g_ik_variant; // 0: auto (two kernels when the frames share the attachments, fused kernel otherwise), 1: two kernels, 2: fused
 } // namespace sb

@@ -23,5 +23,5 @@ int poseblend_tc_prepare(const std::vector<float> & basis, const std::vector<int
 // columns 207..216 of CA_m P_m added to J[.., beta_col + i] when beta_col >= 0
 int launch_poseblend_tc(const PoseBlendTc & pb, const TasksDev & t, cudaStream_t st, int B, int rows, int use_ring, int beta_col,
                         const float * ca, const float * dr, float * J, int ld);
-extern int g_poseblend_variant; // 0: auto (tensor cores where prepared), 1: the FFMA phase inside ik_jacobian_kernel
+extern std::atomic<int> g_poseblend_variant; // 0: auto (tensor cores where prepared), 1: the FFMA phase inside ik_jacobian_kernel
 } // namespace sb

@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(pbtc::THREADS, 1) ik_poseblend_tc_kernel(const
 // ------------------------------------------------------------------------------------------------------------
 namespace sb
 {
-int g_poseblend_variant = 0;
+std::atomic<int> g_poseblend_variant{0};
 
 // stage images of P_m^T for every task from the compact basis rows (3 nUpad, 224) of the task set
 int poseblend_tc_prepare(const std::vector<float> & basis, const std::vector<int32_t> & pair_off,

@@ -35,5 +35,5 @@ struct IkSolveParams
 // shape is one the kernel covers (D + 1 <= 88 unknowns incl. the right-hand side row, no bound can bind); otherwise
 // *handled = false and nothing was launched (the caller falls back to ik_solve_kernel).
 int launch_ik_solve_mma(const IkSolveParams & p, cudaStream_t st, bool * handled);
-extern int g_solve_variant; // 0: auto (tensor-core kernel where it applies), 1: ik_solve_kernel always
+extern std::atomic<int> g_solve_variant; // 0: auto (tensor-core kernel where it applies), 1: ik_solve_kernel always
 } // namespace sb

@@ -18,7 +18,7 @@
 
 namespace sb
 {
-int g_solve_variant = 0;
+std::atomic<int> g_solve_variant{0};
 }
 
 using namespace sb;

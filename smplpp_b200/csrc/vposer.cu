@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(vp::THREADS, 1)
 // ------------------------------------------------------------------------------------------------------------
 namespace sb
 {
-int g_vposer_jac_variant = 0;
+std::atomic<int> g_vposer_jac_variant{0};
 
 int launch_vposer_decode(const smplpp_vposer * vposer, cudaStream_t st, int B, const float * latent,
                          long long latent_stride, float * aa, long long aa_stride, float * jac, float * aux_ws)

@@ -33,5 +33,5 @@ int vposer_tc_prepare(smplpp_vposer & v, const float * w0, const float * w3, con
 void vposer_tc_release(smplpp_vposer & v);
 size_t vposer_tc_aux_floats();
 int launch_vposer_jac_tc(const smplpp_vposer & v, cudaStream_t st, int B, const float * aux, float * jac);
-extern int g_vposer_jac_variant; // 0: tensor cores when available, 1: FFMA kernel
+extern std::atomic<int> g_vposer_jac_variant; // 0: tensor cores when available, 1: FFMA kernel
 } // namespace sb
