@@ -884,34 +884,62 @@ __global__ void __launch_bounds__(TC ? c1::THREADS_TC : c1::THREADS, 2) ik_jacob
 }
 
 // P5e of ik_jacobian_kernel as a kernel of its own (the pose-blend columns are added by ik_poseblend_tc_kernel between
-// the two): contract the 63 body columns with d(axis-angle)/d(latent) (node.cpp:761-772), one CTA per frame
+// the two): contract the 63 body columns with d(axis-angle)/d(latent) (node.cpp:761-772), one CTA per frame.
+// The frame's decoder Jacobian (63 x 32) and the body columns of its live rows sit in shared memory; warp = 16 rows, lane =
+// latent column: per four body columns a lane reads 4 decoder entries and, as broadcasts, one float4 per row for 64 FMAs
+// (the first version re-read both operands from L1 for every task: 0.88 ms per 16384 frames, now 0.3).
 template<int ROWS>
 __global__ void __launch_bounds__(256) ik_vposer_contract_kernel(int n, int extra, const float * __restrict__ jfull, int ldfull,
                                                                  const float * __restrict__ vposer_jac, float * __restrict__ jout,
                                                                  int ld)
 {
-  const int tid = threadIdx.x, f = blockIdx.x;
+  extern __shared__ __align__(16) float s_vc[];
+  float * s_jv = s_vc;            // [64][32]: row 63 is zero
+  float * s_j = s_vc + 64 * 32;   // [128][64]: body columns of up to 128 live rows, column 63 is zero
+  const int tid = threadIdx.x, f = blockIdx.x, warp = tid >> 5, lane = tid & 31;
   const float * Jf = jfull + static_cast<size_t>(f) * 4 * n * ldfull;
   float * Jo = jout + static_cast<size_t>(f) * 4 * n * ld;
   const float * Jv = vposer_jac + static_cast<size_t>(f) * 63 * 32;
-  for(int i = tid; i < n * 32; i += 256)
+  const int nlive = n * ROWS;
+  for(int i = tid; i < 64 * 32; i += 256) s_jv[i] = i < 63 * 32 ? __ldg(Jv + i) : 0.f;
+  auto grow = [&](int l) { return 4 * (l / ROWS) + l % ROWS; }; // global row of live row l
+  for(int l0 = 0; l0 < nlive; l0 += 128)
   {
-    const int m = i >> 5, tt = i & 31;
-    const float * jr = Jf + (4 * m) * ldfull + 6;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 7
-    for(int q = 0; q < 63; q++)
+    const int cnt = min(128, nlive - l0);
+    __syncthreads(); // previous pass consumed
+    for(int i = tid; i < 128 * 64; i += 256)
     {
-      const float v = __ldg(Jv + q * 32 + tt);
+      const int rl = i >> 6, q = i & 63;
+      s_j[i] = (rl < cnt && q < 63) ? Jf[grow(l0 + rl) * ldfull + 6 + q] : 0.f;
+    }
+    __syncthreads();
+    float acc[16];
 #pragma unroll
-      for(int r = 0; r < ROWS; r++) acc[r] = fmaf(jr[r * ldfull + q], v, acc[r]);
+    for(int r = 0; r < 16; r++) acc[r] = 0.f;
+    const float4 * rows = reinterpret_cast<const float4 *>(s_j + warp * 16 * 64);
+#pragma unroll 4
+    for(int q4 = 0; q4 < 16; q4++)
+    {
+      const float v0 = s_jv[(4 * q4) * 32 + lane], v1 = s_jv[(4 * q4 + 1) * 32 + lane], v2 = s_jv[(4 * q4 + 2) * 32 + lane],
+                  v3 = s_jv[(4 * q4 + 3) * 32 + lane];
+#pragma unroll
+      for(int r = 0; r < 16; r++)
+      {
+        const float4 a = rows[r * 16 + q4];
+        acc[r] = fmaf(a.x, v0, fmaf(a.y, v1, fmaf(a.z, v2, fmaf(a.w, v3, acc[r]))));
+      }
     }
 #pragma unroll
-    for(int r = 0; r < 4; r++) Jo[(4 * m + r) * ld + 6 + tt] = acc[r];
+    for(int r = 0; r < 16; r++)
+    {
+      const int rl = warp * 16 + r;
+      if(rl < cnt) Jo[grow(l0 + rl) * ld + 6 + lane] = acc[r];
+    }
   }
-  for(int i = tid; i < 4 * n * (12 + extra); i += 256)
+  // the other columns of the live rows: [trans | root] and the hands move, phi / beta columns follow
+  for(int i = tid; i < nlive * (12 + extra); i += 256)
   {
-    const int row = i / (12 + extra), c = i % (12 + extra);
+    const int row = grow(i / (12 + extra)), c = i % (12 + extra);
     int src, dst;
     if(c < 6)
       src = c, dst = c;
@@ -921,6 +949,9 @@ __global__ void __launch_bounds__(256) ik_vposer_contract_kernel(int n, int extr
       src = 75 + (c - 12), dst = 44 + (c - 12);
     Jo[row * ld + dst] = Jf[row * ldfull + src];
   }
+  // row slots that carry no residual stay zero
+  if(ROWS < 4)
+    for(int i = tid; i < n * ld; i += 256) Jo[(4 * (i / ld) + 3) * ld + i % ld] = 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -2159,9 +2190,9 @@ int run_chunk(const smplpp_model_t * model, const smplpp_vposer_t * vposer, cons
     {
       const int extra = L.phi_cols + L.beta_cols;
       if(L.rows_per_task == 4)
-        ik_vposer_contract_kernel<4><<<B, 256, 0, st>>>(L.n, extra, jp.jfull, jp.ldfull, vjac, jp.jout, jp.ld);
+        ik_vposer_contract_kernel<4><<<B, 256, (64 * 32 + 128 * 64) * sizeof(float), st>>>(L.n, extra, jp.jfull, jp.ldfull, vjac, jp.jout, jp.ld);
       else
-        ik_vposer_contract_kernel<3><<<B, 256, 0, st>>>(L.n, extra, jp.jfull, jp.ldfull, vjac, jp.jout, jp.ld);
+        ik_vposer_contract_kernel<3><<<B, 256, (64 * 32 + 128 * 64) * sizeof(float), st>>>(L.n, extra, jp.jfull, jp.ldfull, vjac, jp.jout, jp.ld);
       SB_LAUNCHED();
     }
   }
