@@ -251,3 +251,39 @@ def test_shared_beta_many_frames_kkt(task_set, marker_tasks, smpl_gpu, ik_varian
     assert (grad[x >= 0.5 - 1e-6] <= 1e-6).all() and (grad[x <= -0.5 + 1e-6] >= -1e-6).all()
     # moving towards the true shape
     assert np.linalg.norm(x - beta_true) < np.linalg.norm(beta_true)
+
+
+@pytest.mark.parametrize("n_tasks,seed", [(77, 1), (5, 2)])
+def test_tensor_core_stages_equal_ffma_on_random_task_sets(smpl_gpu, params, n_tasks, seed):
+    """The tensor-core stages of the two-kernel path (pose-blend columns on tcgen05, normal equations on the fp64 tensor
+    cores) against their FFMA / scalar predecessors on task sets other than the 41 markers of the goldens: random faces,
+    37 frames (one full and one partial frame block), with and without normal rows."""
+    from smplpp_b200 import api, capi, synth
+    rng = np.random.default_rng(seed)
+    faces = rng.choice(params.face_indices.shape[0], size=n_tasks, replace=False).astype(np.int64)
+    ts = api.IkTaskSet(smpl_gpu, faces)
+    F = 37
+    theta = synth.make_motion(F, 7 + seed).reshape(F, 75).astype(f32)
+    theta[:, 3:] += rng.normal(scale=0.2, size=(F, 72)).astype(f32)
+    beta = (rng.normal(size=10) * 0.5).astype(f32)
+    vw = rng.dirichlet(np.ones(3), size=(F, n_tasks)).astype(f32)
+    tgt = rng.normal(scale=0.5, size=(F, n_tasks, 3)).astype(f32)
+    tn = rng.normal(size=(F, n_tasks, 3)).astype(f32)
+    tn /= np.linalg.norm(tn, axis=2, keepdims=True)
+    for kw in (dict(normal_offset=0.015), dict(normal_task_weight=1.0, normal_offset=0.0), dict(normal_offset=0.0)):
+        opt = api.ik_options(update_state=0, skip_if_too_few=0, **kw)
+        outs = {}
+        for variants in ((411, 421), (410, 420)):
+            for v in variants:
+                capi.check(capi.lib().smplpp_set_forward_variant(v))
+            status, out = ts.step(opt, cu(theta), cu(beta), cu(vw), cu(tgt),
+                                  target_normal=cu(tn) if kw.get("normal_task_weight") else None, outputs=True)
+            outs[variants] = (status.cpu().numpy(), out["J"].cpu().numpy(), out["delta"].cpu().numpy(), out["A"].cpu().numpy())
+        for v in (410, 420):
+            capi.check(capi.lib().smplpp_set_forward_variant(v))
+        (s0, J0, d0, A0), (s1, J1, d1, A1) = outs[(411, 421)], outs[(410, 420)]
+        assert np.array_equal(s0, s1) and (s0 == 0).all()
+        scale = np.abs(J0).reshape(F, -1).max(1)
+        assert (np.abs(J1 - J0).reshape(F, -1).max(1) / scale).max() < 2e-6
+        assert np.abs(A1 - A0).max() < 1e-5 * np.abs(A0).max()
+        assert np.abs(d1 - d0).max() < 1e-5
