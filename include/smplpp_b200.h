@@ -126,8 +126,9 @@ int smplpp_host_unregister(void * ptr);
  *   400..402  IK step: auto (two kernels for shared attachments, fused kernel for per-frame ones) / two kernels / fused
  *   410 / 411 normal equations + solve of the two-kernel path: fp64 tensor cores (ik_solve_mma_kernel, default where the
  *             problem shape allows) / scalar ik_solve_kernel
- *   420 / 421 pose-blend columns of the IK Jacobian: tcgen05 (ik_poseblend_tc_kernel, default) / FFMA phase of
- *             ik_jacobian_kernel */
+ *   420..422  pose-blend columns of the IK Jacobian and rest shape of the task vertices: tcgen05 (ik_poseblend_tc_kernel,
+ *             ik_restshape_tc_kernel; default) / FFMA phase of ik_jacobian_kernel + FFMA blend kernel / tcgen05 columns on
+ *             the FFMA rest shape */
 int smplpp_set_forward_variant(int variant);
 
 /* ---------------------------------------------------------------------------------------------------------
@@ -205,6 +206,13 @@ void smplpp_tasks_destroy(smplpp_tasks_t * tasks);
 int32_t smplpp_tasks_count(const smplpp_tasks_t * tasks);
 /* number of distinct mesh vertices the task set depends on (face corners + their 1-rings) */
 int32_t smplpp_tasks_vertex_count(const smplpp_tasks_t * tasks);
+
+/* SMPL::getRestShape (src/SMPL.cpp:446-461, JointRegression.cpp:557) restricted to the vertices the task set depends on:
+ * rest_out (B, n_vertices, 3) device, vertex_ids (n_vertices) host (nullable): the model vertex of every row.  This is the
+ * product the IK step runs per iteration; variant 0 = tcgen05 where available, 1 = FFMA kernel. */
+int smplpp_tasks_rest_shape(const smplpp_model_t * model, const smplpp_tasks_t * tasks, void * stream, int64_t batch,
+                            const float * beta_dev, int64_t beta_stride, const float * theta_dev, float * rest_out_dev,
+                            int32_t * vertex_ids, int32_t variant);
 
 /* calcTriangleVertexWeights on n (pos (n,3), triangle (n,3,3)) pairs -> weights (n,3) */
 int smplpp_triangle_vertex_weights(void * stream, int64_t n, const float * pos_dev, const float * triangles_dev,

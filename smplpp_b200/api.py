@@ -876,6 +876,22 @@ class IkTaskSet:
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.smpl.m__device)
         return self._ws
 
+    def restShape(self, beta, theta, variant: int = 0):
+        """Rest shape of the vertices the task set depends on (SMPL::getRestShape on those rows): returns (rest (B, nU, 3)
+        CUDA tensor, vertex_ids (nU,) int32 numpy).  variant 0: tcgen05 where available, 1: FFMA kernel."""
+        dev = self.smpl.m__device
+        b = _dev_f32(beta, dev).reshape(-1, 10).contiguous()
+        th = _dev_f32(theta, dev).reshape(-1, 75).contiguous()
+        B = th.shape[0]
+        nu = self.vertex_count
+        rest = torch.empty((B, nu, 3), dtype=torch.float32, device=dev)
+        ids = np.zeros(nu, dtype=np.int32)
+        with torch.cuda.device(dev):
+            check(lib().smplpp_tasks_rest_shape(self.smpl.handle, self._h, _stream(dev), C.c_int64(B), _ptr(b),
+                                                C.c_int64(0 if b.shape[0] == 1 else 10), _ptr(th), _ptr(rest),
+                                                ids.ctypes.data_as(capi.c_i32p), C.c_int32(variant)))
+        return rest, ids
+
     def step(self, opt: capi.IkOptions, theta_state: torch.Tensor, beta: torch.Tensor, vertex_weights: torch.Tensor,
              target_pos: torch.Tensor, pos_task_weight: Optional[torch.Tensor] = None,
              target_normal: Optional[torch.Tensor] = None, outputs: bool = False,

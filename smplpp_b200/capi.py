@@ -52,7 +52,7 @@ EXPORTS = [
     "smplpp_blend_shape", "smplpp_joint_regression", "smplpp_world_transformation", "smplpp_linear_blend_skinning",
     "smplpp_model_skinning", "smplpp_model_skinning34", "smplpp_normals",
     "smplpp_vposer_create", "smplpp_vposer_destroy", "smplpp_vposer_decode", "smplpp_rotmat_to_axis_angle",
-    "smplpp_tasks_create", "smplpp_tasks_destroy", "smplpp_tasks_count", "smplpp_tasks_vertex_count",
+    "smplpp_tasks_create", "smplpp_tasks_destroy", "smplpp_tasks_count", "smplpp_tasks_vertex_count", "smplpp_tasks_rest_shape",
     "smplpp_triangle_vertex_weights", "smplpp_ik_options_default", "smplpp_ik_theta_dim", "smplpp_ik_dim",
     "smplpp_task_positions", "smplpp_closest_points", "smplpp_sweep_grid_bounds", "smplpp_sweep_grid_winding", "smplpp_ik_workspace_bytes", "smplpp_ik_step", "smplpp_ik_solve_host",
     "smplpp_ik_faces_workspace_bytes", "smplpp_ik_step_faces", "smplpp_ik_reproject_workspace_bytes", "smplpp_ik_reproject",

@@ -957,7 +957,7 @@ extern "C" int smplpp_set_forward_variant(int variant)
     return SMPLPP_OK;
   }
   // pose-blend columns of the IK Jacobian: 420 auto (ik_poseblend_tc_kernel, tcgen05), 421 the FFMA phase of ik_jacobian_kernel
-  if(variant == 420 || variant == 421)
+  if(variant >= 420 && variant <= 422) // 422: tcgen05 pose-blend columns on the FFMA rest shape (isolates the two in tests)
   {
     g_poseblend_variant = variant - 420;
     return SMPLPP_OK;

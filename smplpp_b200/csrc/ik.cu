@@ -1896,6 +1896,36 @@ extern "C" int32_t smplpp_tasks_count(const smplpp_tasks_t * t)
   return t ? t->d.n : 0;
 }
 
+// Rest shape T + S beta + P c of the task vertices only (SMPL::getRestShape restricted to the rows the IK step reads; the
+// product the step runs on tcgen05).  vertex_ids (host, nullable): model vertex of every row.  variant 0: tensor cores where
+// the task set has the operand images, 1: the FFMA kernel.
+extern "C" int smplpp_tasks_rest_shape(const smplpp_model_t * model, const smplpp_tasks_t * tasks, void * stream, int64_t batch,
+                                       const float * beta, int64_t beta_stride, const float * theta, float * rest_out,
+                                       int32_t * vertex_ids, int32_t variant)
+{
+  if(!model || !tasks || batch < 1 || !beta || !theta || !rest_out) return fail(SMPLPP_ERR_INVALID, "IkTask", "invalid arguments!");
+  cudaStream_t st = as_stream(stream);
+  const int B = static_cast<int>(batch);
+  const size_t cpad = align_up(static_cast<size_t>(B), 128);
+  float * coef = nullptr;
+  float * xf = nullptr;
+  SB_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&coef), cpad * kBlendK * sizeof(float), st));
+  SB_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&xf), cpad * kJoints * 12 * sizeof(float), st));
+  int rc = launch_pose_chain(model->d, st, B, beta, beta_stride, theta, coef, xf, nullptr, nullptr);
+  if(rc == SMPLPP_OK)
+  {
+    if(variant == 0 && tasks->pb.ready && tasks->pb.rest_ready)
+      rc = launch_restshape_tc(tasks->pb, st, B, tasks->d.nU, coef, rest_out);
+    else
+      rc = launch_blend_skin_ffma(tasks->sub, st, B, coef, xf, theta, rest_out, false);
+  }
+  cudaFreeAsync(coef, st);
+  cudaFreeAsync(xf, st);
+  if(rc == SMPLPP_OK && vertex_ids)
+    for(int u = 0; u < tasks->d.nU; u++) vertex_ids[u] = tasks->h_sub_vert[u];
+  return rc;
+}
+
 extern "C" int32_t smplpp_tasks_vertex_count(const smplpp_tasks_t * t)
 {
   return t ? t->d.nU : 0;
@@ -2050,7 +2080,7 @@ IkLayout make_layout(const smplpp_tasks_t * tasks, const smplpp_ik_options * o, 
     L.off_factor = take(static_cast<size_t>(batch) * P * sizeof(double));
   }
   L.off_misc = take(64 * sizeof(double));
-  L.pb_tc = tasks->pb.ready && g_poseblend_variant == 0 && L.phi_cols == 0;
+  L.pb_tc = tasks->pb.ready && g_poseblend_variant != 1 && L.phi_cols == 0;
   L.off_ca = tasks->pb.ready ? take(C * tasks->pb.slots * 128 * sizeof(float)) : 0;
   L.off_dr = tasks->pb.ready ? take(C * 644 * sizeof(float)) : 0;
   L.total = off;
@@ -2119,7 +2149,12 @@ int run_chunk(const smplpp_model_t * model, const smplpp_vposer_t * vposer, cons
   int rc = launch_pose_chain(md, st, B, beta, beta_stride, theta_in, coef, xf, nullptr, nullptr);
   if(rc != SMPLPP_OK) return rc;
   const ModelDev & sub = L.use_ring ? tasks->sub : tasks->sub_corner;
-  rc = launch_blend_skin_ffma(sub, st, B, coef, xf, theta_in, rest, false);
+  // rest shape of the task vertices: tcgen05 (blocked frame layout) where the task set has the operand images
+  const bool rest_tc = L.pb_tc && tasks->pb.rest_ready && g_poseblend_variant == 0;
+  if(rest_tc)
+    rc = launch_restshape_tc(tasks->pb, st, B, L.nUse, coef, rest);
+  else
+    rc = launch_blend_skin_ffma(sub, st, B, coef, xf, theta_in, rest, false);
   if(rc != SMPLPP_OK) return rc;
   // skinning WITHOUT the root translation is what the chain derivatives need (x_uj), the translation is added
   // back analytically: vertices = skinned + trans.  launch_lbs with root = theta row 0.

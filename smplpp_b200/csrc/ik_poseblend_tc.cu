@@ -384,6 +384,217 @@ __global__ void __launch_bounds__(pbtc::THREADS, 1) ik_poseblend_tc_kernel(const
   if(warp == 1) ptx::tmem_dealloc<512>(tmem_base);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Rest shape of the task vertices (BlendShape + the first half of JointRegression on the ~480 rows the tasks touch,
+// src/BlendShape.cpp:670-683, src/JointRegression.cpp:551-565) on tcgen05: rest[f, 3 u + a] = T + sum_c basis[3 u + a, c] coef[f, c].
+// The FFMA kernel of the forward path did this in 0.33 ms per 16384 frames (43 % of the FMA peak); here 128 frames are one
+// M = 128 tile whose coefficient rows (K = 224, fp16 hi | lo) are converted ONCE per CTA and stay in shared memory, the
+// basis rows of 224 coordinates at a time are per-task-set stage images (the array is K-major already) streamed through a
+// three-slot ring, and the epilogue (thread = frame) adds the template in fp32 and transposes 32 x 32 blocks through shared
+// memory so that the (B, 3 nU) result goes out in 128-byte row pieces.
+// ------------------------------------------------------------------------------------------------------------
+namespace rstc
+{
+using pbtc::A_PART;
+using pbtc::B_PART;
+using pbtc::NCOL;
+using pbtc::ROWB;
+using pbtc::swz64;
+constexpr int FPB = 128;                  // frames per CTA
+constexpr int NKB = kBlendK / 32;         // 7 K-blocks
+constexpr int A_BYTES = NKB * 2 * A_PART; // 114688: coefficient rows, all K-blocks, hi | lo
+constexpr int SLOTS = 3;
+constexpr int SLOT = 2 * B_PART;          // 28672: one (coordinate tile, K-block) of the basis, hi | lo
+constexpr int OFF_RING = A_BYTES;
+constexpr int OFF_TMPL = OFF_RING + SLOTS * SLOT;
+constexpr int MAX_TILES = 8;              // 8 x 224 = 1792 coordinates = 597 task vertices
+constexpr int OFF_TR = OFF_TMPL + MAX_TILES * NCOL * 4; // 4 warps x [32 frames][33]: transpose tiles of the epilogue
+constexpr int OFF_BAR = OFF_TR + 4 * 32 * 33 * 4;
+constexpr int SMEM_BYTES = 1024 + OFF_BAR + 128;
+constexpr int THREADS = 256;              // warp 0 TMA, warp 1 MMA, warps 2-3 idle, warps 4-7 builders then epilogue
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+
+struct Params
+{
+  int B, ncoord, ntiles;   // coordinates = 3 * vertices used, tiles of 224
+  const uint8_t * img;     // [tile][K-block][hi | lo][224][64 B]
+  const float * tmpl;      // (ntiles * 224) template coordinate, 0 beyond ncoord
+  const float * coef;      // (B, 224): pose feature | beta | 1 | 0
+  float out_scale;
+  float * rest;            // (B, ncoord)
+};
+} // namespace rstc
+
+__global__ void __launch_bounds__(rstc::THREADS, 1) ik_restshape_tc_kernel(const rstc::Params p)
+{
+  using namespace rstc;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t * smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float * s_tmpl = reinterpret_cast<float *>(smem + OFF_TMPL);
+  uint64_t * bars = reinterpret_cast<uint64_t *>(smem + OFF_BAR);
+  uint64_t * full_b = bars;            // [SLOTS]
+  uint64_t * empty = full_b + SLOTS;   // [SLOTS]
+  uint64_t * acc_full = empty + SLOTS; // [2]
+  uint64_t * acc_empty = acc_full + 2; // [2]
+  uint64_t * a_ready = acc_empty + 2;  // builders -> MMA
+  uint32_t * tmem_slot = reinterpret_cast<uint32_t *>(a_ready + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int f0 = static_cast<int>(blockIdx.x) * FPB;
+
+  if(warp == 0 && lane == 0)
+  {
+    for(int s = 0; s < SLOTS; s++)
+    {
+      ptx::mbar_init(&full_b[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for(int b = 0; b < 2; b++)
+    {
+      ptx::mbar_init(&acc_full[b], 1);
+      ptx::mbar_init(&acc_empty[b], 4);
+    }
+    ptx::mbar_init(a_ready, 4);
+    ptx::fence_barrier_init();
+  }
+  if(warp == 1) ptx::tmem_alloc<512>(tmem_slot);
+  for(int i = threadIdx.x; i < p.ntiles * NCOL; i += THREADS) s_tmpl[i] = __ldg(p.tmpl + i);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int total = p.ntiles * NKB;
+
+  if(warp == 0)
+  {
+    if(ptx::elect_one())
+      for(int it = 0; it < total; it++)
+      {
+        const int s = it % SLOTS;
+        ptx::mbar_wait(&empty[s], ((it / SLOTS) & 1) ^ 1);
+        ptx::mbar_expect_tx(&full_b[s], SLOT);
+        ptx::bulk_load_1d(smem + OFF_RING + s * SLOT, p.img + static_cast<size_t>(it) * SLOT, SLOT, &full_b[s]);
+      }
+  }
+  else if(warp == 1)
+  {
+    if(ptx::elect_one())
+    {
+      constexpr uint32_t DHI = ptx::smem_desc_hi<ROWB>();
+      constexpr uint32_t idesc = ptx::make_idesc_f16(128, NCOL);
+      const uint32_t smem16 = ptx::smem_u32(smem) >> 4;
+      ptx::mbar_wait(a_ready, 0);
+      ptx::tc_fence_after();
+      int it = 0;
+      for(int nt = 0; nt < p.ntiles; nt++)
+      {
+        const int b = nt & 1;
+        if(nt >= 2)
+        {
+          ptx::mbar_wait(&acc_empty[b], ((nt >> 1) - 1) & 1);
+          ptx::tc_fence_after();
+        }
+        for(int kb = 0; kb < NKB; kb++, it++)
+        {
+          const int s = it % SLOTS;
+          ptx::mbar_wait(&full_b[s], (it / SLOTS) & 1);
+          ptx::tc_fence_after();
+          const uint32_t a16 = smem16 + ((kb * 2 * A_PART) >> 4), b16 = smem16 + ((OFF_RING + s * SLOT) >> 4);
+#pragma unroll
+          for(int prod = 0; prod < 3; prod++)
+          {
+            const int pa = prod == 1 ? 1 : 0, pb = prod == 2 ? 1 : 0; // hi.hi, lo.hi, hi.lo
+#pragma unroll
+            for(int ks = 0; ks < 2; ks++)
+              ptx::umma_f16_ss_lo(tmem_base + b * 256, a16 + ((pa * A_PART + ks * 32) >> 4), b16 + ((pb * B_PART + ks * 32) >> 4),
+                                  DHI, idesc, (kb | prod | ks) != 0 ? 1u : 0u);
+          }
+          ptx::tc_commit(&empty[s]);
+        }
+        ptx::tc_commit(&acc_full[b]);
+      }
+    }
+  }
+  else if(warp >= 4)
+  {
+    // ---- coefficient rows of this CTA's 128 frames -> fp16 hi | lo K-block images (thread = frame) ----
+    const int L = (warp - 4) * 32 + lane;
+    const bool live = f0 + L < p.B;
+    const float4 * src = reinterpret_cast<const float4 *>(p.coef + static_cast<size_t>(live ? f0 + L : 0) * kBlendK);
+#pragma unroll 1
+    for(int kb = 0; kb < NKB; kb++)
+    {
+      float x[32];
+#pragma unroll
+      for(int c = 0; c < 8; c++)
+      {
+        const float4 v = live ? __ldg(src + 8 * kb + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        x[4 * c] = v.x, x[4 * c + 1] = v.y, x[4 * c + 2] = v.z, x[4 * c + 3] = v.w;
+      }
+#pragma unroll
+      for(int i = 0; i < 32; i++)
+        if(32 * kb + i >= kBlendKUsed - 1) x[i] = 0.f; // the template column (coefficient 1) is added in fp32
+      uint8_t * dst = smem + kb * 2 * A_PART;
+#pragma unroll
+      for(int c = 0; c < 4; c++)
+      {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for(int e = 0; e < 4; e++)
+        {
+          const float a = x[8 * c + 2 * e], b = x[8 * c + 2 * e + 1];
+          const float ah = __half2float(__float2half_rn(a)), bh = __half2float(__float2half_rn(b));
+          h[e] = skin::pack_half2(ah, bh);
+          l[e] = skin::pack_half2(a - ah, b - bh);
+        }
+        const uint32_t o = static_cast<uint32_t>(L * ROWB + c * 16);
+        *reinterpret_cast<uint4 *>(dst + swz64(o)) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4 *>(dst + swz64(A_PART + o)) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+    }
+    ptx::fence_proxy_async();
+    __syncwarp();
+    if(lane == 0) ptx::mbar_arrive(a_ready);
+    // ---- epilogue: thread = TMEM lane = frame; a 32 x 32 (frame, coordinate) block is transposed through shared memory
+    //      so that every store instruction writes 32 consecutive coordinates of ONE frame (128 contiguous bytes) ----
+    const int q = warp & 3;
+    const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    float * tile = reinterpret_cast<float *>(smem + OFF_TR) + q * 32 * 33;
+    const int fq = f0 + 32 * q; // first frame of this warp
+    for(int nt = 0; nt < p.ntiles; nt++)
+    {
+      const int b = nt & 1;
+      ptx::mbar_wait(&acc_full[b], (nt >> 1) & 1);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for(int ch = 0; ch < NCOL; ch += 32)
+      {
+        float v[32];
+        ptx::tmem_ld_x16(lane_taddr + b * 256 + ch, v);
+        ptx::tmem_ld_x16(lane_taddr + b * 256 + ch + 16, v + 16);
+        ptx::tmem_ld_wait();
+        const int col0 = nt * NCOL + ch;
+#pragma unroll
+        for(int i = 0; i < 32; i++) tile[lane * 33 + i] = fmaf(v[i], p.out_scale, s_tmpl[col0 + i]);
+        __syncwarp();
+        if(col0 + lane < p.ncoord)
+        {
+          const int nfr = min(32, p.B - fq);
+          float * dst = p.rest + static_cast<size_t>(fq) * p.ncoord + col0 + lane;
+          for(int r = 0; r < nfr; r++) dst[static_cast<size_t>(r) * p.ncoord] = tile[r * 33 + lane];
+        }
+        __syncwarp();
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if(lane == 0) ptx::mbar_arrive(&acc_empty[b]);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if(warp == 1) ptx::tmem_dealloc<512>(tmem_base);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
@@ -454,7 +665,63 @@ int poseblend_tc_prepare(const std::vector<float> & basis, const std::vector<int
   out.slot_off = static_cast<const int32_t *>(d_off);
   out.slots = slot_off[n];
   out.basis_exp = e;
+  // rest-shape operand: the K-major basis rows of the nU task vertices, 224 coordinates per tile (the scale e above bounds
+  // every used row: each vertex of the task set belongs to a pair)
+  {
+    const int nU = static_cast<int>(basis.size() / (static_cast<size_t>(3) * kBlendK)); // nUpad; rows beyond nU are zero
+    int used = 0;
+    for(int32_t u : pair_vert) used = std::max(used, u + 1);
+    const int ncoord = 3 * used, ntiles = (ncoord + NCOL - 1) / NCOL;
+    if(ntiles <= rstc::MAX_TILES && used <= nU)
+    {
+      std::vector<uint8_t> rimg(static_cast<size_t>(ntiles) * rstc::NKB * rstc::SLOT, 0);
+      std::vector<float> tmpl(static_cast<size_t>(ntiles) * NCOL, 0.f);
+      for(int r = 0; r < ncoord; r++)
+      {
+        const int nt = r / NCOL, row = r % NCOL;
+        tmpl[r] = basis[static_cast<size_t>(r) * kBlendK + kBlendKUsed - 1];
+        for(int c = 0; c < kBlendKUsed - 1; c++)
+        {
+          const float x = basis[static_cast<size_t>(r) * kBlendK + c] * scale;
+          const __half hi = __float2half_rn(x);
+          const __half lo = __float2half_rn(x - __half2float(hi));
+          uint8_t * blk = rimg.data() + (static_cast<size_t>(nt) * rstc::NKB + c / 32) * rstc::SLOT;
+          const uint32_t o = static_cast<uint32_t>(row * ROWB + (c % 32) * 2);
+          *reinterpret_cast<__half *>(blk + swz64(o)) = hi;
+          *reinterpret_cast<__half *>(blk + swz64(static_cast<uint32_t>(B_PART) + o)) = lo;
+        }
+      }
+      void * d_rimg = nullptr;
+      void * d_tmpl = nullptr;
+      SB_CUDA(cudaMalloc(&d_rimg, rimg.size()));
+      allocations.push_back(d_rimg);
+      SB_CUDA(cudaMemcpy(d_rimg, rimg.data(), rimg.size(), cudaMemcpyHostToDevice));
+      SB_CUDA(cudaMalloc(&d_tmpl, tmpl.size() * sizeof(float)));
+      allocations.push_back(d_tmpl);
+      SB_CUDA(cudaMemcpy(d_tmpl, tmpl.data(), tmpl.size() * sizeof(float), cudaMemcpyHostToDevice));
+      out.rest_img = static_cast<const uint8_t *>(d_rimg);
+      out.rest_tmpl = static_cast<const float *>(d_tmpl);
+      out.rest_ready = true;
+    }
+  }
   out.ready = true;
+  return SMPLPP_OK;
+}
+
+// rest (B, 3 * n_vertices) of the first n_vertices task vertices
+int launch_restshape_tc(const PoseBlendTc & pb, cudaStream_t st, int B, int n_vertices, const float * coef, float * rest)
+{
+  using namespace rstc;
+  static bool attr_done[64] = {};
+  if(first_call_on_device(attr_done))
+    SB_CUDA(cudaFuncSetAttribute(ik_restshape_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  Params p{};
+  p.B = B, p.ncoord = 3 * n_vertices, p.ntiles = (p.ncoord + NCOL - 1) / NCOL;
+  p.img = pb.rest_img, p.tmpl = pb.rest_tmpl, p.coef = coef;
+  p.out_scale = std::ldexp(1.f, -pb.basis_exp);
+  p.rest = rest;
+  ik_restshape_tc_kernel<<<(B + FPB - 1) / FPB, THREADS, SMEM_BYTES, st>>>(p);
+  SB_LAUNCHED();
   return SMPLPP_OK;
 }
 

@@ -273,7 +273,7 @@ def test_tensor_core_stages_equal_ffma_on_random_task_sets(smpl_gpu, params, n_t
     for kw in (dict(normal_offset=0.015), dict(normal_task_weight=1.0, normal_offset=0.0), dict(normal_offset=0.0)):
         opt = api.ik_options(update_state=0, skip_if_too_few=0, **kw)
         outs = {}
-        for variants in ((411, 421), (410, 420)):
+        for variants in ((411, 421), (410, 422), (410, 420)):
             for v in variants:
                 capi.check(capi.lib().smplpp_set_forward_variant(v))
             status, out = ts.step(opt, cu(theta), cu(beta), cu(vw), cu(tgt),
@@ -281,9 +281,32 @@ def test_tensor_core_stages_equal_ffma_on_random_task_sets(smpl_gpu, params, n_t
             outs[variants] = (status.cpu().numpy(), out["J"].cpu().numpy(), out["delta"].cpu().numpy(), out["A"].cpu().numpy())
         for v in (410, 420):
             capi.check(capi.lib().smplpp_set_forward_variant(v))
-        (s0, J0, d0, A0), (s1, J1, d1, A1) = outs[(411, 421)], outs[(410, 420)]
-        assert np.array_equal(s0, s1) and (s0 == 0).all()
-        scale = np.abs(J0).reshape(F, -1).max(1)
-        assert (np.abs(J1 - J0).reshape(F, -1).max(1) / scale).max() < 2e-6
-        assert np.abs(A1 - A0).max() < 1e-5 * np.abs(A0).max()
-        assert np.abs(d1 - d0).max() < 1e-5
+        (s0, J0, d0, A0), (s1, J1, d1, A1), (s2, J2, d2, A2) = outs[(411, 421)], outs[(410, 422)], outs[(410, 420)]
+        assert np.array_equal(s0, s1) and np.array_equal(s0, s2) and (s0 == 0).all()
+        rel = lambda a, b: np.abs(a - b).reshape(F, -1).max(1) / np.abs(b).reshape(F, -1).max(1)
+        # same rest shape (FFMA), tensor-core stages against their predecessors: rounding level in every frame
+        assert rel(J1, J0).max() < 2e-6
+        assert rel(A1, A0).max() < 1e-5 and np.abs(d1 - d0).max() < 1e-5
+        # the default path also takes the rest shape from tcgen05: it differs from the FFMA one in the last bit (3e-8 m,
+        # test_task_rest_shape_kernels).  Where the face normals around a corner nearly cancel (random poses fold the
+        # synthetic mesh) the vertex normal amplifies that a hundred- to a thousandfold (scripts/diag_rest.py), so this
+        # comparison is a sanity bound, not a parity statement
+        assert np.median(rel(J2, J0)) < 1e-4 and rel(J2, J0).max() < 2e-2
+
+
+def test_task_rest_shape_kernels(smpl_gpu, params, task_set):
+    """smplpp_tasks_rest_shape: the rest shape of the task vertices on tcgen05 (what the IK step runs per iteration) against
+    the FFMA kernel and against SMPL::getRestShape of the full model at those vertices."""
+    from smplpp_b200 import synth
+    F = 150  # one full 128-frame tile and a partial one
+    rng = np.random.default_rng(4)
+    theta = synth.make_motion(F, 9).reshape(F, 75).astype(f32)
+    theta[:, 3:] += rng.normal(scale=0.2, size=(F, 72)).astype(f32)
+    beta = (rng.normal(size=(F, 10)) * 0.7).astype(f32)
+    r_tc, ids = task_set.restShape(beta, theta, 0)
+    r_ff, ids2 = task_set.restShape(beta, theta, 1)
+    assert np.array_equal(ids, ids2) and len(ids) == task_set.vertex_count
+    smpl_gpu.launch(beta, theta.reshape(F, 25, 3))
+    full = smpl_gpu.getRestShape()[:, torch.as_tensor(ids.astype(np.int64), device="cuda:0")]
+    assert (r_ff - full).abs().max().item() < 2e-7
+    assert (r_tc - full).abs().max().item() < 2e-7
