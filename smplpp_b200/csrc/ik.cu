@@ -328,40 +328,44 @@ __global__ void __launch_bounds__(TC ? c1::THREADS_TC : c1::THREADS, 2) ik_jacob
       for(int b = 0; b < 3; b++)
         s_M[9 * tid + 3 * a + b] = T[3 * a] * Rk[4 * b] + T[3 * a + 1] * Rk[4 * b + 1] + T[3 * a + 2] * Rk[4 * b + 2];
   }
-  // ---- P2c: d tg_j / d beta and d t'_j / d beta (3x10 per joint) ----
+  // ---- P2c: d tg_j / d beta and d t'_j / d beta (3x10 per joint).  One warp per beta component, lane = joint: the walk down
+  //      the tree needs only warp barriers (it was a block barrier per level: a dozen of them with 240 busy threads) ----
   if(p.beta_cols)
   {
-    const int j = tid / kShapeDim, i = tid % kShapeDim;
-    const bool on = tid < kJoints * kShapeDim;
+    const int j = tid & 31;
+    const bool on = j < kJoints;
     const int parent = on ? p.topo.parent[j] : -1;
     const int depth = on ? p.topo.depth[j] : -1;
-    for(int d = 0; d <= p.topo.max_depth; d++)
+    for(int i = tid >> 5; i < kShapeDim; i += THREADS / 32)
     {
-      if(on && depth == d)
+      for(int d = 0; d <= p.topo.max_depth; d++)
       {
-        if(parent < 0)
+        if(on && depth == d)
         {
-          for(int r = 0; r < 3; r++) s_dTg[(3 * j + r) * kShapeDim + i] = s_JS[(3 * j + r) * kShapeDim + i];
+          if(parent < 0)
+          {
+            for(int r = 0; r < 3; r++) s_dTg[(3 * j + r) * kShapeDim + i] = s_JS[(3 * j + r) * kShapeDim + i];
+          }
+          else
+          {
+            const float * P = s_G + 12 * parent;
+            float dl[3];
+            for(int r = 0; r < 3; r++) dl[r] = s_JS[(3 * j + r) * kShapeDim + i] - s_JS[(3 * parent + r) * kShapeDim + i];
+            for(int r = 0; r < 3; r++)
+              s_dTg[(3 * j + r) * kShapeDim + i] =
+                  s_dTg[(3 * parent + r) * kShapeDim + i] + P[4 * r] * dl[0] + P[4 * r + 1] * dl[1] + P[4 * r + 2] * dl[2];
+          }
         }
-        else
-        {
-          const float * P = s_G + 12 * parent;
-          float dl[3];
-          for(int r = 0; r < 3; r++) dl[r] = s_JS[(3 * j + r) * kShapeDim + i] - s_JS[(3 * parent + r) * kShapeDim + i];
-          for(int r = 0; r < 3; r++)
-            s_dTg[(3 * j + r) * kShapeDim + i] =
-                s_dTg[(3 * parent + r) * kShapeDim + i] + P[4 * r] * dl[0] + P[4 * r + 1] * dl[1] + P[4 * r + 2] * dl[2];
-        }
+        __syncwarp();
       }
-      __syncthreads();
-    }
-    if(on)
-    {
-      const float * G = s_G + 12 * j;
-      float js[3] = {s_JS[(3 * j) * kShapeDim + i], s_JS[(3 * j + 1) * kShapeDim + i], s_JS[(3 * j + 2) * kShapeDim + i]};
-      for(int r = 0; r < 3; r++)
-        s_dTp[(3 * j + r) * kShapeDim + i] =
-            s_dTg[(3 * j + r) * kShapeDim + i] - (G[4 * r] * js[0] + G[4 * r + 1] * js[1] + G[4 * r + 2] * js[2]);
+      if(on)
+      {
+        const float * G = s_G + 12 * j;
+        float js[3] = {s_JS[(3 * j) * kShapeDim + i], s_JS[(3 * j + 1) * kShapeDim + i], s_JS[(3 * j + 2) * kShapeDim + i]};
+        for(int r = 0; r < 3; r++)
+          s_dTp[(3 * j + r) * kShapeDim + i] =
+              s_dTg[(3 * j + r) * kShapeDim + i] - (G[4 * r] * js[0] + G[4 * r + 1] * js[1] + G[4 * r + 2] * js[2]);
+      }
     }
   }
   __syncthreads(); // posed vertices complete
@@ -655,17 +659,23 @@ __global__ void __launch_bounds__(TC ? c1::THREADS_TC : c1::THREADS, 2) ik_jacob
         if(on && !half) Jf[(4 * m + r) * p.ldfull + 3 + 3 * k + c] = out[r][c];
       }
   }
-  // ---- P5c: beta columns, rigid part: sum_u C4_u sum_j wn_j d t'_j / d beta_i ----
+  // ---- P5c: beta columns, rigid part: sum_u C4_u sum_j wn_j d t'_j / d beta_i.  Four lanes per (task, beta component),
+  //      each sums a quarter of the task's vertices (410 items were 1.07 rounds of 384 threads, the second nearly empty) ----
   if(p.beta_cols)
   {
     const int bcol = 75 + p.phi_cols;
-    for(int i = tid; i < n * kShapeDim; i += THREADS)
+    const int nitem4 = 4 * n * kShapeDim;
+    for(int i0 = 0; i0 < nitem4; i0 += THREADS)
     {
-      const int m = i / kShapeDim, ib = i % kShapeDim;
+      const int i4 = i0 + tid;
+      const bool on = i4 < nitem4;
+      const int part = i4 & 3, item = on ? i4 >> 2 : 0;
+      const int m = item / kShapeDim, ib = item % kShapeDim;
       float out[4] = {0.f, 0.f, 0.f, 0.f};
       const int p0 = t.pair_off[m];
       const int np = p.use_ring ? t.pair_off[m + 1] - p0 : 3;
-      for(int q = 0; q < np; q++)
+      const int q0 = on ? part * np / 4 : 0, q1 = on ? (part + 1) * np / 4 : 0;
+      for(int q = q0; q < q1; q++)
       {
         const int u = t.pair_vert[p0 + q];
         f3 y = mk3(0.f, 0.f, 0.f);
@@ -683,7 +693,12 @@ __global__ void __launch_bounds__(TC ? c1::THREADS_TC : c1::THREADS, 2) ik_jacob
         for(int r = 0; r < ROWS; r++) out[r] += C[3 * r] * y.x + C[3 * r + 1] * y.y + C[3 * r + 2] * y.z;
       }
 #pragma unroll
-      for(int r = 0; r < 4; r++) Jf[(4 * m + r) * p.ldfull + bcol + ib] = out[r];
+      for(int r = 0; r < 4; r++)
+      {
+        out[r] += __shfl_xor_sync(0xffffffffu, out[r], 1);
+        out[r] += __shfl_xor_sync(0xffffffffu, out[r], 2);
+        if(on && part == 0) Jf[(4 * m + r) * p.ldfull + bcol + ib] = out[r];
+      }
     }
   }
   __syncthreads();

@@ -57,6 +57,7 @@ struct Params
   const float * theta;          // (B, 25, 3): row 0 = root translation
   float * out;                  // (B, V, 3)
   long long * dbg;              // optional per-CTA timestamps (SMPLPP_TC3_DBG)
+  int dbg_mode;                 // DBG build only (SMPLPP_TC3_DBG = bit mask): 1 no matrix tcgen05.ld, 2 no stores, 4 no GEMM 2 MMAs, 8 no GEMM 1 MMAs, 16 no drain loads (results are wrong: timing decomposition)
 };
 
 } // namespace tc3
@@ -134,7 +135,7 @@ __global__ void frame_images3_kernel(const float * __restrict__ coef, const floa
   }
 }
 
-template<int STAGES, int GSLOTS, int EPI>
+template<int STAGES, int GSLOTS, int EPI, bool DBG = false>
 __global__ void __launch_bounds__(tc3::THREADS, 1)
     blend_skin_tc3_kernel(const tc3::Params p)
 {
@@ -144,6 +145,10 @@ __global__ void __launch_bounds__(tc3::THREADS, 1)
   extern __shared__ uint8_t smem_raw[];
   uint8_t * smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t * bars = reinterpret_cast<uint64_t *>(smem + OFF_BAR);
+  // the same base as a 32-bit shared-window address, aligned in that space (the window base is itself 1 KB aligned): the
+  // hot loops address stages and barriers as smem32 + constant instead of converting a generic pointer at every use
+  const uint32_t smem32 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar32 = smem32 + OFF_BAR;
   uint64_t * full = bars;                // [STAGES]  TMA -> MMA (GEMM 1 stages)
   uint64_t * empty = full + STAGES;      // [STAGES]  MMA -> TMA
   uint64_t * g_full = empty + STAGES;    // [GSLOTS]  TMA -> MMA (transform sub-batches)
@@ -189,7 +194,10 @@ __global__ void __launch_bounds__(tc3::THREADS, 1)
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  long long * dbg = p.dbg ? p.dbg + static_cast<size_t>(blockIdx.x) * 256 : nullptr;
+  long long * dbg = (DBG && p.dbg) ? p.dbg + static_cast<size_t>(blockIdx.x) * 256 : nullptr;
+  // DBG build: cycles the MMA thread / one epilogue warp spend blocked in each kind of wait (SMPLPP_TC3_DBG)
+  long long w_stage = 0, w_gfull = 0, w_mempty = 0, w_rest = 0, w_pfull = 0, w_mfull = 0;
+#define TC3_TIMED(acc, stmt) do { if constexpr(DBG) { const long long t_ = clock64(); stmt; acc += clock64() - t_; } else { stmt; } } while(0)
 
   if(warp < CTRL_WARPS)
   {
@@ -203,6 +211,7 @@ __global__ void __launch_bounds__(tc3::THREADS, 1)
     if(ptx::elect_one())
     {
       const int total_kb = nit * NKB;
+      // (An L2 prefetch of all seven K-blocks of the first item at kernel start was measured: no gain.)
       for(int kbn = 0; kbn < total_kb; kbn++)
       {
         const int item = it0 + kbn / NKB, kb = kbn % NKB, s = kbn % STAGES;
@@ -239,14 +248,22 @@ __global__ void __launch_bounds__(tc3::THREADS, 1)
     {
       constexpr uint32_t idesc1 = ptx::make_idesc_f16(MV, NF);
       constexpr uint32_t idesc2 = ptx::make_idesc_f16(MV, SUBN);
-      // Single-thread issue: every instruction between two tcgen05.mma is on the critical path (a first version that
-      // derived (K-block, product, K-step) from a running triple index spent ~16 instructions per MMA and issued one
-      // every ~105 cycles).  GEMM 1 is issued in HALF K-blocks of 9 MMAs with compile-time operand offsets; only the
-      // stage base is a run-time value.  Descriptor = constant high word | (shared address >> 4).
+      // Single-thread issue: every instruction between two tcgen05.mma is on the critical path.  ncu's source page of the
+      // previous version (r02h) had this thread at 1800 instructions per item for 198 MMAs (a run-time sub-batch loop:
+      // ring slots and parities through divisions, a cvta sequence per barrier) and blocked on a full tensor queue in only
+      // a quarter of its samples: the tensor pipe starved behind the issue loop.  Now the twelve sub-batches of an item are
+      // unrolled, so that ring slots, parities, the half K-block that rides along and its operand offsets are compile-time
+      // constants; only the stage of a K-block (ring position over all items) and the item parity are run-time values,
+      // and barriers are 32-bit shared addresses.  Descriptor = constant high word | (shared address >> 4).
+      static_assert(NSUB % GSLOTS == 0 && ((NSUB / GSLOTS) & 1) == 0, "transform ring: slot and parity of a sub-batch do not depend on the item");
+      static_assert((NSUB & 3) == 0, "matrix buffers: parity of a sub-batch does not depend on the item");
+      static_assert(NSUB + 2 == 2 * NKB, "GEMM 1 schedule: one half K-block per sub-batch, two behind sub-batches 0 and NSUB / 2");
       constexpr uint32_t DHI = ptx::smem_desc_hi<ROWB>();
-      const uint32_t smem16 = ptx::smem_u32(smem) >> 4;
-      int kbn = 0;   // K-blocks of GEMM 1 consumed so far (over all items): ring position
-      int half = 0;  // half K-blocks of the GEMM 1 being issued (0 .. 2 NKB)
+      const uint32_t smem16 = smem32 >> 4;
+      const uint32_t a_full = bar32; // one base register, every other barrier at a compile-time offset
+      const uint32_t a_empty = a_full + 8 * STAGES, a_gfull = a_empty + 8 * STAGES, a_gempty = a_gfull + 8 * GSLOTS,
+                     a_mfull = a_gempty + 8 * GSLOTS, a_mempty = a_mfull + 16, a_pfull = a_mempty + 16, a_rest = a_pfull + 8,
+                     a_wready = a_rest + 8;
       // MMA i (0..8) of a half K-block: triple i / 3 (operand parts and K step), plane i % 3.
       //   half 0: (hi.hi, ks 0), (hi.hi, ks 1), (lo.hi, ks 0)      half 1: (lo.hi, ks 1), (hi.lo, ks 0), (hi.lo, ks 1)
       auto g1_mma = [&](uint32_t st16, int hpar, int i, uint32_t acc) {
@@ -263,45 +280,35 @@ __global__ void __launch_bounds__(tc3::THREADS, 1)
         const int pa = prod == 1 ? 1 : 0, pb = prod == 2 ? 1 : 0;
         ptx::umma_f16_ts_lo(dm, aw + pa * (KJ / 2) + ks * 8, sg16 + ((pb * G_PART + ks * 32) >> 4), DHI, idesc2, j != 0 ? 1u : 0u);
       };
-      // stage of the current half K-block (waits for the TMA data when the half opens a K-block)
-      auto g1_open = [&]() -> uint32_t {
-        const int s = kbn % STAGES;
-        if((half & 1) == 0)
+      // half K-block h (compile-time after unrolling: K-block h / 2, operand half h % 2) of the GEMM 1 whose first K-block
+      // has ring position kbn0 (run-time).  The even half waits for the TMA data, the odd half hands the stage back.
+      auto g1_half = [&](int h, int kbn0) {
+        const int kbn = kbn0 + (h >> 1);
+        const uint32_t s = static_cast<uint32_t>(kbn % STAGES);
+        const uint32_t st16 = smem16 + s * (STAGE >> 4);
+        if((h & 1) == 0)
         {
-          ptx::mbar_wait(&full[s], (kbn / STAGES) & 1);
+          TC3_TIMED(w_stage, ptx::mbar_wait_a(a_full + 8 * s, (kbn / STAGES) & 1));
           ptx::tc_fence_after();
           if(dbg && kbn < 14) dbg[48 + kbn] = clock64();
-        }
-        return smem16 + s * (STAGE >> 4);
-      };
-      auto g1_close = [&]() {
-        if(half & 1)
-        {
-          ptx::tc_commit(&empty[kbn % STAGES]);
-          kbn++;
-        }
-        half++;
-      };
-      auto g1_half_alone = [&]() {
-        const uint32_t st16 = g1_open();
-        const uint32_t acc0 = half != 0 ? 1u : 0u;
-        if((half & 1) == 0)
-        {
 #pragma unroll
-          for(int i = 0; i < 9; i++) g1_mma(st16, 0, i, i < 3 ? acc0 : 1u);
+          for(int i = 0; i < 9; i++)
+            if(!DBG || !(p.dbg_mode & 8)) g1_mma(st16, 0, i, (h == 0 && i < 3) ? 0u : 1u);
         }
         else
         {
 #pragma unroll
-          for(int i = 0; i < 9; i++) g1_mma(st16, 1, i, 1u);
+          for(int i = 0; i < 9; i++)
+            if(!DBG || !(p.dbg_mode & 8)) g1_mma(st16, 1, i, 1u);
+          ptx::tc_commit_a(a_empty + 8 * s);
         }
-        g1_close();
       };
       if(dbg) dbg[0] = clock64();
       if(nit > 0)
       {
-        for(int h = 0; h < 2 * NKB; h++) g1_half_alone();
-        ptx::tc_commit(p_full);
+#pragma unroll
+        for(int h = 0; h < 2 * NKB; h++) g1_half(h, 0);
+        ptx::tc_commit_a(a_pfull);
       }
       if(dbg) dbg[1] = clock64();
       int wcount = 0, prev_tile = -1;
@@ -310,42 +317,50 @@ __global__ void __launch_bounds__(tc3::THREADS, 1)
         const int tile = (it0 + k) / p.nfb;
         if(tile != prev_tile)
         {
-          ptx::mbar_wait(w_ready, wcount & 1);
+          ptx::mbar_wait_a(a_wready, wcount & 1);
           ptx::tc_fence_after();
           wcount++;
           prev_tile = tile;
         }
         const bool more = k + 1 < nit;
-        half = 0;
+        const int kbn_next = (k + 1) * NKB;
+        const uint32_t aw = tmem_base + COL_W;
+#pragma unroll
         for(int sb = 0; sb < NSUB; sb++)
         {
-          const int m = k * NSUB + sb, b = sb & 1, gs = m % GSLOTS;
-          ptx::mbar_wait(&g_full[gs], (m / GSLOTS) & 1);
-          ptx::mbar_wait(&m_empty[b], ((m >> 1) & 1) ^ 1);
+          const int b = sb & 1, gs = sb % GSLOTS;
+          TC3_TIMED(w_gfull, ptx::mbar_wait_a(a_gfull + 8 * gs, (sb / GSLOTS) & 1));
+          TC3_TIMED(w_mempty, ptx::mbar_wait_a(a_mempty + 8 * b, ((sb >> 1) & 1) ^ 1));
           ptx::tc_fence_after();
           const uint32_t sg16 = smem16 + ((OFF_G + gs * G_STAGE) >> 4);
-          const uint32_t dm = tmem_base + COL_M + b * SUBN, aw = tmem_base + COL_W;
+          const uint32_t dm = tmem_base + COL_M + b * SUBN;
 #pragma unroll
-          for(int j = 0; j < 6; j++) g2_mma(dm, aw, sg16, j);
-          ptx::tc_commit(&m_full[b]);
-          ptx::tc_commit(&g_empty[gs]);
+          for(int j = 0; j < 6; j++)
+            if(!DBG || !(p.dbg_mode & 4)) g2_mma(dm, aw, sg16, j);
+          ptx::tc_commit_a(a_mfull + 8 * b);
+          ptx::tc_commit_a(a_gempty + 8 * gs);
           if(more)
           {
-            if(sb == 0)
+            // 14 half K-blocks of the next item's GEMM 1 over the 12 sub-batches: two behind sub-batches 0 and 6, one
+            // behind every other.  (Starting in sub-batch 1, so that two GEMM 2 are queued while the epilogue warps drain
+            // the rest accumulators, measured the same: 0.1720 / 0.1722 ms against 0.1721.)
+            const int nh = (sb == 0 || sb == NSUB / 2) ? 2 : 1, h0 = sb + (sb > 0 ? 1 : 0) + (sb > NSUB / 2 ? 1 : 0);
+            if(h0 == 0)
             {
-              ptx::mbar_wait(rest_free, k & 1); // item k's accumulators now live in the epilogue warps' registers
+              TC3_TIMED(w_rest, ptx::mbar_wait_a(a_rest, k & 1)); // item k's accumulators now live in the epilogue warps' registers
               ptx::tc_fence_after();
             }
             // 14 half K-blocks of the next item's GEMM 1 over the 12 sub-batches.  (Interleaving the 9 MMAs of a half
             // with the 6 GEMM 2 MMAs, to avoid chaining on one accumulator, was measured and is SLOWER: 23 k instead of
             // 17.5 k cycles per item - alternating between the shared-memory-A and TMEM-A forms costs more than the chain.)
-            g1_half_alone();
-            if(sb == 0 || sb == NSUB / 2) g1_half_alone();
+            g1_half(h0, kbn_next);
+            if(nh > 1) g1_half(h0 + 1, kbn_next);
           }
         }
-        if(more) ptx::tc_commit(p_full);
+        if(more) ptx::tc_commit_a(a_pfull);
         if(dbg && k < 30) dbg[2 + k] = clock64();
       }
+      if(dbg) dbg[64] = w_stage, dbg[65] = w_gfull, dbg[66] = w_mempty, dbg[67] = w_rest, dbg[68] = clock64();
     }
   }
   }
@@ -358,6 +373,14 @@ __global__ void __launch_bounds__(tc3::THREADS, 1)
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t my_stg = ptx::smem_u32(smem + OFF_STG) + ew * STG_FLOATS * 4;
     const float sp = p.scale_p;
+    // barriers as 32-bit shared addresses, frame stride and validity bounds hoisted: the r02h source page showed ~120
+    // instructions per sub-batch and warp for 24 FMA + 6 stores (cvta sequences, 64-bit store addresses rebuilt from the
+    // kernel parameters for every frame)
+    const uint32_t a_mfull = bar32 + 16 * (STAGES + GSLOTS); // one base register, compile-time offsets
+    const uint32_t a_mempty = a_mfull + 16, a_pfull = a_mempty + 16, a_rest = a_pfull + 8, a_wready = a_rest + 8;
+    const unsigned fstride = static_cast<unsigned>(p.V) * 3u; // floats per frame of the output
+    // (At 112 registers ptxas rebuilds part of this state in the first sub-batches instead of keeping it; forcing it into
+    // registers with opaque asm operands gave 72 instead of 75-120 instructions per sub-batch and was 2 % SLOWER.)
     int prev_tile = -1;
     int wv0 = 0, nvalid = 0;
     float T0 = 0.f, T1 = 0.f, T2 = 0.f, sm = 0.f;
@@ -379,7 +402,7 @@ __global__ void __launch_bounds__(tc3::THREADS, 1)
           ptx::tmem_st_wait();
           ptx::tc_fence_before();
           __syncwarp();
-          if(lane == 0) ptx::mbar_arrive(w_ready);
+          if(lane == 0) ptx::mbar_arrive_a(a_wready);
         }
         sm = p.scale_m / p.wsum[vc]; // homogeneous divide (LinearBlendSkinning.cpp:545-550) folded into the scale
         const float * tp = p.basis + static_cast<size_t>(3) * vc * kBlendK + KUSED;
@@ -396,18 +419,24 @@ __global__ void __launch_bounds__(tc3::THREADS, 1)
       }
       // ---- drain the rest accumulators of this item: 24 frames x (x, y, z), pre-multiplied by scale / sum w ----
       float R[3][FR_WARP];
-      ptx::mbar_wait(p_full, k & 1);
+      TC3_TIMED(w_pfull, ptx::mbar_wait_a(a_pfull, k & 1));
       ptx::tc_fence_after();
 #pragma unroll
       for(int c = 0; c < 3; c++)
       {
+        if(DBG && (p.dbg_mode & 16))
+        {
+#pragma unroll
+          for(int i = 0; i < FR_WARP; i++) R[c][i] = 1.f;
+          continue;
+        }
         ptx::tmem_ld_x16(lane_taddr + c * NF + fp * FR_WARP, R[c]);
         ptx::tmem_ld_x8p(lane_taddr + c * NF + fp * FR_WARP + 16, R[c] + 16);
       }
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       __syncwarp();
-      if(lane == 0) ptx::mbar_arrive(rest_free);
+      if(lane == 0) ptx::mbar_arrive_a(a_rest);
       {
         const float s = sp * sm;
 #pragma unroll
@@ -419,6 +448,8 @@ __global__ void __launch_bounds__(tc3::THREADS, 1)
         }
       }
       float * outp = p.out + (static_cast<size_t>(f0 + fp * EPI_FR) * p.V + wv0) * 3;
+      float * outl = outp + lane * 3;                                  // this lane's vertex in the warp's first frame
+      const int nfv = lane < nvalid ? p.B - f0 - fp * EPI_FR : 0;      // frame slots (sb * SUBF + t) below nfv are stored
 #pragma unroll
       for(int sb = 0; sb < NSUB; sb++)
       {
@@ -431,16 +462,24 @@ __global__ void __launch_bounds__(tc3::THREADS, 1)
           tr[t][1] = __shfl_sync(0xffffffffu, try_, sb * EPI_FR + t);
           tr[t][2] = __shfl_sync(0xffffffffu, trz, sb * EPI_FR + t);
         }
-        ptx::mbar_wait(&m_full[h], (sb >> 1) & 1); // 6 ring rounds per item: the parity does not depend on the item
+        TC3_TIMED(w_mfull, ptx::mbar_wait_a(a_mfull + 8 * h, (sb >> 1) & 1)); // 6 ring rounds per item: the parity does not depend on the item
         ptx::tc_fence_after();
         float M[EPI_FR * kXformFloats];
         const uint32_t mcol = lane_taddr + COL_M + h * SUBN + fp * (EPI_FR * kXformFloats);
-        ptx::tmem_ld_x16(mcol, M);
-        ptx::tmem_ld_x8p(mcol + 16, M + 16);
+        if(DBG && (p.dbg_mode & 1))
+        {
+#pragma unroll
+          for(int i = 0; i < EPI_FR * kXformFloats; i++) M[i] = 1.f + i;
+        }
+        else
+        {
+          ptx::tmem_ld_x16(mcol, M);
+          ptx::tmem_ld_x8p(mcol + 16, M + 16);
+        }
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         __syncwarp();
-        if(lane == 0) ptx::mbar_arrive(&m_empty[h]); // the MMA warp may overwrite this matrix buffer
+        if(lane == 0) ptx::mbar_arrive_a(a_mempty + 8 * h); // the MMA warp may overwrite this matrix buffer
 #pragma unroll
         for(int t = 0; t < EPI_FR; t++)
         {
@@ -461,8 +500,8 @@ __global__ void __launch_bounds__(tc3::THREADS, 1)
             // no staging: three 4-byte streaming stores per vertex and frame (a warp's 32 vertices are 384 contiguous
             // bytes; L2 merges the sectors).  Measured +2.4 % against the staged float2 stores: the kernel is bound by
             // shared-memory bandwidth (UMMA operand reads + TMA writes), which the staging round trip competes for.
-            float * o = outp + (static_cast<size_t>(sb * SUBF + t) * p.V + lane) * 3;
-            if(f0 + sb * SUBF + fp * EPI_FR + t < p.B && lane < nvalid)
+            float * o = outl + static_cast<size_t>((sb * SUBF + t) * fstride);
+            if(sb * SUBF + t < nfv && (!DBG || !(p.dbg_mode & 2) || ox == 1.2345e30f))
             {
               __stcs(o, ox);
               __stcs(o + 1, oy);
@@ -487,8 +526,13 @@ __global__ void __launch_bounds__(tc3::THREADS, 1)
         __syncwarp();
       }
     }
-    if(dbg && ew == 0 && lane == 0) dbg[33] = clock64();
+    if(dbg && (ew == 0 || ew == 15) && lane == 0)
+    {
+      if(ew == 0) dbg[33] = clock64();
+      dbg[70 + (ew ? 2 : 0)] = w_pfull, dbg[71 + (ew ? 2 : 0)] = w_mfull;
+    }
   }
+#undef TC3_TIMED
   ptx::tc_fence_before();
   __syncthreads();
   if(warp == 1) ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
@@ -517,6 +561,7 @@ int tc3_prepare_model(ModelDev & d)
   SB_LAUNCHED();
   SB_CUDA(cudaDeviceSynchronize());
   SB_CUDA(cudaFuncSetAttribute(blend_skin_tc3_kernel<2, 6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::Layout<2, 6, 1>::SMEM_BYTES));
+  SB_CUDA(cudaFuncSetAttribute(blend_skin_tc3_kernel<2, 6, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::Layout<2, 6, 1>::SMEM_BYTES));
   SB_CUDA(cudaFuncSetAttribute(blend_skin_tc3_kernel<3, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::Layout<3, 3, 1>::SMEM_BYTES));
   SB_CUDA(cudaFuncSetAttribute(blend_skin_tc3_kernel<2, 6, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::Layout<2, 6, 0>::SMEM_BYTES));
   int dev = 0;
@@ -572,6 +617,7 @@ int launch_blend_skin_tc3(const ModelDev & d, cudaStream_t st, int B, const floa
   if(grid_env > 0 && grid_env < grid) grid = grid_env;
   static const bool dbg_on = getenv("SMPLPP_TC3_DBG") != nullptr;
   p.dbg = nullptr;
+  p.dbg_mode = dbg_on ? atoi(getenv("SMPLPP_TC3_DBG")) >> 1 : 0; // SMPLPP_TC3_DBG = 1 + 2 * mode mask
   if(dbg_on)
   {
     SB_CUDA(cudaMalloc(&p.dbg, static_cast<size_t>(grid) * 256 * sizeof(long long)));
@@ -581,6 +627,8 @@ int launch_blend_skin_tc3(const ModelDev & d, cudaStream_t st, int B, const floa
     blend_skin_tc3_kernel<3, 3, 1><<<grid, tc3::THREADS, tc3::Layout<3, 3, 1>::SMEM_BYTES, st>>>(p);
   else if(ring_env == 2)
     blend_skin_tc3_kernel<2, 6, 0><<<grid, tc3::THREADS, tc3::Layout<2, 6, 0>::SMEM_BYTES, st>>>(p);
+  else if(dbg_on)
+    blend_skin_tc3_kernel<2, 6, 1, true><<<grid, tc3::THREADS, tc3::Layout<2, 6, 1>::SMEM_BYTES, st>>>(p);
   else
     blend_skin_tc3_kernel<2, 6, 1><<<grid, tc3::THREADS, tc3::Layout<2, 6, 1>::SMEM_BYTES, st>>>(p);
   SB_LAUNCHED();
@@ -600,7 +648,8 @@ int launch_blend_skin_tc3(const ModelDev & d, cudaStream_t st, int B, const floa
       for(int i = 0; i < 14; i++) fprintf(stderr, " %lld", t[34 + i] - t[0]);
       fprintf(stderr, "\n   stage seen full by the MMA thread:  ");
       for(int i = 0; i < 14; i++) fprintf(stderr, " %lld", t[48 + i] - t[0]);
-      fprintf(stderr, "\n");
+      fprintf(stderr, "\n   MMA thread: total %lld cycles, blocked on stage %lld, transforms %lld, matrix buffer %lld, drain %lld | epilogue warp 0 / 15 blocked on rest accumulators %lld / %lld, on matrices %lld / %lld\n",
+              t[68] - t[0], t[64], t[65], t[66], t[67], t[70], t[72], t[71], t[73]);
     }
   }
   return SMPLPP_OK;

@@ -121,6 +121,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t * bar, uint32_t parity)
   }
 }
 
+// The same operations on a 32-bit shared-memory address computed once (a generic pointer costs a cvta sequence of ~8
+// uniform-datapath instructions at every use: measurable in single-thread issue loops and per-sub-batch epilogues).
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity)
+{
+  uint32_t spins = 0, ok;
+  do
+  {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if(!ok && ++spins > (1u << 26)) __trap();
+  } while(!ok);
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_commit_a(uint32_t bar)
+{
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
 // ---- TMA ----
 __device__ __forceinline__ void prefetch_tensormap(const void * tmap)
 {
