@@ -6,6 +6,7 @@ random walk) -> product forward pass -> 41 marker positions (15 mm normal offset
 Every frame starts from the common initial pose (batched frames cannot warm-start from their predecessor)."""
 from __future__ import annotations
 
+import ctypes as C
 import glob
 import json
 import os
@@ -14,7 +15,7 @@ import time
 import numpy as np
 import torch
 
-from smplpp_b200 import api, synth
+from smplpp_b200 import api, capi, synth
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 # algorithmic FLOPs per frame-iteration of the fused IK step with the 15 mm normal offset (sparse
@@ -134,6 +135,22 @@ def run(dev, rank, world, max_over_ranks, barrier, frames: int = 16384, iters: i
                        "algorithmic_flops_per_frame_iter": FLOPS_DIRECT, "ms_per_launch": ms, "frames_per_launch": frames,
                        "traffic": drb, "l2_to_sm_bytes_per_launch": l2b, "traffic_source": l2src,
                        "hbm_state_bytes_per_frame_iter": 2 * 4 * 75 + 16 * tasks.n}
+
+    # the Jacobian getter alone (smplpp_ik_jacobian, SURVEY 8(d) "Jacobian materialisation"): algorithmic bytes per frame =
+    # the 3 position rows of every marker x D columns in fp32 (4 . 3M . D = 36 900 B at M = 41, D = 75) against the HBM peak.
+    # What it really writes is (B, 4n, dim) with the normal-task row; what binds it is the CUDA-core work of the
+    # linearisation, so the fraction is small by construction and reported for completeness.
+    jac_buf_theta, jac_buf_vw = prob["x0"].clone(), prob["w0"].clone()
+
+    def jac_only():
+        tasks.jacobian(opt, jac_buf_theta, prob["beta"], jac_buf_vw, prob["target"], pos_task_weight=prob["valid"])
+
+    ms_j = time_steps(jac_only, max(3, iters // 2), 2, barrier, max_over_ranks, dev)
+    jb = 4 * 3 * tasks.n * 75
+    out["jacobian"] = {"api": "smplpp_ik_jacobian (e + J in the reference layout, no solve)", "ms_per_call": ms_j,
+                       "frames_per_s": all_frames / (ms_j * 1e-3), "algorithmic_bytes_per_frame": jb,
+                       "written_bytes_per_frame": 4 * 4 * tasks.n * int(capi.lib().smplpp_ik_dim(C.byref(opt), C.c_int32(tasks.n))) + 4 * 4 * tasks.n,
+                       "achieved_gbs": jb * frames / (ms_j * 1e-3) / 1e9, "bound": "fp32 issue / latency (not hbm)"}
 
     # e2e through the host-buffer C-ABI call smplpp_ik_solve_host: theta / attachments / targets / marker weights in
     # page-locked host arrays, H2D + ONE iteration + D2H of theta, weights, status, residual inside the timed region

@@ -302,6 +302,17 @@ int smplpp_ik_step(const smplpp_model_t * model, const smplpp_vposer_t * vposer,
                    float * e_out_dev, float * jac_out_dev, double * a_out_dev, double * b_out_dev,
                    double * delta_out_dev, void * workspace_dev, size_t workspace_bytes);
 
+/* The linearisation of that step alone -- the "Jacobian getter" SURVEY 8(b) asks for, because the reference has none
+ * (callers run Tensor::backward once per residual row and read .grad(), node/node.cpp:823-873): theta assembly (+VPoser),
+ * sparse forward, tangents + re-weighting (vertex_weights is updated in place exactly as the step does, node.cpp:803-804),
+ * residual and Jacobian.  theta_state / beta are read only; no normal equations, no solve, no update.
+ *   e_out (B,4n) f32 and / or jac_out (B,4n,dim) f32 in the layout of smplpp_ik_step; workspace as for smplpp_ik_step. */
+int smplpp_ik_jacobian(const smplpp_model_t * model, const smplpp_vposer_t * vposer, const smplpp_tasks_t * tasks,
+                       const smplpp_ik_options * opt, void * stream, int64_t batch, const float * theta_state_dev,
+                       const float * beta_dev, int64_t beta_stride, float * vertex_weights_dev, const float * target_pos_dev,
+                       const float * target_normal_dev, const float * pos_task_weight_dev, float * e_out_dev,
+                       float * jac_out_dev, void * workspace_dev, size_t workspace_bytes);
+
 /* The same step with PER-FRAME attachments: face_idx_dev (B, n) int32 holds IkTask::faceIdx_ of every (frame, task) as
  * re-seated by the projection of node/node.cpp:993-1001 (smplpp_ik_reproject); the 1-ring topology of every attachment is
  * gathered on the device.  dphi_out_dev (B, n, 2), nullable: the phi part of the step (node.cpp:955-958), which

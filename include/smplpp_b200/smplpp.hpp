@@ -719,6 +719,32 @@ public:
     batch_ = b, dim_ = dim;
     return status;
   }
+  /// The linearisation alone (smplpp_ik_jacobian): what the reference obtains with one Tensor::backward per residual row
+  /// (node.cpp:823-873), without the solve.  theta and beta are not modified; vertexWeights receives the re-weighting of
+  /// node.cpp:803-804; getError() / getJacobian() return the result.
+  void linearize(const SMPL & smpl, const VPoserDecoder * vposer, const smplpp_ik_options & opt, const Array & theta,
+                 const Array & beta, Array & vertexWeights, const Array & targetPos, const Array & posTaskWeight = Array())
+  {
+    const int64_t b = theta.shape.at(0);
+    const int32_t n = size();
+    const int32_t thetaDim = smplpp_ik_theta_dim(&opt), dim = smplpp_ik_dim(&opt, n);
+    if(theta.shape.size() != 2 || theta.shape[1] != thetaDim) throw Exception("IkTask Error: invalid IK step arguments!");
+    if(vertexWeights.data.size() != static_cast<size_t>(b * n * 3) || targetPos.data.size() != static_cast<size_t>(b * n * 3))
+      throw Exception("IkTask Error: invalid task tensors!");
+    const int64_t stride = (beta.shape.at(0) == 1 && b > 1) ? 0 : SHAPE_BASIS_DIM;
+    dTheta_.upload(theta), dBeta_.upload(beta), dVw_.upload(vertexWeights), dTgt_.upload(targetPos);
+    const bool havePw = !posTaskWeight.data.empty();
+    if(havePw) dPw_.upload(posTaskWeight);
+    dE_.reserve(static_cast<size_t>(b * 4 * n) * sizeof(float));
+    dJ_.reserve(static_cast<size_t>(b * 4 * n * dim) * sizeof(float));
+    const size_t ws = smplpp_ik_workspace_bytes(tasks_, &opt, b);
+    dWs_.reserve(ws + 256);
+    check(smplpp_ik_jacobian(smpl.handle(), vposer ? vposer->handle() : nullptr, tasks_, &opt, nullptr, b, dTheta_.as<float>(),
+                             dBeta_.as<float>(), stride, dVw_.as<float>(), dTgt_.as<float>(), nullptr,
+                             havePw ? dPw_.as<float>() : nullptr, dE_.as<float>(), dJ_.as<float>(), dWs_.as<void>(), ws + 256));
+    check(smplpp_copy_to_host(vertexWeights.ptr(), dVw_.as<float>(), vertexWeights.data.size() * sizeof(float), nullptr));
+    batch_ = b, dim_ = dim;
+  }
   /// e (B, 4n): rows 4m..4m+2 = posTaskWeight (actualPos - targetPos), row 4m+3 = the normal task (node.cpp:807-820)
   Array getError() const { return detail::download(dE_.as<float>(), {batch_, 4 * size()}); }
   /// J (B, 4n, dim) in the reference's column layout [theta | phi (2n) | beta] (node.cpp:787-877)

@@ -892,6 +892,37 @@ class IkTaskSet:
                                                 ids.ctypes.data_as(capi.c_i32p), C.c_int32(variant)))
         return rest, ids
 
+    def jacobian(self, opt: capi.IkOptions, theta_state: torch.Tensor, beta: torch.Tensor, vertex_weights: torch.Tensor,
+                 target_pos: torch.Tensor, pos_task_weight: Optional[torch.Tensor] = None,
+                 target_normal: Optional[torch.Tensor] = None, want_jacobian: bool = True):
+        """The linearisation of the IK step alone (smplpp_ik_jacobian; the reference runs one Tensor::backward per residual
+        row for this, node/node.cpp:823-873).  theta_state and beta are read only; vertex_weights receives the re-weighting
+        of node.cpp:803-804.  Returns e (B,4n) and J (B,4n,dim) (None unless want_jacobian) in the layout of step()."""
+        dev = self.smpl.m__device
+        for name, t in (("theta_state", theta_state), ("beta", beta), ("vertex_weights", vertex_weights),
+                        ("target_pos", target_pos)):
+            if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise SmplppError("IkTask Error: %s must be a contiguous float32 CUDA tensor" % name)
+        b = theta_state.shape[0]
+        theta_dim = int(lib().smplpp_ik_theta_dim(C.byref(opt)))
+        if theta_state.shape != (b, theta_dim):
+            raise SmplppError("IkTask Error: theta state must be (B, %d)" % theta_dim)
+        if vertex_weights.shape != (b, self.n, 3) or target_pos.shape != (b, self.n, 3):
+            raise SmplppError("IkTask Error: task tensors must be (B, %d, 3)" % self.n)
+        stride = 0 if beta.numel() == SHAPE_BASIS_DIM and b > 1 else SHAPE_BASIS_DIM
+        dim = int(lib().smplpp_ik_dim(C.byref(opt), C.c_int32(self.n)))
+        e = torch.empty((b, 4 * self.n), dtype=torch.float32, device=dev)
+        jac = torch.empty((b, 4 * self.n, dim), dtype=torch.float32, device=dev) if want_jacobian else None
+        vp = self.vposer.handle if (opt.enable_vposer and self.vposer is not None) else None
+        need = lib().smplpp_ik_workspace_bytes(self._h, C.byref(opt), C.c_int64(b))
+        ws = self._workspace(need)
+        with torch.cuda.device(dev):
+            check(lib().smplpp_ik_jacobian(
+                self.smpl.handle, vp, self._h, C.byref(opt), _stream(dev), C.c_int64(b), _ptr(theta_state), _ptr(beta),
+                C.c_int64(stride), _ptr(vertex_weights), _ptr(target_pos), _ptr(target_normal), _ptr(pos_task_weight),
+                _ptr(e), _ptr(jac), _ptr(ws), C.c_size_t(ws.numel())))
+        return e, jac
+
     def step(self, opt: capi.IkOptions, theta_state: torch.Tensor, beta: torch.Tensor, vertex_weights: torch.Tensor,
              target_pos: torch.Tensor, pos_task_weight: Optional[torch.Tensor] = None,
              target_normal: Optional[torch.Tensor] = None, outputs: bool = False,

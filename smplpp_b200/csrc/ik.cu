@@ -2305,9 +2305,9 @@ static int ik_step_impl(const smplpp_model_t * model, const smplpp_vposer_t * vp
                         int64_t beta_stride, float * vertex_weights, const int32_t * face_idx, const float * target_pos,
                         const float * target_normal, const float * pos_task_weight, int32_t * status, float * e_out,
                         float * jac_out, double * a_out, double * b_out, double * delta_out, float * dphi_out,
-                        void * workspace, size_t workspace_bytes)
+                        void * workspace, size_t workspace_bytes, bool jacobian_only = false)
 {
-  if(!model || !tasks || !opt || batch < 1 || !theta_state || !beta || !vertex_weights || !target_pos || !status)
+  if(!model || !tasks || !opt || batch < 1 || !theta_state || !beta || !vertex_weights || !target_pos || (!status && !jacobian_only))
     return fail(SMPLPP_ERR_INVALID, "IkTask", "invalid IK step arguments!");
   if(opt->enable_vposer && !vposer) return fail(SMPLPP_ERR_INVALID, "VPoser", "VPoser decoder is required!");
   if(opt->optimize_beta && beta_stride == 0 && batch > 1)
@@ -2320,7 +2320,7 @@ static int ik_step_impl(const smplpp_model_t * model, const smplpp_vposer_t * vp
   cudaStream_t st = as_stream(stream);
   char * ws = align_up_ptr<char>(workspace);
   const int n = L.n;
-  if(g_ik_variant == 2 || face_idx) // fused kernel: per-frame attachments always, shared ones when selected
+  if((g_ik_variant == 2 && !jacobian_only) || face_idx) // fused kernel: per-frame attachments always, shared ones when selected
   {
     TaskRec * recs = face_idx ? reinterpret_cast<TaskRec *>(ws + L.total) : nullptr;
     TaskSkin * skins = face_idx ? reinterpret_cast<TaskSkin *>(ws + L.total + rec_only) : nullptr;
@@ -2379,6 +2379,7 @@ static int ik_step_impl(const smplpp_model_t * model, const smplpp_vposer_t * vp
           jac_out + s * 4 * n * L.dim_ref);
       SB_LAUNCHED();
     }
+    if(jacobian_only) continue; // smplpp_ik_jacobian: the linearisation alone
     IkSolveParams sp = make_solve_params(opt, L, B, ws, false);
     sp.theta_state = th;
     sp.beta = be;
@@ -2411,6 +2412,19 @@ extern "C" int smplpp_ik_step(const smplpp_model_t * model, const smplpp_vposer_
   return ik_step_impl(model, vposer, tasks, opt, stream, batch, theta_state, beta, beta_stride, vertex_weights, nullptr,
                       target_pos, target_normal, pos_task_weight, status, e_out, jac_out, a_out, b_out, delta_out, nullptr,
                       workspace, workspace_bytes);
+}
+
+extern "C" int smplpp_ik_jacobian(const smplpp_model_t * model, const smplpp_vposer_t * vposer, const smplpp_tasks_t * tasks,
+                                  const smplpp_ik_options * opt, void * stream, int64_t batch, const float * theta_state,
+                                  const float * beta, int64_t beta_stride, float * vertex_weights, const float * target_pos,
+                                  const float * target_normal, const float * pos_task_weight, float * e_out, float * jac_out,
+                                  void * workspace, size_t workspace_bytes)
+{
+  if(!e_out && !jac_out) return fail(SMPLPP_ERR_INVALID, "IkTask", "invalid IK Jacobian arguments!");
+  // the state is only read on this path (no solve, no update)
+  return ik_step_impl(model, vposer, tasks, opt, stream, batch, const_cast<float *>(theta_state), const_cast<float *>(beta),
+                      beta_stride, vertex_weights, nullptr, target_pos, target_normal, pos_task_weight, nullptr, e_out, jac_out,
+                      nullptr, nullptr, nullptr, nullptr, workspace, workspace_bytes, true);
 }
 
 extern "C" size_t smplpp_ik_faces_workspace_bytes(const smplpp_tasks_t * tasks, const smplpp_ik_options * opt, int64_t batch)

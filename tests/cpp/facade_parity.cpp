@@ -170,6 +170,17 @@ int main(int argc, char ** argv)
       smplpp_ik_options opt = IkTaskSet::defaultOptions();
       opt.skip_if_too_few = 0;
       const Array tgt = arr("ik_motion_target.f32", {1, n, 3}), pw = arr("ik_motion_pos_task_weight.f32", {1, n});
+      {
+        // the getter alone (smplpp_ik_jacobian): same rows, state untouched
+        Array vwLin = vw;
+        const Array thBefore = th;
+        set.linearize(*smpl, nullptr, opt, th, be, vwLin, tgt, pw);
+        const Array Jlin = set.getJacobian(), JrefLin = arr("ik_motion_J.f32", {1, 4 * n, 75 + 2 * n});
+        double jm = 0;
+        for(float x : JrefLin.data) jm = std::fmax(jm, std::fabs(x));
+        expect("linearize: Jacobian vs reference autograd rows (relative)", max_abs(Jlin.ptr(), JrefLin.ptr(), Jlin.data.size()) / jm, 1e-4);
+        expect("linearize leaves theta unchanged", max_abs(th.ptr(), thBefore.ptr(), 75), 0.0);
+      }
       const std::vector<int32_t> status = set.step(*smpl, nullptr, opt, th, be, vw, tgt, pw);
       const std::vector<double> eRef = load<double>("ik_motion_e.f64");
       const Array e = set.getError();

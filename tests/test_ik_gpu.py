@@ -87,6 +87,35 @@ def ik_variant(request):
 
 
 @pytest.mark.parametrize("mode", list(MODES))
+def test_ik_jacobian_getter_vs_reference_golden(task_set, golden_ik, mode):
+    """smplpp_ik_jacobian (SURVEY 8b: the reference has no getter, callers harvest Tensor::backward rows,
+    node/node.cpp:823-873): e and J against the compiled reference's rows, state untouched, weights re-seated as by step."""
+    from smplpp_b200 import api
+    g = golden_ik
+    n = task_set.n
+    opt = api.ik_options(skip_if_too_few=0, **MODES[mode])
+    theta = cu(g["theta_in"].reshape(1, 75))
+    beta = cu(g["beta_in"].reshape(1, 10))
+    vw = cu(g["vertex_weights_in"].reshape(1, n, 3))
+    tgt = cu(g[mode + "_target"].reshape(1, n, 3))
+    pw = cu(g[mode + "_pos_task_weight"].reshape(1, n).astype(f32)) if (mode + "_pos_task_weight") in g else None
+    theta0, beta0 = theta.clone(), beta.clone()
+    e, J = task_set.jacobian(opt, theta, beta, vw, tgt, pos_task_weight=pw)
+    assert torch.equal(theta, theta0) and torch.equal(beta, beta0)
+    Jref = g[mode + "_J"]
+    assert np.abs(e[0].cpu().numpy() - g[mode + "_e"]).max() < (2e-5 if mode == "interactive" else TOL_VERTEX_M)
+    assert np.abs(J[0].cpu().numpy() - Jref).max() / np.abs(Jref).max() <= TOL_JACOBIAN_REL
+    assert np.abs(vw[0].cpu().numpy() - g[mode + "_vertex_weights_out"]).max() < 1e-4
+    # bitwise the rows the full step materialises
+    vw2 = cu(g["vertex_weights_in"].reshape(1, n, 3))
+    _, out = task_set.step(opt, theta.clone(), beta.clone(), vw2, tgt, pos_task_weight=pw, outputs=True)
+    assert torch.equal(out["e"], e) and torch.equal(out["J"], J)
+    e_only, none = task_set.jacobian(opt, theta, beta, cu(g["vertex_weights_in"].reshape(1, n, 3)), tgt, pos_task_weight=pw,
+                                     want_jacobian=False)
+    assert none is None and torch.equal(e_only, e)
+
+
+@pytest.mark.parametrize("mode", list(MODES))
 def test_ik_step_vs_reference_golden(task_set, golden_ik, mode, ik_variant):
     from smplpp_b200 import api
     g = golden_ik
