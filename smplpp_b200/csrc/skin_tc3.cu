@@ -12,8 +12,8 @@
 // back to back with the tensor pipe idle for two thirds of the time:
 //   * one persistent CTA per SM walks a contiguous range of (vertex tile, frame block) work items;
 //   * when GEMM 1 of an item completes, the sixteen epilogue warps DRAIN its 288 accumulator columns into registers
-//     (72 per thread, pre-scaled by 1 / sum_j W), which frees the TMEM columns: the MMA thread then interleaves the
-//     126 MMAs of the NEXT item's GEMM 1 with the 12 sub-batches of this item's GEMM 2 (3-4 MMA triples per sub-batch);
+//     (72 per thread, pre-scaled by 1 / sum_j W), which frees the TMEM columns: one thread then issues the 126 MMAs of
+//     the NEXT item's GEMM 1 while another issues the 12 sub-batches of this item's GEMM 2;
 //   * two TMA producer threads, one per ring (2 x 60 KB GEMM 1 stages, 6 x 12 KB transform sub-batches), so neither
 //     ring can starve the other;
 //   * the frames of a 96-frame block are permuted in the fp16 coefficient operand so that the 24 frames an epilogue
@@ -25,9 +25,9 @@
 //
 // TMEM (512 columns): [0,288) rest accumulators (x | y | z planes x 96 frames), [288,480) two 96-column buffers of
 // skinning matrices (8 frames x 12), [480,512) the W tile (A operand of GEMM 2, fp16 hi | lo).
-// warp 0: TMA producer of the GEMM 1 stages | warp 1: TMEM allocator + MMA issuer | warp 2: TMA producer of the transform
-// sub-batches | warp 3: idle (the first warpgroup hands its registers back with setmaxnreg) | warps 4-19: epilogue, 112 registers each (four per TMEM lane quadrant, one
-// per frame pair of an 8-frame sub-batch).
+// warp 0: TMA producer of the GEMM 1 stages | warp 1: TMEM allocator + issuer of GEMM 2 | warp 2: TMA producer of the transform
+// sub-batches | warp 3: issuer of GEMM 1 (the first warpgroup hands its registers back with setmaxnreg) | warps 4-19: epilogue,
+// 112 registers each (four per TMEM lane quadrant, one per frame pair of an 8-frame sub-batch).
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -57,7 +57,7 @@ struct Params
   const float * theta;          // (B, 25, 3): row 0 = root translation
   float * out;                  // (B, V, 3)
   long long * dbg;              // optional per-CTA timestamps (SMPLPP_TC3_DBG)
-  int dbg_mode;                 // DBG build only (SMPLPP_TC3_DBG = bit mask): 1 no matrix tcgen05.ld, 2 no stores, 4 no GEMM 2 MMAs, 8 no GEMM 1 MMAs, 16 no drain loads (results are wrong: timing decomposition)
+  int dbg_mode;                 // DBG build only (SMPLPP_TC3_DBG = bit mask): 1 no matrix tcgen05.ld, 2 no stores, 4 no GEMM 2 MMAs, 8 no GEMM 1 MMAs, 16 no drain loads, 32 no stage ring, 64 no transform ring, 128 no epilogue arithmetic, 256 no matrix-buffer hand-off, 512 no drain hand-off (results are wrong: timing decomposition)
 };
 
 } // namespace tc3
@@ -197,6 +197,7 @@ __global__ void __launch_bounds__(tc3::THREADS, 1)
   long long * dbg = (DBG && p.dbg) ? p.dbg + static_cast<size_t>(blockIdx.x) * 256 : nullptr;
   // DBG build: cycles the MMA thread / one epilogue warp spend blocked in each kind of wait (SMPLPP_TC3_DBG)
   long long w_stage = 0, w_gfull = 0, w_mempty = 0, w_rest = 0, w_pfull = 0, w_mfull = 0;
+#define TC3_OFF(bit) (DBG && (p.dbg_mode & (bit)))
 #define TC3_TIMED(acc, stmt) do { if constexpr(DBG) { const long long t_ = clock64(); stmt; acc += clock64() - t_; } else { stmt; } } while(0)
 
   if(warp < CTRL_WARPS)
@@ -210,19 +211,27 @@ __global__ void __launch_bounds__(tc3::THREADS, 1)
     // producer thread with plain blocking waits.  A single polling producer over both rings performed the same.)
     if(ptx::elect_one())
     {
-      const int total_kb = nit * NKB;
+      const int total_kb = TC3_OFF(32) ? 0 : nit * NKB;
       // (An L2 prefetch of all seven K-blocks of the first item at kernel start was measured: no gain.)
+      // The reload of a stage is on the critical path of the GEMM 1 issuer (a quarter of its samples are stage waits):
+      // source addresses (two integer divisions) are ready BEFORE the wait, barriers and stages are 32-bit shared addresses.
+      int kb = 0, tile = it0 / p.nfb, fb = it0 % p.nfb;
       for(int kbn = 0; kbn < total_kb; kbn++)
       {
-        const int item = it0 + kbn / NKB, kb = kbn % NKB, s = kbn % STAGES;
-        const int tile = item / p.nfb, fb = item % p.nfb;
-        ptx::mbar_wait(&empty[s], ((kbn / STAGES) & 1) ^ 1);
-        ptx::mbar_expect_tx(&full[s], STAGE);
-        uint8_t * dst = smem + s * STAGE;
+        const uint32_t s = static_cast<uint32_t>(kbn % STAGES);
         const uint8_t * srca = p.img_a + (static_cast<size_t>(tile) * NKB + kb) * (2 * A_PART);
-        ptx::bulk_load_1d(dst, srca, 2 * A_PART, &full[s]);
-        ptx::bulk_load_1d(dst + 2 * A_PART, p.img_b + (static_cast<size_t>(fb) * NKB + kb) * (2 * B_PART), 2 * B_PART, &full[s]);
+        const uint8_t * srcb = p.img_b + (static_cast<size_t>(fb) * NKB + kb) * (2 * B_PART);
+        const uint32_t dst = smem32 + s * STAGE, fbar = bar32 + 8 * s;
+        ptx::mbar_wait_a(bar32 + 8 * (STAGES + s), ((kbn / STAGES) & 1) ^ 1);
+        ptx::mbar_expect_tx_a(fbar, STAGE);
+        ptx::bulk_load_1d_a(dst, srca, 2 * A_PART, fbar);
+        ptx::bulk_load_1d_a(dst + 2 * A_PART, srcb, 2 * B_PART, fbar);
         if(dbg && kbn < 14) dbg[34 + kbn] = clock64();
+        if(++kb == NKB)
+        {
+          kb = 0;
+          if(++fb == p.nfb) fb = 0, tile++;
+        }
       }
     }
   }
@@ -231,33 +240,40 @@ __global__ void __launch_bounds__(tc3::THREADS, 1)
     // ---- producer of the transform sub-batch ring ----
     if(ptx::elect_one())
     {
-      const int total_g = nit * NSUB;
+      const int total_g = TC3_OFF(64) ? 0 : nit * NSUB;
+      int sb = 0, fb = it0 % p.nfb;
       for(int gn = 0; gn < total_g; gn++)
       {
-        const int item = it0 + gn / NSUB, sb = gn % NSUB, s = gn % GSLOTS;
-        ptx::mbar_wait(&g_empty[s], ((gn / GSLOTS) & 1) ^ 1);
-        ptx::mbar_expect_tx(&g_full[s], G_STAGE);
-        ptx::bulk_load_1d(smem + OFF_G + s * G_STAGE, p.img_g + (static_cast<size_t>(item % p.nfb) * NSUB + sb) * G_STAGE, G_STAGE,
-                          &g_full[s]);
+        const uint32_t s = static_cast<uint32_t>(gn % GSLOTS);
+        const uint8_t * src = p.img_g + (static_cast<size_t>(fb) * NSUB + sb) * G_STAGE;
+        const uint32_t fbar = bar32 + 8 * (2 * STAGES + s);
+        ptx::mbar_wait_a(bar32 + 8 * (2 * STAGES + GSLOTS + s), ((gn / GSLOTS) & 1) ^ 1);
+        ptx::mbar_expect_tx_a(fbar, G_STAGE);
+        ptx::bulk_load_1d_a(smem32 + OFF_G + s * G_STAGE, src, G_STAGE, fbar);
+        if(++sb == NSUB)
+        {
+          sb = 0;
+          if(++fb == p.nfb) fb = 0;
+        }
       }
     }
   }
-  else if(warp == 1)
+  else if(warp == 1 || warp == 3)
   {
     if(ptx::elect_one())
     {
       constexpr uint32_t idesc1 = ptx::make_idesc_f16(MV, NF);
       constexpr uint32_t idesc2 = ptx::make_idesc_f16(MV, SUBN);
-      // Single-thread issue: every instruction between two tcgen05.mma is on the critical path.  ncu's source page of the
-      // previous version (r02h) had this thread at 1800 instructions per item for 198 MMAs (a run-time sub-batch loop:
-      // ring slots and parities through divisions, a cvta sequence per barrier) and blocked on a full tensor queue in only
-      // a quarter of its samples: the tensor pipe starved behind the issue loop.  Now the twelve sub-batches of an item are
-      // unrolled, so that ring slots, parities, the half K-block that rides along and its operand offsets are compile-time
-      // constants; only the stage of a K-block (ring position over all items) and the item parity are run-time values,
-      // and barriers are 32-bit shared addresses.  Descriptor = constant high word | (shared address >> 4).
+      // Every instruction between two tcgen05.mma is on the critical path of its issuing thread.  ncu's source page of the
+      // single-issuer version (r02h) had that thread at 1800 instructions per item for 198 MMAs and blocked on a full
+      // tensor queue in only a quarter of its samples: the tensor pipe starved behind the issue loop.  Hence (a) TWO
+      // issuing threads - warp 3 the 126 GEMM 1 MMAs of the next item, warp 1 the 72 GEMM 2 MMAs of this one; the tensor
+      // queue interleaves them (0.1725 -> 0.1607 ms per launch) - and (b) lean streams: the sub-batches and half K-blocks
+      // are unrolled, so that ring slots, parities and operand offsets are compile-time constants; only the stage of a
+      // K-block (ring position over all items) and the item parity are run-time values, and barriers are 32-bit shared
+      // addresses.  Descriptor = constant high word | (shared address >> 4).
       static_assert(NSUB % GSLOTS == 0 && ((NSUB / GSLOTS) & 1) == 0, "transform ring: slot and parity of a sub-batch do not depend on the item");
       static_assert((NSUB & 3) == 0, "matrix buffers: parity of a sub-batch does not depend on the item");
-      static_assert(NSUB + 2 == 2 * NKB, "GEMM 1 schedule: one half K-block per sub-batch, two behind sub-batches 0 and NSUB / 2");
       constexpr uint32_t DHI = ptx::smem_desc_hi<ROWB>();
       const uint32_t smem16 = smem32 >> 4;
       const uint32_t a_full = bar32; // one base register, every other barrier at a compile-time offset
@@ -288,7 +304,7 @@ __global__ void __launch_bounds__(tc3::THREADS, 1)
         const uint32_t st16 = smem16 + s * (STAGE >> 4);
         if((h & 1) == 0)
         {
-          TC3_TIMED(w_stage, ptx::mbar_wait_a(a_full + 8 * s, (kbn / STAGES) & 1));
+          if(!TC3_OFF(32)) TC3_TIMED(w_stage, ptx::mbar_wait_a(a_full + 8 * s, (kbn / STAGES) & 1));
           ptx::tc_fence_after();
           if(dbg && kbn < 14) dbg[48 + kbn] = clock64();
 #pragma unroll
@@ -300,19 +316,34 @@ __global__ void __launch_bounds__(tc3::THREADS, 1)
 #pragma unroll
           for(int i = 0; i < 9; i++)
             if(!DBG || !(p.dbg_mode & 8)) g1_mma(st16, 1, i, 1u);
-          ptx::tc_commit_a(a_empty + 8 * s);
+          if(!TC3_OFF(32)) ptx::tc_commit_a(a_empty + 8 * s);
         }
       };
       if(dbg) dbg[0] = clock64();
-      if(nit > 0)
+      if(nit > 0 && warp == 3)
       {
 #pragma unroll
         for(int h = 0; h < 2 * NKB; h++) g1_half(h, 0);
-        ptx::tc_commit_a(a_pfull);
+        if(!TC3_OFF(512)) ptx::tc_commit_a(a_pfull);
       }
       if(dbg) dbg[1] = clock64();
+      if(warp == 3)
+      {
+        // ---- GEMM 1 issuer: the 126 MMAs of item k + 1 as soon as item k's accumulators have been drained into the epilogue
+        //      warps' registers; the stage ring and the tensor queue pace it ----
+        for(int k = 0; k + 1 < nit; k++)
+        {
+          if(!TC3_OFF(512)) TC3_TIMED(w_rest, ptx::mbar_wait_a(a_rest, k & 1));
+          ptx::tc_fence_after();
+#pragma unroll
+          for(int h = 0; h < 2 * NKB; h++) g1_half(h, (k + 1) * NKB);
+          if(!TC3_OFF(512)) ptx::tc_commit_a(a_pfull);
+        }
+        if(dbg) dbg[64] = w_stage, dbg[67] = w_rest, dbg[69] = clock64();
+      }
+      // ---- GEMM 2 issuer (warp 1): the twelve sub-batches of every item, two matrix buffers ----
       int wcount = 0, prev_tile = -1;
-      for(int k = 0; k < nit; k++)
+      for(int k = 0; k < (warp == 3 ? 0 : nit); k++)
       {
         const int tile = (it0 + k) / p.nfb;
         if(tile != prev_tile)
@@ -322,45 +353,25 @@ __global__ void __launch_bounds__(tc3::THREADS, 1)
           wcount++;
           prev_tile = tile;
         }
-        const bool more = k + 1 < nit;
-        const int kbn_next = (k + 1) * NKB;
         const uint32_t aw = tmem_base + COL_W;
 #pragma unroll
         for(int sb = 0; sb < NSUB; sb++)
         {
           const int b = sb & 1, gs = sb % GSLOTS;
-          TC3_TIMED(w_gfull, ptx::mbar_wait_a(a_gfull + 8 * gs, (sb / GSLOTS) & 1));
-          TC3_TIMED(w_mempty, ptx::mbar_wait_a(a_mempty + 8 * b, ((sb >> 1) & 1) ^ 1));
+          if(!TC3_OFF(64)) TC3_TIMED(w_gfull, ptx::mbar_wait_a(a_gfull + 8 * gs, (sb / GSLOTS) & 1));
+          if(!TC3_OFF(256)) TC3_TIMED(w_mempty, ptx::mbar_wait_a(a_mempty + 8 * b, ((sb >> 1) & 1) ^ 1));
           ptx::tc_fence_after();
           const uint32_t sg16 = smem16 + ((OFF_G + gs * G_STAGE) >> 4);
           const uint32_t dm = tmem_base + COL_M + b * SUBN;
 #pragma unroll
           for(int j = 0; j < 6; j++)
             if(!DBG || !(p.dbg_mode & 4)) g2_mma(dm, aw, sg16, j);
-          ptx::tc_commit_a(a_mfull + 8 * b);
-          ptx::tc_commit_a(a_gempty + 8 * gs);
-          if(more)
-          {
-            // 14 half K-blocks of the next item's GEMM 1 over the 12 sub-batches: two behind sub-batches 0 and 6, one
-            // behind every other.  (Starting in sub-batch 1, so that two GEMM 2 are queued while the epilogue warps drain
-            // the rest accumulators, measured the same: 0.1720 / 0.1722 ms against 0.1721.)
-            const int nh = (sb == 0 || sb == NSUB / 2) ? 2 : 1, h0 = sb + (sb > 0 ? 1 : 0) + (sb > NSUB / 2 ? 1 : 0);
-            if(h0 == 0)
-            {
-              TC3_TIMED(w_rest, ptx::mbar_wait_a(a_rest, k & 1)); // item k's accumulators now live in the epilogue warps' registers
-              ptx::tc_fence_after();
-            }
-            // 14 half K-blocks of the next item's GEMM 1 over the 12 sub-batches.  (Interleaving the 9 MMAs of a half
-            // with the 6 GEMM 2 MMAs, to avoid chaining on one accumulator, was measured and is SLOWER: 23 k instead of
-            // 17.5 k cycles per item - alternating between the shared-memory-A and TMEM-A forms costs more than the chain.)
-            g1_half(h0, kbn_next);
-            if(nh > 1) g1_half(h0 + 1, kbn_next);
-          }
+          if(!TC3_OFF(256)) ptx::tc_commit_a(a_mfull + 8 * b);
+          if(!TC3_OFF(64)) ptx::tc_commit_a(a_gempty + 8 * gs);
         }
-        if(more) ptx::tc_commit_a(a_pfull);
         if(dbg && k < 30) dbg[2 + k] = clock64();
       }
-      if(dbg) dbg[64] = w_stage, dbg[65] = w_gfull, dbg[66] = w_mempty, dbg[67] = w_rest, dbg[68] = clock64();
+      if(dbg && warp == 1) dbg[65] = w_gfull, dbg[66] = w_mempty, dbg[68] = clock64();
     }
   }
   }
@@ -419,7 +430,7 @@ __global__ void __launch_bounds__(tc3::THREADS, 1)
       }
       // ---- drain the rest accumulators of this item: 24 frames x (x, y, z), pre-multiplied by scale / sum w ----
       float R[3][FR_WARP];
-      TC3_TIMED(w_pfull, ptx::mbar_wait_a(a_pfull, k & 1));
+      if(!TC3_OFF(512)) TC3_TIMED(w_pfull, ptx::mbar_wait_a(a_pfull, k & 1));
       ptx::tc_fence_after();
 #pragma unroll
       for(int c = 0; c < 3; c++)
@@ -436,7 +447,7 @@ __global__ void __launch_bounds__(tc3::THREADS, 1)
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       __syncwarp();
-      if(lane == 0) ptx::mbar_arrive_a(a_rest);
+      if(lane == 0 && !TC3_OFF(512)) ptx::mbar_arrive_a(a_rest);
       {
         const float s = sp * sm;
 #pragma unroll
@@ -462,7 +473,7 @@ __global__ void __launch_bounds__(tc3::THREADS, 1)
           tr[t][1] = __shfl_sync(0xffffffffu, try_, sb * EPI_FR + t);
           tr[t][2] = __shfl_sync(0xffffffffu, trz, sb * EPI_FR + t);
         }
-        TC3_TIMED(w_mfull, ptx::mbar_wait_a(a_mfull + 8 * h, (sb >> 1) & 1)); // 6 ring rounds per item: the parity does not depend on the item
+        if(!TC3_OFF(256)) TC3_TIMED(w_mfull, ptx::mbar_wait_a(a_mfull + 8 * h, (sb >> 1) & 1)); // 6 ring rounds per item: the parity does not depend on the item
         ptx::tc_fence_after();
         float M[EPI_FR * kXformFloats];
         const uint32_t mcol = lane_taddr + COL_M + h * SUBN + fp * (EPI_FR * kXformFloats);
@@ -479,7 +490,8 @@ __global__ void __launch_bounds__(tc3::THREADS, 1)
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         __syncwarp();
-        if(lane == 0) ptx::mbar_arrive_a(a_mempty + 8 * h); // the MMA warp may overwrite this matrix buffer
+        if(lane == 0 && !TC3_OFF(256)) ptx::mbar_arrive_a(a_mempty + 8 * h); // the MMA warp may overwrite this matrix buffer
+        if(TC3_OFF(128)) continue;
 #pragma unroll
         for(int t = 0; t < EPI_FR; t++)
         {
@@ -533,6 +545,7 @@ __global__ void __launch_bounds__(tc3::THREADS, 1)
     }
   }
 #undef TC3_TIMED
+#undef TC3_OFF
   ptx::tc_fence_before();
   __syncthreads();
   if(warp == 1) ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
@@ -648,8 +661,8 @@ int launch_blend_skin_tc3(const ModelDev & d, cudaStream_t st, int B, const floa
       for(int i = 0; i < 14; i++) fprintf(stderr, " %lld", t[34 + i] - t[0]);
       fprintf(stderr, "\n   stage seen full by the MMA thread:  ");
       for(int i = 0; i < 14; i++) fprintf(stderr, " %lld", t[48 + i] - t[0]);
-      fprintf(stderr, "\n   MMA thread: total %lld cycles, blocked on stage %lld, transforms %lld, matrix buffer %lld, drain %lld | epilogue warp 0 / 15 blocked on rest accumulators %lld / %lld, on matrices %lld / %lld\n",
-              t[68] - t[0], t[64], t[65], t[66], t[67], t[70], t[72], t[71], t[73]);
+      fprintf(stderr, "\n   GEMM 1 issuer: total %lld cycles, blocked on stage %lld, drain %lld | GEMM 2 issuer: total %lld, blocked on transforms %lld, matrix buffer %lld | epilogue warp 0 / 15 blocked on rest accumulators %lld / %lld, on matrices %lld / %lld\n",
+              t[69] - t[0], t[64], t[67], t[68] - t[0], t[65], t[66], t[70], t[72], t[71], t[73]);
     }
   }
   return SMPLPP_OK;
