@@ -287,7 +287,7 @@ def run_config4(dev, rank, world, max_over_ranks, barrier, frames_total: int = 1
 
 
 def kernel_names():
-    return ("ik_jacobian_kernel", "ik_poseblend_tc_kernel", "ik_solve_mma_kernel")
+    return ("ik_restshape_tc_kernel", "ik_jacobian_kernel", "ik_poseblend_tc_kernel", "ik_solve_mma_kernel")
 
 
 def cpu_reference_ik(frames: int = 2, iters: int = 2):
