@@ -205,12 +205,8 @@ __global__ void __launch_bounds__(TC ? c1::THREADS_TC : c1::THREADS, 2) ik_jacob
   // compact list of the (task, joint) pairs whose joint moves the task (P5b), 2-byte aligned after s_sj
   uint16_t * s_act = reinterpret_cast<uint16_t *>(s_sj + ((p.nUse * t.kmax + 1) & ~1));
   __shared__ int s_valid, s_bad, s_nact;
-  // ancestor masks in shared memory: P5b indexes them per lane (a per-lane index into the constant bank is replayed once per
-  // distinct joint of the warp; the line was 7 % of the kernel's stall samples)
-  __shared__ uint32_t s_anc[kJoints];
 
   if(tid == 0) s_valid = 0, s_bad = 0, s_nact = 0;
-  if(tid < kJoints) s_anc[tid] = p.anc_mask[tid];
   for(int i = tid; i < 75; i += THREADS) s_theta[i] = p.theta[static_cast<size_t>(f) * 75 + i];
   if(tid < kShapeDim) s_beta[tid] = p.beta[static_cast<size_t>(f) * p.beta_stride + tid];
   {
@@ -627,7 +623,7 @@ __global__ void __launch_bounds__(TC ? c1::THREADS_TC : c1::THREADS, 2) ik_jacob
         {
           const int i = u * t.kmax + sl;
           const float wj = s_sw[i];
-          if(wj != 0.f && ((s_anc[s_sj[i]] >> k) & 1u)) y = y + (ld3(s_xw + 3 * i) - wj * tgk);
+          if(wj != 0.f && ((p.anc_mask[s_sj[i]] >> k) & 1u)) y = y + (ld3(s_xw + 3 * i) - wj * tgk);
         }
         const float * C = s_C4 + 12 * (p0 + q);
 #pragma unroll
