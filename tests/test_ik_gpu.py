@@ -175,6 +175,30 @@ def test_ik_step_vposer_vs_reference_golden(task_set, golden_ik, ik_variant):
     assert np.abs(theta[0].cpu().numpy() - g["vposer_theta_out"]).max() < 5e-4
 
 
+def test_ik_jacobian_getter_vposer_and_batch(task_set, golden_ik):
+    """smplpp_ik_jacobian in VPoser mode (latent columns through the decoder Jacobian) against the compiled reference's
+    rows, and on a batch of identical frames: every frame bitwise equal to the single-frame call."""
+    from smplpp_b200 import api
+    g = golden_ik
+    n = task_set.n
+    opt = api.ik_options(skip_if_too_few=0, enable_vposer=1, **MODES["motion"])
+    theta = cu(g["vposer_theta_in"].reshape(1, 44))
+    beta = cu(g["beta_in"].reshape(1, 10))
+    vw = cu(g["vertex_weights_in"].reshape(1, n, 3))
+    tgt = cu(g["target_pos"].reshape(1, n, 3))
+    e, J = task_set.jacobian(opt, theta, beta, vw, tgt)
+    Jref = g["vposer_J"]
+    assert np.abs(e[0].cpu().numpy() - g["vposer_e"]).max() < 5e-5
+    assert np.abs(J[0].cpu().numpy() - Jref).max() / np.abs(Jref).max() <= 2 * TOL_JACOBIAN_REL
+    B = 37
+    thB = theta.repeat(B, 1).contiguous()
+    vwB = cu(np.repeat(g["vertex_weights_in"].reshape(1, n, 3), B, axis=0))
+    tgB = tgt.repeat(B, 1, 1).contiguous()
+    eB, JB = task_set.jacobian(opt, thB, beta.repeat(B, 1).contiguous(), vwB, tgB)
+    assert torch.equal(eB, e.expand(B, -1)) and torch.equal(JB, J.expand(B, -1, -1))
+    assert torch.equal(vwB, vw.expand(B, -1, -1))
+
+
 def test_ik_converges_like_oracle(task_set, oracle_model, marker_tasks, smpl_gpu):
     """Run K iterations of the motion-mode step on 3 frames and compare the marker residual trajectory with the
     oracle's (converged residual within 1e-4 m)."""
